@@ -1,0 +1,107 @@
+// Shared helpers for libchap_b200 (sm_100a).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/chap_b200.h"
+
+namespace chap {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_force_simt;
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// call after every kernel launch: counts it and converts launch errors (capture safe)
+inline int launched(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CHAP_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return CHAP_OK;
+}
+
+#define CHAP_REQUIRE(cond, code, ...) \
+    do { if (!(cond)) return ::chap::fail(code, __VA_ARGS__); } while (0)
+#define CHAP_CUDA(call) \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+        return ::chap::fail(CHAP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+#define CHAP_TRY(call) do { int rc_ = (call); if (rc_ != CHAP_OK) return rc_; } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;   // B200
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
+    int64_t b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming 128-bit load (read once) / store
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+struct Geom {           // resolved convolution geometry (D = 1 for 2D)
+    int kind, nd, n;
+    int iD, iH, iW, oD, oH, oW;
+    int cin, cout;
+    int taps;           // 3^nd, 1, 2^nd, 2^nd
+    int64_t in_rows, out_rows;   // N * spatial
+};
+
+inline int resolve(const chap_conv_desc* d, Geom& g) {
+    CHAP_REQUIRE(d != nullptr, CHAP_ERR_BAD_ARG, "conv desc is NULL");
+    CHAP_REQUIRE(d->nd == 2 || d->nd == 3, CHAP_ERR_BAD_ARG, "conv nd must be 2 or 3 (got %d)", d->nd);
+    CHAP_REQUIRE(d->n > 0 && d->in_h > 0 && d->in_w > 0 && d->in_d > 0 && d->cin > 0 && d->cout > 0,
+                 CHAP_ERR_BAD_ARG, "conv desc has a non-positive size");
+    CHAP_REQUIRE(d->nd == 3 || d->in_d == 1, CHAP_ERR_BAD_ARG, "2D conv needs in_d == 1");
+    g.kind = d->kind; g.nd = d->nd; g.n = d->n;
+    g.iD = d->in_d; g.iH = d->in_h; g.iW = d->in_w;
+    g.cin = d->cin; g.cout = d->cout;
+    const int p2 = d->nd == 2 ? 4 : 8, p3 = d->nd == 2 ? 9 : 27;
+    switch (d->kind) {
+        case CHAP_CONV_K3: g.oD = g.iD; g.oH = g.iH; g.oW = g.iW; g.taps = p3; break;
+        case CHAP_CONV_K1: g.oD = g.iD; g.oH = g.iH; g.oW = g.iW; g.taps = 1; break;
+        case CHAP_CONV_DOWN2:
+            CHAP_REQUIRE(g.iH % 2 == 0 && g.iW % 2 == 0 && (d->nd == 2 || g.iD % 2 == 0), CHAP_ERR_BAD_ARG,
+                         "k2s2 conv needs even input size");
+            g.oD = d->nd == 3 ? g.iD / 2 : 1; g.oH = g.iH / 2; g.oW = g.iW / 2; g.taps = p2; break;
+        case CHAP_CONV_UP2:
+            g.oD = d->nd == 3 ? g.iD * 2 : 1; g.oH = g.iH * 2; g.oW = g.iW * 2; g.taps = p2; break;
+        default: return fail(CHAP_ERR_BAD_ARG, "unknown conv kind %d", d->kind);
+    }
+    g.in_rows = (int64_t)g.n * g.iD * g.iH * g.iW;
+    g.out_rows = (int64_t)g.n * g.oD * g.oH * g.oW;
+    return CHAP_OK;
+}
+
+}  // namespace chap

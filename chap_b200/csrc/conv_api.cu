@@ -1,0 +1,80 @@
+// extern "C" convolution entry points: shape validation + dispatch (tcgen05 path / CUDA-core path).
+#include "common.cuh"
+#include "conv_plan.cuh"
+
+using namespace chap;
+
+static bool use_tc(const Geom& g, bool dgrad) {
+    return g_force_simt.load() == 0 && tc_supports(g, dgrad);
+}
+
+extern "C" size_t chap_conv_packed_elems(const chap_conv_desc* d) {
+    Geom g{};
+    if (resolve(d, g) != CHAP_OK) return 0;
+    return (size_t)g.taps * g.cin * g.cout;
+}
+
+extern "C" int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(w != nullptr, CHAP_ERR_BAD_ARG, "pack_weights: w is NULL");
+    if (w_fwd) {
+        PackSpec p = fwd_pack(g);
+        CHAP_TRY(launch_pack(w, w_fwd, p.taps, p.K, p.N, p.sk, p.sn, p.flip, use_tc(g, false) ? 0 : 1, S(stream)));
+    }
+    if (w_dgrad) {
+        PackSpec p = dgrad_pack(g);
+        CHAP_TRY(launch_pack(w, w_dgrad, p.taps, p.K, p.N, p.sk, p.sn, p.flip, use_tc(g, true) ? 0 : 1, S(stream)));
+    }
+    return CHAP_OK;
+}
+
+extern "C" int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
+                             float* y, double* ch_sums, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(x && w_fwd && y, CHAP_ERR_BAD_ARG, "conv_fwd: NULL pointer");
+    if (use_tc(g, false)) {
+        int rc = tc_conv(g, false, x, w_fwd, bias, y, ch_sums, S(stream));
+        if (rc < 0) return rc;
+        if (rc == 1) return CHAP_OK;
+    }
+    CHAP_TRY(simt_conv(fwd_op(g), x, w_fwd, bias, y, S(stream)));
+    if (ch_sums) CHAP_TRY(channel_stats(y, g.out_rows, g.cout, ch_sums, S(stream)));
+    return CHAP_OK;
+}
+
+extern "C" int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(dy && w_dgrad && dx, CHAP_ERR_BAD_ARG, "conv_dgrad: NULL pointer");
+    if (use_tc(g, true)) {
+        int rc = tc_conv(g, true, dy, w_dgrad, nullptr, dx, nullptr, S(stream));
+        if (rc < 0) return rc;
+        if (rc == 1) return CHAP_OK;
+    }
+    return simt_conv(dgrad_op(g), dy, w_dgrad, nullptr, dx, S(stream));
+}
+
+extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
+    Geom g{};
+    if (resolve(d, g) != CHAP_OK) return 0;
+    return (size_t)2 * g.cout * sizeof(double);
+}
+
+extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(x && dy && dw, CHAP_ERR_BAD_ARG, "conv_wgrad: NULL pointer");
+    SimtOp op = fwd_op(g);
+    PackSpec p = fwd_pack(g);          // dw has the torch layout: same strides as reading w
+    CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream)));
+    if (dbias) {
+        CHAP_REQUIRE(workspace && workspace_bytes >= (size_t)2 * g.cout * sizeof(double), CHAP_ERR_WORKSPACE,
+                     "conv_wgrad: workspace too small (%zu bytes)", workspace_bytes);
+        CHAP_TRY(channel_stats(dy, g.out_rows, g.cout, (double*)workspace, S(stream)));
+        CHAP_TRY(sums_to_float((const double*)workspace, dbias, g.cout, S(stream)));
+    }
+    return CHAP_OK;
+}

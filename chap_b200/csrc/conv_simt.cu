@@ -1,0 +1,257 @@
+// CUDA-core (fp32 FMA) convolution kernels: the permanent path for the layers that cannot
+// feed a tensor-core tile (Cin = 1 stems: K = 9/27; Cout = 4/2 heads) and the debug path
+// (chap_set_force_simt) for every other layer.  All four conv kinds of chap_b200.h are expressed
+// as one of two generic forms over channels-last rows:
+//   gather : out[m, n] = sum_t sum_k in[src(m, t), k] * Wp[t][k][n]      (K3, K1, DOWN2 and their
+//            stride-1 data gradients; dgrad of UP2)
+//   up2    : out[dst(p, t), n] = sum_k in[p, k] * Wp[t][k][n]            (UP2; dgrad of DOWN2)
+// Wp is the packed weight [tap][K][N] (N contiguous) produced by pack_weights_kernel.
+#include "common.cuh"
+#include "conv_plan.cuh"
+
+namespace chap {
+
+__device__ __forceinline__ void decode_row(int64_t m, int D, int H, int W, int& n, int& d, int& h, int& w) {
+    w = (int)(m % W); m /= W;
+    h = (int)(m % H); m /= H;
+    d = (int)(m % D); n = (int)(m / D);
+}
+
+// ---------------------------------------------------------------- weight packing
+// out[t][k][n] (kn_order = 1) or out[t][n][k] (kn_order = 0) = w[k*sk + n*sn + tmap(t)]
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out,
+                                    int taps, int K, int N, int64_t sk, int64_t sn, int flip, int kn_order) {
+    int64_t total = (int64_t)taps * K * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i / ((int64_t)K * N));
+        int r = (int)(i % ((int64_t)K * N));
+        int k, n;
+        if (kn_order) { k = r / N; n = r % N; } else { n = r / K; k = r % K; }
+        int ts = flip ? (taps - 1 - t) : t;
+        out[i] = w[k * sk + n * sn + ts];
+    }
+}
+
+int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, int64_t sn, int flip,
+                int kn_order, cudaStream_t st) {
+    int64_t total = (int64_t)taps * K * N;
+    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, sk, sn, flip, kn_order);
+    return launched("pack_weights_kernel");
+}
+
+// ---------------------------------------------------------------- gather conv
+template <int CO_T, bool VEC4>
+__global__ void __launch_bounds__(128)
+conv_gather_kernel(SimtOp op, const float* __restrict__ in, const float* __restrict__ wp,
+                   const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ float ws[];                  // [K][CO_T]
+    const int n0 = blockIdx.y * CO_T;
+    const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool live = m < op.out_rows;
+    int bn = 0, od = 0, oh = 0, ow = 0;
+    if (live) decode_row(m, op.oD, op.oH, op.oW, bn, od, oh, ow);
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+
+    const int kd_n = op.nd == 3 ? op.ksz : 1;
+    int t = 0;
+    for (int kz = 0; kz < kd_n; ++kz)
+        for (int ky = 0; ky < op.ksz; ++ky)
+            for (int kx = 0; kx < op.ksz; ++kx, ++t) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < op.K * CO_T; i += 128) {
+                    int k = i / CO_T, j = i % CO_T;
+                    ws[i] = (n0 + j < op.N) ? wp[((int64_t)t * op.K + k) * op.N + n0 + j] : 0.f;
+                }
+                __syncthreads();
+                int id = od * op.stride + kz - (op.nd == 3 ? op.pad : 0);
+                int ih = oh * op.stride + ky - op.pad;
+                int iw = ow * op.stride + kx - op.pad;
+                bool ok = live && id >= 0 && id < op.iD && ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW;
+                if (!ok) continue;
+                const float* src = in + ((((int64_t)bn * op.iD + id) * op.iH + ih) * op.iW + iw) * op.K;
+                if (VEC4) {
+                    for (int k = 0; k < op.K; k += 4) {
+                        float4 x = __ldg(reinterpret_cast<const float4*>(src + k));
+                        const float* wr = ws + k * CO_T;
+#pragma unroll
+                        for (int j = 0; j < CO_T; ++j) {
+                            acc[j] = fmaf(x.x, wr[j], acc[j]);
+                            acc[j] = fmaf(x.y, wr[CO_T + j], acc[j]);
+                            acc[j] = fmaf(x.z, wr[2 * CO_T + j], acc[j]);
+                            acc[j] = fmaf(x.w, wr[3 * CO_T + j], acc[j]);
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < op.K; ++k) {
+                        float x = __ldg(src + k);
+                        const float* wr = ws + k * CO_T;
+#pragma unroll
+                        for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, wr[j], acc[j]);
+                    }
+                }
+            }
+    if (!live) return;
+    float* dst = out + m * op.N + n0;
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+        if (n0 + j < op.N) dst[j] = acc[j] + (bias ? bias[n0 + j] : 0.f);
+}
+
+// ---------------------------------------------------------------- up2 (transposed k2 s2) conv
+template <int CO_T, bool VEC4>
+__global__ void __launch_bounds__(128)
+conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, const float* __restrict__ wp,
+                const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ float ws[];                  // [K][CO_T]
+    const int t = blockIdx.x / blocks_per_tap;
+    const int n0 = blockIdx.y * CO_T;
+    const int64_t p = (int64_t)(blockIdx.x % blocks_per_tap) * 128 + threadIdx.x;
+    for (int i = threadIdx.x; i < op.K * CO_T; i += 128) {
+        int k = i / CO_T, j = i % CO_T;
+        ws[i] = (n0 + j < op.N) ? wp[((int64_t)t * op.K + k) * op.N + n0 + j] : 0.f;
+    }
+    __syncthreads();
+    if (p >= op.in_rows) return;
+    int bn, id, ih, iw;
+    decode_row(p, op.iD, op.iH, op.iW, bn, id, ih, iw);
+    int kz = op.nd == 3 ? (t >> 2) : 0, ky = (t >> 1) & 1, kx = t & 1;
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
+    const float* src = in + p * op.K;
+    if (VEC4) {
+        for (int k = 0; k < op.K; k += 4) {
+            float4 x = __ldg(reinterpret_cast<const float4*>(src + k));
+            const float* wr = ws + k * CO_T;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) {
+                acc[j] = fmaf(x.x, wr[j], acc[j]);
+                acc[j] = fmaf(x.y, wr[CO_T + j], acc[j]);
+                acc[j] = fmaf(x.z, wr[2 * CO_T + j], acc[j]);
+                acc[j] = fmaf(x.w, wr[3 * CO_T + j], acc[j]);
+            }
+        }
+    } else {
+        for (int k = 0; k < op.K; ++k) {
+            float x = __ldg(src + k);
+            const float* wr = ws + k * CO_T;
+#pragma unroll
+            for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(x, wr[j], acc[j]);
+        }
+    }
+    int od = op.nd == 3 ? 2 * id + kz : 0, oh = 2 * ih + ky, ow = 2 * iw + kx;
+    float* dst = out + ((((int64_t)bn * op.oD + od) * op.oH + oh) * op.oW + ow) * op.N + n0;
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j)
+        if (n0 + j < op.N) dst[j] = acc[j] + (bias ? bias[n0 + j] : 0.f);
+}
+
+int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st) {
+    const bool vec4 = (op.K % 4 == 0) && aligned16(in);
+    const bool small = op.N <= 4;
+    const int co_t = small ? 4 : 16;
+    const size_t smem = (size_t)op.K * co_t * sizeof(float);
+    dim3 block(128);
+    if (op.up2) {
+        int bpt = (int)((op.in_rows + 127) / 128);
+        dim3 grid((unsigned)(bpt * op.taps), (unsigned)((op.N + co_t - 1) / co_t));
+        if (small) {
+            if (vec4) conv_up2_kernel<4, true><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+            else conv_up2_kernel<4, false><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+        } else {
+            if (vec4) conv_up2_kernel<16, true><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+            else conv_up2_kernel<16, false><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+        }
+        return launched("conv_up2_kernel");
+    }
+    dim3 grid((unsigned)((op.out_rows + 127) / 128), (unsigned)((op.N + co_t - 1) / co_t));
+    if (small) {
+        if (vec4) conv_gather_kernel<4, true><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+        else conv_gather_kernel<4, false><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+    } else {
+        if (vec4) conv_gather_kernel<16, true><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+        else conv_gather_kernel<16, false><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+    }
+    return launched("conv_gather_kernel");
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dW[t][k][n] = sum_rows A[rowA(r, t), k] * B[rowB(r, t), n]; written with torch-layout strides.
+//   gather form: r = output row of the forward op, rowA = src(r, t) (may be out of range -> 0), rowB = r
+//   up2 form   : r = input row p,                   rowA = p,                          rowB = dst(p, t)
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(SimtOp op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dw,
+                  int64_t sk, int64_t sn, int64_t rows_per_split) {
+    __shared__ float As[64][16];
+    __shared__ float Bs[64][16];
+    __shared__ int64_t rowA[64], rowB[64];
+    const int k_tiles = (op.K + 15) / 16;
+    const int k0 = (blockIdx.x % k_tiles) * 16, n0 = (blockIdx.x / k_tiles) * 16;
+    const int t = blockIdx.y;
+    const int64_t total_rows = op.up2 ? op.in_rows : op.out_rows;
+    const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r_end = min(total_rows, r_begin + rows_per_split);
+    const int kk = threadIdx.x & 15, nn = threadIdx.x >> 4;
+    int kz, ky, kx;
+    if (op.up2 || op.ksz == 2) { kz = op.nd == 3 ? (t >> 2) : 0; ky = (t >> 1) & 1; kx = t & 1; }
+    else if (op.ksz == 3) { kz = op.nd == 3 ? t / 9 : 0; ky = (t / 3) % 3; kx = t % 3; }
+    else { kz = ky = kx = 0; }
+    float acc = 0.f;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += 64) {
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            int64_t r = r0 + threadIdx.x, ra = -1, rb = -1;
+            if (r < r_end) {
+                int bn, d, h, w;
+                if (op.up2) {
+                    decode_row(r, op.iD, op.iH, op.iW, bn, d, h, w);
+                    ra = r;
+                    int od = op.nd == 3 ? 2 * d + kz : 0;
+                    rb = (((int64_t)bn * op.oD + od) * op.oH + 2 * h + ky) * op.oW + 2 * w + kx;
+                } else {
+                    decode_row(r, op.oD, op.oH, op.oW, bn, d, h, w);
+                    rb = r;
+                    int id = d * op.stride + kz - (op.nd == 3 ? op.pad : 0);
+                    int ih = h * op.stride + ky - op.pad;
+                    int iw = w * op.stride + kx - op.pad;
+                    if (id >= 0 && id < op.iD && ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW)
+                        ra = (((int64_t)bn * op.iD + id) * op.iH + ih) * op.iW + iw;
+                }
+            }
+            rowA[threadIdx.x] = ra; rowB[threadIdx.x] = rb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = threadIdx.x + i * 256, r = idx >> 4, c = idx & 15;
+            int64_t ra = rowA[r], rb = rowB[r];
+            As[r][c] = (ra >= 0 && k0 + c < op.K) ? __ldg(a + ra * op.K + k0 + c) : 0.f;
+            Bs[r][c] = (rb >= 0 && n0 + c < op.N) ? __ldg(b + rb * op.N + n0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int r = 0; r < 64; ++r) acc = fmaf(As[r][kk], Bs[r][nn], acc);
+    }
+    if (k0 + kk < op.K && n0 + nn < op.N)
+        atomicAdd(dw + (k0 + kk) * sk + (n0 + nn) * sn + t, acc);
+}
+
+int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
+               int64_t sk, int64_t sn, cudaStream_t st) {
+    CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
+    const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
+    const int tiles = ((op.K + 15) / 16) * ((op.N + 15) / 16);
+    int64_t want_splits = (kNumSMs * 4 + (int64_t)tiles * op.taps - 1) / ((int64_t)tiles * op.taps);
+    int64_t max_splits = (rows + 511) / 512;
+    int64_t splits = want_splits < 1 ? 1 : (want_splits > max_splits ? max_splits : want_splits);
+    if (splits > 65535) splits = 65535;
+    int64_t rps = ((rows + splits - 1) / splits + 63) / 64 * 64;
+    splits = (rows + rps - 1) / rps;
+    dim3 grid((unsigned)tiles, (unsigned)op.taps, (unsigned)splits);
+    conv_wgrad_kernel<<<grid, 256, 0, st>>>(op, a, b, dw, sk, sn, rps);
+    return launched("conv_wgrad_kernel");
+}
+
+}  // namespace chap

@@ -1,0 +1,528 @@
+// Bandwidth-bound kernels around the convolutions: BatchNorm statistics / apply / backward fused
+// with (Leaky)ReLU, dropout factors and the additive skip; 2x2 max pooling; align_corners x2
+// upsampling; channel concat / split; small elementwise helpers.
+// All tensors are channels-last rows [rows, C]; 128-bit accesses whenever C % 4 == 0.
+#include "common.cuh"
+#include "conv_plan.cuh"
+
+namespace chap {
+
+// ------------------------------------------------------------------ per-channel sums
+// sums[0:c] += sum_r f(r,c), sums[c:2c] += sum_r g(r,c); thread = (row lane, channel group)
+template <int VEC, typename F>
+__device__ __forceinline__ void channel_reduce(int64_t rows, int c, double* sums, F&& load2) {
+    __shared__ float part[256 * 2 * 4];
+    const int cg = c / VEC;                    // channel groups
+    const int rpb = 256 / cg;                  // row lanes per block
+    const int g = threadIdx.x % cg, rl = threadIdx.x / cg;
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s[v] = q[v] = 0.f;
+    if (rl < rpb) {
+        for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < rows; r += (int64_t)gridDim.x * rpb)
+            load2(r, g, s, q);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        part[(threadIdx.x * 2 + 0) * VEC + v] = s[v];
+        part[(threadIdx.x * 2 + 1) * VEC + v] = q[v];
+    }
+    __syncthreads();
+    if (threadIdx.x < cg) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            double a = 0.0, b = 0.0;
+            for (int l = 0; l < rpb; ++l) {
+                int t = l * cg + threadIdx.x;
+                a += (double)part[(t * 2 + 0) * VEC + v];
+                b += (double)part[(t * 2 + 1) * VEC + v];
+            }
+            atomicAdd(sums + threadIdx.x * VEC + v, a);
+            atomicAdd(sums + c + threadIdx.x * VEC + v, b);
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ y, int64_t rows, int c, double* sums) {
+    channel_reduce<VEC>(rows, c, sums, [&](int64_t r, int g, float* s, float* q) {
+        if (VEC == 4) {
+            float4 v = ldg_stream(reinterpret_cast<const float4*>(y + r * c) + g);
+            s[0] += v.x; s[1 % VEC] += v.y; s[2 % VEC] += v.z; s[3 % VEC] += v.w;
+            q[0] += v.x * v.x; q[1 % VEC] += v.y * v.y; q[2 % VEC] += v.z * v.z; q[3 % VEC] += v.w * v.w;
+        } else {
+            float v = y[r * c + g];
+            s[0] += v; q[0] += v * v;
+        }
+    });
+}
+
+int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_t st) {
+    CHAP_REQUIRE(y && sums && rows > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_stats: bad argument");
+    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    const bool v4 = (c % 4 == 0) && aligned16(y);
+    const int cg = v4 ? c / 4 : c;
+    CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "channel_stats: too many channels (%d)", c);
+    const int rpb = 256 / cg;
+    int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
+    if (v4) channel_stats_kernel<4><<<grid, 256, 0, st>>>(y, rows, c, sums);
+    else channel_stats_kernel<1><<<grid, 256, 0, st>>>(y, rows, c, sums);
+    return launched("channel_stats_kernel");
+}
+
+__global__ void sums_to_float_kernel(const double* sums, float* out, int c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) out[i] = (float)sums[i];
+}
+int sums_to_float(const double* sums, float* out, int c, cudaStream_t st) {
+    sums_to_float_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, out, c);
+    return launched("sums_to_float_kernel");
+}
+
+// ------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(const double* sums, int64_t count, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* rmean, float* rvar, int64_t* nbt,
+                                   float* mean_invstd, float* scale_shift, int c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && nbt) *nbt += 1;
+    if (i >= c) return;
+    double mean = sums[i] / (double)count;
+    double var = sums[c + i] / (double)count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = gamma[i] * invstd;
+    mean_invstd[i] = (float)mean; mean_invstd[c + i] = invstd;
+    scale_shift[i] = sc; scale_shift[c + i] = beta[i] - (float)mean * sc;
+    if (rmean) {
+        double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        rmean[i] = (1.f - momentum) * rmean[i] + momentum * (float)mean;
+        rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void bn_eval_params_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar,
+                                      float eps, float* mean_invstd, float* scale_shift, int c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float invstd = 1.f / sqrtf(rvar[i] + eps);
+    float sc = gamma[i] * invstd;
+    mean_invstd[i] = rmean[i]; mean_invstd[c + i] = invstd;
+    scale_shift[i] = sc; scale_shift[c + i] = beta[i] - rmean[i] * sc;
+}
+
+// ------------------------------------------------------------------ BN apply + act (+drop, +residual)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ ss, float slope,
+                  const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
+                  const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec,
+                  float* __restrict__ out) {
+    const int cg = c / VEC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const int64_t n = i / (rows_per_sample * cg);
+        float v[VEC], o[VEC];
+        if (VEC == 4) { float4 t = ldg_stream(reinterpret_cast<const float4*>(y) + i); v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w; }
+        else v[0] = y[i];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            int ch = g * VEC + k;
+            float z = fmaf(v[k], ss[ch], ss[c + ch]);
+            float a = z > 0.f ? z : slope * z;
+            if (drop_nc) a *= drop_nc[n * c + ch];
+            o[k] = a;
+        }
+        if (drop_el) {
+            if (VEC == 4) { float4 t = ldg_stream(reinterpret_cast<const float4*>(drop_el) + i); o[0] *= t.x; o[1 % VEC] *= t.y; o[2 % VEC] *= t.z; o[3 % VEC] *= t.w; }
+            else o[0] *= drop_el[i];
+        }
+        if (res) {
+            if (VEC == 4) { float4 t = ldg_stream(reinterpret_cast<const float4*>(res) + i); o[0] += t.x; o[1 % VEC] += t.y; o[2 % VEC] += t.z; o[3 % VEC] += t.w; }
+            else o[0] += res[i];
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+        else out[i] = o[0];
+    }
+}
+
+// dz for one element
+__device__ __forceinline__ float bn_dz(float dout, float yv, float sc, float sh, float slope) {
+    float z = fmaf(yv, sc, sh);
+    return z > 0.f ? dout : slope * dout;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
+                         const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
+                         const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t rows, int c, double* sums) {
+    channel_reduce<VEC>(rows, c, sums, [&](int64_t r, int g, float* s, float* q) {
+        const int64_t n = r / rows_per_sample;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            int ch = g * VEC + k;
+            int64_t e = r * c + ch;
+            float d = dout[e];
+            if (drop_nc) d *= drop_nc[n * c + ch];
+            if (drop_el) d *= drop_el[e];
+            float yv = y[e];
+            float dz = bn_dz(d, yv, ss[ch], ss[c + ch], slope);
+            float xh = (yv - mi[ch]) * mi[c + ch];
+            s[k] += dz; q[k] += dz * xh;
+        }
+    });
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
+                        const float* __restrict__ mi, float slope,
+                        const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
+                        int64_t rows_per_sample, int c, int64_t total_vec, int train, double inv_count,
+                        const double* __restrict__ sums, float* __restrict__ dy,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int cg = c / VEC;
+    if (blockIdx.x == 0 && dgamma) {
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) { dbeta[ch] = (float)sums[ch]; dgamma[ch] = (float)sums[c + ch]; }
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const int64_t n = i / (rows_per_sample * cg);
+        float d[VEC], yv[VEC], o[VEC];
+        if (VEC == 4) {
+            float4 t = ldg_stream(reinterpret_cast<const float4*>(dout) + i); d[0] = t.x; d[1 % VEC] = t.y; d[2 % VEC] = t.z; d[3 % VEC] = t.w;
+            float4 u = ldg_stream(reinterpret_cast<const float4*>(y) + i); yv[0] = u.x; yv[1 % VEC] = u.y; yv[2 % VEC] = u.z; yv[3 % VEC] = u.w;
+        } else { d[0] = dout[i]; yv[0] = y[i]; }
+        if (drop_el) {
+            if (VEC == 4) { float4 t = ldg_stream(reinterpret_cast<const float4*>(drop_el) + i); d[0] *= t.x; d[1 % VEC] *= t.y; d[2 % VEC] *= t.z; d[3 % VEC] *= t.w; }
+            else d[0] *= drop_el[i];
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            int ch = g * VEC + k;
+            float dd = d[k];
+            if (drop_nc) dd *= drop_nc[n * c + ch];
+            float sc = ss[ch];
+            float dz = bn_dz(dd, yv[k], sc, ss[c + ch], slope);
+            if (train) {
+                float xh = (yv[k] - mi[ch]) * mi[c + ch];
+                float mean_dz = (float)(sums[ch] * inv_count), mean_dzx = (float)(sums[c + ch] * inv_count);
+                o[k] = sc * (dz - mean_dz - xh * mean_dzx);
+            } else {
+                o[k] = sc * dz;
+            }
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+        else dy[i] = o[0];
+    }
+}
+
+// ------------------------------------------------------------------ max pool 2x2 (2D)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const float* __restrict__ x, int h, int w, int c, int64_t total_vec, float* __restrict__ y) {
+    const int cg = c / VEC, oh = h / 2, ow = w / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg); int64_t r = i / cg;
+        int xo = (int)(r % ow); r /= ow; int yo = (int)(r % oh); int64_t n = r / oh;
+        const float* p = x + (((n * h + 2 * yo) * w + 2 * xo) * (int64_t)c) + g * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float m = p[k];
+            m = fmaxf(m, p[c + k]); m = fmaxf(m, p[(int64_t)w * c + k]); m = fmaxf(m, p[(int64_t)w * c + c + k]);
+            y[i * VEC + k] = m;
+        }
+    }
+}
+template <int VEC>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int h, int w, int c,
+                    int64_t total_vec, float* __restrict__ dx) {
+    const int cg = c / VEC, oh = h / 2, ow = w / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg); int64_t r = i / cg;
+        int xo = (int)(r % ow); r /= ow; int yo = (int)(r % oh); int64_t n = r / oh;
+        const int64_t base = (((n * h + 2 * yo) * w + 2 * xo) * (int64_t)c) + g * VEC;
+        const int64_t off[4] = {0, (int64_t)c, (int64_t)w * c, (int64_t)w * c + c};
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            int best = 0; float m = x[base + k];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) { float v = x[base + off[j] + k]; if (v > m) { m = v; best = j; } }
+            float gy = dy[i * VEC + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dx[base + off[j] + k] = (j == best) ? gy : 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ x2 upsample, align_corners=True
+__device__ __forceinline__ void lerp_src(int o, int in, int out, int& i0, int& i1, float& l1) {
+    float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    float src = scale * (float)o;
+    i0 = (int)src;                        // src >= 0
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const float* __restrict__ x, int d, int h, int w, int c, int nd, int64_t total_vec, float* __restrict__ y) {
+    const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg); int64_t r = i / cg;
+        int xo = (int)(r % ow); r /= ow; int yo = (int)(r % oh); r /= oh; int zo = (int)(r % od); int64_t n = r / od;
+        int z0 = 0, z1 = 0, y0, y1, x0, x1; float lz = 0.f, ly, lx;
+        if (nd == 3) lerp_src(zo, d, od, z0, z1, lz);
+        lerp_src(yo, h, oh, y0, y1, ly);
+        lerp_src(xo, w, ow, x0, x1, lx);
+        const float* b = x + n * (int64_t)d * h * w * c + g * VEC;
+        auto at = [&](int zz, int yy, int xx, int k) { return b[(((int64_t)zz * h + yy) * w + xx) * c + k]; };
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float a00 = at(z0, y0, x0, k) * (1.f - lx) + at(z0, y0, x1, k) * lx;
+            float a01 = at(z0, y1, x0, k) * (1.f - lx) + at(z0, y1, x1, k) * lx;
+            float v0 = a00 * (1.f - ly) + a01 * ly;
+            if (nd == 3) {
+                float a10 = at(z1, y0, x0, k) * (1.f - lx) + at(z1, y0, x1, k) * lx;
+                float a11 = at(z1, y1, x0, k) * (1.f - lx) + at(z1, y1, x1, k) * lx;
+                float v1 = a10 * (1.f - ly) + a11 * ly;
+                v0 = v0 * (1.f - lz) + v1 * lz;
+            }
+            y[i * VEC + k] = v0;
+        }
+    }
+}
+
+// contributions of the outputs along one dim to input index i: list of (o, weight)
+__device__ __forceinline__ int contrib(int i, int in, int out, int* oi, float* wt) {
+    int cnt = 0;
+    int lo = 2 * i - 4 < 0 ? 0 : 2 * i - 4, hi = 2 * i + 5 > out - 1 ? out - 1 : 2 * i + 5;
+    if (in == 1) { lo = 0; hi = out - 1; }
+    for (int o = lo; o <= hi && cnt < 8; ++o) {
+        int i0, i1; float l1;
+        lerp_src(o, in, out, i0, i1, l1);
+        float wgt = 0.f;
+        if (i0 == i) wgt += 1.f - l1;
+        if (i1 == i) wgt += l1;
+        if (i0 == i || i1 == i) { oi[cnt] = o; wt[cnt] = wgt; ++cnt; }
+    }
+    return cnt;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, int nd, int64_t total_vec, float* __restrict__ dx) {
+    const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = (int)(i % cg); int64_t r = i / cg;
+        int xi = (int)(r % w); r /= w; int yi = (int)(r % h); r /= h; int zi = (int)(r % d); int64_t n = r / d;
+        int oz[8], oy[8], ox[8]; float wz[8], wy[8], wx[8];
+        int nz = 1; oz[0] = 0; wz[0] = 1.f;
+        if (nd == 3) nz = contrib(zi, d, od, oz, wz);
+        int ny = contrib(yi, h, oh, oy, wy);
+        int nx = contrib(xi, w, ow, ox, wx);
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+        const float* b = dy + n * (int64_t)od * oh * ow * c + g * VEC;
+        for (int a = 0; a < nz; ++a)
+            for (int bb = 0; bb < ny; ++bb) {
+                float wzy = wz[a] * wy[bb];
+                const float* row = b + (((int64_t)oz[a] * oh + oy[bb]) * ow) * c;
+                for (int cc = 0; cc < nx; ++cc) {
+                    float wt = wzy * wx[cc];
+                    const float* p = row + (int64_t)ox[cc] * c;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wt, p[k], acc[k]);
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) dx[i * VEC + k] = acc[k];
+    }
+}
+
+// ------------------------------------------------------------------ concat / split / misc
+__global__ void __launch_bounds__(256)
+concat_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int ca, int cb, float* __restrict__ out) {
+    const int ct = ca + cb;
+    const int64_t total = rows * ct;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ct; int ch = (int)(i % ct);
+        out[i] = ch < ca ? a[r * ca + ch] : b[r * cb + ch - ca];
+    }
+}
+__global__ void __launch_bounds__(256)
+concat4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t rows, int ca4, int cb4, float4* __restrict__ out) {
+    const int ct = ca4 + cb4;
+    const int64_t total = rows * ct;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ct; int ch = (int)(i % ct);
+        out[i] = ch < ca4 ? ldg_stream(a + r * ca4 + ch) : ldg_stream(b + r * cb4 + ch - ca4);
+    }
+}
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ in, int64_t rows, int ca, int cb, float* __restrict__ a, float* __restrict__ b) {
+    const int ct = ca + cb;
+    const int64_t total = rows * ct;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ct; int ch = (int)(i % ct);
+        float v = in[i];
+        if (ch < ca) { if (a) a[r * ca + ch] = v; } else { if (b) b[r * cb + ch - ca] = v; }
+    }
+}
+__global__ void __launch_bounds__(256)
+channel_scale_kernel(const float* __restrict__ x, const float* __restrict__ s, int64_t rows_per_sample, int c, int64_t total, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ch = (int)(i % c); int64_t n = i / (rows_per_sample * c);
+        out[i] = x[i] * s[n * c + ch];
+    }
+}
+__global__ void __launch_bounds__(256)
+axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, int64_t total, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = fmaf(alpha, b[i], a[i]);
+}
+__global__ void __launch_bounds__(256)
+mask_mix_kernel(const float* __restrict__ a, const float* __restrict__ b, const int64_t* __restrict__ m,
+                int64_t rows_per_sample, int c, int64_t total, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = (i / c) % rows_per_sample;
+        float mm = (float)m[r];
+        out[i] = a[i] * mm + b[i] * (1.f - mm);
+    }
+}
+
+}  // namespace chap
+
+using namespace chap;
+
+extern "C" int chap_channel_stats(const float* y, int64_t rows, int32_t c, double* sums, void* stream) {
+    return channel_stats(y, rows, c, sums, S(stream));
+}
+
+extern "C" int chap_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, int64_t* nbt,
+                                float* mean_invstd, float* scale_shift, int32_t c, void* stream) {
+    CHAP_REQUIRE(sums && gamma && beta && mean_invstd && scale_shift && c > 0 && count > 0, CHAP_ERR_BAD_ARG, "bn_finalize: bad argument");
+    CHAP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CHAP_ERR_BAD_ARG, "bn_finalize: running stats must both be set or both NULL");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, count, gamma, beta, eps, momentum, running_mean,
+                                                               running_var, running_mean ? nbt : nullptr, mean_invstd, scale_shift, c);
+    return launched("bn_finalize_kernel");
+}
+
+extern "C" int chap_bn_eval_params(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                   float* mean_invstd, float* scale_shift, int32_t c, void* stream) {
+    CHAP_REQUIRE(gamma && beta && rm && rv && mean_invstd && scale_shift && c > 0, CHAP_ERR_BAD_ARG, "bn_eval_params: bad argument");
+    bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(gamma, beta, rm, rv, eps, mean_invstd, scale_shift, c);
+    return launched("bn_eval_params_kernel");
+}
+
+static bool all16(std::initializer_list<const void*> ps) {
+    for (const void* p : ps) if (p && !aligned16(p)) return false;
+    return true;
+}
+
+extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, const float* drop_nc, const float* drop_el,
+                               const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    CHAP_REQUIRE(y && ss && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_fwd: bad argument");
+    const int64_t total = (int64_t)n * rps * c;
+    if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
+        bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, out);
+    } else {
+        bn_act_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total, out);
+    }
+    return launched("bn_act_fwd_kernel");
+}
+
+extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* ss, const float* mi, const float* gamma,
+                               float slope, const float* drop_nc, const float* drop_el, int32_t n, int64_t rps, int32_t c,
+                               int32_t train, double* sums, float* dy, float* dgamma, float* dbeta, void* stream) {
+    (void)gamma;
+    CHAP_REQUIRE(dout && y && ss && mi && sums && dy && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_bwd: bad argument");
+    CHAP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), CHAP_ERR_BAD_ARG, "bn_act_bwd: dgamma/dbeta must both be set or both NULL");
+    const int64_t rows = (int64_t)n * rps, total = rows * c;
+    cudaStream_t st = S(stream);
+    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    const bool v4 = c % 4 == 0 && all16({dout, y, drop_el, dy});
+    const int cg = v4 ? c / 4 : c;
+    CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);
+    const int rpb = 256 / cg;
+    int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
+    if (v4) bn_act_bwd_reduce_kernel<4><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
+    else bn_act_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
+    CHAP_TRY(launched("bn_act_bwd_reduce_kernel"));
+    const double inv_count = 1.0 / (double)rows;
+    if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
+    else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, inv_count, sums, dy, dgamma, dbeta);
+    return launched("bn_act_bwd_apply_kernel");
+}
+
+extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, void* stream) {
+    CHAP_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_fwd: bad argument (h, w must be even)");
+    const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
+    if (c % 4 == 0) maxpool2_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, h, w, c, total / 4, y);
+    else maxpool2_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, h, w, c, total, y);
+    return launched("maxpool2_fwd_kernel");
+}
+
+extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, void* stream) {
+    CHAP_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_bwd: bad argument (h, w must be even)");
+    const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
+    if (c % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, dy, h, w, c, total / 4, dx);
+    else maxpool2_bwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, dy, h, w, c, total, dx);
+    return launched("maxpool2_bwd_kernel");
+}
+
+extern "C" int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* y, void* stream) {
+    CHAP_REQUIRE(x && y && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_fwd: bad argument");
+    const int64_t total = (int64_t)n * (nd == 3 ? 2 * d : 1) * 2 * h * 2 * w * c;
+    if (c % 4 == 0) upsample2x_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total / 4, y);
+    else upsample2x_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total, y);
+    return launched("upsample2x_fwd_kernel");
+}
+
+extern "C" int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* dx, void* stream) {
+    CHAP_REQUIRE(dy && dx && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_bwd: bad argument");
+    const int64_t total = (int64_t)n * d * h * w * c;
+    if (c % 4 == 0) upsample2x_bwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total / 4, dx);
+    else upsample2x_bwd_kernel<1><<<grid_for(total, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total, dx);
+    return launched("upsample2x_bwd_kernel");
+}
+
+extern "C" int chap_concat_channels(const float* a, const float* b, int64_t rows, int32_t ca, int32_t cb, float* out, void* stream) {
+    CHAP_REQUIRE(a && b && out && rows > 0 && ca > 0 && cb > 0, CHAP_ERR_BAD_ARG, "concat_channels: bad argument");
+    const int64_t total = rows * (ca + cb);
+    if (ca % 4 == 0 && cb % 4 == 0 && all16({a, b, out}))
+        concat4_kernel<<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>((const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
+    else
+        concat_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(a, b, rows, ca, cb, out);
+    return launched("concat_kernel");
+}
+
+extern "C" int chap_split_channels(const float* in, int64_t rows, int32_t ca, int32_t cb, float* a, float* b, void* stream) {
+    CHAP_REQUIRE(in && rows > 0 && ca > 0 && cb > 0 && (a || b), CHAP_ERR_BAD_ARG, "split_channels: bad argument");
+    split_kernel<<<grid_for(rows * (ca + cb), 256 * 4), 256, 0, S(stream)>>>(in, rows, ca, cb, a, b);
+    return launched("split_kernel");
+}
+
+extern "C" int chap_channel_scale(const float* x, const float* s, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    CHAP_REQUIRE(x && s && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_scale: bad argument");
+    const int64_t total = (int64_t)n * rps * c;
+    channel_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(x, s, rps, c, total, out);
+    return launched("channel_scale_kernel");
+}
+
+extern "C" int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream) {
+    CHAP_REQUIRE(a && b && out && elems > 0, CHAP_ERR_BAD_ARG, "axpy: bad argument");
+    axpy_kernel<<<grid_for(elems, 256 * 4), 256, 0, S(stream)>>>(a, b, alpha, elems, out);
+    return launched("axpy_kernel");
+}
+
+extern "C" int chap_mask_mix(const float* a, const float* b, const int64_t* mask, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    CHAP_REQUIRE(a && b && mask && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "mask_mix: bad argument");
+    const int64_t total = (int64_t)n * rps * c;
+    mask_mix_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(a, b, mask, rps, c, total, out);
+    return launched("mask_mix_kernel");
+}

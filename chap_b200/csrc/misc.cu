@@ -1,0 +1,180 @@
+// Library state (errors, launch counter), fused SGD-momentum, sliding-window aggregation.
+#include "common.cuh"
+
+namespace chap {
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_force_simt{0};
+
+// ------------------------------------------------------------------ SGD momentum on a flat arena
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n4, int64_t n,
+           float lr, float mom, float wd, float gs, int first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        float4 gv = ldg_stream(reinterpret_cast<const float4*>(g) + i);
+        float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(buf)[i];
+        float g0 = fmaf(wd, pv.x, gs * gv.x), g1 = fmaf(wd, pv.y, gs * gv.y);
+        float g2 = fmaf(wd, pv.z, gs * gv.z), g3 = fmaf(wd, pv.w, gs * gv.w);
+        bv.x = first ? g0 : fmaf(mom, bv.x, g0); bv.y = first ? g1 : fmaf(mom, bv.y, g1);
+        bv.z = first ? g2 : fmaf(mom, bv.z, g2); bv.w = first ? g3 : fmaf(mom, bv.w, g3);
+        pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+        reinterpret_cast<float4*>(buf)[i] = bv;
+        reinterpret_cast<float4*>(p)[i] = pv;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gg = fmaf(wd, p[i], gs * g[i]);
+        float b = first ? gg : fmaf(mom, buf[i], gg);
+        buf[i] = b; p[i] -= lr * b;
+    }
+}
+
+// ------------------------------------------------------------------ sliding window
+__device__ __forceinline__ int win_start(int i, int stride, int vol, int patch) {
+    int s = stride * i;
+    int lim = vol - patch;
+    return s < lim ? s : lim;
+}
+
+__global__ void __launch_bounds__(256)
+sw_extract_kernel(chap_sw_desc d, const float* __restrict__ vol, int first, int64_t total, float* __restrict__ patches) {
+    const int64_t pvol = (int64_t)d.patch[0] * d.patch[1] * d.patch[2];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int wi = first + (int)(i / pvol);
+        int64_t r = i % pvol;
+        int z = (int)(r % d.patch[2]); r /= d.patch[2]; int y = (int)(r % d.patch[1]); int x = (int)(r / d.patch[1]);
+        int wz = wi % d.nwin[2], wy = (wi / d.nwin[2]) % d.nwin[1], wx = wi / (d.nwin[2] * d.nwin[1]);
+        int xs = win_start(wx, d.stride[0], d.vol[0], d.patch[0]);
+        int ys = win_start(wy, d.stride[1], d.vol[1], d.patch[1]);
+        int zs = win_start(wz, d.stride[2], d.vol[2], d.patch[2]);
+        patches[i] = vol[((int64_t)(xs + x) * d.vol[1] + ys + y) * d.vol[2] + zs + z];
+    }
+}
+
+// Tile-owned, atomic-free accumulate: one thread owns one output voxel and visits the windows that
+// cover it in the reference's x -> y -> z loop order, so the fp32 sums are bit-identical to the
+// host `score_map[...] += y` of code/test_3D_util.py:67-70; then score/cnt and first-max argmax.
+template <int C>
+__global__ void __launch_bounds__(256)
+sw_aggregate_kernel(chap_sw_desc d, const float* __restrict__ win, int is_prob, float* __restrict__ score,
+                    float* __restrict__ cnt, int64_t* __restrict__ label) {
+    const int64_t nvox = (int64_t)d.vol[0] * d.vol[1] * d.vol[2];
+    const int64_t pvol = (int64_t)d.patch[0] * d.patch[1] * d.patch[2];
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+        int z = (int)(v % d.vol[2]); int y = (int)((v / d.vol[2]) % d.vol[1]); int x = (int)(v / ((int64_t)d.vol[2] * d.vol[1]));
+        float acc[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) acc[k] = 0.f;
+        float n = 0.f;
+        for (int wx = 0; wx < d.nwin[0]; ++wx) {
+            int xs = win_start(wx, d.stride[0], d.vol[0], d.patch[0]);
+            if (x < xs || x >= xs + d.patch[0]) continue;
+            for (int wy = 0; wy < d.nwin[1]; ++wy) {
+                int ys = win_start(wy, d.stride[1], d.vol[1], d.patch[1]);
+                if (y < ys || y >= ys + d.patch[1]) continue;
+                for (int wz = 0; wz < d.nwin[2]; ++wz) {
+                    int zs = win_start(wz, d.stride[2], d.vol[2], d.patch[2]);
+                    if (z < zs || z >= zs + d.patch[2]) continue;
+                    int64_t wi = ((int64_t)wx * d.nwin[1] + wy) * d.nwin[2] + wz;
+                    int64_t e = wi * pvol + ((int64_t)(x - xs) * d.patch[1] + (y - ys)) * d.patch[2] + (z - zs);
+                    float p[C];
+                    if (C == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(win) + e); p[0] = t.x; p[1 % C] = t.y; }
+                    else if (C == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(win) + e); p[0] = t.x; p[1 % C] = t.y; p[2 % C] = t.z; p[3 % C] = t.w; }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < C; ++k) p[k] = __ldg(win + e * C + k);
+                    }
+                    if (!is_prob) {
+                        float m = p[0];
+#pragma unroll
+                        for (int k = 1; k < C; ++k) m = fmaxf(m, p[k]);
+                        float s = 0.f;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) { p[k] = expf(p[k] - m); s += p[k]; }
+                        float inv = 1.f / s;
+#pragma unroll
+                        for (int k = 0; k < C; ++k) p[k] *= inv;
+                    }
+#pragma unroll
+                    for (int k = 0; k < C; ++k) acc[k] = acc[k] + p[k];
+                    n = n + 1.f;
+                }
+            }
+        }
+        int best = 0; float bm = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            float q = acc[k] / n;                       // division BEFORE argmax (test_3D_util.py:71-72)
+            if (score) score[(int64_t)k * nvox + v] = q;
+            if (k == 0 || q > bm) { bm = q; best = k; }
+        }
+        if (cnt) cnt[v] = n;
+        label[v] = best;
+    }
+}
+
+}  // namespace chap
+
+using namespace chap;
+
+extern "C" const char* chap_last_error(void) { return g_err; }
+extern "C" int chap_abi_version(void) { return CHAP_ABI_VERSION; }
+extern "C" uint64_t chap_launch_count(void) { return g_launches.load(); }
+extern "C" void chap_reset_launch_count(void) { g_launches.store(0); }
+extern "C" void chap_set_force_simt(int flag) { g_force_simt.store(flag ? 1 : 0); }
+extern "C" int chap_get_force_simt(void) { return g_force_simt.load(); }
+
+extern "C" int chap_check_device(void) {
+    int dev = 0;
+    CHAP_CUDA(cudaGetDevice(&dev));
+    int major = 0, minor = 0;
+    CHAP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CHAP_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    CHAP_REQUIRE(major == 10, CHAP_ERR_ARCH, "libchap_b200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+    return CHAP_OK;
+}
+
+extern "C" int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t elems, float lr, float momentum,
+                                 float weight_decay, float grad_scale, int32_t first_step, void* stream) {
+    CHAP_REQUIRE(p && g && buf && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum: bad argument");
+    CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum: buffers must be 16-byte aligned");
+    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, lr, momentum, weight_decay, grad_scale, first_step);
+    return launched("sgd_kernel");
+}
+
+static int check_sw(const chap_sw_desc* d) {
+    CHAP_REQUIRE(d != nullptr, CHAP_ERR_BAD_ARG, "sliding window desc is NULL");
+    for (int a = 0; a < 3; ++a) {
+        CHAP_REQUIRE(d->vol[a] >= d->patch[a] && d->patch[a] > 0 && d->nwin[a] > 0 && d->stride[a] > 0, CHAP_ERR_BAD_ARG,
+                     "sliding window axis %d: vol %d patch %d nwin %d stride %d", a, d->vol[a], d->patch[a], d->nwin[a], d->stride[a]);
+    }
+    CHAP_REQUIRE(d->c >= 1, CHAP_ERR_BAD_ARG, "sliding window: classes %d", d->c);
+    return CHAP_OK;
+}
+
+extern "C" int chap_sw_extract(const chap_sw_desc* d, const float* volume, int32_t first, int32_t count, float* patches, void* stream) {
+    CHAP_TRY(check_sw(d));
+    const int total_win = d->nwin[0] * d->nwin[1] * d->nwin[2];
+    CHAP_REQUIRE(volume && patches && first >= 0 && count > 0 && first + count <= total_win, CHAP_ERR_BAD_ARG, "sw_extract: bad window range");
+    const int64_t total = (int64_t)count * d->patch[0] * d->patch[1] * d->patch[2];
+    sw_extract_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(*d, volume, first, total, patches);
+    return launched("sw_extract_kernel");
+}
+
+extern "C" int chap_sw_aggregate(const chap_sw_desc* d, const float* win, int32_t is_prob, float* score, float* cnt,
+                                 int64_t* label, void* stream) {
+    CHAP_TRY(check_sw(d));
+    CHAP_REQUIRE(win && label, CHAP_ERR_BAD_ARG, "sw_aggregate: NULL pointer");
+    const int64_t nvox = (int64_t)d->vol[0] * d->vol[1] * d->vol[2];
+    int grid = grid_for(nvox, 256);
+    switch (d->c) {
+        case 2: CHAP_REQUIRE(((uintptr_t)win & 7u) == 0, CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
+                sw_aggregate_kernel<2><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
+        case 3: sw_aggregate_kernel<3><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
+        case 4: CHAP_REQUIRE(aligned16(win), CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
+                sw_aggregate_kernel<4><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
+        default: return fail(CHAP_ERR_BAD_ARG, "sw_aggregate: unsupported class count %d", d->c);
+    }
+    return launched("sw_aggregate_kernel");
+}

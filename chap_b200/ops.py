@@ -1,0 +1,577 @@
+"""Host-side operators: torch.autograd.Function wrappers over the C ABI of libchap_b200.so.
+
+PyTorch is plumbing here (device memory, streams, autograd tape); every device computation
+is a kernel of this repository launched through ctypes with raw pointers.  Tensors are fp32
+and channels-last (logical [N, C, *spatial], physical [N, *spatial, C]).  There is no CPU
+path: every operator raises if its inputs are not CUDA tensors.
+"""
+import contextlib
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+_state = {"epoch": 0, "bn_tracking": True, "weight_grad": True}
+_pack_cache = {}
+
+
+def lib():
+    return _lib.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("chap_b200 operators need CUDA tensors (there is no CPU fallback)")
+
+
+def mem_format(ndim):
+    return torch.channels_last if ndim == 4 else torch.channels_last_3d
+
+
+def cl(x):
+    """fp32, channels-last contiguous view/copy of a [N, C, *spatial] tensor."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous(memory_format=mem_format(x.dim()))
+
+
+def empty_cl(shape, device):
+    return torch.empty(shape, dtype=torch.float32, device=device, memory_format=mem_format(len(shape)))
+
+
+def _spatial3(x):
+    """(nd, D, H, W) with D = 1 for 2D tensors."""
+    if x.dim() == 4:
+        return 2, 1, x.shape[2], x.shape[3]
+    return 3, x.shape[2], x.shape[3], x.shape[4]
+
+
+# ----------------------------------------------------------------------------- global switches
+def invalidate_weight_cache():
+    """Call after parameters were modified behind autograd's back (the fused SGD kernel)."""
+    _state["epoch"] += 1
+    _pack_cache.clear()
+
+
+@contextlib.contextmanager
+def bn_tracking(flag):
+    """BatchNorm keeps using batch statistics in train mode but does not touch the running
+    statistics while flag is False (the VAT passes)."""
+    old, _state["bn_tracking"] = _state["bn_tracking"], flag
+    try:
+        yield
+    finally:
+        _state["bn_tracking"] = old
+
+
+@contextlib.contextmanager
+def no_weight_grad():
+    """Convolutions record data gradients only (the decoder data-grad pass of VAT)."""
+    old, _state["weight_grad"] = _state["weight_grad"], False
+    try:
+        yield
+    finally:
+        _state["weight_grad"] = old
+
+
+def set_force_simt(flag):
+    lib().chap_set_force_simt(1 if flag else 0)
+    invalidate_weight_cache()
+
+
+# ----------------------------------------------------------------------------- convolution
+def _conv_desc(kind, x, cin, cout):
+    nd, d, h, w = _spatial3(x)
+    return ConvDesc(kind, nd, x.shape[0], d, h, w, cin, cout)
+
+
+def _packs(weight, desc):
+    key = (weight.data_ptr(), weight._version, _state["epoch"], desc.kind, desc.nd, lib().chap_get_force_simt())
+    hit = _pack_cache.get(key)
+    if hit is not None:
+        return hit
+    n = lib().chap_conv_packed_elems(ctypes.byref(desc))
+    wf = torch.empty(n, dtype=torch.float32, device=weight.device)
+    wd = torch.empty(n, dtype=torch.float32, device=weight.device)
+    w = weight.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    check(lib().chap_conv_pack_weights(ctypes.byref(desc), _p(w), _p(wf), _p(wd), _stream()))
+    _pack_cache[key] = (wf, wd)
+    return wf, wd
+
+
+def _out_shape(kind, x, cout):
+    sp = list(x.shape[2:])
+    if kind == _lib.CONV_DOWN2:
+        sp = [s // 2 for s in sp]
+    elif kind == _lib.CONV_UP2:
+        sp = [s * 2 for s in sp]
+    return [x.shape[0], cout] + sp
+
+
+class _Conv(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, kind, want_stats):
+        _require_cuda(x, weight, bias)
+        x = cl(x)
+        transposed = kind == _lib.CONV_UP2
+        cin = weight.shape[0] if transposed else weight.shape[1]
+        cout = weight.shape[1] if transposed else weight.shape[0]
+        if x.shape[1] != cin:
+            raise RuntimeError("conv: input has %d channels, weight expects %d" % (x.shape[1], cin))
+        desc = _conv_desc(kind, x, cin, cout)
+        wf, wd = _packs(weight, desc)
+        y = empty_cl(_out_shape(kind, x, cout), x.device)
+        sums = torch.empty(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+        b = None if bias is None else bias.detach()
+        check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
+        ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
+        ctx.wshape = tuple(weight.shape)
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None)
+        if want_stats:
+            ctx.mark_non_differentiable(sums)
+            return y, sums
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dsums):
+        (x,) = ctx.saved_tensors
+        desc = ctx.desc
+        dy = cl(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            nd = desc.nd
+            shape = [desc.n, desc.cin] + ([desc.in_h, desc.in_w] if nd == 2 else [desc.in_d, desc.in_h, desc.in_w])
+            dx = empty_cl(shape, dy.device)
+            check(lib().chap_conv_dgrad(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(dx), _stream()))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dy.device)
+            want_b = ctx.has_bias and ctx.needs_input_grad[2]
+            db = torch.empty(desc.cout, dtype=torch.float32, device=dy.device) if want_b else None
+            ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))
+            ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
+            check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
+        return dx, dw, db, None, None
+
+
+def conv_stats(x, weight, bias, kind, want_stats=True):
+    """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted)."""
+    if not _state["weight_grad"]:
+        weight = weight.detach()
+        bias = None if bias is None else bias.detach()
+    return _Conv.apply(x, weight, bias, kind, bool(want_stats))
+
+
+def conv(x, weight, bias, kind):
+    return conv_stats(x, weight, bias, kind, False)[0]
+
+
+# ----------------------------------------------------------------------------- BN + activation
+class _BnAct(Function):
+    @staticmethod
+    def forward(ctx, y, gamma, beta, residual, sums, running, train, update, slope, eps, momentum, drop_nc, drop_el):
+        _require_cuda(y, gamma, beta)
+        y = cl(y)
+        n, c = y.shape[0], y.shape[1]
+        rps = y.numel() // (n * c)
+        dev = y.device
+        mi = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        ss = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        g, b = gamma.detach(), beta.detach()
+        if train:
+            if sums is None:
+                sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+                check(lib().chap_channel_stats(_p(y), n * rps, c, _p(sums), _stream()))
+            rm, rv, nbt = running if (update and running is not None) else (None, None, None)
+            check(lib().chap_bn_finalize(_p(sums), n * rps, _p(g), _p(b), eps, momentum, _p(rm), _p(rv), _p(nbt),
+                                         _p(mi), _p(ss), c, _stream()))
+        else:
+            rm, rv, _ = running
+            check(lib().chap_bn_eval_params(_p(g), _p(b), _p(rm), _p(rv), eps, _p(mi), _p(ss), c, _stream()))
+        if residual is not None:
+            residual = cl(residual)
+        if drop_el is not None:
+            drop_el = cl(drop_el)
+        out = empty_cl(y.shape, dev)
+        check(lib().chap_bn_act_fwd(_p(y), _p(ss), slope, _p(drop_nc), _p(drop_el), _p(residual), n, rps, c, _p(out), _stream()))
+        ctx.save_for_backward(y, ss, mi, g, drop_nc, drop_el)
+        ctx.cfg = (n, rps, c, bool(train), float(slope), residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, ss, mi, g, drop_nc, drop_el = ctx.saved_tensors
+        n, rps, c, train, slope, has_res = ctx.cfg
+        dout = cl(dout)
+        dev = dout.device
+        dy = empty_cl(y.shape, dev)
+        want_pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,
+                                    1 if train else 0, _p(sums), _p(dy), _p(dgamma), _p(dbeta), _stream()))
+        dres = dout if (has_res and ctx.needs_input_grad[3]) else None
+        return (dy, dgamma, dbeta, dres) + (None,) * 9
+
+
+def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
+    """act(BatchNorm(y)) * drop + residual with the semantics of the nn.BatchNormNd holder `bn`
+    (train/eval, eps, momentum, running statistics)."""
+    train = bn.training or not bn.track_running_stats
+    running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else None
+    update = bn.training and bn.track_running_stats and _state["bn_tracking"]
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return _BnAct.apply(y, bn.weight, bn.bias, residual, sums, running, train, update, float(slope), float(bn.eps),
+                        float(momentum), drop_nc, drop_el)
+
+
+# ----------------------------------------------------------------------------- pooling / upsampling / concat
+class _MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = cl(x)
+        n, c, h, w = x.shape
+        y = empty_cl([n, c, h // 2, w // 2], x.device)
+        check(lib().chap_maxpool2_fwd(_p(x), n, h, w, c, _p(y), _stream()))
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = cl(dy)
+        dx = empty_cl(x.shape, x.device)
+        check(lib().chap_maxpool2_bwd(_p(x), _p(dy), n, h, w, c, _p(dx), _stream()))
+        return dx
+
+
+def maxpool2(x):
+    return _MaxPool2.apply(x)
+
+
+class _Upsample2x(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = cl(x)
+        nd, d, h, w = _spatial3(x)
+        n, c = x.shape[0], x.shape[1]
+        y = empty_cl([n, c] + [2 * s for s in x.shape[2:]], x.device)
+        check(lib().chap_upsample2x_fwd(_p(x), nd, n, d, h, w, c, _p(y), _stream()))
+        ctx.cfg = (nd, n, d, h, w, c, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        nd, n, d, h, w, c, shape = ctx.cfg
+        dy = cl(dy)
+        dx = empty_cl(list(shape), dy.device)
+        check(lib().chap_upsample2x_bwd(_p(dy), nd, n, d, h, w, c, _p(dx), _stream()))
+        return dx
+
+
+def upsample2x(x):
+    """bilinear (4D) / trilinear (5D) x2, align_corners=True."""
+    return _Upsample2x.apply(x)
+
+
+class _Concat(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, b)
+        a, b = cl(a), cl(b)
+        ca, cb = a.shape[1], b.shape[1]
+        rows = a.numel() // ca
+        out = empty_cl([a.shape[0], ca + cb] + list(a.shape[2:]), a.device)
+        check(lib().chap_concat_channels(_p(a), _p(b), rows, ca, cb, _p(out), _stream()))
+        ctx.cfg = (tuple(a.shape), tuple(b.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        sa, sb = ctx.cfg
+        dout = cl(dout)
+        rows = dout.numel() // dout.shape[1]
+        da = empty_cl(list(sa), dout.device) if ctx.needs_input_grad[0] else None
+        db = empty_cl(list(sb), dout.device) if ctx.needs_input_grad[1] else None
+        if da is not None or db is not None:
+            check(lib().chap_split_channels(_p(dout), rows, sa[1], sb[1], _p(da), _p(db), _stream()))
+        return da, db
+
+
+def concat_channels(a, b):
+    return _Concat.apply(a, b)
+
+
+class _ChannelScale(Function):
+    @staticmethod
+    def forward(ctx, x, scale_nc):
+        _require_cuda(x, scale_nc)
+        x = cl(x)
+        s = scale_nc.detach().reshape(x.shape[0], x.shape[1]).float().contiguous()
+        n, c = x.shape[0], x.shape[1]
+        out = empty_cl(x.shape, x.device)
+        check(lib().chap_channel_scale(_p(x), _p(s), n, x.numel() // (n * c), c, _p(out), _stream()))
+        ctx.save_for_backward(s)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (s,) = ctx.saved_tensors
+        dout = cl(dout)
+        n, c = dout.shape[0], dout.shape[1]
+        dx = empty_cl(dout.shape, dout.device)
+        check(lib().chap_channel_scale(_p(dout), _p(s), n, dout.numel() // (n * c), c, _p(dx), _stream()))
+        return dx, None
+
+
+def channel_scale(x, scale_nc):
+    """x * scale[n, c] (Dropout2d/3d-style channel masks; the mask itself is not differentiated)."""
+    return _ChannelScale.apply(x, scale_nc)
+
+
+def axpy(a, b, alpha):
+    """a + alpha * b (flat, no autograd)."""
+    _require_cuda(a, b)
+    a, b = cl(a.detach()), cl(b.detach())
+    out = torch.empty_like(a)
+    check(lib().chap_axpy(_p(a), _p(b), float(alpha), a.numel(), _p(out), _stream()))
+    return out
+
+
+def mask_mix(a, b, mask):
+    """a*m + b*(1-m) with an int64 spatial mask broadcast over batch and channels (no grad)."""
+    _require_cuda(a, b, mask)
+    a, b = cl(a.detach()), cl(b.detach())
+    m = mask.to(torch.int64).contiguous()
+    n, c = a.shape[0], a.shape[1]
+    out = torch.empty_like(a)
+    check(lib().chap_mask_mix(_p(a), _p(b), _p(m), n, a.numel() // (n * c), c, _p(out), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- losses
+def _rows_c(logits):
+    c = logits.shape[1]
+    return logits.numel() // c, c
+
+
+def pseudo_label(pre1, pre2):
+    """softmax1, softmax2, argmax1, argmax2 (int64), knowledge = CE(pre1, arg2) + CE(pre2, arg1)."""
+    _require_cuda(pre1, pre2)
+    pre1, pre2 = cl(pre1.detach()), cl(pre2.detach())
+    rows, c = _rows_c(pre1)
+    sp = [pre1.shape[0]] + list(pre1.shape[2:])
+    s1, s2 = torch.empty_like(pre1), torch.empty_like(pre2)
+    a1 = torch.empty(sp, dtype=torch.int64, device=pre1.device)
+    a2 = torch.empty(sp, dtype=torch.int64, device=pre1.device)
+    k = torch.empty(sp, dtype=torch.float32, device=pre1.device)
+    check(lib().chap_pseudo_label(_p(pre1), _p(pre2), rows, c, _p(s1), _p(s2), _p(a1), _p(a2), _p(k), _stream()))
+    return s1, s2, a1, a2, k
+
+
+def softmax(logits):
+    _require_cuda(logits)
+    x = cl(logits.detach())
+    rows, c = _rows_c(x)
+    out = torch.empty_like(x)
+    check(lib().chap_softmax(_p(x), rows, c, _p(out), _stream()))
+    return out
+
+
+def argmax(a, b=None):
+    """argmax over classes of softmax(a) or of softmax((a + b) / 2); int64 [N, *spatial]."""
+    _require_cuda(a, b)
+    a = cl(a.detach())
+    b = None if b is None else cl(b.detach())
+    rows, c = _rows_c(a)
+    out = torch.empty([a.shape[0]] + list(a.shape[2:]), dtype=torch.int64, device=a.device)
+    check(lib().chap_argmax(_p(a), _p(b), rows, c, _p(out), _stream()))
+    return out
+
+
+def _label_arg(labels):
+    if labels.dtype == torch.int64:
+        return labels.contiguous(), _lib.LABEL_I64
+    return labels.float().contiguous(), _lib.LABEL_F32
+
+
+class _DiceCeSums(Function):
+    @staticmethod
+    def forward(ctx, logits, labels, mask, invert):
+        _require_cuda(logits, labels, mask)
+        x = cl(logits)
+        n, c = x.shape[0], x.shape[1]
+        rps = x.numel() // (n * c)
+        lab, dt = _label_arg(labels)
+        m = mask.to(torch.int64).contiguous()
+        if m.numel() != rps:
+            raise RuntimeError("dice_ce: mask must have one entry per spatial position")
+        sums = torch.empty(3 * c + 2, dtype=torch.float64, device=x.device)
+        check(lib().chap_dice_ce_fwd(_p(x), _p(lab), dt, _p(m), invert, n, rps, c, _p(sums), _stream()))
+        ctx.save_for_backward(x, lab, m)
+        ctx.cfg = (dt, invert, n, rps, c)
+        return sums
+
+    @staticmethod
+    def backward(ctx, dsums):
+        x, lab, m = ctx.saved_tensors
+        dt, invert, n, rps, c = ctx.cfg
+        coef = torch.cat([dsums[:2 * c], dsums[3 * c:3 * c + 1]]).float().contiguous()
+        dl = torch.empty_like(x)
+        check(lib().chap_dice_ce_bwd(_p(x), _p(lab), dt, _p(m), invert, n, rps, c, _p(coef), 0, _p(dl), _stream()))
+        return dl, None, None, None
+
+
+def dice_ce_sums(logits, labels, mask, invert=False):
+    """float64[3C+2]: inter[C], sum(s^2 m)[C], sum(t m)[C], sum(CE m), sum(m); differentiable in logits."""
+    return _DiceCeSums.apply(logits, labels, mask, 1 if invert else 0)
+
+
+class _ConsistencySums(Function):
+    @staticmethod
+    def forward(ctx, logits, target, mask, dist):
+        _require_cuda(logits, target, mask)
+        x, t = cl(logits), cl(target.detach())
+        rows, c = _rows_c(x)
+        m = None if mask is None else mask.detach().float().contiguous()
+        sums = torch.empty(3 * c + 1, dtype=torch.float64, device=x.device)
+        check(lib().chap_consistency_fwd(_p(x), _p(t), _p(m), dist, rows, c, _p(sums), _stream()))
+        ctx.save_for_backward(x, t, m)
+        ctx.cfg = (dist, rows, c)
+        return sums
+
+    @staticmethod
+    def backward(ctx, dsums):
+        x, t, m = ctx.saved_tensors
+        dist, rows, c = ctx.cfg
+        coef = dsums[:2 * c].float().contiguous()
+        dl = torch.empty_like(x)
+        check(lib().chap_consistency_bwd(_p(x), _p(t), _p(m), dist, rows, c, _p(coef), _p(dl), _stream()))
+        return dl, None, None, None
+
+
+def consistency_sums(logits, target, mask, dist):
+    return _ConsistencySums.apply(logits, target, mask, dist)
+
+
+def patch_topk_mask(knowledge, arg1, arg2, scale_factor, topk):
+    """create_maskV1 (frozen spec, oracle/chap_losses.py create_mask_v1): float mask [N, *spatial]."""
+    _require_cuda(knowledge, arg1, arg2)
+    k = knowledge.detach().float().contiguous()
+    a1, a2 = arg1.contiguous(), arg2.contiguous()
+    n = k.shape[0]
+    nd = k.dim() - 1
+    d, h, w = (1, k.shape[1], k.shape[2]) if nd == 2 else tuple(k.shape[1:])
+    s = scale_factor
+    npatch = (d // s if nd == 3 else 1) * (h // s) * (w // s)
+    score = torch.empty(n, npatch, dtype=torch.float32, device=k.device)
+    check(lib().chap_patch_score(_p(k), _p(a1), _p(a2), nd, n, d, h, w, s, _p(score), _stream()))
+    kk = max(1, int(topk * npatch))
+    kth = torch.topk(score, kk, dim=1).values[:, -1].contiguous()     # selection on a [N, P] tensor: plumbing
+    mask = torch.empty_like(k)
+    check(lib().chap_patch_mask(_p(score), _p(kth), nd, n, d, h, w, s, _p(mask), _stream()))
+    return mask
+
+
+# ----------------------------------------------------------------------------- perturbation generator
+def perturb(grads, feats, eps, mode="channel_spatial", g_scale=1.0):
+    """[f_l + eps * normalise(g_l)] for all levels in one library call (f_l may be None -> r_l only).
+    g is multiplied by g_scale on load (VAT differentiates w.r.t. f + xi*d, so dL/dd = xi * dL/d(f + xi d)).
+    The perturbation is a constant w.r.t. autograd (g is detached by the frozen spec); the caller restores
+    d out / d f = I with attach_identity_grad()."""
+    n = grads[0].shape[0]
+    levels = (_lib.Level * len(grads))()
+    keep, outs = [], []
+    for i, g in enumerate(grads):
+        _require_cuda(g)
+        g = cl(g.detach())
+        f = None if feats is None or feats[i] is None else cl(feats[i].detach())
+        out = torch.empty_like(g)
+        c = g.shape[1]
+        levels[i] = _lib.Level(g.data_ptr(), 0 if f is None else f.data_ptr(), out.data_ptr(), g.numel() // (n * c), c, 0)
+        keep += [g, f]
+        outs.append(out)
+    n_ws = lib().chap_perturb_workspace_elems(levels, len(grads), n)
+    ws = torch.empty(n_ws, dtype=torch.float64, device=grads[0].device)
+    check(lib().chap_perturb_fwd(levels, len(grads), n, _lib.PERTURB_MODES[mode], float(eps), float(g_scale), _p(ws), n_ws,
+                                 _stream()))
+    return outs
+
+
+class _ReplaceValue(Function):
+    """Forward: returns `value` (computed from f by a kernel as f + const); backward: identity to f."""
+    @staticmethod
+    def forward(ctx, f, value):
+        return value.view_as(value)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, None
+
+
+def attach_identity_grad(f, value):
+    return _ReplaceValue.apply(f, value)
+
+
+def l2n_sample_axpy(d, base, xi):
+    """base + xi * d / (||d||_2 per sample + 1e-8); no autograd (inputs are leaves of VAT step 2)."""
+    _require_cuda(d, base)
+    d = cl(d.detach())
+    base = None if base is None else cl(base.detach())
+    n = d.shape[0]
+    norms = torch.empty(n, dtype=torch.float64, device=d.device)
+    out = torch.empty_like(d)
+    check(lib().chap_l2n_sample_axpy(_p(d), _p(base), float(xi), n, d.numel() // n, _p(norms), _p(out), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- optimiser
+def sgd_momentum_(flat_p, flat_g, flat_buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
+    _require_cuda(flat_p, flat_g, flat_buf)
+    check(lib().chap_sgd_momentum(_p(flat_p), _p(flat_g), _p(flat_buf), flat_p.numel(), float(lr), float(momentum),
+                                  float(weight_decay), float(grad_scale), 1 if first_step else 0, _stream()))
+    invalidate_weight_cache()
+
+
+# ----------------------------------------------------------------------------- sliding window
+def sw_desc(vol, patch, nwin, stride, c):
+    d = _lib.SwDesc()
+    for a in range(3):
+        d.vol[a], d.patch[a], d.nwin[a], d.stride[a] = int(vol[a]), int(patch[a]), int(nwin[a]), int(stride[a])
+    d.c = int(c)
+    return d
+
+
+def sw_extract(desc, volume, first, count):
+    _require_cuda(volume)
+    out = torch.empty([count, 1, desc.patch[0], desc.patch[1], desc.patch[2]], dtype=torch.float32, device=volume.device)
+    check(lib().chap_sw_extract(ctypes.byref(desc), _p(volume), first, count, _p(out), _stream()))
+    return out
+
+
+def sw_aggregate(desc, win, is_prob, want_maps=False):
+    _require_cuda(win)
+    dev = win.device
+    vol = (desc.vol[0], desc.vol[1], desc.vol[2])
+    label = torch.empty(vol, dtype=torch.int64, device=dev)
+    score = torch.empty((desc.c,) + vol, dtype=torch.float32, device=dev) if want_maps else None
+    cnt = torch.empty(vol, dtype=torch.float32, device=dev) if want_maps else None
+    check(lib().chap_sw_aggregate(ctypes.byref(desc), _p(win), 1 if is_prob else 0, _p(score), _p(cnt), _p(label), _stream()))
+    return (label, score, cnt) if want_maps else label

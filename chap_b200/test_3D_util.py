@@ -1,0 +1,159 @@
+"""3D sliding-window inference on the sm_100a kernels.
+
+Same entry points as the reference's code/test_3D_util.py (`test_single_case` :14-79,
+`calculate_metric_percase` :147-152, `cal_dice` :132-144) and code/val_3D.py (`test_single_case`
+:14-79, `cal_metric` :82-88).  The reference runs one window per forward, copies every window's
+softmax to the host (8 MB at the LA configuration) and accumulates with numpy; here
+  * windows are gathered on the device (`chap_sw_extract`) and run through the net in batches,
+  * the logits of all windows stay in HBM (channels-last), and
+  * ONE tile-owned, atomic-free kernel (`chap_sw_aggregate`) applies the softmax on load, adds the
+    windows covering each voxel in the reference's x->y->z order (bit-identical fp32 sums), divides
+    by the count and takes the first-max argmax.
+Only the int64 label map (and optionally score / count maps) returns to the host.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _pad_amounts(shape, patch_size):
+    pads = []
+    for s, p in zip(shape, patch_size):
+        tot = max(p - s, 0)
+        pads.append((tot // 2, tot - tot // 2))
+    return pads
+
+
+def _net_logits(net, patches, output_index=0):
+    y = net(patches)
+    if isinstance(y, (tuple, list)):            # DualDecoder3d returns (o1, o2); test_LA.py:50 uses num_outputs=1
+        return y[output_index]
+    return y
+
+
+def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, batch_windows=4,
+                     device=None, return_maps=False, window_logits_hook=None):
+    """image: numpy [W, H, D] float; returns label_map int64 numpy [W, H, D] (and, with
+    return_maps, score_map [C, W, H, D] and cnt [W, H, D] float32) -- code/test_3D_util.py:14-79."""
+    if device is None:
+        device = next(net.parameters()).device
+    w, h, d = image.shape
+    pads = _pad_amounts(image.shape, patch_size)
+    add_pad = any(a + b > 0 for a, b in pads)
+    if add_pad:
+        image = np.pad(image, pads, mode='constant', constant_values=0)
+    ww, hh, dd = image.shape
+    sx = math.ceil((ww - patch_size[0]) / stride_xy) + 1
+    sy = math.ceil((hh - patch_size[1]) / stride_xy) + 1
+    sz = math.ceil((dd - patch_size[2]) / stride_z) + 1
+    desc = ops.sw_desc((ww, hh, dd), patch_size, (sx, sy, sz), (stride_xy, stride_xy, stride_z), num_classes)
+    vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(device)
+    n_win = sx * sy * sz
+    pw, ph, pd = patch_size
+    win = torch.empty((n_win, pw, ph, pd, num_classes), dtype=torch.float32, device=device)   # channels-last logits
+    was_training = net.training
+    net.eval()
+    with torch.no_grad():
+        for first in range(0, n_win, batch_windows):
+            count = min(batch_windows, n_win - first)
+            patches = ops.sw_extract(desc, vol, first, count)
+            logits = ops.cl(_net_logits(net, patches))
+            if window_logits_hook is not None:
+                window_logits_hook(first, logits)
+            win[first:first + count].copy_(logits.permute(0, 2, 3, 4, 1))      # same memory order: plain copy
+        out = ops.sw_aggregate(desc, win, is_prob=False, want_maps=return_maps)
+    if was_training:
+        net.train()
+    if return_maps:
+        label, score, cnt = out
+        label_map, score_map, cnt_map = label.cpu().numpy(), score.cpu().numpy(), cnt.cpu().numpy()
+    else:
+        label_map = out.cpu().numpy()
+    if add_pad:
+        (wl, _), (hl, _), (dl, _) = pads
+        label_map = label_map[wl:wl + w, hl:hl + h, dl:dl + d]
+        if return_maps:
+            score_map = score_map[:, wl:wl + w, hl:hl + h, dl:dl + d]
+            cnt_map = cnt_map[wl:wl + w, hl:hl + h, dl:dl + d]
+    if return_maps:
+        return label_map, score_map, cnt_map
+    return label_map
+
+
+def dice_coefficient(pred, gt):
+    """medpy.metric.binary.dc: 2|A&B| / (|A| + |B|); 0.0 when both are empty."""
+    pred, gt = np.asarray(pred).astype(bool), np.asarray(gt).astype(bool)
+    size = np.count_nonzero(pred) + np.count_nonzero(gt)
+    return 2.0 * np.count_nonzero(pred & gt) / float(size) if size > 0 else 0.0
+
+
+def _surface_distances(a, b, spacing=None):
+    from scipy import ndimage
+    a, b = np.asarray(a).astype(bool), np.asarray(b).astype(bool)
+    if not a.any() or not b.any():
+        raise RuntimeError("surface distance is undefined for an empty mask")
+    fp = ndimage.generate_binary_structure(a.ndim, 1)
+    a_border = a ^ ndimage.binary_erosion(a, structure=fp, iterations=1)
+    b_border = b ^ ndimage.binary_erosion(b, structure=fp, iterations=1)
+    dt = ndimage.distance_transform_edt(~b_border, sampling=spacing)
+    return dt[a_border]
+
+
+def hd95(pred, gt, spacing=None):
+    """medpy.metric.binary.hd95: 95th percentile of the symmetric surface distances."""
+    return float(np.percentile(np.hstack((_surface_distances(pred, gt, spacing), _surface_distances(gt, pred, spacing))), 95))
+
+
+def asd(pred, gt, spacing=None):
+    """medpy.metric.binary.asd: average surface distance from pred to gt."""
+    return float(_surface_distances(pred, gt, spacing).mean())
+
+
+def jc(pred, gt):
+    """medpy.metric.binary.jc: Jaccard coefficient."""
+    pred, gt = np.asarray(pred).astype(bool), np.asarray(gt).astype(bool)
+    union = np.count_nonzero(pred | gt)
+    return float(np.count_nonzero(pred & gt)) / float(union) if union > 0 else 0.0
+
+
+def cal_metric(gt, pred):
+    """code/test_3D_util.py:82-88 / code/val_3D.py:82-88: [dice, hd95] or zeros."""
+    if pred.sum() > 0 and gt.sum() > 0:
+        return np.array([dice_coefficient(pred, gt), hd95(pred, gt)])
+    return np.zeros(2)
+
+
+def cal_dice(prediction, label, num=2):
+    """code/test_3D_util.py:132-144 (np.float replaced by float)."""
+    total_dice = np.zeros(num - 1)
+    for i in range(1, num):
+        p, l = (prediction == i).astype(float), (label == i).astype(float)
+        total_dice[i - 1] += 2 * np.sum(p * l) / (np.sum(p) + np.sum(l))
+    return total_dice
+
+
+def calculate_metric_percase(pred, gt):
+    """code/test_3D_util.py:147-152: dice, jaccard, hd95, asd."""
+    return dice_coefficient(pred, gt), jc(pred, gt), hd95(pred, gt), asd(pred, gt)
+
+
+def test_all_case(net, image_list, num_classes=2, patch_size=(112, 112, 80), stride_xy=18, stride_z=4,
+                  batch_windows=4, rank=0, world_size=1):
+    """Evaluate a list of (image, label) numpy volumes; cases are sharded round-robin over ranks
+    (replicas only, no collective -- SURVEY.md section 8e).  Returns the per-case metric rows
+    [dice, jc, hd95, asd] of this rank's cases and their indices."""
+    rows, idx = [], []
+    for i, (image, label) in enumerate(image_list):
+        if i % world_size != rank:
+            continue
+        pred = test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes, batch_windows)
+        if pred.sum() == 0 or (label > 0).sum() == 0:
+            rows.append((0.0, 0.0, 0.0, 0.0))
+        else:
+            rows.append(calculate_metric_percase(pred == 1, label == 1) if num_classes == 2 else
+                        tuple(np.mean([calculate_metric_percase(pred == c, label == c) for c in range(1, num_classes)], axis=0)))
+        idx.append(i)
+    return np.array(rows, dtype=np.float64).reshape(-1, 4), idx

@@ -1,0 +1,180 @@
+"""One CHAP training iteration (2D ACDC-shaped U-Net or 3D LA-shaped V-Net) on the sm_100a kernels.
+
+Host-side orchestration mirroring the body of the reference's training loop,
+code/train_ours_2D.py:304-389 (flags --adv_noise, --adv_losstype kl|dice; the --dropout branch is
+not part of this step).  The reference has no 3D trainer; the 3D step is the same
+procedure on DualDecoder3d with a cubic copy-paste mask (frozen in oracle/train_step.py).
+
+Device work: conv/BN/activation stacks, pseudo-label block, mix losses, patch mask, the perturbation
+generator, consistency losses and the fused SGD-momentum update are all libchap_b200 kernels.  The
+largest-connected-component filter of get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144) runs on
+the host like the reference (skimage there, scipy.ndimage here; one D2H/H2D round trip per step).
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .utils import losses, patch, ramps
+
+
+def generate_mask(img, offsets=None):
+    """generate_mask, code/train_ours_2D.py:91-101 (dimension generic).  Returns (mask[*spatial] int64,
+    loss_mask[N, *spatial] int64); offsets = the np.random.randint draws, drawn here when None."""
+    spatial = tuple(img.shape[2:])
+    if offsets is None:
+        offsets = tuple(int(np.random.randint(0, s - int(s * 2 / 3))) for s in spatial)
+    mask = torch.ones(spatial, dtype=torch.int64, device=img.device)
+    mask[tuple(slice(o, o + int(s * 2 / 3)) for o, s in zip(offsets, spatial))] = 0
+    return mask, mask.unsqueeze(0).expand((img.shape[0],) + spatial)
+
+
+def largest_cc_labels(seg, n_classes):
+    """get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144): keep the largest connected component of
+    every foreground class per sample (full connectivity, first component wins ties).  Host side."""
+    from scipy import ndimage
+    seg_np = seg.detach().cpu().numpy()
+    structure = np.ones((3,) * (seg_np.ndim - 1), dtype=bool)
+    out = np.zeros(seg_np.shape, dtype=np.float32)
+    for i in range(seg_np.shape[0]):
+        for c in range(1, n_classes):
+            labels, n = ndimage.label(seg_np[i] == c, structure=structure)
+            if n != 0:
+                keep = labels == (np.argmax(np.bincount(labels.ravel())[1:]) + 1)
+                out[i] += keep.astype(np.float32) * c
+    return torch.from_numpy(out).to(seg.device, non_blocking=True)
+
+
+def get_masks(output, n_classes, nms=1):
+    """get_ACDC_masks, code/train_ours_2D.py:103-108."""
+    probs = ops.argmax(output)
+    return largest_cc_labels(probs, n_classes) if nms == 1 else probs
+
+
+def consistency_weight(iter_num, consistency=1.0, rampup=50.0):
+    """get_current_consistency_weight, code/train_ours_2D.py:34-36 with the call at :356."""
+    return consistency * ramps.sigmoid_rampup(iter_num // 150, rampup)
+
+
+def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, vat=None, adv_losstype="kl",
+                        topk=0.1, use_diff_mask=True, consistency=1.0, rampup=50.0, mask_offsets=None,
+                        d_init=None, trace=None):
+    """Forward part of the iteration; returns (loss, aux).  Line numbers: code/train_ours_2D.py."""
+    n = volume.shape[0]
+    sub_l, sub_u = labeled_bs // 2, (n - labeled_bs) // 2                               # :295
+    img_a, img_b = volume[:sub_l], volume[sub_l:labeled_bs]                             # :307
+    uimg_a, uimg_b = volume[labeled_bs:labeled_bs + sub_u], volume[labeled_bs + sub_u:]
+    lab_a, lab_b = label[:sub_l], label[sub_l:labeled_bs]                               # :310
+    uimg_ab = volume[labeled_bs:]                                                       # :312 (cat of adjacent rows)
+
+    with torch.no_grad():                                                               # :314-333
+        pre1, pre2 = model(uimg_ab)
+        soft1, soft2, ps1, ps2, knowledge = ops.pseudo_label(pre1, pre2)
+        plab1 = largest_cc_labels(ps1, n_classes)          # argmax(softmax) + largest CC, all 2*sub_u rows at once
+        plab2 = largest_cc_labels(ps2, n_classes)
+        plab_a1, plab_b1 = plab1[:sub_u], plab1[sub_u:]
+        plab_a2, plab_b2 = plab2[:sub_u], plab2[sub_u:]
+        img_mask, loss_mask = generate_mask(img_a, mask_offsets)
+        net_input_unl = ops.mask_mix(uimg_a, img_a, img_mask)                           # :335
+        net_input_l = ops.mask_mix(img_b, uimg_b, img_mask)                             # :336
+        net_input_mix = torch.cat((net_input_l, net_input_unl))                         # :338
+
+    out1, out2 = model(net_input_mix)                                                   # :339
+    out_l1, out_unl1 = out1[:sub_l], out1[sub_l:]
+    out_l2, out_unl2 = out2[:sub_l], out2[sub_l:]
+    lu_o1, ll_i1, m1 = losses.mix_loss(out_unl1, plab_a2, lab_a, loss_mask, u_weight=0.5, unlab=True)   # :345
+    lu_o2, ll_i2, m2 = losses.mix_loss(out_unl2, plab_a1, lab_a, loss_mask, u_weight=0.5, unlab=True)   # :346
+    ll_o1, lu_i1, m3 = losses.mix_loss(out_l1, lab_b, plab_b2, loss_mask, u_weight=0.5)                 # :348
+    ll_o2, lu_i2, m4 = losses.mix_loss(out_l2, lab_b, plab_b1, loss_mask, u_weight=0.5)                 # :349
+    bcp_loss = m1 + m2 + m3 + m4                                                        # :351
+    loss_l = ll_i1 + ll_i2 + ll_o1 + ll_o2
+    loss_u = lu_i1 + lu_i2 + lu_o1 + lu_o2
+    cw = consistency_weight(iter_num, consistency, rampup)                              # :356
+
+    if vat is not None:                                                                 # :369-372
+        diff_mask = patch.create_maskV1(ps1, ps2, knowledge, scale_factor=4, topk=topk) if use_diff_mask else None
+        vat_loss = vat(model, volume, soft1, soft2, diff_mask, adv_losstype, d_init=d_init, trace=trace)
+    else:
+        vat_loss = torch.zeros((), device=volume.device)
+    loss = bcp_loss + cw * vat_loss                                                     # :378
+    aux = dict(bcp_loss=bcp_loss.detach(), vat_loss=vat_loss.detach(), loss_l=loss_l.detach(),
+               loss_u=loss_u.detach(), cw=cw, soft1=soft1, soft2=soft2, knowledge=knowledge,
+               plab=(plab_a1, plab_b1, plab_a2, plab_b2), out_mix=(out1.detach(), out2.detach()))
+    return loss, aux
+
+
+class FlatSGD:
+    """torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4) semantics (code/train_ours_2D.py:278,383)
+    on one flat fp32 arena: parameters are re-pointed at views of a single buffer, gradients are
+    gathered into a matching flat buffer, and ONE fused kernel updates everything.  `grad_hook`
+    (optional) is called on the flat gradient before the update -- the data-parallel all-reduce."""
+
+    def __init__(self, params, lr, momentum=0.9, weight_decay=1e-4, grad_hook=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.momentum, self.weight_decay, self.grad_hook = lr, momentum, weight_decay, grad_hook
+        dev = self.params[0].device
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4                     # keep every slot 16-byte aligned
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+        self.grad_views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        self.first = True
+        ops.invalidate_weight_cache()
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        with torch.no_grad():
+            missing = [v for p, v in zip(self.params, self.grad_views) if p.grad is None]
+            have = [(v, p.grad) for p, v in zip(self.params, self.grad_views) if p.grad is not None]
+            if missing:
+                torch._foreach_zero_(missing)
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+
+    def step(self, grad_scale=1.0):
+        self.gather_grads()
+        if self.grad_hook is not None:
+            self.grad_hook(self.flat_g)
+        ops.sgd_momentum_(self.flat_p, self.flat_g, self.flat_buf, self.lr, self.momentum, self.weight_decay,
+                          grad_scale, self.first)
+        self.first = False
+
+
+class ChapTrainer:
+    """State + `step(volume, label)` for CHAP training of a DualDecoder (2D) or DualDecoder3d (3D)."""
+
+    def __init__(self, model, n_classes, labeled_bs, base_lr=0.01, max_iterations=30000, adv_noise=True,
+                 adv_losstype="kl", noise_mag=10.0, epi=6.0, topk=0.1, consistency=1.0, consistency_rampup=50.0,
+                 use_diff_mask=True, grad_hook=None, grad_scale=1.0):
+        self.model, self.n_classes, self.labeled_bs = model, n_classes, labeled_bs
+        self.base_lr, self.max_iterations = base_lr, max_iterations
+        self.vat = losses.VAT2d(xi=noise_mag, epi=epi, num_classes=n_classes) if adv_noise else None
+        self.adv_losstype, self.topk, self.use_diff_mask = adv_losstype, topk, use_diff_mask
+        self.consistency, self.rampup = consistency, consistency_rampup
+        self.opt = FlatSGD(model.parameters(), base_lr, grad_hook=grad_hook)
+        self.grad_scale = grad_scale
+        self.iter_num = 0
+        model.train()
+
+    def step(self, volume, label, mask_offsets=None, d_init=None, trace=None):
+        loss, aux = chap_losses_forward(self.model, volume, label, self.labeled_bs, self.n_classes, self.iter_num,
+                                        vat=self.vat, adv_losstype=self.adv_losstype, topk=self.topk,
+                                        use_diff_mask=self.use_diff_mask, consistency=self.consistency,
+                                        rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace)
+        self.opt.zero_grad()                                                            # :381
+        loss.backward()                                                                 # :382
+        self.opt.lr = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9   # lr set at :387-389 of the previous iteration
+        self.opt.step(self.grad_scale)                                                  # :383
+        self.iter_num += 1                                                              # :385
+        aux["loss"] = loss.detach()
+        return aux

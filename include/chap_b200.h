@@ -1,0 +1,248 @@
+/*
+ * chap_b200.h -- C ABI of libchap_b200.so (sm_100a only).
+ *
+ * The reference (gardnerzhou/CHAP) has no FFI layer: its device work is ATen/cuDNN calls made
+ * from nn.Module.forward and from the training script.  Each entry point below names the
+ * reference interface (file:line under /root/reference) whose device work it replaces; the
+ * Python host side (chap_b200/ops.py) binds them with ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every device buffer (workspaces included) is owned by the
+ *    caller; the library never allocates or frees device memory and keeps no pointer after
+ *    return.  Descriptors are PODs copied on entry.
+ *  - Activations are fp32, channels-last: [N, (D,) H, W, C] (a torch tensor of logical shape
+ *    [N, C, (D,) H, W] in torch.channels_last / channels_last_3d memory format).  For 2D, D = 1.
+ *  - Convolution weights / gradients use the torch parameter layout
+ *    ([Cout, Cin, k..] for conv, [Cin, Cout, k..] for transposed conv); packed copies are opaque.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *    synchronisation and is CUDA-graph capturable.
+ *  - Return 0 on success, a negative chap_status on failure; chap_last_error() returns a
+ *    thread-local message.  No exceptions cross the ABI.  There is no CPU fallback.
+ */
+#ifndef CHAP_B200_H
+#define CHAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHAP_ABI_VERSION 1
+
+typedef enum {
+    CHAP_OK = 0,
+    CHAP_ERR_BAD_ARG = -1,      /* null pointer, bad shape, unsupported combination */
+    CHAP_ERR_ALIGNMENT = -2,    /* pointer / channel count not aligned as required */
+    CHAP_ERR_WORKSPACE = -3,    /* workspace too small */
+    CHAP_ERR_CUDA = -4,         /* a CUDA runtime / driver call failed */
+    CHAP_ERR_ARCH = -5          /* device is not sm_100 */
+} chap_status;
+
+const char* chap_last_error(void);
+int chap_abi_version(void);
+/* 0 when the current device is a compute-capability 10.x part, CHAP_ERR_ARCH otherwise. */
+int chap_check_device(void);
+/* Number of kernels this library has launched in this process (bench.py `gpu_launches`). */
+uint64_t chap_launch_count(void);
+void chap_reset_launch_count(void);
+/* 1: route every convolution through the CUDA-core kernels (debug aid), 0: tcgen05 where supported. */
+void chap_set_force_simt(int flag);
+int chap_get_force_simt(void);
+
+/* ------------------------------------------------------------------ convolutions
+ * Replaces nn.Conv2d/Conv3d/ConvTranspose2d/ConvTranspose3d forward + backward inside
+ *   unet.ConvBlock code/networks/unet.py:44-60, unet.UpBlock :78-99, unet.Decoder.out_conv :168,
+ *   vnet.ConvBlock code/networks/vnet.py:8-34, DownsamplingConvBlock :70-94,
+ *   Upsampling_function :97-125, vnet.Decoder.out_conv :189.
+ */
+typedef enum {
+    CHAP_CONV_K3 = 0,     /* k=3, stride 1, pad 1 */
+    CHAP_CONV_K1 = 1,     /* k=1, stride 1, pad 0 */
+    CHAP_CONV_DOWN2 = 2,  /* k=2, stride 2, pad 0 (out spatial = in/2) */
+    CHAP_CONV_UP2 = 3     /* transposed, k=2, stride 2 (out spatial = 2*in) */
+} chap_conv_kind;
+
+typedef struct {
+    int32_t kind;       /* chap_conv_kind */
+    int32_t nd;         /* 2 or 3 spatial dims */
+    int32_t n;          /* batch */
+    int32_t in_d, in_h, in_w;   /* INPUT spatial size (in_d = 1 for nd == 2) */
+    int32_t cin, cout;
+} chap_conv_desc;
+
+/* number of floats in one packed weight buffer (same for the fwd and the dgrad packing) */
+size_t chap_conv_packed_elems(const chap_conv_desc* d);
+/* torch-layout weight -> packed forward operand and packed data-gradient operand (either may be NULL) */
+int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream);
+/* y = conv(x) + bias.  ch_sums (nullable): double[2*cout], receives per-channel sum(y), sum(y*y)
+ * (zeroed by the call) -- the BatchNorm batch statistics of the following layer. */
+int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
+                  float* y, double* ch_sums, void* stream);
+/* dx = conv^T(dy) (data gradient), dx has the input shape */
+int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream);
+/* dw (torch layout, overwritten) and dbias (nullable) from x and dy.
+ * workspace: caller-owned scratch of chap_conv_wgrad_workspace_bytes(d) bytes (may be 0 -> NULL ok). */
+size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d);
+int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ BatchNorm + activation (+dropout, +skip add)
+ * Replaces BatchNorm2d/3d (train and eval) + LeakyReLU(0.01)/ReLU + Dropout + the additive skip of
+ * vnet.Decoder (code/networks/unet.py:51-56, code/networks/vnet.py:21-28,202-215).
+ */
+/* per-channel sum / sum of squares of y[rows, c] into double[2c] (zeroed by the call) */
+int chap_channel_stats(const float* y, int64_t rows, int32_t c, double* sums, void* stream);
+/* train mode: batch mean / biased var from sums -> mean_invstd[2c], scale_shift[2c]
+ * (scale = gamma*invstd, shift = beta - mean*scale); if running_mean != NULL update
+ * running = (1-m)*running + m*stat (unbiased var) and ++(*num_batches_tracked). */
+int chap_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float* mean_invstd, float* scale_shift,
+                     int32_t c, void* stream);
+/* eval mode: scale/shift (and mean_invstd) from the running statistics */
+int chap_bn_eval_params(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* mean_invstd, float* scale_shift,
+                        int32_t c, void* stream);
+/* out = act(y*scale+shift) * drop + residual;   act(z) = z>0 ? z : slope*z
+ * drop_nc (nullable): float[n*c] per-(sample,channel) factor (Dropout2d/3d);
+ * drop_el (nullable): float[n*rows_per_sample*c] elementwise factor (nn.Dropout); residual nullable. */
+int chap_bn_act_fwd(const float* y, const float* scale_shift, float slope, const float* drop_nc,
+                    const float* drop_el, const float* residual, int32_t n, int64_t rows_per_sample,
+                    int32_t c, float* out, void* stream);
+/* backward of the above.  Pass 1 accumulates sums[2c] = (sum dz, sum dz*xhat) (doubles, zeroed by the
+ * call); pass 2 writes dy and (train) dgamma, dbeta.  train = 0: BN constants are fixed (eval). */
+int chap_bn_act_bwd(const float* dout, const float* y, const float* scale_shift, const float* mean_invstd,
+                    const float* gamma, float slope, const float* drop_nc, const float* drop_el,
+                    int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
+                    double* sums, float* dy, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------ pooling / upsampling / concat
+ * MaxPool2d(2) code/networks/unet.py:69; Upsample(x2, bilinear|trilinear, align_corners=True)
+ * unet.py:87-88, vnet.py:105; torch.cat([skip, up], 1) unet.py:98.
+ */
+int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, void* stream);
+int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, void* stream);
+/* nd = 2: d must be 1.  out spatial = 2 * in spatial. */
+int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* y, void* stream);
+int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* dx, void* stream);
+/* out[r, 0:ca] = a[r, :], out[r, ca:ca+cb] = b[r, :] */
+int chap_concat_channels(const float* a, const float* b, int64_t rows, int32_t ca, int32_t cb, float* out, void* stream);
+/* inverse: a (nullable), b (nullable) <- slices of in */
+int chap_split_channels(const float* in, int64_t rows, int32_t ca, int32_t cb, float* a, float* b, void* stream);
+/* out[n, r, c] = x[n, r, c] * scale_nc[n, c]  (Dropout2d of FilterDropout.perform_dropout,
+ * code/networks/FilterDropout.py:45-89, and unet.UNet.perform_dropout unet.py:532-552) */
+int chap_channel_scale(const float* x, const float* scale_nc, int32_t n, int64_t rows_per_sample, int32_t c, float* out, void* stream);
+/* out = a + alpha*b (flat) */
+int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream);
+/* out = a*m + b*(1-m), m int64/broadcast spatial mask [rows_per_sample] (copy-paste mixing,
+ * code/train_ours_2D.py:335-336) */
+int chap_mask_mix(const float* a, const float* b, const int64_t* mask, int32_t n, int64_t rows_per_sample,
+                  int32_t c, float* out, void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * softmax / argmax / cross-entropy / masked Dice of code/train_ours_2D.py:198-216,319-325 and the
+ * 'kl' | 'dice' consistency distance of losses.VAT2d (call site :372).  logits are channels-last
+ * [n, rows_per_sample, c], c <= 8.
+ */
+/* soft1/soft2 (nullable) = softmax, arg1/arg2 (nullable) = argmax (int64, first max wins),
+ * knowledge (nullable) = CE(pre1, arg2) + CE(pre2, arg1) per position */
+int chap_pseudo_label(const float* pre1, const float* pre2, int64_t rows, int32_t c,
+                      float* soft1, float* soft2, int64_t* arg1, int64_t* arg2, float* knowledge, void* stream);
+/* softmax over c for each row (inference, code/test_3D_util.py:64, code/val_2D.py:68-80) */
+int chap_softmax(const float* logits, int64_t rows, int32_t c, float* out, void* stream);
+/* argmax over c of (a + b)/2 (b nullable -> argmax of a); first max wins (code/val_2D.py:72-83) */
+int chap_argmax(const float* a, const float* b, int64_t rows, int32_t c, int64_t* out, void* stream);
+
+/* label dtype codes */
+#define CHAP_LABEL_I64 0
+#define CHAP_LABEL_F32 1
+/* Masked Dice + CE partial sums against hard labels.
+ * mask: int64 [rows_per_sample] (broadcast over n), used as m (invert=0) or 1-m (invert=1).
+ * sums (double[3c+2], zeroed by the call): inter[c], sum s^2 m [c], sum t m [c], sum CE m, sum m */
+int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t label_dtype, const int64_t* mask,
+                     int32_t invert, int32_t n, int64_t rows_per_sample, int32_t c, double* sums, void* stream);
+/* dlogits (+)= d/dlogits of  sum_c [coef_i[c]*inter_c + coef_s[c]*(sum s^2 m)_c] + coef_ce * sum(CE m);
+ * coef: float[2c+1] on device = (coef_i[c], coef_s[c], coef_ce); accumulate != 0 adds into dlogits */
+int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t label_dtype, const int64_t* mask,
+                     int32_t invert, int32_t n, int64_t rows_per_sample, int32_t c, const float* coef,
+                     int32_t accumulate, float* dlogits, void* stream);
+
+#define CHAP_DIST_KL 0
+#define CHAP_DIST_DICE 1
+/* consistency distance between softmax(logits) and a soft target; mask: float [n*rows_per_sample] or NULL.
+ * sums (double[3c+1], zeroed by the call): KL: sums[0] = sum m * KL(t || p);
+ * DICE: inter[c], sum p^2 m[c], sum t^2 m[c]. */
+int chap_consistency_fwd(const float* logits, const float* target, const float* mask, int32_t dist,
+                         int64_t rows, int32_t c, double* sums, void* stream);
+/* KL: dlogits = coef[0] * m * (p*sum(t) - t);  DICE: through the softmax Jacobian with
+ * coef = (coef_i[c], coef_p[c]) multiplying inter_c and (sum p^2 m)_c */
+int chap_consistency_bwd(const float* logits, const float* target, const float* mask, int32_t dist,
+                         int64_t rows, int32_t c, const float* coef, float* dlogits, void* stream);
+/* patch scores of patch.create_maskV1 (call site code/train_ours_2D.py:371):
+ * score[n, patch] = mean(knowledge) + mean(arg1 != arg2) over s^nd patches */
+int chap_patch_score(const float* knowledge, const int64_t* arg1, const int64_t* arg2, int32_t nd, int32_t n,
+                     int32_t d, int32_t h, int32_t w, int32_t s, float* score, void* stream);
+/* mask[n, voxel] = score[n, patch(voxel)] >= kth[n] */
+int chap_patch_mask(const float* score, const float* kth, int32_t nd, int32_t n, int32_t d, int32_t h,
+                    int32_t w, int32_t s, float* mask, void* stream);
+
+/* ------------------------------------------------------------------ perturbation generator
+ * The channel-spatial hierarchical adversarial perturbation of losses.VAT2d (absent in the
+ * reference; ctor code/train_ours_2D.py:290, call :372; BASELINE.json north_star).
+ */
+typedef struct {
+    const float* g;     /* gradient w.r.t. the level's perturbation direction [n, rows, c] */
+    const float* f;     /* encoder feature of the level (nullable: out = r only) */
+    float* out;         /* f + eps * normalise(g) */
+    int64_t rows;       /* positions per sample */
+    int32_t c;
+    int32_t pad_;
+} chap_level;
+
+#define CHAP_PERTURB_SAMPLE 0
+#define CHAP_PERTURB_CHANNEL 1
+#define CHAP_PERTURB_SPATIAL 2
+#define CHAP_PERTURB_CHANNEL_SPATIAL 3
+/* workspace: double[ws_elems], ws_elems >= chap_perturb_workspace_elems(levels, n_levels, n) */
+size_t chap_perturb_workspace_elems(const chap_level* levels, int32_t n_levels, int32_t n);
+/* g is multiplied by g_scale when loaded (chain-rule factor of the probing step) */
+int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int32_t n, int32_t mode, float eps, float g_scale,
+                     double* workspace, size_t ws_elems, void* stream);
+/* out = base + xi * d / (||d||_2 per sample + 1e-8)  (base nullable); norms: double[n] scratch */
+int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n, int64_t elems_per_sample,
+                         double* norms, float* out, void* stream);
+
+/* ------------------------------------------------------------------ optimiser
+ * torch.optim.SGD(momentum, weight_decay) step of code/train_ours_2D.py:278,383 on flat buffers:
+ * g' = grad_scale*g + wd*p ; buf = first ? g' : mom*buf + g' ; p -= lr*buf */
+int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t elems, float lr, float momentum,
+                      float weight_decay, float grad_scale, int32_t first_step, void* stream);
+
+/* ------------------------------------------------------------------ sliding-window aggregation
+ * The score_map / cnt accumulation, division and argmax of test_single_case,
+ * code/test_3D_util.py:46-72 (identical: code/val_3D.py:46-72).
+ */
+typedef struct {
+    int32_t vol[3];      /* padded volume size (ww, hh, dd) */
+    int32_t patch[3];    /* patch size (pw, ph, pd) */
+    int32_t nwin[3];     /* windows per axis (sx, sy, sz) */
+    int32_t stride[3];   /* (stride_xy, stride_xy, stride_z) */
+    int32_t c;           /* classes */
+    int32_t pad_;
+} chap_sw_desc;
+/* gather windows [first, first+count) of the padded volume into patches[count, pw, ph, pd] */
+int chap_sw_extract(const chap_sw_desc* d, const float* volume, int32_t first, int32_t count, float* patches, void* stream);
+/* win: window logits (is_prob = 0: softmax fused on load) or probabilities (is_prob = 1),
+ * channels-last [nwin_total, pw, ph, pd, c], windows ordered x-major then y then z like the
+ * reference loops.  Each output voxel is owned by one thread which adds its windows in the reference
+ * order (bit-identical fp32 sums), divides by cnt and takes the first-max argmax.
+ * score (nullable): [c, ww, hh, dd] (already divided by cnt); cnt (nullable): [ww, hh, dd]. */
+int chap_sw_aggregate(const chap_sw_desc* d, const float* win, int32_t is_prob, float* score, float* cnt,
+                      int64_t* label, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHAP_B200_H */
