@@ -1,0 +1,265 @@
+"""GPU: every kernel of libchap_b200 against a plain PyTorch fp32 restatement of the same op
+(run on the CPU in float64/float32) -- through the public ops / the C ABI."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, max_err, rel_err
+from oracle import chap_losses as L
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+# tolerance on convolution results: the tensor-core path multiplies in TF32 (10-bit mantissa, the
+# reference's default cudnn.allow_tf32 behaviour), accumulates in fp32; CUDA-core path is fp32.
+CONV_TOL = 3e-3
+SIMT_TOL = 2e-5
+
+
+def _ops():
+    from chap_b200 import ops
+    return ops
+
+
+def _to_cl(x):
+    return _ops().cl(x.to(DEV))
+
+
+CONV_CASES = [
+    # kind, nd, n, spatial, cin, cout
+    ("k3", 2, 2, (12, 16), 1, 16), ("k3", 2, 3, (9, 7), 16, 16), ("k3", 2, 2, (16, 16), 32, 64),
+    ("k3", 2, 1, (8, 8), 16, 4), ("k3", 2, 2, (5, 6), 256, 128),
+    ("k1", 2, 2, (8, 8), 64, 32), ("k1", 3, 2, (4, 6, 5), 16, 2),
+    ("up2", 2, 2, (6, 5), 32, 16), ("up2", 3, 2, (3, 4, 5), 32, 16),
+    ("down2", 3, 2, (4, 6, 8), 16, 32), ("down2", 2, 2, (6, 8), 16, 32),
+    ("k3", 3, 2, (6, 5, 7), 1, 16), ("k3", 3, 1, (5, 8, 6), 16, 16), ("k3", 3, 2, (4, 4, 5), 64, 32),
+]
+
+
+def _torch_conv(kind, nd, x, w, b):
+    conv = F.conv2d if nd == 2 else F.conv3d
+    convt = F.conv_transpose2d if nd == 2 else F.conv_transpose3d
+    if kind == "k3":
+        return conv(x, w, b, padding=1)
+    if kind == "k1":
+        return conv(x, w, b)
+    if kind == "down2":
+        return conv(x, w, b, stride=2)
+    return convt(x, w, b, stride=2)
+
+
+@pytest.mark.parametrize("force_simt", [True, False])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "%s-%dd-n%d-%s-%d-%d" % (c[0], c[1], c[2], "x".join(map(str, c[3])), c[4], c[5]))
+def test_conv_fwd_dgrad_wgrad(case, force_simt):
+    from chap_b200 import _lib
+    ops = _ops()
+    kind, nd, n, sp, cin, cout = case
+    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1, "down2": _lib.CONV_DOWN2, "up2": _lib.CONV_UP2}[kind]
+    k = {"k3": 3, "k1": 1, "down2": 2, "up2": 2}[kind]
+    g = torch.Generator().manual_seed(CONV_CASES.index(case))
+    x = torch.randn((n, cin) + sp, generator=g, dtype=torch.float64)
+    wshape = ((cin, cout) if kind == "up2" else (cout, cin)) + (k,) * nd
+    w = torch.randn(wshape, generator=g, dtype=torch.float64) / (cin * k ** nd) ** 0.5
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y_ref = _torch_conv(kind, nd, x, w, b)
+    gy = torch.randn(y_ref.shape, generator=g, dtype=torch.float64)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(y_ref, (x, w, b), gy)
+    ops.set_force_simt(force_simt)
+    try:
+        xg = _to_cl(x.detach().float()).requires_grad_(True)
+        wg = w.detach().float().to(DEV).requires_grad_(True)
+        bg = b.detach().float().to(DEV).requires_grad_(True)
+        y, sums = ops.conv_stats(xg, wg, bg, kcode, True)
+        gx, gw, gb = torch.autograd.grad(y, (xg, wg, bg), gy.float().to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_force_simt(False)
+    tol = SIMT_TOL if force_simt else CONV_TOL
+    assert y.shape == y_ref.shape
+    assert rel_err(y, y_ref) < tol, "fwd"
+    assert rel_err(gx, gx_ref) < tol, "dgrad"
+    assert rel_err(gw, gw_ref) < tol, "wgrad"
+    assert rel_err(gb, gb_ref) < tol, "dbias"
+    yd = y.detach().double().cpu()
+    dims = (0,) + tuple(range(2, 2 + nd))
+    assert rel_err(sums[:cout], yd.sum(dims)) < 1e-4 + tol and rel_err(sums[cout:], (yd * yd).sum(dims)) < 1e-4 + tol, "fused BN statistics"
+
+
+@pytest.mark.parametrize("nd,train,with_res,drop", list(itertools.product([2, 3], [True, False], [False, True], ["none", "nc", "el"])))
+def test_bn_act_fwd_bwd(nd, train, with_res, drop):
+    ops = _ops()
+    torch.manual_seed(nd * 7 + int(train))
+    n, c = 3, 16
+    sp = (6, 5) if nd == 2 else (3, 4, 5)
+    y = torch.randn((n, c) + sp, dtype=torch.float64) * 2 + 0.5
+    bn = (torch.nn.BatchNorm2d if nd == 2 else torch.nn.BatchNorm3d)(c).double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+        bn.running_mean.uniform_(-0.2, 0.2); bn.running_var.uniform_(0.5, 1.5)
+    bn.train(train)
+    res = torch.randn_like(y) if with_res else None
+    dnc = (torch.rand(n, c, dtype=torch.float64) > 0.5).double() * 2 if drop == "nc" else None
+    dele = (torch.rand_like(y) > 0.3).double() / 0.7 if drop == "el" else None
+    slope = 0.01 if nd == 2 else 0.0
+    bn_g = (torch.nn.BatchNorm2d if nd == 2 else torch.nn.BatchNorm3d)(c).to(DEV)
+    bn_g.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    bn_g.train(train)
+    yr = y.clone().requires_grad_(True)
+    resr = res.clone().requires_grad_(True) if with_res else None
+    out_ref = F.leaky_relu(bn(yr), slope)
+    if dnc is not None:
+        out_ref = out_ref * dnc.reshape((n, c) + (1,) * nd)
+    if dele is not None:
+        out_ref = out_ref * dele
+    if with_res:
+        out_ref = out_ref + resr
+    gout = torch.randn_like(out_ref)
+    ins = [yr, bn.weight, bn.bias] + ([resr] if with_res else [])
+    grads_ref = torch.autograd.grad(out_ref, ins, gout)
+    yg = _to_cl(y.float()).requires_grad_(True)
+    resg = _to_cl(res.float()).requires_grad_(True) if with_res else None
+    out = ops.bn_act(yg, bn_g, slope, residual=resg, drop_nc=None if dnc is None else dnc.float().to(DEV),
+                     drop_el=None if dele is None else _to_cl(dele.float()))
+    ins_g = [yg, bn_g.weight, bn_g.bias] + ([resg] if with_res else [])
+    grads = torch.autograd.grad(out, ins_g, gout.float().to(DEV))
+    assert rel_err(out, out_ref) < 1e-5
+    for a, b_, nm in zip(grads, grads_ref, ["dy", "dgamma", "dbeta", "dres"]):
+        assert rel_err(a, b_) < 2e-5, nm
+    if train:
+        assert rel_err(bn_g.running_mean, bn.running_mean) < 1e-6 and rel_err(bn_g.running_var, bn.running_var) < 1e-6
+        assert int(bn_g.num_batches_tracked) == int(bn.num_batches_tracked) == 1
+
+
+def test_bn_tracking_disabled_keeps_running_stats():
+    ops = _ops()
+    bn = torch.nn.BatchNorm2d(16).to(DEV).train()
+    y = _to_cl(torch.randn(2, 16, 4, 4))
+    with ops.bn_tracking(False):
+        ops.bn_act(y, bn, 0.01)
+    assert float(bn.running_mean.abs().sum()) == 0.0 and int(bn.num_batches_tracked) == 0
+
+
+def test_maxpool_upsample_concat():
+    ops = _ops()
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 8, 6, dtype=torch.float64, requires_grad=True)
+    ref = F.max_pool2d(x, 2)
+    g = torch.randn_like(ref)
+    (gx_ref,) = torch.autograd.grad(ref, x, g)
+    xg = _to_cl(x.detach().float()).requires_grad_(True)
+    out = ops.maxpool2(xg)
+    (gx,) = torch.autograd.grad(out, xg, g.float().to(DEV))
+    assert max_err(out, ref) < 1e-6 and max_err(gx, gx_ref) < 1e-6
+    for nd, shape in ((2, (2, 8, 5, 7)), (3, (2, 4, 3, 5, 4)), (3, (1, 8, 1, 2, 3)), (2, (1, 4, 1, 1))):
+        x = torch.randn(shape, dtype=torch.float64, requires_grad=True)
+        ref = F.interpolate(x, scale_factor=2, mode="bilinear" if nd == 2 else "trilinear", align_corners=True)
+        g = torch.randn_like(ref)
+        (gx_ref,) = torch.autograd.grad(ref, x, g)
+        xg = _to_cl(x.detach().float()).requires_grad_(True)
+        out = ops.upsample2x(xg)
+        (gx,) = torch.autograd.grad(out, xg, g.float().to(DEV))
+        assert rel_err(out, ref) < 1e-6, shape
+        assert rel_err(gx, gx_ref) < 1e-6, shape
+    a = torch.randn(2, 16, 4, 5, requires_grad=True)
+    b = torch.randn(2, 32, 4, 5, requires_grad=True)
+    ag, bg = _to_cl(a.detach()).requires_grad_(True), _to_cl(b.detach()).requires_grad_(True)
+    out = ops.concat_channels(ag, bg)
+    g = torch.randn(2, 48, 4, 5)
+    ga, gb = torch.autograd.grad(out, (ag, bg), g.to(DEV))
+    assert torch.equal(out.cpu(), torch.cat([a, b], 1)) and torch.equal(ga.cpu(), g[:, :16]) and torch.equal(gb.cpu(), g[:, 16:])
+    s = torch.rand(2, 16)
+    assert rel_err(ops.channel_scale(ag, s.to(DEV)), a.detach() * s[:, :, None, None]) < 1e-7
+    m = (torch.rand(4, 5) > 0.5).long()
+    c1, c2 = torch.randn(2, 1, 4, 5), torch.randn(2, 1, 4, 5)
+    assert torch.equal(ops.mask_mix(c1.to(DEV), c2.to(DEV), m.to(DEV)).cpu(), c1 * m + c2 * (1 - m))
+
+
+@pytest.mark.parametrize("c,nd", [(4, 2), (2, 3)])
+def test_loss_kernels_match_frozen_oracle(c, nd):
+    ops = _ops()
+    from chap_b200.utils import losses
+    torch.manual_seed(c)
+    sp = (12, 16) if nd == 2 else (4, 8, 8)
+    n = 3
+    logits = (torch.randn((n, c) + sp) * 2).requires_grad_(True)
+    logits2 = torch.randn((n, c) + sp) * 2
+    lab_a, lab_b = torch.randint(0, c, (n,) + sp), torch.randint(0, c, (n,) + sp).float()
+    mask = L.generate_mask(sp, tuple(1 for _ in sp))
+    lmask = mask.unsqueeze(0).expand((n,) + sp)
+    ref = L.mix_loss(logits, lab_a, lab_b, lmask, c, unlab=True)
+    (gref,) = torch.autograd.grad(ref[2] + 0.3 * ref[0], logits)
+    lg = _to_cl(logits.detach()).requires_grad_(True)
+    out = losses.mix_loss(lg, lab_a.to(DEV), lab_b.to(DEV), lmask.to(DEV), unlab=True)
+    (gg,) = torch.autograd.grad(out[2] + 0.3 * out[0], lg)
+    for a, b in zip(out, ref):
+        assert abs(float(a) - float(b)) < 1e-5 * max(1.0, abs(float(b)))
+    assert rel_err(gg, gref) < 1e-4
+    # pseudo-label block + patch mask
+    s1, s2, a1, a2, know = ops.pseudo_label(_to_cl(logits.detach()), _to_cl(logits2))
+    rs1, rs2, ra1, ra2, rknow = L.pseudo_label_block(logits.detach(), logits2)
+    assert rel_err(s1, rs1) < 1e-6 and rel_err(s2, rs2) < 1e-6 and rel_err(know, rknow) < 1e-5
+    assert torch.equal(a1.cpu(), ra1) and torch.equal(a2.cpu(), ra2)
+    dm = ops.patch_topk_mask(know, a1, a2, 4, 0.25)
+    rdm = L.create_mask_v1(ra1, ra2, rknow, 4, 0.25)
+    assert float((dm.cpu() != rdm).float().mean()) < 0.02          # a patch can flip only through a float tie at the threshold
+    # consistency distances, masked and unmasked, both types
+    for losstype, m in itertools.product(("kl", "dice"), (None, rdm)):
+        r = L.consistency_distance(logits, rs2, m, losstype)
+        (gr,) = torch.autograd.grad(r, logits)
+        o = losses.consistency_distance(lg, s2, None if m is None else m.to(DEV), losstype)
+        (go,) = torch.autograd.grad(o, lg)
+        assert abs(float(o) - float(r)) < 1e-5 * max(1.0, abs(float(r))), (losstype, m is None)
+        assert rel_err(go, gr) < 1e-4, (losstype, m is None)
+    assert torch.equal(ops.argmax(lg).cpu(), logits.detach().argmax(1))
+    assert rel_err(ops.softmax(lg), torch.softmax(logits.detach(), 1)) < 1e-6
+
+
+def test_loss_kernels_match_frozen_fixture():
+    from chap_b200.utils import losses
+    g = golden("frozen_losses.npz")
+    lg = _to_cl(torch.from_numpy(g["logits"]))
+    out = losses.mix_loss(lg, torch.from_numpy(g["lab_a"]).to(DEV), torch.from_numpy(g["lab_b"]).to(DEV),
+                          torch.from_numpy(g["mask"]).to(DEV), unlab=True)
+    np.testing.assert_allclose([float(v) for v in out], g["mix"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["channel_spatial", "channel", "spatial", "sample"])
+def test_perturbation_generator(mode):
+    """tolerance from BASELINE.json north_star: <= 1e-4 relative on perturbation tensors."""
+    ops = _ops()
+    torch.manual_seed(1)
+    shapes = [(3, 16, 16, 16), (3, 32, 8, 8), (3, 64, 4, 4), (3, 128, 2, 2), (3, 256, 1, 1)]
+    gs = [torch.randn(s) * (10.0 ** -i) for i, s in enumerate(shapes)]
+    fs = [torch.randn(s) for s in shapes]
+    outs = ops.perturb([_to_cl(t) for t in gs], [_to_cl(t) for t in fs], 6.0, mode, g_scale=10.0)
+    for o, g_, f in zip(outs, gs, fs):
+        r_ref = L.perturbation(g_ * 10.0, 6.0, mode)
+        r = o.cpu() - f
+        assert rel_err(r, r_ref) < 1e-4
+        assert rel_err(o, f + r_ref) < 1e-6
+    g3 = torch.randn(2, 16, 4, 6, 5)
+    (o3,) = ops.perturb([_to_cl(g3)], None, 2.0, mode)
+    assert rel_err(o3, L.perturbation(g3, 2.0, mode)) < 1e-4
+    gf = golden("frozen_losses.npz")
+    key = {"channel_spatial": "r_cs", "channel": "r_c", "spatial": "r_s", "sample": "r_n"}[mode]
+    (og,) = ops.perturb([_to_cl(torch.from_numpy(gf["gfield"]))], None, 6.0, mode)
+    assert rel_err(og, gf[key]) < 1e-4
+
+
+def test_l2n_axpy_and_sgd():
+    ops = _ops()
+    torch.manual_seed(2)
+    d, base = torch.randn(3, 16, 5, 7) - 0.5, torch.randn(3, 16, 5, 7)
+    out = ops.l2n_sample_axpy(_to_cl(d), _to_cl(base), 10.0)
+    assert rel_err(out, base + 10.0 * L.l2n_sample(d)) < 1e-6
+    p, g = torch.randn(1003), torch.randn(1003)
+    pr, buf = p.clone(), [None]
+    pg, gg, bg = p.to(DEV), g.to(DEV), torch.zeros(1003, device=DEV)
+    for it in range(3):
+        L.sgd_momentum_step([pr], [g * (it + 1)], buf, 0.01 * (it + 1))
+        ops.sgd_momentum_(pg, gg * (it + 1), bg, 0.01 * (it + 1), 0.9, 1e-4, 1.0, it == 0)
+    assert rel_err(pg, pr) < 1e-6 and rel_err(bg, buf[0]) < 1e-6

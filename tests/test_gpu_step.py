@@ -1,0 +1,127 @@
+"""GPU: the perturbation step (VAT2d) and the full CHAP training iteration against the frozen
+oracle (oracle/train_step.py) on the same weights, inputs, copy-paste offsets and probing noise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, seeded_model
+from oracle import chap_losses as L
+from oracle import nets
+from oracle import train_step as oracle_step
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _batch2d(n=8, size=32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.rand(n, 1, size, size, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
+    lab = torch.zeros(n, size, size, dtype=torch.int64)
+    for i in range(n):                                   # blobby labels so that connected components exist
+        for c in range(1, 4):
+            cy, cx = torch.randint(6, size - 6, (2,), generator=g)
+            lab[i][((yy - cy) ** 2 + (xx - cx) ** 2) < (3 + c) ** 2] = c
+    return vol, lab
+
+
+@pytest.mark.parametrize("losstype", ["kl", "dice"])
+def test_vat_matches_oracle(losstype):
+    """perturbation tensors <= 1e-4 relative GIVEN the same gradient field (kernel boundary), VAT loss
+    <= 1e-3 (BASELINE.json north_star tolerances)."""
+    from chap_b200 import ops
+    from chap_b200.utils import losses
+    m = seeded_model("dualdecoder2d", seed=11).to(DEV).train()
+    sd = nets.clone_state_dict(m.state_dict(), requires_grad=True)
+    om = oracle_step.OracleModel(sd, dims=2)
+    vol, _ = _batch2d(8, 32)
+    with torch.no_grad():
+        p1, p2 = om(vol[4:])
+    soft1, soft2, ps1, ps2, know = L.pseudo_label_block(p1, p2)
+    mask = L.create_mask_v1(ps1, ps2, know, 4, 0.25)
+    g = torch.Generator().manual_seed(3)
+    d_init = [torch.rand(4, c, s, s, generator=g) - 0.5 for c, s in zip((16, 32, 64, 128, 256), (32, 16, 8, 4, 2))]
+    tr_o, tr_g = {}, {}
+    lo = L.VAT(10.0, 6.0, 4)(om, vol, soft1, soft2, mask, losstype, d_init=d_init, trace=tr_o)
+    lg = losses.VAT2d(10.0, 6.0, 4)(m, vol.to(DEV), soft1.to(DEV), soft2.to(DEV), mask.to(DEV), losstype,
+                                     d_init=[ops.cl(t.to(DEV)) for t in d_init], trace=tr_g)
+    assert abs(float(tr_g["dist"]) - float(tr_o["dist"])) < 2e-3 * max(1.0, abs(float(tr_o["dist"])))
+    for lvl in range(5):
+        # kernel-boundary parity: feed the ORACLE's gradient field through the CUDA generator
+        (adv,) = ops.perturb([ops.cl(tr_o["g"][lvl].to(DEV))], None, 6.0, "channel_spatial", g_scale=1.0)
+        assert rel_err(adv, tr_o["r"][lvl]) < 1e-4, lvl
+        assert rel_err(tr_g["feats"][lvl], tr_o["feats"][lvl]) < 2e-3, lvl
+    assert abs(float(lg) - float(lo)) < 5e-3 * max(1.0, abs(float(lo)))
+    names = [n for n, _ in m.named_parameters()]
+    go = torch.autograd.grad(lo, [sd[n] for n in names], allow_unused=True)
+    gg = torch.autograd.grad(lg, list(m.parameters()), allow_unused=True)
+    assert all((a is None) == (b is None) for a, b in zip(gg, go))
+    tot_o = sum(float(t.double().pow(2).sum()) for t in go if t is not None) ** 0.5
+    tot_g = sum(float(t.double().pow(2).sum()) for t in gg if t is not None) ** 0.5
+    assert abs(tot_g - tot_o) < 0.05 * tot_o        # adversarial direction is chaotic in TF32: norms agree, not bits
+
+
+def test_bn_running_stats_untouched_by_vat():
+    from chap_b200.utils import losses
+    m = seeded_model("dualdecoder2d", seed=11).to(DEV).train()
+    before = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+    vol, _ = _batch2d(4, 32)
+    soft = torch.softmax(torch.randn(2, 4, 32, 32), 1).to(DEV)
+    losses.VAT2d()(m, vol.to(DEV), soft, soft, None, "kl").backward()
+    after = m.state_dict()
+    assert all(torch.equal(v, after[k]) for k, v in before.items())
+
+
+def test_chap_training_iterations_match_oracle():
+    """3 full iterations (pseudo-labels + largest CC + copy-paste mix + 4 mix losses + VAT + backward
+    + SGD momentum/poly LR) in fp32 CUDA-core mode: losses <= 1e-3, parameters after 3 steps close."""
+    from chap_b200 import ops
+    from chap_b200.train_step import ChapTrainer
+    ops.set_force_simt(True)
+    try:
+        m = seeded_model("dualdecoder2d", seed=8).to(DEV)
+        sd = nets.clone_state_dict(m.state_dict(), requires_grad=True)
+        om = oracle_step.OracleModel(sd, dims=2)
+        trainer = ChapTrainer(m, n_classes=4, labeled_bs=4, base_lr=0.01, max_iterations=100, topk=0.25)
+        bufs = [None] * len(om.params())
+        g = torch.Generator().manual_seed(1)
+        for it in range(3):
+            vol, lab = _batch2d(8, 32, seed=it)
+            offs = (3 + it, 5 - it)
+            d_init = [torch.rand(4, c, s, s, generator=g) - 0.5 for c, s in zip((16, 32, 64, 128, 256), (32, 16, 8, 4, 2))]
+            ref = oracle_step.chap_train_step(om, bufs, vol, lab, 4, 4, offs, it, base_lr=0.01, max_iterations=100,
+                                              vat=L.VAT(10.0, 6.0, 4), topk=0.25, d_init=d_init)
+            out = trainer.step(vol.to(DEV), lab.to(DEV), mask_offsets=offs, d_init=[ops.cl(t.to(DEV)) for t in d_init])
+            for key in ("bcp_loss", "loss_l", "loss_u"):
+                assert abs(float(out[key]) - float(ref[key])) < 1e-3 * max(1.0, abs(float(ref[key]))), (it, key)
+            assert abs(float(out["vat_loss"]) - float(ref["vat_loss"])) < 2e-2 * max(1.0, abs(float(ref["vat_loss"]))), it
+            for a, b in zip(out["plab"], ref["plab"]):
+                assert float((a.cpu() != b).float().mean()) < 0.01
+        worst = max(rel_err(p, sd[n]) for n, p in m.named_parameters())
+        assert worst < 2e-2, worst
+        assert trainer.iter_num == 3
+    finally:
+        ops.set_force_simt(False)
+
+
+def test_chap_training_iteration_3d_runs_and_matches_oracle_losses():
+    from chap_b200 import ops
+    from chap_b200.train_step import ChapTrainer
+    ops.set_force_simt(True)
+    try:
+        m = seeded_model("dualdecoder3d", seed=2).to(DEV)
+        sd = nets.clone_state_dict(m.state_dict(), requires_grad=True)
+        om = oracle_step.OracleModel(sd, dims=3, has_dropout=False)
+        trainer = ChapTrainer(m, n_classes=2, labeled_bs=2, base_lr=0.01, max_iterations=100, topk=0.25)
+        g = torch.Generator().manual_seed(5)
+        vol = torch.randn(4, 1, 16, 16, 16, generator=g)
+        lab = (torch.rand(4, 16, 16, 16, generator=g) > 0.6).long()
+        d_init = [torch.rand(2, c, s, s, s, generator=g) - 0.5 for c, s in zip((16, 32, 64, 128, 256), (16, 8, 4, 2, 1))]
+        ref = oracle_step.chap_train_step(om, [None] * len(om.params()), vol, lab, 2, 2, (1, 2, 3), 0, base_lr=0.01,
+                                          max_iterations=100, vat=L.VAT(10.0, 6.0, 2), topk=0.25, d_init=d_init)
+        out = trainer.step(vol.to(DEV), lab.to(DEV), mask_offsets=(1, 2, 3), d_init=[ops.cl(t.to(DEV)) for t in d_init])
+        for key in ("bcp_loss", "loss_l", "loss_u"):
+            assert abs(float(out[key]) - float(ref[key])) < 1e-3 * max(1.0, abs(float(ref[key]))), key
+        assert np.isfinite(float(out["vat_loss"]))
+    finally:
+        ops.set_force_simt(False)
