@@ -15,7 +15,6 @@ from . import _lib
 from ._lib import ConvDesc, check
 
 _state = {"epoch": 0, "bn_tracking": True, "weight_grad": True}
-_pack_cache = {}
 
 
 def lib():
@@ -62,7 +61,6 @@ def _spatial3(x):
 def invalidate_weight_cache():
     """Call after parameters were modified behind autograd's back (the fused SGD kernel)."""
     _state["epoch"] += 1
-    _pack_cache.clear()
 
 
 @contextlib.contextmanager
@@ -97,11 +95,18 @@ def _conv_desc(kind, x, cin, cout):
     return ConvDesc(kind, nd, x.shape[0], d, h, w, cin, cout)
 
 
-def _packs(weight, desc):
-    key = (weight.data_ptr(), weight._version, _state["epoch"], desc.kind, desc.nd, lib().chap_get_force_simt())
-    hit = _pack_cache.get(key)
-    if hit is not None:
-        return hit
+def _packs(weight, kind, nd):
+    """Packed forward / data-gradient operands of a conv weight.  Cached ON the tensor object (an
+    nn.Parameter lives as long as its module), keyed by the tensor version, the global epoch bumped
+    by the fused optimiser, and the dispatch mode -- never by address, which the allocator reuses."""
+    tag = (weight._version, _state["epoch"], kind, nd, lib().chap_get_force_simt())
+    hit = getattr(weight, "_chap_pack", None)
+    if hit is not None and hit[0] == tag:
+        return hit[1], hit[2]
+    transposed = kind == _lib.CONV_UP2
+    cin = weight.shape[0] if transposed else weight.shape[1]
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    desc = ConvDesc(kind, nd, 1, 2, 2, 2, cin, cout) if nd == 3 else ConvDesc(kind, nd, 1, 1, 2, 2, cin, cout)
     n = lib().chap_conv_packed_elems(ctypes.byref(desc))
     wf = torch.empty(n, dtype=torch.float32, device=weight.device)
     wd = torch.empty(n, dtype=torch.float32, device=weight.device)
@@ -109,7 +114,10 @@ def _packs(weight, desc):
     if not w.is_contiguous():
         w = w.contiguous()
     check(lib().chap_conv_pack_weights(ctypes.byref(desc), _p(w), _p(wf), _p(wd), _stream()))
-    _pack_cache[key] = (wf, wd)
+    try:
+        weight._chap_pack = (tag, wf, wd)
+    except AttributeError:
+        pass
     return wf, wd
 
 
@@ -124,7 +132,7 @@ def _out_shape(kind, x, cout):
 
 class _Conv(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, want_stats):
+    def forward(ctx, x, weight, bias, kind, want_stats, wf, wd):
         _require_cuda(x, weight, bias)
         x = cl(x)
         transposed = kind == _lib.CONV_UP2
@@ -133,7 +141,6 @@ class _Conv(Function):
         if x.shape[1] != cin:
             raise RuntimeError("conv: input has %d channels, weight expects %d" % (x.shape[1], cin))
         desc = _conv_desc(kind, x, cin, cout)
-        wf, wd = _packs(weight, desc)
         y = empty_cl(_out_shape(kind, x, cout), x.device)
         sums = torch.empty(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
         b = None if bias is None else bias.detach()
@@ -164,15 +171,17 @@ class _Conv(Function):
             ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
             check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def conv_stats(x, weight, bias, kind, want_stats=True):
     """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted)."""
+    _require_cuda(x, weight)
+    wf, wd = _packs(weight, kind, x.dim() - 2)
     if not _state["weight_grad"]:
         weight = weight.detach()
         bias = None if bias is None else bias.detach()
-    return _Conv.apply(x, weight, bias, kind, bool(want_stats))
+    return _Conv.apply(x, weight, bias, kind, bool(want_stats), wf, wd)
 
 
 def conv(x, weight, bias, kind):

