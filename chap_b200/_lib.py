@@ -42,6 +42,8 @@ SIGNATURES = {
     "chap_check_device": (I, []),
     "chap_launch_count": (c_uint64, []),
     "chap_reset_launch_count": (None, []),
+    "chap_timing_enable": (None, [I]),
+    "chap_timing_report": (I, [ctypes.c_char_p, c_size_t]),
     "chap_set_force_simt": (None, [I]),
     "chap_get_force_simt": (I, []),
     "chap_conv_packed_elems": (c_size_t, [_CD]),
@@ -108,6 +110,21 @@ def check(rc):
     if rc != 0:
         msg = load().chap_last_error()
         raise RuntimeError("libchap_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def timing_enable(on):
+    load().chap_timing_enable(1 if on else 0)
+
+
+def timing_report():
+    """{kernel family: dict(launches, ms, flops, bytes)} for the launches since timing_enable(True)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().chap_timing_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, fl, by = line.split()
+        out[name] = dict(launches=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out
 
 
 def launch_count():

@@ -39,6 +39,15 @@ inline int launched(const char* what) {
         return ::chap::fail(CHAP_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 #define CHAP_TRY(call) do { int rc_ = (call); if (rc_ != CHAP_OK) return rc_; } while (0)
 
+// Optional live timing of kernel families (bench.py roofline): CUDA events recorded on the launching
+// stream around a launch while chap_timing_enable(1) is in effect; aggregated by chap_timing_report().
+struct KernelTimer {
+    int slot;
+    cudaStream_t st;
+    KernelTimer(const char* name, double flops, double bytes, cudaStream_t stream);
+    ~KernelTimer();
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -149,6 +149,9 @@ conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, con
 }
 
 int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st) {
+    const double rows_mac = (double)(op.up2 ? op.in_rows : op.out_rows);
+    KernelTimer timer(op.up2 ? "conv_simt_up2" : "conv_simt_gather", 2.0 * rows_mac * op.K * op.N * op.taps,
+                      4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);
     const bool vec4 = (op.K % 4 == 0) && aligned16(in);
     const bool small = op.N <= 4;
     const int co_t = small ? 4 : 16;
@@ -242,6 +245,8 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
                int64_t sk, int64_t sn, cudaStream_t st) {
     CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
     const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
+    KernelTimer timer("conv_simt_wgrad", 2.0 * (double)rows * op.K * op.N * op.taps,
+                      4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);
     const int tiles = ((op.K + 15) / 16) * ((op.N + 15) / 16);
     int64_t want_splits = (kNumSMs * 4 + (int64_t)tiles * op.taps - 1) / ((int64_t)tiles * op.taps);
     int64_t max_splits = (rows + 511) / 512;

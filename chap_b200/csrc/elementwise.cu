@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
 int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_t st) {
     CHAP_REQUIRE(y && sums && rows > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_stats: bad argument");
     CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    KernelTimer timer("channel_stats", 0.0, 4.0 * (double)rows * c, st);
     const bool v4 = (c % 4 == 0) && aligned16(y);
     const int cg = v4 ? c / 4 : c;
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "channel_stats: too many channels (%d)", c);
@@ -428,6 +429,7 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
                                const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
     CHAP_REQUIRE(y && ss && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_fwd: bad argument");
     const int64_t total = (int64_t)n * rps * c;
+    KernelTimer timer("bn_act_fwd", 0.0, 4.0 * total * (2 + (drop_el ? 1 : 0) + (residual ? 1 : 0)), S(stream));
     if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
         bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, out);
     } else {
@@ -445,6 +447,7 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
     const int64_t rows = (int64_t)n * rps, total = rows * c;
     cudaStream_t st = S(stream);
     CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    KernelTimer timer("bn_act_bwd", 0.0, 4.0 * total * (3 + (drop_el ? 1 : 0)), st);   // algorithmic: read dout, y; write dy
     const bool v4 = c % 4 == 0 && all16({dout, y, drop_el, dy});
     const int cg = v4 ? c / 4 : c;
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);

@@ -1,10 +1,33 @@
 // Library state (errors, launch counter), fused SGD-momentum, sliding-window aggregation.
 #include "common.cuh"
+#include <string.h>
 
 namespace chap {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_force_simt{0};
+
+// ------------------------------------------------------------------ live kernel timing
+namespace {
+constexpr int kMaxTimed = 1 << 15;
+struct TimedLaunch { cudaEvent_t a, b; const char* name; double flops, bytes; };
+TimedLaunch* g_timed = nullptr;
+std::atomic<int> g_timed_n{0};
+std::atomic<int> g_timing_on{0};
+}
+KernelTimer::KernelTimer(const char* name, double flops, double bytes, cudaStream_t stream) : slot(-1), st(stream) {
+    if (!g_timing_on.load(std::memory_order_relaxed) || !g_timed) return;
+    int i = g_timed_n.fetch_add(1);
+    if (i >= kMaxTimed) return;
+    TimedLaunch& t = g_timed[i];
+    if (!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+    t.name = name; t.flops = flops; t.bytes = bytes;
+    cudaEventRecord(t.a, st);
+    slot = i;
+}
+KernelTimer::~KernelTimer() {
+    if (slot >= 0) cudaEventRecord(g_timed[slot].b, st);
+}
 
 // ------------------------------------------------------------------ SGD momentum on a flat arena
 __global__ void __launch_bounds__(256)
@@ -124,6 +147,40 @@ extern "C" uint64_t chap_launch_count(void) { return g_launches.load(); }
 extern "C" void chap_reset_launch_count(void) { g_launches.store(0); }
 extern "C" void chap_set_force_simt(int flag) { g_force_simt.store(flag ? 1 : 0); }
 extern "C" int chap_get_force_simt(void) { return g_force_simt.load(); }
+
+extern "C" void chap_timing_enable(int on) {
+    if (on && !g_timed) g_timed = new TimedLaunch[kMaxTimed]();
+    if (on) g_timed_n.store(0);
+    g_timing_on.store(on ? 1 : 0);
+}
+
+// Synchronises the device and writes one line per kernel family:
+//   name launches total_ms flops bytes\n     (flops / bytes are sums of the algorithmic figures passed at launch)
+extern "C" int chap_timing_report(char* buf, size_t cap) {
+    CHAP_REQUIRE(buf && cap > 0, CHAP_ERR_BAD_ARG, "timing_report: bad buffer");
+    buf[0] = 0;
+    if (!g_timed) return CHAP_OK;
+    CHAP_CUDA(cudaDeviceSynchronize());
+    int n = g_timed_n.load();
+    if (n > kMaxTimed) n = kMaxTimed;
+    struct Agg { const char* name; int count; double ms, flops, bytes; };
+    Agg agg[64]; int na = 0;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_timed[i].a, g_timed[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
+        int j = 0;
+        for (; j < na; ++j) if (agg[j].name == g_timed[i].name || strcmp(agg[j].name, g_timed[i].name) == 0) break;
+        if (j == na) { if (na == 64) continue; agg[na++] = Agg{g_timed[i].name, 0, 0.0, 0.0, 0.0}; }
+        agg[j].count++; agg[j].ms += ms; agg[j].flops += g_timed[i].flops; agg[j].bytes += g_timed[i].bytes;
+    }
+    size_t off = 0;
+    for (int j = 0; j < na; ++j) {
+        int w = snprintf(buf + off, cap - off, "%s %d %.6f %.6e %.6e\n", agg[j].name, agg[j].count, agg[j].ms, agg[j].flops, agg[j].bytes);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+    return CHAP_OK;
+}
 
 extern "C" int chap_check_device(void) {
     int dev = 0;

@@ -133,6 +133,7 @@ perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, fl
 template <int MODE>
 static int run_level(const chap_level& L, int n, float eps, float gs, double* chan_sq, double* samp_sq, cudaStream_t st) {
     const int c = L.c;
+    KernelTimer timer("perturb_level", 0.0, 12.0 * (double)n * L.rows * c, st);   // algorithmic: read g, read f, write out
     int tpr = 1;                                   // lanes per row: keep <= 16 channels (4 float4) per lane
     while (tpr < 32 && c / tpr > 16 && (c / (tpr * 2)) % 4 == 0) tpr *= 2;
     const int rpb = 256 / tpr;

@@ -48,6 +48,11 @@ int chap_check_device(void);
 uint64_t chap_launch_count(void);
 void chap_reset_launch_count(void);
 /* 1: route every convolution through the CUDA-core kernels (debug aid), 0: tcgen05 where supported. */
+/* Live timing of kernel families with CUDA events on the launching stream (bench.py roofline).
+ * enable(1) resets the record; report() synchronises the device and writes lines
+ * "name launches total_ms algorithmic_flops algorithmic_bytes" into buf. */
+void chap_timing_enable(int on);
+int chap_timing_report(char* buf, size_t cap);
 void chap_set_force_simt(int flag);
 int chap_get_force_simt(void);
 
