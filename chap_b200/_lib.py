@@ -29,6 +29,7 @@ class SwDesc(ctypes.Structure):
 CONV_K3, CONV_K1, CONV_DOWN2, CONV_UP2 = 0, 1, 2, 3
 LABEL_I64, LABEL_F32 = 0, 1
 DIST_KL, DIST_DICE = 0, 1
+STAT_SLOTS = 16
 PERTURB_MODES = {"sample": 0, "channel": 1, "spatial": 2, "channel_spatial": 3}
 
 P = c_void_p
@@ -53,7 +54,7 @@ SIGNATURES = {
     "chap_conv_wgrad_workspace_bytes": (c_size_t, [_CD]),
     "chap_conv_wgrad": (I, [_CD, P, P, P, P, P, c_size_t, P]),
     "chap_channel_stats": (I, [P, L, I, P, P]),
-    "chap_bn_finalize": (I, [P, L, P, P, F, F, P, P, P, P, P, I, P]),
+    "chap_bn_finalize": (I, [P, I, L, P, P, F, F, P, P, P, P, P, I, P]),
     "chap_bn_eval_params": (I, [P, P, P, P, F, P, P, I, P]),
     "chap_bn_act_fwd": (I, [P, P, F, P, P, P, I, L, I, P, P]),
     "chap_bn_act_bwd": (I, [P, P, P, P, P, F, P, P, I, L, I, I, P, P, P, P, P]),

@@ -1,7 +1,379 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution path (placeholder until the kernel lands).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Forward and data-gradient of the stride-1 convolutions (k=3 pad 1, k=1; 2D and 3D) as
+//     D[m, n] = sum_{tap} sum_{k} A_tap[m, k] * B_tap[n, k]
+//   m : 128 output positions of one spatial box (tw x th x td) of one image      -> TMEM lanes
+//   n : up to 256 output channels                                                -> TMEM columns (fp32 accumulators)
+//   k : input channels in chunks of 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B)
+// A_tap is the channels-last activation box shifted by the tap offset: ONE tiled TMA load per (tap, k-chunk) with
+// the box origin moved by (kx-1, ky-1, kz-1); out-of-bounds coordinates are zero-filled by the TMA unit, which IS the
+// convolution's zero padding -- no im2col buffer, no halo handling in the kernel.  B_tap is the packed weight
+// [tap][n][k] (K-major).  Operands are fp32 in memory, converted to TF32 (round-to-nearest) by the TMA unit
+// (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32) and multiplied by tcgen05.mma.kind::tf32 with fp32 accumulation in TMEM.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected lane) + TMEM allocator, warps 2..5 epilogue
+// (tcgen05.ld -> +bias -> 128-bit stores, and the per-channel sum / sum-of-squares of the BatchNorm that follows,
+// reduced warp-shuffle -> smem -> one double atomic per CTA and channel into one of CHAP_STAT_SLOTS slots).
+// smem ring of `stages` {A, B} buffers with full/empty mbarriers; the accumulator is handed to the epilogue through a
+// tcgen05.commit on a third mbarrier.  Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's
+// epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 #include "conv_plan.cuh"
+
 namespace chap {
-bool tc_supports(const Geom&, bool) { return false; }
-int tc_conv(const Geom&, bool, const float*, const float*, const float*, float*, double*, cudaStream_t) { return 0; }
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major operand with 128B / 64B swizzle (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows) | [46,48) version=1 |
+//   [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t sbo = (8u * row_bytes) >> 4;
+    const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+struct TcParams {
+    int nd, ksz, pad, taps;
+    int W, H, D;                  // spatial size (output == input for these kinds)
+    int tw, th, td;               // spatial box of one M tile (tw*th*td <= 128)
+    int tiles_w, tiles_h, tiles_d;
+    int kc, kchunks;              // channels per k chunk (32 or 16), chunks per tap
+    int n_total, nt;              // output channels, channels per CTA
+    int stages, tmem_cols;
+    uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes;
+    float* out;
+    const float* bias;
+    double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
+};
+
+constexpr int kTcThreads = 192;
+
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + (size_t)p.stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.stages * p.b_stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);          // [4 warps][2][nt] epilogue statistics
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_w; t /= p.tiles_w;
+    const int ty = t % p.tiles_h; t /= p.tiles_h;
+    const int tz = t % p.tiles_d;
+    const int img = t / p.tiles_d;
+    const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
+    const int n0 = blockIdx.y * p.nt;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int iters = p.taps * p.kchunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                const int tap = it / p.kchunks, kci = it - tap * p.kchunks;
+                int kx, ky, kz;
+                if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], p.a_box_bytes + p.b_box_bytes);
+                uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
+                uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
+                if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
+                tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, tap * p.n_total + n0);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t row_bytes = (uint32_t)p.kc * 4u;
+            const int ksteps = p.kc / 8;
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t a_desc = make_kmajor_desc(smem_u32(a_base + (size_t)s * p.a_stage_bytes), row_bytes);
+                const uint64_t b_desc = make_kmajor_desc(smem_u32(b_base + (size_t)s * p.b_stage_bytes), row_bytes);
+                for (int k = 0; k < ksteps; ++k)          // +32 bytes (= 8 tf32) along K inside the swizzled row: +2 in the >>4 address field
+                    tc_mma_tf32(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+                tc_commit(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+        const int lg = warp & 3;
+        const int m = lg * 32 + lane;                                  // accumulator row == position inside the box
+        const int dx = m % p.tw, dy = (m / p.tw) % p.th, dz = m / (p.tw * p.th);
+        const int ow = w0 + dx, oh = h0 + dy, od = d0 + dz;
+        const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
+        float* dst = p.out + ((((int64_t)img * p.D + od) * p.H + oh) * p.W + ow) * (int64_t)p.n_total + n0;
+        float* red_s = red + (size_t)(lg * 2 + 0) * p.nt;
+        float* red_q = red + (size_t)(lg * 2 + 1) * p.nt;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.nt; c0 += 16) {
+            float v[16];
+            tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.stats) {
+                // column sums over the 32 rows of this warp: butterfly reduce-scatter, 16 columns -> lanes 0..15
+                float s16[16], q16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { float x = valid ? v[j] : 0.f; s16[j] = x; q16[j] = x * x; }
+#pragma unroll
+                for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                    const bool upper = (lane & bit) != 0;
+#pragma unroll
+                    for (int j = 0; j < half; ++j) {
+                        float keep_s = upper ? s16[j + half] : s16[j], send_s = upper ? s16[j] : s16[j + half];
+                        float keep_q = upper ? q16[j + half] : q16[j], send_q = upper ? q16[j] : q16[j + half];
+                        s16[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                        q16[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                    }
+                }
+                // lane l now holds column (bit-reversed assignment): col = 8*b4 + 4*b3 + 2*b2 + b1 of the lane, rows split by b0
+                float cs = s16[0] + __shfl_xor_sync(0xffffffffu, s16[0], 1);
+                float cq = q16[0] + __shfl_xor_sync(0xffffffffu, q16[0], 1);
+                if ((lane & 1) == 0) {
+                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    red_s[c0 + col] = cs; red_q[c0 + col] = cq;
+                }
+            }
+        }
+        tc_fence_before();
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps only
+            const int e = threadIdx.x - 64;
+            double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * p.n_total;
+            for (int c = e; c < p.nt; c += 128) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
+                atomicAdd(slot + n0 + c, (double)a);
+                atomicAdd(slot + p.n_total + n0 + c, (double)b);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int kc) {
+    EncodeTiledFn fn = encode_fn();
+    CHAP_REQUIRE(fn != nullptr, CHAP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CHAP_REQUIRE(r == CUDA_SUCCESS, CHAP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return CHAP_OK;
+}
+
+static int tc_channels(const Geom& g, bool dgrad, int& K, int& N) {
+    K = dgrad ? g.cout : g.cin;
+    N = dgrad ? g.cin : g.cout;
+    return 0;
+}
+
+bool tc_supports(const Geom& g, bool dgrad) {
+    if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
+    int K, N;
+    tc_channels(g, dgrad, K, N);
+    if (!(K == 16 || K % 32 == 0)) return false;
+    if (N < 16 || N % 16 != 0) return false;
+    if (N > 256 && N % 256 != 0) return false;
+    return true;
+}
+
+// choose the spatial box (tw, th, td), tw*th*td <= 128, that covers the volume with the fewest tiles
+static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
+    long best = -1;
+    for (int w = 1; w <= W && w <= 128; ++w)
+        for (int h = 1; h <= H && w * h <= 128; ++h) {
+            int d = 128 / (w * h);
+            if (d > D) d = D;
+            if (d < 1) continue;
+            long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
+            long score = tiles * 1024 - w;                 // fewest tiles, then the widest contiguous run
+            if (best < 0 || score < best) { best = score; tw = w; th = h; td = d; }
+        }
+}
+
+int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
+            double* ch_sums, cudaStream_t st) {
+    if (!tc_supports(g, dgrad)) return 0;
+    CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
+    int K, N;
+    tc_channels(g, dgrad, K, N);
+    TcParams p{};
+    p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
+    p.W = g.iW; p.H = g.iH; p.D = g.iD;
+    choose_box(p.W, p.H, p.D, p.tw, p.th, p.td);
+    p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
+    p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
+    p.n_total = N; p.nt = N > 256 ? 256 : N;
+    p.tmem_cols = 32; while (p.tmem_cols < p.nt) p.tmem_cols *= 2;
+    p.a_stage_bytes = 128u * p.kc * 4u;                                  // always room for 128 rows
+    p.a_box_bytes = (uint32_t)(p.tw * p.th * p.td) * p.kc * 4u;
+    p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
+    p.b_stage_bytes = (p.b_box_bytes + 1023u) & ~1023u;
+    const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    int stages = (int)((96 * 1024) / stage);
+    const int iters = p.taps * p.kchunks;
+    if (stages > 6) stages = 6;
+    if (stages > iters) stages = iters;
+    if (stages < 2) stages = iters < 2 ? 1 : 2;
+    p.stages = stages;
+    p.out = out; p.bias = bias; p.stats = ch_sums;
+    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 + (size_t)8 * p.nt * sizeof(float);
+
+    // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[5], str[4]; uint32_t box[5];
+        const uint64_t C = (uint64_t)K;
+        if (g.nd == 2) {
+            dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
+            str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+            CHAP_TRY(make_map(&tmA, in, 4, dims, str, box, p.kc));
+        } else {
+            dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
+            str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+            CHAP_TRY(make_map(&tmA, in, 5, dims, str, box, p.kc));
+        }
+        uint64_t wd[2] = {(uint64_t)K, (uint64_t)g.taps * N};
+        uint64_t ws[1] = {(uint64_t)K * 4};
+        uint32_t wb[2] = {(uint32_t)p.kc, (uint32_t)p.nt};
+        CHAP_TRY(make_map(&tmB, wp, 2, wd, ws, wb, p.kc));
+    }
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * N * sizeof(double), st));
+    const double rows = (double)g.out_rows;
+    KernelTimer timer(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", 2.0 * rows * K * N * g.taps,
+                      4.0 * (rows * K + rows * N + (double)g.taps * K * N), st);
+    dim3 grid((unsigned)(g.n * p.tiles_d * p.tiles_h * p.tiles_w), (unsigned)(N / p.nt));
+    conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+    CHAP_TRY(launched("conv_tc_kernel"));
+    return 1;
+}
+
+}  // namespace chap

@@ -81,14 +81,16 @@ int sums_to_float(const double* sums, float* out, int c, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ BN finalize
-__global__ void bn_finalize_kernel(const double* sums, int64_t count, const float* gamma, const float* beta,
+__global__ void bn_finalize_kernel(const double* sums, int slots, int64_t count, const float* gamma, const float* beta,
                                    float eps, float momentum, float* rmean, float* rvar, int64_t* nbt,
                                    float* mean_invstd, float* scale_shift, int c) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && nbt) *nbt += 1;
     if (i >= c) return;
-    double mean = sums[i] / (double)count;
-    double var = sums[c + i] / (double)count - mean * mean;
+    double s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < slots; ++s) { s1 += sums[(size_t)s * 2 * c + i]; s2 += sums[(size_t)s * 2 * c + c + i]; }
+    double mean = s1 / (double)count;
+    double var = s2 / (double)count - mean * mean;
     if (var < 0.0) var = 0.0;
     float invstd = (float)(1.0 / sqrt(var + (double)eps));
     float sc = gamma[i] * invstd;
@@ -403,12 +405,12 @@ extern "C" int chap_channel_stats(const float* y, int64_t rows, int32_t c, doubl
     return channel_stats(y, rows, c, sums, S(stream));
 }
 
-extern "C" int chap_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta, float eps,
+extern "C" int chap_bn_finalize(const double* sums, int32_t slots, int64_t count, const float* gamma, const float* beta, float eps,
                                 float momentum, float* running_mean, float* running_var, int64_t* nbt,
                                 float* mean_invstd, float* scale_shift, int32_t c, void* stream) {
-    CHAP_REQUIRE(sums && gamma && beta && mean_invstd && scale_shift && c > 0 && count > 0, CHAP_ERR_BAD_ARG, "bn_finalize: bad argument");
+    CHAP_REQUIRE(sums && gamma && beta && mean_invstd && scale_shift && c > 0 && count > 0 && slots >= 1, CHAP_ERR_BAD_ARG, "bn_finalize: bad argument");
     CHAP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CHAP_ERR_BAD_ARG, "bn_finalize: running stats must both be set or both NULL");
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, count, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slots, count, gamma, beta, eps, momentum, running_mean,
                                                                running_var, running_mean ? nbt : nullptr, mean_invstd, scale_shift, c);
     return launched("bn_finalize_kernel");
 }

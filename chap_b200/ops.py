@@ -142,7 +142,7 @@ class _Conv(Function):
             raise RuntimeError("conv: input has %d channels, weight expects %d" % (x.shape[1], cin))
         desc = _conv_desc(kind, x, cin, cout)
         y = empty_cl(_out_shape(kind, x, cout), x.device)
-        sums = torch.empty(2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+        sums = torch.empty(_lib.STAT_SLOTS * 2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
         b = None if bias is None else bias.detach()
         check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
         ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
@@ -201,11 +201,13 @@ class _BnAct(Function):
         ss = torch.empty(2 * c, dtype=torch.float32, device=dev)
         g, b = gamma.detach(), beta.detach()
         if train:
+            slots = _lib.STAT_SLOTS
             if sums is None:
+                slots = 1
                 sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
                 check(lib().chap_channel_stats(_p(y), n * rps, c, _p(sums), _stream()))
             rm, rv, nbt = running if (update and running is not None) else (None, None, None)
-            check(lib().chap_bn_finalize(_p(sums), n * rps, _p(g), _p(b), eps, momentum, _p(rm), _p(rv), _p(nbt),
+            check(lib().chap_bn_finalize(_p(sums), slots, n * rps, _p(g), _p(b), eps, momentum, _p(rm), _p(rv), _p(nbt),
                                          _p(mi), _p(ss), c, _stream()))
         else:
             rm, rv, _ = running

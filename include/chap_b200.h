@@ -77,12 +77,16 @@ typedef struct {
     int32_t cin, cout;
 } chap_conv_desc;
 
+/* Per-channel statistics produced by a convolution epilogue are spread over CHAP_STAT_SLOTS partial
+ * buffers (fewer colliding atomics); layout double[CHAP_STAT_SLOTS][2*cout], summed by chap_bn_finalize. */
+#define CHAP_STAT_SLOTS 16
+
 /* number of floats in one packed weight buffer (same for the fwd and the dgrad packing) */
 size_t chap_conv_packed_elems(const chap_conv_desc* d);
 /* torch-layout weight -> packed forward operand and packed data-gradient operand (either may be NULL) */
 int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream);
-/* y = conv(x) + bias.  ch_sums (nullable): double[2*cout], receives per-channel sum(y), sum(y*y)
- * (zeroed by the call) -- the BatchNorm batch statistics of the following layer. */
+/* y = conv(x) + bias.  ch_sums (nullable): double[CHAP_STAT_SLOTS][2*cout], receives partial per-channel
+ * sum(y), sum(y*y) (zeroed by the call) -- the BatchNorm batch statistics of the following layer. */
 int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
                   float* y, double* ch_sums, void* stream);
 /* dx = conv^T(dy) (data gradient), dx has the input shape */
@@ -99,10 +103,10 @@ int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, fl
  */
 /* per-channel sum / sum of squares of y[rows, c] into double[2c] (zeroed by the call) */
 int chap_channel_stats(const float* y, int64_t rows, int32_t c, double* sums, void* stream);
-/* train mode: batch mean / biased var from sums -> mean_invstd[2c], scale_shift[2c]
+/* train mode: batch mean / biased var from sums[slots][2c] (slots summed) -> mean_invstd[2c], scale_shift[2c]
  * (scale = gamma*invstd, shift = beta - mean*scale); if running_mean != NULL update
  * running = (1-m)*running + m*stat (unbiased var) and ++(*num_batches_tracked). */
-int chap_bn_finalize(const double* sums, int64_t count, const float* gamma, const float* beta,
+int chap_bn_finalize(const double* sums, int32_t slots, int64_t count, const float* gamma, const float* beta,
                      float eps, float momentum, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float* mean_invstd, float* scale_shift,
                      int32_t c, void* stream);
