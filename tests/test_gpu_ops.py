@@ -86,6 +86,7 @@ def test_conv_fwd_dgrad_wgrad(case, force_simt):
     assert rel_err(gb, gb_ref) < tol, "dbias"
     yd = y.detach().double().cpu()
     dims = (0,) + tuple(range(2, 2 + nd))
+    sums = sums.reshape(_lib.STAT_SLOTS, 2 * cout).sum(0)          # partial statistics slots of the conv epilogue
     assert rel_err(sums[:cout], yd.sum(dims)) < 1e-4 + tol and rel_err(sums[cout:], (yd * yd).sum(dims)) < 1e-4 + tol, "fused BN statistics"
 
 
@@ -263,3 +264,29 @@ def test_l2n_axpy_and_sgd():
         L.sgd_momentum_step([pr], [g * (it + 1)], buf, 0.01 * (it + 1))
         ops.sgd_momentum_(pg, gg * (it + 1), bg, 0.01 * (it + 1), 0.9, 1e-4, 1.0, it == 0)
     assert rel_err(pg, pr) < 1e-6 and rel_err(bg, buf[0]) < 1e-6
+
+
+def test_tensor_core_path_is_taken_and_accurate_to_tf32():
+    """Supported layers must run on the tcgen05 kernel (not silently on CUDA cores) and agree with the fp32
+    CUDA-core result to TF32 rounding (10-bit mantissa products, fp32 accumulation)."""
+    from chap_b200 import _lib
+    ops = _ops()
+    torch.manual_seed(0)
+    x = _to_cl(torch.randn(2, 64, 24, 40))
+    w = (torch.randn(128, 64, 3, 3) / 24.0).to(DEV)
+    b = torch.randn(128).to(DEV)
+    _lib.timing_enable(True)
+    y_tc, s_tc = ops.conv_stats(x, w, b, _lib.CONV_K3, True)
+    fam = _lib.timing_report()
+    _lib.timing_enable(False)
+    assert "conv_tc_fwd" in fam and fam["conv_tc_fwd"]["launches"] == 1, fam
+    ops.set_force_simt(True)
+    try:
+        y_ref, s_ref = ops.conv_stats(x, w.clone(), b, _lib.CONV_K3, True)
+    finally:
+        ops.set_force_simt(False)
+    err = rel_err(y_tc, y_ref)
+    assert 1e-6 < err < 1e-3, err                       # > 1e-6: it really went through TF32; < 1e-3: correct
+    s_tc = s_tc.reshape(_lib.STAT_SLOTS, -1).sum(0)
+    s_ref = s_ref.reshape(_lib.STAT_SLOTS, -1).sum(0)
+    assert rel_err(s_tc, s_ref) < 1e-3
