@@ -71,6 +71,22 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Round-to-nearest conversion to TF32 (kept in an fp32 container, low 13 mantissa bits zero).  tcgen05.mma
+// kind::tf32 IGNORES the low 13 bits of its fp32 operands (truncation, biased); producers of tensors that feed a
+// tensor-core convolution therefore round on store when the tensor-core path is active (`on`), which is what
+// cuDNN's TF32 path does with cvt.rna and halves the rounding error (measured, DESIGN.md "precision").
+__device__ __forceinline__ float tf32_rn(float x, int on) {
+    if (!on) return x;
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+// Measured on B200 (round 1): rounding the producers' outputs to TF32 did NOT change the network-level error of the
+// tensor-core path (2D logits 1.49e-3 with, 1.46e-3 without, vs the fp32 oracle) -- the CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+// tensor maps / the MMA unit already round -- while it costs the fp32 precision of tensors that are also consumed
+// elementwise (the perturbed features f + r lose r below TF32 resolution).  Producer-side rounding is therefore OFF.
+inline int round_tf32_on() { return 0; }
+
 // streaming 128-bit load (read once) / store
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;

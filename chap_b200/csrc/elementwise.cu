@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ ss, float slope,
                   const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
                   const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec,
-                  float* __restrict__ out) {
+                  int rt, float* __restrict__ out) {
     const int cg = c / VEC;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % cg);
@@ -143,6 +143,8 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ ss, flo
             if (VEC == 4) { float4 t = ldg_stream(reinterpret_cast<const float4*>(res) + i); o[0] += t.x; o[1 % VEC] += t.y; o[2 % VEC] += t.z; o[3 % VEC] += t.w; }
             else o[0] += res[i];
         }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = tf32_rn(o[k], rt);
         if (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
         else out[i] = o[0];
     }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
                         const float* __restrict__ mi, float slope,
                         const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
-                        int64_t rows_per_sample, int c, int64_t total_vec, int train, double inv_count,
+                        int64_t rows_per_sample, int c, int64_t total_vec, int train, int rt, double inv_count,
                         const double* __restrict__ sums, float* __restrict__ dy,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c / VEC;
@@ -215,6 +217,8 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                 o[k] = sc * dz;
             }
         }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = tf32_rn(o[k], rt);
         if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
         else dy[i] = o[0];
     }
@@ -271,7 +275,7 @@ __device__ __forceinline__ void lerp_src(int o, int in, int out, int& i0, int& i
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-upsample2x_fwd_kernel(const float* __restrict__ x, int d, int h, int w, int c, int nd, int64_t total_vec, float* __restrict__ y) {
+upsample2x_fwd_kernel(const float* __restrict__ x, int d, int h, int w, int c, int nd, int64_t total_vec, int rt, float* __restrict__ y) {
     const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -293,7 +297,7 @@ upsample2x_fwd_kernel(const float* __restrict__ x, int d, int h, int w, int c, i
                 float v1 = a10 * (1.f - ly) + a11 * ly;
                 v0 = v0 * (1.f - lz) + v1 * lz;
             }
-            y[i * VEC + k] = v0;
+            y[i * VEC + k] = tf32_rn(v0, rt);
         }
     }
 }
@@ -316,7 +320,7 @@ __device__ __forceinline__ int contrib(int i, int in, int out, int* oi, float* w
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, int nd, int64_t total_vec, float* __restrict__ dx) {
+upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, int nd, int64_t total_vec, int rt, float* __restrict__ dx) {
     const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -342,7 +346,7 @@ upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, 
                 }
             }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) dx[i * VEC + k] = acc[k];
+        for (int k = 0; k < VEC; ++k) dx[i * VEC + k] = tf32_rn(acc[k], rt);
     }
 }
 
@@ -433,9 +437,9 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     const int64_t total = (int64_t)n * rps * c;
     KernelTimer timer("bn_act_fwd", 0.0, 4.0 * total * (2 + (drop_el ? 1 : 0) + (residual ? 1 : 0)), S(stream));
     if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
-        bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, out);
+        bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, round_tf32_on(), out);
     } else {
-        bn_act_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total, out);
+        bn_act_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total, round_tf32_on(), out);
     }
     return launched("bn_act_fwd_kernel");
 }
@@ -459,8 +463,8 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
     else bn_act_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
     CHAP_TRY(launched("bn_act_bwd_reduce_kernel"));
     const double inv_count = 1.0 / (double)rows;
-    if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
-    else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, inv_count, sums, dy, dgamma, dbeta);
+    if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
+    else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
     return launched("bn_act_bwd_apply_kernel");
 }
 
@@ -483,16 +487,16 @@ extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int
 extern "C" int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* y, void* stream) {
     CHAP_REQUIRE(x && y && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_fwd: bad argument");
     const int64_t total = (int64_t)n * (nd == 3 ? 2 * d : 1) * 2 * h * 2 * w * c;
-    if (c % 4 == 0) upsample2x_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total / 4, y);
-    else upsample2x_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total, y);
+    if (c % 4 == 0) upsample2x_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total / 4, round_tf32_on(), y);
+    else upsample2x_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total, round_tf32_on(), y);
     return launched("upsample2x_fwd_kernel");
 }
 
 extern "C" int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* dx, void* stream) {
     CHAP_REQUIRE(dy && dx && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_bwd: bad argument");
     const int64_t total = (int64_t)n * d * h * w * c;
-    if (c % 4 == 0) upsample2x_bwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total / 4, dx);
-    else upsample2x_bwd_kernel<1><<<grid_for(total, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total, dx);
+    if (c % 4 == 0) upsample2x_bwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total / 4, round_tf32_on(), dx);
+    else upsample2x_bwd_kernel<1><<<grid_for(total, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total, round_tf32_on(), dx);
     return launched("upsample2x_bwd_kernel");
 }
 

