@@ -72,7 +72,12 @@ extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const fl
     CHAP_REQUIRE(x && dy && dw, CHAP_ERR_BAD_ARG, "conv_wgrad: NULL pointer");
     SimtOp op = fwd_op(g);
     PackSpec p = fwd_pack(g);          // dw has the torch layout: same strides as reading w
-    CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream)));
+    int handled = 0;
+    if (g_force_simt.load() == 0 && tc_wgrad_supports(g)) {
+        handled = tc_wgrad(g, x, dy, dw, S(stream));
+        if (handled < 0) return handled;
+    }
+    if (!handled) CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream)));
     if (dbias) {
         CHAP_REQUIRE(workspace && workspace_bytes >= (size_t)2 * g.cout * sizeof(double), CHAP_ERR_WORKSPACE,
                      "conv_wgrad: workspace too small (%zu bytes)", workspace_bytes);

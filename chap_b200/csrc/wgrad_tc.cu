@@ -1,0 +1,271 @@
+// tcgen05 weight-gradient kernel for the stride-1 convolutions (k=3 pad 1, k=1; 2D and 3D).
+//
+//     dW[tap][co][ci] = sum_p dy[p, co] * x[p + tap, ci]
+// is, per tap, a GEMM whose reduction dimension is the pixel index p.  Both operands are channels-last, i.e. the
+// M (= co) and N (= ci) dimensions are the contiguous ones: "MN-major" UMMA operands.  A spatial box of P pixels
+// (P % 8 == 0, P <= 64) is one K block: the dy box [co-chunk x P] and, per tap, the x box shifted by the tap offset
+// [ci-chunk x P] are fetched by tiled TMA loads (out-of-bounds pixels are zero-filled = the conv padding), 32 channels
+// (128 B rows, SWIZZLE_128B) or 16 channels (64 B rows, SWIZZLE_64B) per load.  In smem a load is P rows of one
+// swizzle-atom width: exactly the canonical MN-major layout ((atom,n),(8,k)) with SBO = 8 rows, LBO = the distance
+// between channel chunks; one tcgen05.mma.kind::tf32 (K = 8) consumes one 8-row group.
+//
+// Work split: blockIdx.z = (co tile, ci tile), blockIdx.y = tap group (as many taps as fit 512 TMEM columns),
+// blockIdx.x = slice of the pixel blocks.  Each CTA accumulates its slice in TMEM (fp32) and adds it to the
+// torch-layout gradient with red.global.add.f32 (the gradient buffer is zeroed first).
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+#include "conv_plan.cuh"
+#include "tc_common.cuh"
+
+namespace chap {
+
+struct WgParams {
+    int nd, ksz, pad, taps;
+    int W, H, D, n_img;
+    int tw, th, td, tiles_w, tiles_h, tiles_d;
+    int P;                          // pixels per K block (= tw*th*td, multiple of 8)
+    int cout, cin;                  // full channel counts (gradient strides)
+    int m_tile, n_tile;             // channels of dy / x handled by this CTA
+    int mma_m;                      // 64 or 128
+    int a_cpg, a_groups;            // channels per TMA chunk (32|16) and chunks per m_tile
+    int b_cpg, b_groups;
+    int tg;                         // taps per CTA
+    int stages, tmem_cols;
+    int blocks_total, blocks_per_cta;
+    uint32_t a_stage_bytes, b_stage_bytes;
+    int64_t s_co, s_ci;             // gradient strides in floats (torch layout), tap stride is 1
+    float* dw;
+};
+
+constexpr int kWgThreads = 192;
+
+// MN-major TF32 operand descriptor (cute::UMMA::SmemDescriptor), layout type 1 = SWIZZLE_128B_BASE32B, the only smem
+// layout tcgen05 accepts for MN-major 32-bit operands: rows of 128 B (32 channels), K atom = 4 rows, so
+// SBO = 4 rows = 512 B (stride between K atoms), LBO = stride between 32-channel chunks.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t row_bytes, uint32_t lbo_bytes) {
+    const uint64_t sbo = (4u * row_bytes) >> 4;
+    const uint64_t layout = 1ull;
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + (size_t)p.stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.stages * p.b_stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = p.cout / p.m_tile;
+    const int m0 = (blockIdx.z % m_tiles) * p.m_tile, n0 = (blockIdx.z / m_tiles) * p.n_tile;      // n0 > 0 only when cin > 256
+    const int tap0 = blockIdx.y * p.tg;
+    const int ntaps = min(p.tg, p.taps - tap0);
+    const int blk0 = blockIdx.x * p.blocks_per_cta;
+    const int nblk = min(p.blocks_per_cta, p.blocks_total - blk0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_row = (uint32_t)p.a_cpg * 4u, b_row = (uint32_t)p.b_cpg * 4u;
+    const uint32_t a_chunk = (uint32_t)p.P * a_row, b_chunk = (uint32_t)p.P * b_row;     // bytes of one channel chunk
+
+    if (nblk > 0 && warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int b = 0; b < nblk; ++b) {
+                int t = blk0 + b;
+                const int tx = t % p.tiles_w; t /= p.tiles_w;
+                const int ty = t % p.tiles_h; t /= p.tiles_h;
+                const int tz = t % p.tiles_d;
+                const int img = t / p.tiles_d;
+                const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    const int tap = tap0 + ti;
+                    int kx, ky, kz;
+                    if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)p.a_groups * a_chunk + (uint32_t)p.b_groups * b_chunk);
+                    uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
+                    uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
+                    for (int g = 0; g < p.a_groups; ++g) {
+                        if (p.nd == 2) tma_load_4d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, img);
+                        else tma_load_5d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, d0, img);
+                    }
+                    for (int g = 0; g < p.b_groups; ++g) {
+                        if (p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                        else tma_load_5d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (nblk > 0 && warp == 1) {
+        if (lane == 0) {
+            // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(p.mma_m >> 4) << 24);
+            // M is always 128 rows; when the tile has fewer channels the extra channel chunks alias chunk 0 (one chunk,
+            // LBO = 0) or read whatever follows in shared memory (two chunks): those accumulator rows are never stored
+            const uint32_t a_lbo = p.a_groups >= 2 ? a_chunk : 0u;
+            const int ksteps = p.P / 8;
+            int s = 0; uint32_t ph = 0;
+            for (int b = 0; b < nblk; ++b) {
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * p.a_stage_bytes);
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * p.b_stage_bytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(ti * p.n_tile);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
+                        const uint64_t b_desc = make_mnmajor_desc(b_addr + (uint32_t)k * 8u * b_row, b_row, b_chunk);
+                        tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, (uint32_t)((b | k) != 0));
+                    }
+                    tc_commit(&empty[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+            tc_commit(tmem_full);
+        }
+    } else if (nblk > 0 && warp >= 2) {
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;                  // accumulator row = output channel inside the tile
+        const bool valid = row < p.m_tile && row < p.mma_m;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (lg * 32 < p.mma_m) {                         // M = 64: lane groups 2,3 hold nothing
+            float* dst_row = p.dw + (int64_t)(m0 + row) * p.s_co;
+            for (int ti = 0; ti < ntaps; ++ti) {
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                    float v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * p.n_tile + c0), v);
+                    if (valid && n0 + c0 < p.cin) {                 // columns beyond cin are the zero-filled channels
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            atomicAdd(dst_row + (int64_t)(n0 + c0 + j) * p.s_ci + (tap0 + ti), v[j]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+bool tc_wgrad_supports(const Geom& g) {
+    if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
+    auto ok = [](int c) { return c == 16 || (c % 32 == 0 && c <= 1024); };
+    return ok(g.cin) && ok(g.cout);
+}
+
+// spatial box with P = w*h*d a multiple of 8 and <= 64, minimising the padded pixel count
+static void choose_box8(int W, int H, int D, int& tw, int& th, int& td) {
+    long best = -1;
+    const int Wp = (W + 7) / 8 * 8, Hp = (H + 7) / 8 * 8, Dp = (D + 7) / 8 * 8;
+    for (int w = 1; w <= Wp && w <= 64; ++w)
+        for (int h = 1; h <= Hp && w * h <= 64; ++h)
+            for (int d = 1; d <= Dp && w * h * d <= 64; ++d) {
+                const int P = w * h * d;
+                if (P % 8 != 0) continue;
+                long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
+                long score = tiles * P * 64 - P;            // least padded work, then the larger block
+                if (best < 0 || score < best) { best = score; tw = w; th = h; td = d; }
+            }
+}
+
+int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st) {
+    if (!tc_wgrad_supports(g)) return 0;
+    CHAP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dw), CHAP_ERR_ALIGNMENT, "tc_wgrad: buffers must be 16-byte aligned");
+    WgParams p{};
+    p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
+    p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
+    choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
+    p.P = p.tw * p.th * p.td;
+    p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
+    p.cout = g.cout; p.cin = g.cin;
+    p.m_tile = g.cout > 128 ? 128 : g.cout;
+    p.n_tile = g.cin > 256 ? 256 : (g.cin < 32 ? 32 : g.cin);     // 16-channel tensors: the TMA box is 32 wide, channels 16..31 zero-filled
+    p.mma_m = 128;           // M = 64 has a different TMEM lane mapping; M = 128 costs the same tensor time
+    p.a_cpg = 32; p.a_groups = (p.m_tile + 31) / 32;
+    p.b_cpg = 32; p.b_groups = p.n_tile / 32;
+    int tg = 512 / p.n_tile;
+    if (tg > g.taps) tg = g.taps;
+    // balance the tap groups (e.g. 9 taps, room for 4 -> 3 groups of 3)
+    const int groups = (g.taps + tg - 1) / tg;
+    tg = (g.taps + groups - 1) / groups;
+    p.tg = tg;
+    p.tmem_cols = 32; while (p.tmem_cols < tg * p.n_tile) p.tmem_cols *= 2;
+    p.a_stage_bytes = ((uint32_t)p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
+    p.b_stage_bytes = ((uint32_t)p.n_tile * p.P * 4u + 1023u) & ~1023u;
+    const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    int stages = (int)((200 * 1024 - 2048) / stage);
+    if (stages > 6) stages = 6;
+    CHAP_REQUIRE(stages >= 2, CHAP_ERR_BAD_ARG, "tc_wgrad: tile does not fit shared memory");
+    p.stages = stages;
+    p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    const int n_tiles = g.cin > 256 ? g.cin / 256 : 1;
+    const int zdim = (g.cout / p.m_tile) * n_tiles;
+    int splits = (2 * kNumSMs + groups * zdim - 1) / (groups * zdim);
+    if (splits > p.blocks_total) splits = p.blocks_total;
+    if (splits < 1) splits = 1;
+    p.blocks_per_cta = (p.blocks_total + splits - 1) / splits;
+    splits = (p.blocks_total + p.blocks_per_cta - 1) / p.blocks_per_cta;
+    const PackSpec ps = fwd_pack(g);          // torch [co][ci][tap]: s_ci = T, s_co = Cin*T
+    p.s_ci = ps.sk; p.s_co = ps.sn;
+    p.dw = dw;
+
+    CUtensorMap tmA, tmB;
+    for (int which = 0; which < 2; ++which) {
+        const float* base = which == 0 ? dy : x;
+        const uint64_t C = which == 0 ? g.cout : g.cin;
+        const int cpg = which == 0 ? p.a_cpg : p.b_cpg;
+        uint64_t dims[5], str[4]; uint32_t box[5];
+        if (g.nd == 2) {
+            dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
+            str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
+            box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+            CHAP_TRY(make_tensor_map(which == 0 ? &tmA : &tmB, base, 4, dims, str, box, cpg, true));
+        } else {
+            dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
+            str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
+            box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+            CHAP_TRY(make_tensor_map(which == 0 ? &tmA : &tmB, base, 5, dims, str, box, cpg, true));
+        }
+    }
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * g.cin * g.cout * sizeof(float), st));
+    const double rows = (double)g.out_rows;
+    KernelTimer timer("conv_tc_wgrad", 2.0 * rows * g.cin * g.cout * g.taps,
+                      4.0 * (rows * g.cin + rows * g.cout + (double)g.taps * g.cin * g.cout), st);
+    dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
+    wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
+    CHAP_TRY(launched("wgrad_tc_kernel"));
+    return 1;
+}
+
+}  // namespace chap
