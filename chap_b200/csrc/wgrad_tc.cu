@@ -24,7 +24,8 @@ struct WgParams {
     int nd, ksz, pad, taps;
     int W, H, D, n_img;
     int tw, th, td, tiles_w, tiles_h, tiles_d;
-    int P;                          // pixels per K block (= tw*th*td, multiple of 8)
+    int P;                          // pixels per K block padded to a multiple of 8 (smem rows per channel chunk)
+    int p_box;                      // pixels actually loaded per block (= tw*th*td <= P); rows p_box..P stay zero
     int cout, cin;                  // full channel counts (gradient strides)
     int m_tile, n_tile;             // channels of dy / x handled by this CTA
     int mma_m;                      // 64 or 128
@@ -77,6 +78,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (p.p_box != p.P) {
+        // the TMA boxes cover p_box < P rows of every channel chunk: the remaining rows of the last K atom must read as zero
+        float4* z = reinterpret_cast<float4*>(smem);
+        const int n16 = (int)(((size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes)) >> 4);
+        for (int i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -103,7 +111,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     int kx, ky, kz;
                     if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)p.a_groups * a_chunk + (uint32_t)p.b_groups * b_chunk);
+                    mbar_expect_tx(&full[s], (uint32_t)(p.a_groups + p.b_groups) * (uint32_t)p.p_box * 128u);
                     uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
                     uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
                     for (int g = 0; g < p.a_groups; ++g) {
@@ -181,17 +189,15 @@ bool tc_wgrad_supports(const Geom& g) {
     return ok(g.cin) && ok(g.cout);
 }
 
-// spatial box with P = w*h*d a multiple of 8 and <= 64, minimising the padded pixel count
+// spatial box inside the image (w <= W, h <= H, d <= D), at most 64 pixels, minimising the padded reduction length
 static void choose_box8(int W, int H, int D, int& tw, int& th, int& td) {
     long best = -1;
-    const int Wp = (W + 7) / 8 * 8, Hp = (H + 7) / 8 * 8, Dp = (D + 7) / 8 * 8;
-    for (int w = 1; w <= Wp && w <= 64; ++w)
-        for (int h = 1; h <= Hp && w * h <= 64; ++h)
-            for (int d = 1; d <= Dp && w * h * d <= 64; ++d) {
-                const int P = w * h * d;
-                if (P % 8 != 0) continue;
+    for (int w = 1; w <= W && w <= 64; ++w)
+        for (int h = 1; h <= H && w * h <= 64; ++h)
+            for (int d = 1; d <= D && w * h * d <= 64; ++d) {
+                const int P = (w * h * d + 7) / 8 * 8;
                 long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
-                long score = tiles * P * 64 - P;            // least padded work, then the larger block
+                long score = tiles * P * 64 - w * h * d;    // least padded work, then the larger block
                 if (best < 0 || score < best) { best = score; tw = w; th = h; td = d; }
             }
 }
@@ -203,7 +209,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
     choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
-    p.P = p.tw * p.th * p.td;
+    p.p_box = p.tw * p.th * p.td;
+    p.P = (p.p_box + 7) / 8 * 8;
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.cout = g.cout; p.cin = g.cin;
     p.m_tile = g.cout > 128 ? 128 : g.cout;
