@@ -76,9 +76,12 @@ SIGNATURES = {
     "chap_consistency_bwd": (I, [P, P, P, I, L, I, P, P, P]),
     "chap_patch_score": (I, [P, P, P, I, I, I, I, I, I, P, P]),
     "chap_patch_mask": (I, [P, P, I, I, I, I, I, I, P, P]),
+    "chap_largest_cc_workspace_bytes": (c_size_t, [I, I, I, I, I]),
+    "chap_largest_cc": (I, [P, I, I, I, I, I, I, P, P, c_size_t, P]),
     "chap_perturb_workspace_elems": (c_size_t, [POINTER(Level), I, I]),
     "chap_perturb_fwd": (I, [POINTER(Level), I, I, I, F, F, P, c_size_t, P]),
     "chap_l2n_sample_axpy": (I, [P, P, F, I, L, P, P, P]),
+    "chap_sgd_momentum_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
     "chap_sgd_momentum": (I, [P, P, P, L, F, F, F, F, I, P]),
     "chap_sw_extract": (I, [_SW, P, I, I, P, P]),
     "chap_sw_aggregate": (I, [_SW, P, I, P, P, P, P]),

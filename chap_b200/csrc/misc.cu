@@ -32,7 +32,8 @@ KernelTimer::~KernelTimer() {
 // ------------------------------------------------------------------ SGD momentum on a flat arena
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n4, int64_t n,
-           float lr, float mom, float wd, float gs, int first) {
+           float lr, const float* __restrict__ lr_dev, float mom, float wd, float gs, int first) {
+    if (lr_dev) lr = *lr_dev;          // learning rate read from device memory: the launch is CUDA-graph replayable
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -196,7 +197,15 @@ extern "C" int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t e
                                  float weight_decay, float grad_scale, int32_t first_step, void* stream) {
     CHAP_REQUIRE(p && g && buf && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum: bad argument");
     CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum: buffers must be 16-byte aligned");
-    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, lr, momentum, weight_decay, grad_scale, first_step);
+    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, lr, nullptr, momentum, weight_decay, grad_scale, first_step);
+    return launched("sgd_kernel");
+}
+
+extern "C" int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int64_t elems, const float* lr_dev, float momentum,
+                                       float weight_decay, float grad_scale, void* stream) {
+    CHAP_REQUIRE(p && g && buf && lr_dev && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum_lrdev: bad argument");
+    CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum_lrdev: buffers must be 16-byte aligned");
+    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, 0.f, lr_dev, momentum, weight_decay, grad_scale, 0);
     return launched("sgd_kernel");
 }
 

@@ -501,6 +501,21 @@ def patch_topk_mask(knowledge, arg1, arg2, scale_factor, topk):
     return mask
 
 
+def largest_cc(seg, n_classes):
+    """get_ACDC_2DLargestCC on the device: int64 class map [N, *spatial] -> float32 map keeping, per sample and
+    foreground class, only the largest connected component (full connectivity, first component wins ties)."""
+    _require_cuda(seg)
+    seg = seg.to(torch.int64).contiguous()
+    n = seg.shape[0]
+    nd = seg.dim() - 1
+    d, h, w = (1, seg.shape[1], seg.shape[2]) if nd == 2 else tuple(seg.shape[1:])
+    nbytes = lib().chap_largest_cc_workspace_bytes(n, d, h, w, n_classes)
+    ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=seg.device)
+    out = torch.empty(seg.shape, dtype=torch.float32, device=seg.device)
+    check(lib().chap_largest_cc(_p(seg), nd, n, d, h, w, n_classes, _p(out), _p(ws), nbytes, _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------- perturbation generator
 def perturb(grads, feats, eps, mode="channel_spatial", g_scale=1.0):
     """[f_l + eps * normalise(g_l)] for all levels in one library call (f_l may be None -> r_l only).
@@ -558,6 +573,14 @@ def sgd_momentum_(flat_p, flat_g, flat_buf, lr, momentum, weight_decay, grad_sca
     _require_cuda(flat_p, flat_g, flat_buf)
     check(lib().chap_sgd_momentum(_p(flat_p), _p(flat_g), _p(flat_buf), flat_p.numel(), float(lr), float(momentum),
                                   float(weight_decay), float(grad_scale), 1 if first_step else 0, _stream()))
+    invalidate_weight_cache()
+
+
+def sgd_momentum_lrdev_(flat_p, flat_g, flat_buf, lr_dev, momentum, weight_decay, grad_scale=1.0):
+    """SGD-momentum with the learning rate in a device tensor (CUDA-graph replayable); flat_buf starts as zeros."""
+    _require_cuda(flat_p, flat_g, flat_buf, lr_dev)
+    check(lib().chap_sgd_momentum_lrdev(_p(flat_p), _p(flat_g), _p(flat_buf), flat_p.numel(), _p(lr_dev), float(momentum),
+                                        float(weight_decay), float(grad_scale), _stream()))
     invalidate_weight_cache()
 
 

@@ -29,8 +29,13 @@ def generate_mask(img, offsets=None):
 
 
 def largest_cc_labels(seg, n_classes):
-    """get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144): keep the largest connected component of
-    every foreground class per sample (full connectivity, first component wins ties).  Host side."""
+    """get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144): keep the largest connected component of every
+    foreground class per sample (full connectivity, first component wins ties) -- union-find kernel, no host sync."""
+    return ops.largest_cc(seg, n_classes)
+
+
+def largest_cc_labels_host(seg, n_classes):
+    """Same filter on the host with scipy (what the reference does with skimage: one D2H/H2D round trip)."""
     from scipy import ndimage
     seg_np = seg.detach().cpu().numpy()
     structure = np.ones((3,) * (seg_np.ndim - 1), dtype=bool)
@@ -57,8 +62,10 @@ def consistency_weight(iter_num, consistency=1.0, rampup=50.0):
 
 def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, vat=None, adv_losstype="kl",
                         topk=0.1, use_diff_mask=True, consistency=1.0, rampup=50.0, mask_offsets=None,
-                        d_init=None, trace=None):
-    """Forward part of the iteration; returns (loss, aux).  Line numbers: code/train_ours_2D.py."""
+                        d_init=None, trace=None, img_mask=None, cw=None):
+    """Forward part of the iteration; returns (loss, aux).  Line numbers: code/train_ours_2D.py.
+    img_mask (int64 [*spatial]) / cw (float or 0-dim device tensor) may be supplied by the caller (the CUDA-graph
+    trainer keeps them in static device buffers); otherwise they are drawn / computed here like the reference does."""
     n = volume.shape[0]
     sub_l, sub_u = labeled_bs // 2, (n - labeled_bs) // 2                               # :295
     img_a, img_b = volume[:sub_l], volume[sub_l:labeled_bs]                             # :307
@@ -73,7 +80,9 @@ def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, v
         plab2 = largest_cc_labels(ps2, n_classes)
         plab_a1, plab_b1 = plab1[:sub_u], plab1[sub_u:]
         plab_a2, plab_b2 = plab2[:sub_u], plab2[sub_u:]
-        img_mask, loss_mask = generate_mask(img_a, mask_offsets)
+        if img_mask is None:
+            img_mask, _ = generate_mask(img_a, mask_offsets)
+        loss_mask = img_mask
         net_input_unl = ops.mask_mix(uimg_a, img_a, img_mask)                           # :335
         net_input_l = ops.mask_mix(img_b, uimg_b, img_mask)                             # :336
         net_input_mix = torch.cat((net_input_l, net_input_unl))                         # :338
@@ -88,7 +97,8 @@ def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, v
     bcp_loss = m1 + m2 + m3 + m4                                                        # :351
     loss_l = ll_i1 + ll_i2 + ll_o1 + ll_o2
     loss_u = lu_i1 + lu_i2 + lu_o1 + lu_o2
-    cw = consistency_weight(iter_num, consistency, rampup)                              # :356
+    if cw is None:
+        cw = consistency_weight(iter_num, consistency, rampup)                          # :356
 
     if vat is not None:                                                                 # :369-372
         diff_mask = patch.create_maskV1(ps1, ps2, knowledge, scale_factor=4, topk=topk) if use_diff_mask else None
@@ -106,11 +116,12 @@ class FlatSGD:
     """torch.optim.SGD(lr, momentum=0.9, weight_decay=1e-4) semantics (code/train_ours_2D.py:278,383)
     on one flat fp32 arena: parameters are re-pointed at views of a single buffer, gradients are
     gathered into a matching flat buffer, and ONE fused kernel updates everything.  `grad_hook`
-    (optional) is called on the flat gradient before the update -- the data-parallel all-reduce."""
+    (optional) is called on the flat gradient before the update -- the data-parallel all-reduce.
+    The learning rate lives in a device scalar so that the update can be replayed from a CUDA graph."""
 
     def __init__(self, params, lr, momentum=0.9, weight_decay=1e-4, grad_hook=None):
         self.params = [p for p in params if p.requires_grad]
-        self.lr, self.momentum, self.weight_decay, self.grad_hook = lr, momentum, weight_decay, grad_hook
+        self.momentum, self.weight_decay, self.grad_hook = momentum, weight_decay, grad_hook
         dev = self.params[0].device
         self.offsets, total = [], 0
         for p in self.params:
@@ -118,15 +129,25 @@ class FlatSGD:
             total += (p.numel() + 3) // 4 * 4                     # keep every slot 16-byte aligned
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)     # zeros: first step gives buf = g
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = torch.empty(1, dtype=torch.float32).pin_memory()
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
                 view = self.flat_p[off:off + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view
         self.grad_views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
-        self.first = True
         ops.invalidate_weight_cache()
+
+    @property
+    def lr(self):
+        return float(self._lr_host[0])
+
+    @lr.setter
+    def lr(self, value):
+        self._lr_host[0] = float(value)
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
 
     def zero_grad(self):
         for p in self.params:
@@ -145,17 +166,21 @@ class FlatSGD:
         self.gather_grads()
         if self.grad_hook is not None:
             self.grad_hook(self.flat_g)
-        ops.sgd_momentum_(self.flat_p, self.flat_g, self.flat_buf, self.lr, self.momentum, self.weight_decay,
-                          grad_scale, self.first)
-        self.first = False
+        ops.sgd_momentum_lrdev_(self.flat_p, self.flat_g, self.flat_buf, self.lr_dev, self.momentum, self.weight_decay, grad_scale)
 
 
 class ChapTrainer:
-    """State + `step(volume, label)` for CHAP training of a DualDecoder (2D) or DualDecoder3d (3D)."""
+    """State + `step(volume, label)` for CHAP training of a DualDecoder (2D) or DualDecoder3d (3D).
+
+    use_graph=True: after `graph_warmup` eager iterations the whole iteration (3 network passes + the VAT probe,
+    pseudo-labels, largest-CC filter, losses, backward, gradient gather, all-reduce hook, fused SGD) is captured ONCE
+    into a CUDA graph and replayed; per-iteration host work is three tiny H2D scalars/masks plus the input copy into
+    static buffers.  Everything that changes between iterations lives in device memory: inputs, the copy-paste mask
+    (np.random offsets, code/train_ours_2D.py:97-98), the consistency weight (:356) and the learning rate (:387)."""
 
     def __init__(self, model, n_classes, labeled_bs, base_lr=0.01, max_iterations=30000, adv_noise=True,
                  adv_losstype="kl", noise_mag=10.0, epi=6.0, topk=0.1, consistency=1.0, consistency_rampup=50.0,
-                 use_diff_mask=True, grad_hook=None, grad_scale=1.0):
+                 use_diff_mask=True, grad_hook=None, grad_scale=1.0, use_graph=False, graph_warmup=3):
         self.model, self.n_classes, self.labeled_bs = model, n_classes, labeled_bs
         self.base_lr, self.max_iterations = base_lr, max_iterations
         self.vat = losses.VAT2d(xi=noise_mag, epi=epi, num_classes=n_classes) if adv_noise else None
@@ -164,17 +189,57 @@ class ChapTrainer:
         self.opt = FlatSGD(model.parameters(), base_lr, grad_hook=grad_hook)
         self.grad_scale = grad_scale
         self.iter_num = 0
+        self.use_graph, self.graph_warmup = use_graph, graph_warmup
+        self.graph, self.static = None, None
         model.train()
 
-    def step(self, volume, label, mask_offsets=None, d_init=None, trace=None):
+    # ------------------------------------------------------------------ one iteration on given device tensors
+    def _iteration(self, volume, label, img_mask=None, cw=None, mask_offsets=None, d_init=None, trace=None):
         loss, aux = chap_losses_forward(self.model, volume, label, self.labeled_bs, self.n_classes, self.iter_num,
                                         vat=self.vat, adv_losstype=self.adv_losstype, topk=self.topk,
                                         use_diff_mask=self.use_diff_mask, consistency=self.consistency,
-                                        rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace)
+                                        rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace,
+                                        img_mask=img_mask, cw=cw)
         self.opt.zero_grad()                                                            # :381
         loss.backward()                                                                 # :382
-        self.opt.lr = self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9   # lr set at :387-389 of the previous iteration
         self.opt.step(self.grad_scale)                                                  # :383
-        self.iter_num += 1                                                              # :385
         aux["loss"] = loss.detach()
         return aux
+
+    def _poly_lr(self):
+        return self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9        # set at :387-389 of the previous iteration
+
+    def step(self, volume, label, mask_offsets=None, d_init=None, trace=None):
+        self.opt.lr = self._poly_lr()
+        eager = (not self.use_graph) or d_init is not None or trace is not None
+        if eager or self.iter_num < self.graph_warmup:
+            aux = self._iteration(volume, label, mask_offsets=mask_offsets, d_init=d_init, trace=trace)
+            self.iter_num += 1                                                          # :385
+            return aux
+        if self.graph is None:
+            self._capture(volume, label)
+        st = self.static
+        st["volume"].copy_(volume, non_blocking=True)
+        st["label"].copy_(label, non_blocking=True)
+        mask, _ = generate_mask(volume[:1], mask_offsets)
+        st["mask"].copy_(mask, non_blocking=True)
+        st["cw_host"].fill_(consistency_weight(self.iter_num, self.consistency, self.rampup))
+        st["cw"].copy_(st["cw_host"], non_blocking=True)
+        self.graph.replay()
+        ops.invalidate_weight_cache()          # the replay updated the weights behind the Python-side pack cache
+        self.iter_num += 1
+        return st["aux"]
+
+    def _capture(self, volume, label):
+        dev = volume.device
+        st = dict(volume=torch.empty_like(volume), label=torch.empty_like(label),
+                  mask=torch.ones(tuple(volume.shape[2:]), dtype=torch.int64, device=dev),
+                  cw=torch.zeros((), dtype=torch.float32, device=dev), cw_host=torch.zeros(()).pin_memory())
+        st["volume"].copy_(volume)
+        st["label"].copy_(label)
+        ops.invalidate_weight_cache()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"])
+        self.static = st

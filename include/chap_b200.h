@@ -197,6 +197,14 @@ int chap_patch_score(const float* knowledge, const int64_t* arg1, const int64_t*
 int chap_patch_mask(const float* score, const float* kth, int32_t nd, int32_t n, int32_t d, int32_t h,
                     int32_t w, int32_t s, float* mask, void* stream);
 
+/* Largest-connected-component filter of get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144) on the device:
+ * seg int64 [n, d, h, w] class map -> out float32 [n, d, h, w]: per sample and foreground class (1..n_classes-1) the
+ * largest component (8- / 26-connectivity) keeps its class value, everything else is 0; among equally large components
+ * the one that comes first in scan order wins (np.argmax over np.bincount of skimage labels).  nd = 2: d must be 1. */
+size_t chap_largest_cc_workspace_bytes(int32_t n, int32_t d, int32_t h, int32_t w, int32_t n_classes);
+int chap_largest_cc(const int64_t* seg, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t n_classes,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ perturbation generator
  * The channel-spatial hierarchical adversarial perturbation of losses.VAT2d (absent in the
  * reference; ctor code/train_ours_2D.py:290, call :372; BASELINE.json north_star).
@@ -226,6 +234,10 @@ int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n,
 /* ------------------------------------------------------------------ optimiser
  * torch.optim.SGD(momentum, weight_decay) step of code/train_ours_2D.py:278,383 on flat buffers:
  * g' = grad_scale*g + wd*p ; buf = first ? g' : mom*buf + g' ; p -= lr*buf */
+/* same with the learning rate read from device memory at run time and buf assumed initialised (zeros before the first
+ * step give buf = g'): the launch can be captured once in a CUDA graph and replayed with a changing learning rate */
+int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int64_t elems, const float* lr_dev, float momentum,
+                            float weight_decay, float grad_scale, void* stream);
 int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t elems, float lr, float momentum,
                       float weight_decay, float grad_scale, int32_t first_step, void* stream);
 

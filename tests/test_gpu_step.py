@@ -136,3 +136,61 @@ def test_chap_training_iteration_3d_runs_and_matches_oracle_losses():
         assert np.isfinite(float(out["vat_loss"]))
     finally:
         ops.set_force_simt(False)
+
+
+def test_largest_cc_kernel_matches_host_oracle():
+    """bit-exact label maps vs the scipy restatement of get_ACDC_2DLargestCC, incl. ties, empty classes, 2D and 3D."""
+    from chap_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for shape, ncls in (((5, 64, 64), 4), ((3, 24, 20, 16), 2), ((2, 33, 17), 3)):
+        noise = torch.rand(shape, generator=g)
+        seg = (noise * ncls * 1.7).long().clamp_(0, ncls - 1)           # speckled maps: many small components, ties
+        seg[0] = 0                                                       # an empty sample
+        if len(shape) == 3:
+            seg[1, :8, :8] = 1; seg[1, 20:28, 20:28] = 1                 # two equal squares of class 1 -> first one wins
+            seg[1, 8:20] = 0; seg[1, :, 8:20] = 0
+        want = L.largest_cc_labels(seg, ncls)
+        got = ops.largest_cc(seg.to(DEV), ncls).cpu()
+        assert got.dtype == torch.float32 and torch.equal(got, want), shape
+    _, lab = _batch2d(6, 48)
+    assert torch.equal(ops.largest_cc(lab.to(DEV), 4).cpu(), L.largest_cc_labels(lab, 4))
+
+
+def test_cuda_graph_trainer_equals_eager_trainer():
+    """The captured iteration must be the same computation as the eager one: two trainers from the same weights, no
+    stochastic parts (dropout p = 0, no VAT noise), 6 iterations -> parameters agree to float rounding."""
+    from chap_b200 import ops
+    from chap_b200.train_step import ChapTrainer
+    ops.set_force_simt(True)
+    try:
+        ma = seeded_model("dualdecoder2d", seed=8).to(DEV)
+        mb = seeded_model("dualdecoder2d", seed=8).to(DEV)
+        ta = ChapTrainer(ma, 4, 4, max_iterations=100, adv_noise=False, use_graph=False)
+        tb = ChapTrainer(mb, 4, 4, max_iterations=100, adv_noise=False, use_graph=True, graph_warmup=2)
+        for it in range(6):
+            vol, lab = _batch2d(8, 32, seed=it)
+            offs = (2 + it % 3, 4)
+            la = ta.step(vol.to(DEV), lab.to(DEV), mask_offsets=offs)["loss"].clone()
+            lb = tb.step(vol.to(DEV), lab.to(DEV), mask_offsets=offs)["loss"].clone()
+            assert abs(float(la) - float(lb)) < 1e-4 * max(1.0, abs(float(la))), it
+        assert tb.graph is not None and tb.iter_num == 6
+        errs = np.array([rel_err(pb, pa) for pa, pb in zip(ma.parameters(), mb.parameters())])
+        # same computation; float atomics reorder sums between runs and a flipped activation kink shows up as a
+        # percent-level difference in a few small tensors (BatchNorm betas start at 0): median at rounding level
+        assert np.median(errs) < 1e-5 and errs.max() < 0.1, (np.median(errs), errs.max())
+    finally:
+        ops.set_force_simt(False)
+
+
+def test_cuda_graph_trainer_full_chap_step_runs():
+    """graph capture of the FULL step (VAT with in-graph RNG, largest-CC kernel, TF32 tensor-core convs)."""
+    from chap_b200.train_step import ChapTrainer
+    m = seeded_model("dualdecoder2d", seed=3).to(DEV)
+    t = ChapTrainer(m, 4, 4, max_iterations=100, use_graph=True, graph_warmup=2, topk=0.25)
+    losses_seen = []
+    for it in range(5):
+        vol, lab = _batch2d(8, 32, seed=it)
+        out = t.step(vol.to(DEV), lab.to(DEV))
+        losses_seen.append(float(out["loss"]))
+    assert t.graph is not None and all(np.isfinite(v) for v in losses_seen), losses_seen
+    assert len(set(losses_seen)) == 5            # every replay saw new inputs / weights
