@@ -90,3 +90,28 @@ def test_vnet_sliding_window_end_to_end_vs_oracle():
     assert diff.mean() < 0.02
     if diff.any():
         assert np.abs(wscore[0][diff] - wscore[1][diff]).max() < 5e-3     # ties only
+
+
+def test_val_2d_test_single_volume_batched_equals_slice_loop():
+    """chap_b200.val_2D.test_single_volume (all slices in one forward) vs the reference's per-slice protocol
+    (code/val_2D.py:57-92) run with the same product net: identical label volume, Dice interface preserved."""
+    from scipy.ndimage import zoom
+    from conftest import seeded_model
+    from chap_b200 import ops
+    from chap_b200.val_2D import predict_volume, test_single_volume
+    m = seeded_model("dualdecoder2d", seed=9).to(DEV).eval()
+    rng = np.random.RandomState(1)
+    image = rng.rand(5, 40, 36).astype(np.float32)
+    label = (rng.rand(5, 40, 36) * 4).astype(np.int64)
+    got = predict_volume(image, m, (64, 64), 'logit_ensemble', DEV)
+    want = np.zeros_like(label)
+    with torch.no_grad():
+        for i in range(5):
+            sl = zoom(image[i], (64 / 40, 64 / 36), order=0)
+            o1, o2 = m(torch.from_numpy(sl)[None, None].float().to(DEV))
+            out = ops.argmax(o1, o2)[0].cpu().numpy()
+            want[i] = zoom(out, (40 / 64, 36 / 64), order=0)
+    assert (got != want).mean() < 1e-3          # batch-1 vs batch-5 convolutions may differ in the last bit of a tie
+    res = test_single_volume(torch.from_numpy(image)[None], torch.from_numpy(label)[None], m, classes=4,
+                             patch_size=[64, 64], model_type='logit_ensemble', device=DEV)
+    assert len(res) == 3 and all(len(r) == 2 for r in res)

@@ -1,0 +1,64 @@
+"""CPU: host-side logic of the product package that needs no GPU (schedules, masks, metrics, window geometry) and
+its agreement with the oracle restatement."""
+import numpy as np
+import torch
+
+from oracle import chap_losses as L
+from oracle import sliding_window as osw
+
+
+def test_schedules_match_oracle():
+    from chap_b200.train_step import consistency_weight
+    from chap_b200.utils import ramps
+    for t in (0, 1, 149, 150, 3000, 7500, 29999):
+        assert consistency_weight(t, 1.0, 50.0) == L.consistency_weight(t, 1.0, 50.0)
+    assert ramps.sigmoid_rampup(0, 50.0) == float(np.exp(-5.0)) and ramps.sigmoid_rampup(50, 50.0) == 1.0
+    assert ramps.sigmoid_rampup(3, 0) == 1.0
+
+
+def test_generate_mask_matches_reference_semantics():
+    from chap_b200.train_step import generate_mask
+    img = torch.zeros(6, 1, 256, 256)
+    mask, loss_mask = generate_mask(img, (10, 20))
+    assert mask.dtype == torch.int64 and loss_mask.shape == (6, 256, 256)
+    assert int((mask == 0).sum()) == 170 * 170 and mask[10, 20] == 0 and mask[9, 20] == 1 and mask[179, 189] == 0 and mask[180, 189] == 1
+    assert torch.equal(mask, L.generate_mask((256, 256), (10, 20)))
+    m3, _ = generate_mask(torch.zeros(1, 1, 112, 112, 80), (1, 2, 3))
+    assert int((m3 == 0).sum()) == 74 * 74 * 53
+    np.random.seed(0)
+    a, _ = generate_mask(img)
+    np.random.seed(0)
+    assert L.draw_mask_offsets((256, 256)) == tuple(int(torch.nonzero(a == 0)[0][i]) for i in range(2))
+
+
+def test_host_largest_cc_and_metrics():
+    from chap_b200.test_3D_util import asd, cal_dice, dice_coefficient, hd95, jc
+    from chap_b200.train_step import largest_cc_labels_host
+    seg = torch.zeros(1, 8, 8, dtype=torch.int64)
+    seg[0, 0:2, 0:2] = 1; seg[0, 4:7, 4:7] = 1; seg[0, 0, 7] = 2
+    out = largest_cc_labels_host(seg, 3)
+    assert torch.equal(out, L.largest_cc_labels(seg, 3)) and out.sum() == 9 + 2 and out[0, 0, 0] == 0
+    a = np.zeros((8, 8, 8), bool); a[2:6, 2:6, 2:6] = True
+    b = np.zeros((8, 8, 8), bool); b[3:7, 2:6, 2:6] = True
+    assert abs(dice_coefficient(a, b) - 0.75) < 1e-12 and abs(jc(a, b) - 0.6) < 1e-12
+    assert dice_coefficient(a, a) == 1.0 and dice_coefficient(np.zeros(3), np.zeros(3)) == 0.0
+    assert hd95(a, a) == 0.0 and hd95(a, b) == 1.0 and 0.0 < asd(a, b) < 1.0
+    assert abs(cal_dice(a.astype(int), b.astype(int), 2)[0] - 0.75) < 1e-12
+    assert L.dice_coefficient(a, b) == dice_coefficient(a, b)
+
+
+def test_window_geometry_matches_oracle():
+    from chap_b200.test_3D_util import _pad_amounts
+    for shape in ((192, 192, 88), (177, 203, 88), (100, 120, 70)):
+        assert _pad_amounts(shape, (112, 112, 80)) == osw.pad_amounts(shape, (112, 112, 80))
+    assert len(osw.window_starts(192, 112, 18)) ** 2 * len(osw.window_starts(88, 80, 4)) == 108
+
+
+def test_filter_dropout_mask_helpers():
+    from chap_b200.networks import FilterDropout as fd
+    torch.manual_seed(0)
+    probs = torch.rand(6, 32)
+    m1, m2 = fd.drop_based_on_prob(probs, False)
+    assert m1.shape == (6, 32) and abs(float(m1.mean()) - 1.0) < 1e-5 and abs(float(m2.mean()) - 1.0) < 1e-5
+    m1, m2 = fd.scores_dropoutV2(torch.rand(32), torch.rand(6, 32), True, 'sigmoid')
+    assert set(torch.unique(m1 > 0).tolist()) <= {True, False} and m1.shape == (6, 32)
