@@ -42,9 +42,9 @@ int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, 
 // ---------------------------------------------------------------- gather conv
 template <int CO_T, bool VEC4>
 __global__ void __launch_bounds__(128)
-conv_gather_kernel(SimtOp op, const float* __restrict__ in, const float* __restrict__ wp,
+conv_gather_kernel(SimtOp op, int all_w, const float* __restrict__ in, const float* __restrict__ wp,
                    const float* __restrict__ bias, float* __restrict__ out) {
-    extern __shared__ float ws[];                  // [K][CO_T]
+    extern __shared__ float ws_all[];              // [K][CO_T] per tap, or [taps][K][CO_T] when everything fits (all_w)
     const int n0 = blockIdx.y * CO_T;
     const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const bool live = m < op.out_rows;
@@ -55,16 +55,26 @@ conv_gather_kernel(SimtOp op, const float* __restrict__ in, const float* __restr
     for (int j = 0; j < CO_T; ++j) acc[j] = 0.f;
 
     const int kd_n = op.nd == 3 ? op.ksz : 1;
+    if (all_w) {
+        for (int i = threadIdx.x; i < op.taps * op.K * CO_T; i += 128) {
+            int tk = i / CO_T, j = i % CO_T;
+            ws_all[i] = (n0 + j < op.N) ? wp[(int64_t)tk * op.N + n0 + j] : 0.f;
+        }
+        __syncthreads();
+    }
     int t = 0;
     for (int kz = 0; kz < kd_n; ++kz)
         for (int ky = 0; ky < op.ksz; ++ky)
             for (int kx = 0; kx < op.ksz; ++kx, ++t) {
-                __syncthreads();
-                for (int i = threadIdx.x; i < op.K * CO_T; i += 128) {
-                    int k = i / CO_T, j = i % CO_T;
-                    ws[i] = (n0 + j < op.N) ? wp[((int64_t)t * op.K + k) * op.N + n0 + j] : 0.f;
+                const float* ws = all_w ? ws_all + (size_t)t * op.K * CO_T : ws_all;
+                if (!all_w) {
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < op.K * CO_T; i += 128) {
+                        int k = i / CO_T, j = i % CO_T;
+                        ws_all[i] = (n0 + j < op.N) ? wp[((int64_t)t * op.K + k) * op.N + n0 + j] : 0.f;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 int id = od * op.stride + kz - (op.nd == 3 ? op.pad : 0);
                 int ih = oh * op.stride + ky - op.pad;
                 int iw = ow * op.stride + kx - op.pad;
@@ -170,12 +180,14 @@ int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* b
         return launched("conv_up2_kernel");
     }
     dim3 grid((unsigned)((op.out_rows + 127) / 128), (unsigned)((op.N + co_t - 1) / co_t));
+    const int all_w = (size_t)op.taps * smem <= 40 * 1024 ? 1 : 0;      // all taps' weights resident: no per-tap barrier
+    const size_t gsmem = all_w ? (size_t)op.taps * smem : smem;
     if (small) {
-        if (vec4) conv_gather_kernel<4, true><<<grid, block, smem, st>>>(op, in, wp, bias, out);
-        else conv_gather_kernel<4, false><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+        if (vec4) conv_gather_kernel<4, true><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
+        else conv_gather_kernel<4, false><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
     } else {
-        if (vec4) conv_gather_kernel<16, true><<<grid, block, smem, st>>>(op, in, wp, bias, out);
-        else conv_gather_kernel<16, false><<<grid, block, smem, st>>>(op, in, wp, bias, out);
+        if (vec4) conv_gather_kernel<16, true><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
+        else conv_gather_kernel<16, false><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
     }
     return launched("conv_gather_kernel");
 }
@@ -241,9 +253,70 @@ conv_wgrad_kernel(SimtOp op, const float* __restrict__ a, const float* __restric
         atomicAdd(dw + (k0 + kk) * sk + (n0 + nn) * sn + t, acc);
 }
 
+// Weight gradient of the Cin = 1 stems (k = 3): dW[co][0][tap] = sum_p x[p + tap] * dy[p, co].  The generic kernel would
+// re-read dy once per tap; here one thread owns a pixel, reads its 16-channel dy vector ONCE and the 9 neighbouring
+// inputs of one kz-plane, and keeps 9 x 16 partial sums in registers across a grid-stride loop; then warp shuffle ->
+// smem -> one atomic per (tap, channel) and block.  grid = (pixel slices, kz planes, Cout / 16).
+__global__ void __launch_bounds__(128)
+stem_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t sn) {
+    __shared__ float red[144];
+    const int kz = blockIdx.y, c0 = blockIdx.z * 16;
+    float acc[9][16];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[t][c] = 0.f;
+    for (int i = threadIdx.x; i < 144; i += 128) red[i] = 0.f;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < op.out_rows; r += (int64_t)gridDim.x * 128) {
+        int bn, d, h, w;
+        decode_row(r, op.oD, op.oH, op.oW, bn, d, h, w);
+        const int id = op.nd == 3 ? d + kz - 1 : 0;
+        if (id < 0 || id >= op.iD) continue;
+        float g[16];
+        const float4* gp = reinterpret_cast<const float4*>(dy + r * op.N + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { float4 v = __ldg(gp + q); g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w; }
+        const float* xb = x + (((int64_t)bn * op.iD + id) * op.iH) * op.iW;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ih = h + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iw = w + kx - 1;
+                const float xv = (ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW) ? __ldg(xb + (int64_t)ih * op.iW + iw) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[ky * 3 + kx][c] = fmaf(xv, g[c], acc[ky * 3 + kx][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float v = warp_sum(acc[t][c]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&red[t * 16 + c], v);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 144; i += 128) {
+        const int t = i / 16, c = i % 16;
+        atomicAdd(dw + (int64_t)(c0 + c) * sn + (kz * 9 + t), red[i]);
+    }
+}
+
 int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
                int64_t sk, int64_t sn, cudaStream_t st) {
     CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
+    if (!op.up2 && op.K == 1 && op.ksz == 3 && op.stride == 1 && op.N % 16 == 0 && aligned16(b)) {
+        KernelTimer timer("conv_stem_wgrad", 2.0 * (double)op.out_rows * op.N * op.taps,
+                          4.0 * ((double)op.in_rows + (double)op.out_rows * op.N), st);
+        int slices = (int)((op.out_rows + 128 * 8 - 1) / (128 * 8));
+        const int planes = op.nd == 3 ? 3 : 1;
+        const int cap = (kNumSMs * 6) / (planes * (op.N / 16));
+        if (slices > cap) slices = cap < 1 ? 1 : cap;
+        stem_wgrad_kernel<<<dim3((unsigned)slices, (unsigned)planes, (unsigned)(op.N / 16)), 128, 0, st>>>(op, a, b, dw, sn);
+        return launched("stem_wgrad_kernel");
+    }
     const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
     KernelTimer timer("conv_simt_wgrad", 2.0 * (double)rows * op.K * op.N * op.taps,
                       4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);

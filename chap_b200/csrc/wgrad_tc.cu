@@ -218,26 +218,41 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.mma_m = 128;           // M = 64 has a different TMEM lane mapping; M = 128 costs the same tensor time
     p.a_cpg = 32; p.a_groups = (p.m_tile + 31) / 32;
     p.b_cpg = 32; p.b_groups = p.n_tile / 32;
-    int tg = 512 / p.n_tile;
-    if (tg > g.taps) tg = g.taps;
-    // balance the tap groups (e.g. 9 taps, room for 4 -> 3 groups of 3)
-    const int groups = (g.taps + tg - 1) / tg;
-    tg = (g.taps + groups - 1) / groups;
-    p.tg = tg;
-    p.tmem_cols = 32; while (p.tmem_cols < tg * p.n_tile) p.tmem_cols *= 2;
     p.a_stage_bytes = ((uint32_t)p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
     p.b_stage_bytes = ((uint32_t)p.n_tile * p.P * 4u + 1023u) & ~1023u;
     const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
-    int stages = (int)((200 * 1024 - 2048) / stage);
-    if (stages > 6) stages = 6;
-    CHAP_REQUIRE(stages >= 2, CHAP_ERR_BAD_ARG, "tc_wgrad: tile does not fit shared memory");
-    p.stages = stages;
     p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
     const int n_tiles = g.cin > 256 ? g.cin / 256 : 1;
     const int zdim = (g.cout / p.m_tile) * n_tiles;
-    int splits = (2 * kNumSMs + groups * zdim - 1) / (groups * zdim);
-    if (splits > p.blocks_total) splits = p.blocks_total;
-    if (splits < 1) splits = 1;
+    // Work split.  Parallelism comes from (channel tiles) x (tap groups) x (pixel splits).  Every pixel split adds one
+    // fp32 atomic per (padded) weight element in the epilogue, so splits are capped by an atomic budget (measured: a
+    // 256x256x9 layer with 24 splits spent >80% of its 106 us in 14 M atomics); tap groups are made smaller instead.
+    // Two CTAs share an SM when a CTA needs <= 256 TMEM columns and <= 100 KB of smem.
+    const long weights_pad = (long)g.cout * p.n_tile * n_tiles * g.taps;
+    long max_splits = 4000000L / weights_pad;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > p.blocks_total) max_splits = p.blocks_total;
+    int best_tg = 1, best_ctas = -1, best_splits = 1, best_groups = g.taps;
+    for (int tg = (512 / p.n_tile < g.taps ? 512 / p.n_tile : g.taps); tg >= 1; --tg) {
+        const int groups = (g.taps + tg - 1) / tg;
+        if ((g.taps + groups - 1) / groups != tg) continue;                    // keep the groups balanced
+        const bool two = tg * p.n_tile <= 256 && 3 * stage <= 100 * 1024;
+        const int target = two ? 2 * kNumSMs : kNumSMs;
+        long splits = (target + groups * zdim - 1) / (groups * zdim);
+        if (splits > max_splits) splits = max_splits;
+        const int ctas = (int)(splits * groups * zdim);
+        const int score = ctas >= (target * 3) / 4 ? 1000000 + tg : ctas;      // enough CTAs: prefer the largest tap group
+        if (score > best_ctas) { best_ctas = score; best_tg = tg; best_splits = (int)splits; best_groups = groups; }
+    }
+    const int tg = best_tg, groups = best_groups;
+    int splits = best_splits;
+    p.tg = tg;
+    p.tmem_cols = 32; while (p.tmem_cols < tg * p.n_tile) p.tmem_cols *= 2;
+    const bool two_per_sm = p.tmem_cols <= 256 && 3 * stage <= 100 * 1024;
+    int stages = (int)(((two_per_sm ? 100 : 200) * 1024 - 2048) / stage);
+    if (stages > 8) stages = 8;
+    CHAP_REQUIRE(stages >= 2, CHAP_ERR_BAD_ARG, "tc_wgrad: tile does not fit shared memory");
+    p.stages = stages;
     p.blocks_per_cta = (p.blocks_total + splits - 1) / splits;
     splits = (p.blocks_total + p.blocks_per_cta - 1) / p.blocks_per_cta;
     const PackSpec ps = fwd_pack(g);          // torch [co][ci][tap]: s_ci = T, s_co = Cin*T
