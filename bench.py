@@ -142,7 +142,7 @@ def run_reference(args, w):
     threads = os.cpu_count() or 1
     # bounded sample: the full batch is 24 (12 labelled); time a batch-4 (2 labelled) slice of the same iteration
     sample_batch, sample_labeled = (4, 2) if w["dims"] == 2 else (4, 2)
-    sample_shape = w["shape"] if w["dims"] == 2 else (56, 56, 40)
+    sample_shape = w["shape"] if w["dims"] == 2 else (64, 64, 48)
     ws = dict(w, shape=sample_shape)
     sec = cpu_chap_iteration(ws, sample_batch, sample_labeled, threads, args.steps, min(args.warmup, 1))
     vox_full = w["batch"] * float(np.prod(w["shape"]))
@@ -278,7 +278,7 @@ def run_gpu(args, w):
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sb, sl = 4, 2
-            sshape = w["shape"] if w["dims"] == 2 else (56, 56, 40)
+            sshape = w["shape"] if w["dims"] == 2 else (64, 64, 48)
             sec = cpu_chap_iteration(dict(w, shape=sshape), sb, sl, threads, 2, 1)
             sec_full = sec * (w["batch"] * vox) / (sb * float(np.prod(sshape)))
             cpu = {"value": 1.0 / sec_full, "unit": "it/s", "cores": threads, "kind": "port",

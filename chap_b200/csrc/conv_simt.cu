@@ -253,69 +253,93 @@ conv_wgrad_kernel(SimtOp op, const float* __restrict__ a, const float* __restric
         atomicAdd(dw + (k0 + kk) * sk + (n0 + nn) * sn + t, acc);
 }
 
-// Weight gradient of the Cin = 1 stems (k = 3): dW[co][0][tap] = sum_p x[p + tap] * dy[p, co].  The generic kernel would
-// re-read dy once per tap; here one thread owns a pixel, reads its 16-channel dy vector ONCE and the 9 neighbouring
-// inputs of one kz-plane, and keeps 9 x 16 partial sums in registers across a grid-stride loop; then warp shuffle ->
-// smem -> one atomic per (tap, channel) and block.  grid = (pixel slices, kz planes, Cout / 16).
+// Weight gradient of the thin k = 3 layers: the Cin = 1 stems (KC = 1, NC = 16) and the Cout = 4 heads (KC = 4, NC = 4):
+//   dW[co][ci][tap] = sum_p x[p + tap, ci] * dy[p, co].
+// The generic kernel would re-read dy once per tap; here one thread owns a pixel, reads its NC-channel dy vector ONCE
+// and the 9 neighbouring KC-channel inputs of one kz-plane, and keeps 9 x KC x NC partial sums in registers across a
+// grid-stride loop; then warp shuffle -> smem -> one atomic per weight and block.
+// grid = (pixel slices, kz planes, (Cin / KC) * (Cout / NC)).
+template <int KC, int NC>
 __global__ void __launch_bounds__(128)
-stem_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t sn) {
-    __shared__ float red[144];
-    const int kz = blockIdx.y, c0 = blockIdx.z * 16;
-    float acc[9][16];
+thin_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t sk, int64_t sn) {
+    constexpr int NA = 9 * KC * NC;
+    __shared__ float red[NA];
+    const int kz = blockIdx.y;
+    const int kchunks = op.K / KC;
+    const int k0 = (blockIdx.z % kchunks) * KC, c0 = (blockIdx.z / kchunks) * NC;
+    float acc[9][KC][NC];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[t][c] = 0.f;
-    for (int i = threadIdx.x; i < 144; i += 128) red[i] = 0.f;
+        for (int k = 0; k < KC; ++k)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[t][k][c] = 0.f;
+    for (int i = threadIdx.x; i < NA; i += 128) red[i] = 0.f;
     __syncthreads();
     for (int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x; r < op.out_rows; r += (int64_t)gridDim.x * 128) {
         int bn, d, h, w;
         decode_row(r, op.oD, op.oH, op.oW, bn, d, h, w);
         const int id = op.nd == 3 ? d + kz - 1 : 0;
         if (id < 0 || id >= op.iD) continue;
-        float g[16];
+        float g[NC];
         const float4* gp = reinterpret_cast<const float4*>(dy + r * op.N + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { float4 v = __ldg(gp + q); g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w; }
-        const float* xb = x + (((int64_t)bn * op.iD + id) * op.iH) * op.iW;
+        for (int q = 0; q < NC / 4; ++q) { float4 v = __ldg(gp + q); g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w; }
+        const float* xb = x + ((((int64_t)bn * op.iD + id) * op.iH) * op.iW) * op.K + k0;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int ih = h + ky - 1;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int iw = w + kx - 1;
-                const float xv = (ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW) ? __ldg(xb + (int64_t)ih * op.iW + iw) : 0.f;
+                const bool ok = ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW;
+                float xv[KC];
+                if (KC == 4) {
+                    float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xb + ((int64_t)ih * op.iW + iw) * op.K)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[0] = v.x; xv[1 % KC] = v.y; xv[2 % KC] = v.z; xv[3 % KC] = v.w;
+                } else {
+                    xv[0] = ok ? __ldg(xb + ((int64_t)ih * op.iW + iw) * op.K) : 0.f;
+                }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) acc[ky * 3 + kx][c] = fmaf(xv, g[c], acc[ky * 3 + kx][c]);
+                for (int k = 0; k < KC; ++k)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) acc[ky * 3 + kx][k][c] = fmaf(xv[k], g[c], acc[ky * 3 + kx][k][c]);
             }
         }
     }
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            float v = warp_sum(acc[t][c]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&red[t * 16 + c], v);
-        }
+        for (int k = 0; k < KC; ++k)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float v = warp_sum(acc[t][k][c]);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&red[(t * KC + k) * NC + c], v);
+            }
     __syncthreads();
-    for (int i = threadIdx.x; i < 144; i += 128) {
-        const int t = i / 16, c = i % 16;
-        atomicAdd(dw + (int64_t)(c0 + c) * sn + (kz * 9 + t), red[i]);
+    for (int i = threadIdx.x; i < NA; i += 128) {
+        const int t = i / (KC * NC), k = (i / NC) % KC, c = i % NC;
+        atomicAdd(dw + (int64_t)(c0 + c) * sn + (int64_t)(k0 + k) * sk + (kz * 9 + t), red[i]);
     }
 }
 
 int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
                int64_t sk, int64_t sn, cudaStream_t st) {
     CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
-    if (!op.up2 && op.K == 1 && op.ksz == 3 && op.stride == 1 && op.N % 16 == 0 && aligned16(b)) {
-        KernelTimer timer("conv_stem_wgrad", 2.0 * (double)op.out_rows * op.N * op.taps,
-                          4.0 * ((double)op.in_rows + (double)op.out_rows * op.N), st);
-        int slices = (int)((op.out_rows + 128 * 8 - 1) / (128 * 8));
+    const bool stem = op.K == 1 && op.N % 16 == 0;
+    const bool head = op.N == 4 && op.K % 4 == 0 && aligned16(a);
+    if (!op.up2 && op.ksz == 3 && op.stride == 1 && (stem || head) && aligned16(b)) {
+        KernelTimer timer("conv_thin_wgrad", 2.0 * (double)op.out_rows * op.K * op.N * op.taps,
+                          4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N), st);
         const int planes = op.nd == 3 ? 3 : 1;
-        const int cap = (kNumSMs * 6) / (planes * (op.N / 16));
+        const int zdim = stem ? op.N / 16 : op.K / 4;
+        int slices = (int)((op.out_rows + 128 * 8 - 1) / (128 * 8));
+        const int cap = (kNumSMs * 6) / (planes * zdim);
         if (slices > cap) slices = cap < 1 ? 1 : cap;
-        stem_wgrad_kernel<<<dim3((unsigned)slices, (unsigned)planes, (unsigned)(op.N / 16)), 128, 0, st>>>(op, a, b, dw, sn);
-        return launched("stem_wgrad_kernel");
+        dim3 grid((unsigned)slices, (unsigned)planes, (unsigned)zdim);
+        if (stem) thin_wgrad_kernel<1, 16><<<grid, 128, 0, st>>>(op, a, b, dw, sk, sn);
+        else thin_wgrad_kernel<4, 4><<<grid, 128, 0, st>>>(op, a, b, dw, sk, sn);
+        return launched("thin_wgrad_kernel");
     }
     const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
     KernelTimer timer("conv_simt_wgrad", 2.0 * (double)rows * op.K * op.N * op.taps,

@@ -18,6 +18,7 @@
 // tcgen05.commit on a third mbarrier.  Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -43,6 +44,7 @@ struct TcParams {
     int kc, kchunks;              // channels per k chunk (32 or 16), chunks per tap
     int n_total, nt;              // output channels, channels per CTA
     int stages, tmem_cols;
+    int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
     uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes;
     float* out;
     const float* bias;
@@ -91,23 +93,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int iters = p.taps * p.kchunks;
+    // reuse mode: one iteration = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
+    const int iters = (p.reuse ? p.taps / 3 : p.taps) * p.kchunks;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
-                const int tap = it / p.kchunks, kci = it - tap * p.kchunks;
-                int kx, ky, kz;
-                if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
+                const int grp = it / p.kchunks, kci = it - grp * p.kchunks;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], p.a_box_bytes + p.b_box_bytes);
                 uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
                 uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
-                if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
-                tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, tap * p.n_total + n0);
+                if (p.reuse) {
+                    const int kx = grp % 3, kz = grp / 3;              // grp enumerates (kz, kx)
+                    mbar_expect_tx(&full[s], p.a_box_bytes + 3u * p.b_box_bytes);
+                    if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - 1, h0 - 1, img);
+                    else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - 1, h0 - 1, d0 + kz - 1, img);
+                    for (int ky = 0; ky < 3; ++ky)
+                        tma_load_2d(b_dst + (size_t)ky * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + ky) * 3 + kx) * p.n_total + n0);
+                } else {
+                    const int tap = grp;
+                    int kx, ky, kz;
+                    if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
+                    mbar_expect_tx(&full[s], p.a_box_bytes + p.b_box_bytes);
+                    if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                    else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
+                    tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, tap * p.n_total + n0);
+                }
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
@@ -122,10 +135,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t a_desc = make_kmajor_desc(smem_u32(a_base + (size_t)s * p.a_stage_bytes), row_bytes);
-                const uint64_t b_desc = make_kmajor_desc(smem_u32(b_base + (size_t)s * p.b_stage_bytes), row_bytes);
-                for (int k = 0; k < ksteps; ++k)          // +32 bytes (= 8 tf32) along K inside the swizzled row: +2 in the >>4 address field
-                    tc_mma_tf32(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
+                const uint32_t a_addr = smem_u32(a_base + (size_t)s * p.a_stage_bytes);
+                const uint32_t b_addr = smem_u32(b_base + (size_t)s * p.b_stage_bytes);
+                const int nky = p.reuse ? 3 : 1;
+                for (int ky = 0; ky < nky; ++ky) {
+                    // reuse mode: the rows of tap ky start ky * tw rows into the h-haloed box (tw % 8 == 0 keeps the swizzle phase)
+                    const uint64_t a_desc = make_kmajor_desc(a_addr + (uint32_t)(ky * p.tw) * row_bytes, row_bytes);
+                    const uint64_t b_desc = make_kmajor_desc(b_addr + (uint32_t)ky * p.b_box_bytes, row_bytes);
+                    for (int k = 0; k < ksteps; ++k)      // +32 bytes (= 8 tf32) along K inside the swizzled row: +2 in the >>4 address field
+                        tc_mma_tf32(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((it | ky | k) != 0));
+                }
                 tc_commit(&empty[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
@@ -278,17 +297,37 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD;
     choose_box(p.W, p.H, p.D, p.tw, p.th, p.td);
+    // Row-reuse mode for the activation-bound layers (few output channels): in-plane 128-pixel tile (tw x th, tw % 8 == 0)
+    // and ONE TMA box with an h-halo (th + 2 rows) per (kz, kx); the three ky taps read it at row offsets ky * tw.
+    // L2 -> smem traffic for A drops from 9 (27) boxes of th rows to 3 (9) boxes of th + 2 rows.
+    p.reuse = 0;
+    if (g.kind == CHAP_CONV_K3 && N <= 64 && getenv("CHAP_NO_ROW_REUSE") == nullptr) {
+        int best_tw = 0; long best_tiles = -1;
+        for (int tw : {8, 16, 32}) {
+            const int th = 128 / tw;
+            if (p.W < tw || p.H < th + 2) continue;                 // the TMA box must fit inside the tensor extents
+            long tiles = (long)((p.W + tw - 1) / tw) * ((p.H + th - 1) / th);
+            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && th > 128 / best_tw)) { best_tiles = tiles; best_tw = tw; }
+        }
+        if (best_tw) { p.reuse = 1; p.tw = best_tw; p.th = 128 / best_tw; p.td = 1; }
+    }
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
     p.n_total = N; p.nt = N > 256 ? 256 : N;
     p.tmem_cols = 32; while (p.tmem_cols < p.nt) p.tmem_cols *= 2;
-    p.a_stage_bytes = 128u * p.kc * 4u;                                  // always room for 128 rows
-    p.a_box_bytes = (uint32_t)(p.tw * p.th * p.td) * p.kc * 4u;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
-    p.b_stage_bytes = (p.b_box_bytes + 1023u) & ~1023u;
+    if (p.reuse) {
+        p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
+        p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
+        p.b_stage_bytes = 3u * p.b_box_bytes;
+    } else {
+        p.a_stage_bytes = 128u * p.kc * 4u;                              // always room for 128 rows
+        p.a_box_bytes = (uint32_t)(p.tw * p.th * p.td) * p.kc * 4u;
+        p.b_stage_bytes = (p.b_box_bytes + 1023u) & ~1023u;
+    }
     const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     int stages = (int)((96 * 1024) / stage);
-    const int iters = p.taps * p.kchunks;
+    const int iters = (p.reuse ? p.taps / 3 : p.taps) * p.kchunks;
     if (stages > 6) stages = 6;
     if (stages > iters) stages = iters;
     if (stages < 2) stages = iters < 2 ? 1 : 2;
@@ -304,12 +343,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
-            box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = 1;
             CHAP_TRY(make_tensor_map(&tmA, in, 4, dims, str, box, p.kc));
         } else {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
-            box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = p.td; box[4] = 1;
             CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc));
         }
         uint64_t wd[2] = {(uint64_t)K, (uint64_t)g.taps * N};
