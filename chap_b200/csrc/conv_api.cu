@@ -1,4 +1,5 @@
 // extern "C" convolution entry points: shape validation + dispatch (tcgen05 path / CUDA-core path).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_plan.cuh"
 
@@ -73,7 +74,11 @@ extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const fl
     SimtOp op = fwd_op(g);
     PackSpec p = fwd_pack(g);          // dw has the torch layout: same strides as reading w
     int handled = 0;
-    if (g_force_simt.load() == 0 && tc_wgrad_supports(g)) {
+    // thin layers (Cin * Cout small): the tensor core cannot be filled (output 16 x 144) and every K = 8 MMA costs
+    // ~130 cycles, so the register-tiled CUDA-core kernel wins (measured; threshold overridable for experiments)
+    static const int thin_max = getenv("CHAP_THIN_MAX") ? atoi(getenv("CHAP_THIN_MAX")) : 0;
+    const bool thin = g.kind == CHAP_CONV_K3 && g.cin % 4 == 0 && g.cout % 4 == 0 && g.cin * g.cout <= thin_max;
+    if (g_force_simt.load() == 0 && tc_wgrad_supports(g) && !thin) {
         handled = tc_wgrad(g, x, dy, dw, S(stream));
         if (handled < 0) return handled;
     }

@@ -327,12 +327,12 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
                int64_t sk, int64_t sn, cudaStream_t st) {
     CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
     const bool stem = op.K == 1 && op.N % 16 == 0;
-    const bool head = op.N == 4 && op.K % 4 == 0 && aligned16(a);
+    const bool head = op.N % 4 == 0 && op.K % 4 == 0 && op.K * op.N <= 1024 && aligned16(a);     // heads and other thin layers
     if (!op.up2 && op.ksz == 3 && op.stride == 1 && (stem || head) && aligned16(b)) {
         KernelTimer timer("conv_thin_wgrad", 2.0 * (double)op.out_rows * op.K * op.N * op.taps,
                           4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N), st);
         const int planes = op.nd == 3 ? 3 : 1;
-        const int zdim = stem ? op.N / 16 : op.K / 4;
+        const int zdim = stem ? op.N / 16 : (op.K / 4) * (op.N / 4);
         int slices = (int)((op.out_rows + 128 * 8 - 1) / (128 * 8));
         const int cap = (kNumSMs * 6) / (planes * zdim);
         if (slices > cap) slices = cap < 1 ? 1 : cap;

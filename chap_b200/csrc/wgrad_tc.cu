@@ -13,6 +13,7 @@
 // blockIdx.x = slice of the pixel blocks.  Each CTA accumulates its slice in TMEM (fp32) and adds it to the
 // torch-layout gradient with red.global.add.f32 (the gradient buffer is zeroed first).
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 #include "conv_plan.cuh"
@@ -31,7 +32,10 @@ struct WgParams {
     int mma_m;                      // 64 or 128
     int a_cpg, a_groups;            // channels per TMA chunk (32|16) and chunks per m_tile
     int b_cpg, b_groups;
-    int tg;                         // taps per CTA
+    int tg;                         // taps per CTA (reuse mode: (kz, kx) pairs per CTA, each pair = 3 ky taps)
+    int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
+    int b_rows;                     // rows (pixels) per x channel chunk in smem
+    int debug;                      // CHAP_WG_DEBUG bit 0: skip the MMAs, bit 1: skip the TMA loads (timing experiments only)
     int stages, tmem_cols;
     int blocks_total, blocks_per_cta;
     uint32_t a_stage_bytes, b_stage_bytes;
@@ -66,7 +70,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int m_tiles = p.cout / p.m_tile;
     const int m0 = (blockIdx.z % m_tiles) * p.m_tile, n0 = (blockIdx.z / m_tiles) * p.n_tile;      // n0 > 0 only when cin > 256
     const int tap0 = blockIdx.y * p.tg;
-    const int ntaps = min(p.tg, p.taps - tap0);
+    const int units = p.reuse ? p.taps / 3 : p.taps;               // scheduling units: taps, or (kz, kx) pairs
+    const int ntaps = min(p.tg, units - tap0);
+    const int nky = p.reuse ? 3 : 1;
     const int blk0 = blockIdx.x * p.blocks_per_cta;
     const int nblk = min(p.blocks_per_cta, p.blocks_total - blk0);
 
@@ -94,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_row = (uint32_t)p.a_cpg * 4u, b_row = (uint32_t)p.b_cpg * 4u;
-    const uint32_t a_chunk = (uint32_t)p.P * a_row, b_chunk = (uint32_t)p.P * b_row;     // bytes of one channel chunk
+    const uint32_t a_chunk = (uint32_t)p.P * a_row, b_chunk = (uint32_t)p.b_rows * b_row;     // bytes of one channel chunk
 
     if (nblk > 0 && warp == 0) {
         if (lane == 0) {
@@ -109,9 +115,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int ti = 0; ti < ntaps; ++ti) {
                     const int tap = tap0 + ti;
                     int kx, ky, kz;
-                    if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
+                    if (p.reuse) { kx = tap % 3; kz = tap / 3; ky = 0; }               // box origin one row above the tile
+                    else if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)(p.a_groups + p.b_groups) * (uint32_t)p.p_box * 128u);
+                    if (p.debug & 2) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory"); if (++s == p.stages) { s = 0; ph ^= 1; } continue; }
+                    mbar_expect_tx(&full[s], ((uint32_t)p.a_groups * (uint32_t)p.p_box + (uint32_t)p.b_groups * (uint32_t)(p.reuse ? p.b_rows : p.p_box)) * 128u);
                     uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
                     uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
                     for (int g = 0; g < p.a_groups; ++g) {
@@ -142,11 +150,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(a_base + (size_t)s * p.a_stage_bytes);
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * p.b_stage_bytes);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(ti * p.n_tile);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
-                        const uint64_t b_desc = make_mnmajor_desc(b_addr + (uint32_t)k * 8u * b_row, b_row, b_chunk);
-                        tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, (uint32_t)((b | k) != 0));
+                    if (p.reuse && p.b_groups == 1) {
+                        // One tcgen05.mma costs ~130 cycles whatever N is (measured: 5976 M128 N32 K8 MMAs per CTA = 522 us),
+                        // so the three ky taps are issued as ONE MMA with N = 96: the "channel chunk" stride (LBO) of the B
+                        // descriptor is set to tw rows, chunk g IS tap ky = g, and the accumulator columns come out as [ky][ci].
+                        const uint32_t idesc3 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(96 >> 3) << 17);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(ti * 3 * p.n_tile);
+                        for (int k = 0; k < ksteps && !(p.debug & 1); ++k) {
+                            const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
+                            const uint64_t b_desc = make_mnmajor_desc(b_addr + (uint32_t)k * 8u * b_row, b_row, (uint32_t)p.tw * b_row);
+                            tc_mma_tf32(d_tmem, a_desc, b_desc, idesc3, (uint32_t)((b | k) != 0));
+                        }
+                    } else
+                    for (int ky = 0; ky < nky; ++ky) {
+                        // reuse mode: tap ky reads the haloed x box ky * tw rows further down (tw % 4 == 0 keeps the K atoms aligned)
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((ti * nky + ky) * p.n_tile);
+                        const uint32_t b_tap = b_addr + (uint32_t)(ky * p.tw) * b_row;
+                        for (int k = 0; k < ksteps && !(p.debug & 1); ++k) {
+                            const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
+                            const uint64_t b_desc = make_mnmajor_desc(b_tap + (uint32_t)k * 8u * b_row, b_row, b_chunk);
+                            tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, (uint32_t)((b | k) != 0));
+                        }
                     }
                     tc_commit(&empty[s]);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -162,14 +186,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         if (lg * 32 < p.mma_m) {                         // M = 64: lane groups 2,3 hold nothing
             float* dst_row = p.dw + (int64_t)(m0 + row) * p.s_co;
-            for (int ti = 0; ti < ntaps; ++ti) {
+            for (int ti = 0; ti < ntaps * nky; ++ti) {
+                int tap = tap0 + ti;
+                if (p.reuse) { const int q = tap0 + ti / 3, ky = ti % 3; tap = ((q / 3) * 3 + ky) * 3 + (q % 3); }
                 for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
                     float v[16];
                     tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * p.n_tile + c0), v);
                     if (valid && n0 + c0 < p.cin) {                 // columns beyond cin are the zero-filled channels
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            atomicAdd(dst_row + (int64_t)(n0 + c0 + j) * p.s_ci + (tap0 + ti), v[j]);
+                            atomicAdd(dst_row + (int64_t)(n0 + c0 + j) * p.s_ci + tap, v[j]);
                     }
                 }
             }
@@ -209,8 +235,18 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
     choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
+    const int n_tile_pre = g.cin > 256 ? 256 : (g.cin < 32 ? 32 : g.cin);
+    // Row-reuse mode (large images, <= 128 input channels per CTA): in-plane 8 x 8 pixel block; the x box is loaded once
+    // per (kz, kx) with an h-halo of one row above and below and serves the three ky taps -> 3 (9) x-boxes of 10 rows
+    // instead of 9 (27) boxes of 8 rows per block.
+    p.reuse = 0;
+    if (g.kind == CHAP_CONV_K3 && n_tile_pre <= 128 && p.W >= 8 && p.H >= 10 && getenv("CHAP_NO_ROW_REUSE") == nullptr) {
+        p.reuse = 1; p.tw = 8; p.th = 8; p.td = 1;
+    }
     p.p_box = p.tw * p.th * p.td;
     p.P = (p.p_box + 7) / 8 * 8;
+    p.b_rows = p.reuse ? p.tw * (p.th + 2) : p.P;
+    p.debug = getenv("CHAP_WG_DEBUG") ? atoi(getenv("CHAP_WG_DEBUG")) : 0;
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.cout = g.cout; p.cin = g.cin;
     p.m_tile = g.cout > 128 ? 128 : g.cout;
@@ -219,7 +255,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.a_cpg = 32; p.a_groups = (p.m_tile + 31) / 32;
     p.b_cpg = 32; p.b_groups = p.n_tile / 32;
     p.a_stage_bytes = ((uint32_t)p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
-    p.b_stage_bytes = ((uint32_t)p.n_tile * p.P * 4u + 1023u) & ~1023u;
+    p.b_stage_bytes = ((uint32_t)p.n_tile * p.b_rows * 4u + 1023u) & ~1023u;
     const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
     const int n_tiles = g.cin > 256 ? g.cin / 256 : 1;
@@ -229,14 +265,16 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     // 256x256x9 layer with 24 splits spent >80% of its 106 us in 14 M atomics); tap groups are made smaller instead.
     // Two CTAs share an SM when a CTA needs <= 256 TMEM columns and <= 100 KB of smem.
     const long weights_pad = (long)g.cout * p.n_tile * n_tiles * g.taps;
+    const int units = p.reuse ? g.taps / 3 : g.taps;          // what a CTA's tap group is made of
+    const int cols_per_unit = (p.reuse ? 3 : 1) * p.n_tile;
     long max_splits = 4000000L / weights_pad;
     if (max_splits < 1) max_splits = 1;
     if (max_splits > p.blocks_total) max_splits = p.blocks_total;
-    int best_tg = 1, best_ctas = -1, best_splits = 1, best_groups = g.taps;
-    for (int tg = (512 / p.n_tile < g.taps ? 512 / p.n_tile : g.taps); tg >= 1; --tg) {
-        const int groups = (g.taps + tg - 1) / tg;
-        if ((g.taps + groups - 1) / groups != tg) continue;                    // keep the groups balanced
-        const bool two = tg * p.n_tile <= 256 && 3 * stage <= 100 * 1024;
+    int best_tg = 1, best_ctas = -1, best_splits = 1, best_groups = units;
+    for (int tg = (512 / cols_per_unit < units ? 512 / cols_per_unit : units); tg >= 1; --tg) {
+        const int groups = (units + tg - 1) / tg;
+        if ((units + groups - 1) / groups != tg) continue;                     // keep the groups balanced
+        const bool two = tg * cols_per_unit <= 256 && 3 * stage <= 100 * 1024;
         const int target = two ? 2 * kNumSMs : kNumSMs;
         long splits = (target + groups * zdim - 1) / (groups * zdim);
         if (splits > max_splits) splits = max_splits;
@@ -247,7 +285,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     const int tg = best_tg, groups = best_groups;
     int splits = best_splits;
     p.tg = tg;
-    p.tmem_cols = 32; while (p.tmem_cols < tg * p.n_tile) p.tmem_cols *= 2;
+    p.tmem_cols = 32; while (p.tmem_cols < tg * cols_per_unit) p.tmem_cols *= 2;
     const bool two_per_sm = p.tmem_cols <= 256 && 3 * stage <= 100 * 1024;
     int stages = (int)(((two_per_sm ? 100 : 200) * 1024 - 2048) / stage);
     if (stages > 8) stages = 8;
@@ -268,12 +306,12 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
         if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
-            box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+            box[0] = cpg; box[1] = p.tw; box[2] = (which == 1 && p.reuse) ? p.th + 2 : p.th; box[3] = 1;
             CHAP_TRY(make_tensor_map(which == 0 ? &tmA : &tmB, base, 4, dims, str, box, cpg, true));
         } else {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
-            box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+            box[0] = cpg; box[1] = p.tw; box[2] = (which == 1 && p.reuse) ? p.th + 2 : p.th; box[3] = p.td; box[4] = 1;
             CHAP_TRY(make_tensor_map(which == 0 ? &tmA : &tmB, base, 5, dims, str, box, cpg, true));
         }
     }
