@@ -132,7 +132,7 @@ def _out_shape(kind, x, cout):
 
 class _Conv(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, want_stats, wf, wd):
+    def forward(ctx, x, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False):
         _require_cuda(x, weight, bias)
         x = cl(x)
         transposed = kind == _lib.CONV_UP2
@@ -146,6 +146,7 @@ class _Conv(Function):
         b = None if bias is None else bias.detach()
         check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
         ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
+        ctx.zero_bias_grad = zero_bias_grad
         ctx.wshape = tuple(weight.shape)
         ctx.save_for_backward(x if ctx.needs_input_grad[1] else None)
         if want_stats:
@@ -166,22 +167,28 @@ class _Conv(Function):
             check(lib().chap_conv_dgrad(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(dx), _stream()))
         if ctx.needs_input_grad[1]:
             dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dy.device)
-            want_b = ctx.has_bias and ctx.needs_input_grad[2]
+            # A bias that feeds a train-mode BatchNorm has an analytically ZERO gradient (BN subtracts the batch mean:
+            # sum_r dy = scale * (sum dz - N mean(dz) - mean(dz xhat) * sum xhat) = 0); the reference computes rounding
+            # noise there.  The gradient is returned as exact zeros (weight decay still applies in the optimiser).
+            want_b = ctx.has_bias and ctx.needs_input_grad[2] and not ctx.zero_bias_grad
             db = torch.empty(desc.cout, dtype=torch.float32, device=dy.device) if want_b else None
             ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
             check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
-        return dx, dw, db, None, None, None, None
+            if ctx.has_bias and ctx.needs_input_grad[2] and ctx.zero_bias_grad:
+                db = torch.zeros(desc.cout, dtype=torch.float32, device=dy.device)
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv_stats(x, weight, bias, kind, want_stats=True):
-    """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted)."""
+def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False):
+    """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted).
+    feeds_train_bn: y goes straight into a train-mode BatchNorm -> the bias gradient is exactly zero and is not computed."""
     _require_cuda(x, weight)
     wf, wd = _packs(weight, kind, x.dim() - 2)
     if not _state["weight_grad"]:
         weight = weight.detach()
         bias = None if bias is None else bias.detach()
-    return _Conv.apply(x, weight, bias, kind, bool(want_stats), wf, wd)
+    return _Conv.apply(x, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn))
 
 
 def conv(x, weight, bias, kind):
