@@ -66,6 +66,10 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
             double* ch_sums, cudaStream_t st);
 bool tc_supports(const Geom& g, bool dgrad);
+// thin-layer tensor-core path (thin_tc.cu): taps in the N dimension + shift-add epilogue, Cin/Cout in {16, 32}
+int thin_tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
+                 double* ch_sums, cudaStream_t st);
+bool thin_tc_supports(const Geom& g, bool dgrad);
 // tensor-core weight gradient (wgrad_tc.cu): 1 handled, 0 unsupported shape, <0 error.  dw is overwritten.
 int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st);
 bool tc_wgrad_supports(const Geom& g);

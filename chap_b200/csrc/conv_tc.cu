@@ -53,6 +53,46 @@ struct TcParams {
 
 constexpr int kTcThreads = 192;
 
+// The single MMA-issuing thread.  Its own instruction stream is on the critical path (a runtime modulo per MMA cost 30 %
+// of the kernel), so the body is straight-line per stage: KSTEPS x NKY tcgen05.mma with descriptors formed by integer adds
+// on the lo word (+2 per 8 tf32 along K inside the swizzled row, + tw rows / one weight box per ky tap).
+template <int KSTEPS, int NKY>
+__device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
+                                           uint64_t* tmem_full, uint32_t tmem_base, int iters) {
+    // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t row_bytes = KSTEPS * 32u;
+    // descriptor hi word: SBO >> 4 (8 rows) | version 1 (bit 46) | layout (bit 61: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+    constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+    const uint32_t a_lo0 = ((smem_u32(a_base) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t b_lo0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4;
+    const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4, b_ky = p.b_box_bytes >> 4;
+    int s = 0; uint32_t ph = 0;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0, accum = 0;
+    for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+            for (int ky = 0; ky < NKY; ++ky) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                    tc_mma_tf32_lh(tmem_base, a_lo + (uint32_t)ky * a_ky + 2u * k, hi, b_lo + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
+                                   (ky | k) == 0 ? accum : 1u);
+                }
+            }
+            tc_commit(&empty[s]);
+        }
+        __syncwarp();
+        accum = 1;
+        a_lo += a_stage; b_lo += b_stage;
+        if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+    }
+    if (elect_one()) tc_commit(tmem_full);
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -126,30 +166,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t row_bytes = (uint32_t)p.kc * 4u;
-            const int ksteps = p.kc / 8;
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(a_base + (size_t)s * p.a_stage_bytes);
-                const uint32_t b_addr = smem_u32(b_base + (size_t)s * p.b_stage_bytes);
-                const int nky = p.reuse ? 3 : 1;
-                for (int ky = 0; ky < nky; ++ky) {
-                    // reuse mode: the rows of tap ky start ky * tw rows into the h-haloed box (tw % 8 == 0 keeps the swizzle phase)
-                    const uint64_t a_desc = make_kmajor_desc(a_addr + (uint32_t)(ky * p.tw) * row_bytes, row_bytes);
-                    const uint64_t b_desc = make_kmajor_desc(b_addr + (uint32_t)ky * p.b_box_bytes, row_bytes);
-                    for (int k = 0; k < ksteps; ++k)      // +32 bytes (= 8 tf32) along K inside the swizzled row: +2 in the >>4 address field
-                        tc_mma_tf32(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (uint32_t)((it | ky | k) != 0));
-                }
-                tc_commit(&empty[s]);
-                if (++s == p.stages) { s = 0; ph ^= 1; }
-            }
-            tc_commit(tmem_full);
-        }
+        // the whole warp runs the (uniform) loop, one elected lane issues: descriptors stay in uniform registers
+        if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters);
+                          else issue_mmas<4, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters); }
+        else            { if (p.reuse) issue_mmas<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters);
+                          else issue_mmas<2, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters); }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
         const int lg = warp & 3;
@@ -290,6 +311,7 @@ static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
             double* ch_sums, cudaStream_t st) {
     if (!tc_supports(g, dgrad)) return 0;
+    if (thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
     CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
     int K, N;
     tc_channels(g, dgrad, K, N);

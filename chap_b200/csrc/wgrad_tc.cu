@@ -135,49 +135,62 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (nblk > 0 && warp == 1) {
-        if (lane == 0) {
-            // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(p.mma_m >> 4) << 24);
-            // M is always 128 rows; when the tile has fewer channels the extra channel chunks alias chunk 0 (one chunk,
-            // LBO = 0) or read whatever follows in shared memory (two chunks): those accumulator rows are never stored
-            const uint32_t a_lbo = p.a_groups >= 2 ? a_chunk : 0u;
-            const int ksteps = p.P / 8;
-            int s = 0; uint32_t ph = 0;
-            for (int b = 0; b < nblk; ++b) {
-                for (int ti = 0; ti < ntaps; ++ti) {
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_base + (size_t)s * p.a_stage_bytes);
-                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * p.b_stage_bytes);
-                    if (p.reuse && p.b_groups == 1) {
-                        // One tcgen05.mma costs ~130 cycles whatever N is (measured: 5976 M128 N32 K8 MMAs per CTA = 522 us),
-                        // so the three ky taps are issued as ONE MMA with N = 96: the "channel chunk" stride (LBO) of the B
-                        // descriptor is set to tw rows, chunk g IS tap ky = g, and the accumulator columns come out as [ky][ci].
-                        const uint32_t idesc3 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(96 >> 3) << 17);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(ti * 3 * p.n_tile);
-                        for (int k = 0; k < ksteps && !(p.debug & 1); ++k) {
-                            const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
-                            const uint64_t b_desc = make_mnmajor_desc(b_addr + (uint32_t)k * 8u * b_row, b_row, (uint32_t)p.tw * b_row);
-                            tc_mma_tf32(d_tmem, a_desc, b_desc, idesc3, (uint32_t)((b | k) != 0));
-                        }
-                    } else
-                    for (int ky = 0; ky < nky; ++ky) {
-                        // reuse mode: tap ky reads the haloed x box ky * tw rows further down (tw % 4 == 0 keeps the K atoms aligned)
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((ti * nky + ky) * p.n_tile);
-                        const uint32_t b_tap = b_addr + (uint32_t)(ky * p.tw) * b_row;
-                        for (int k = 0; k < ksteps && !(p.debug & 1); ++k) {
-                            const uint64_t a_desc = make_mnmajor_desc(a_addr + (uint32_t)k * 8u * a_row, a_row, a_lbo);
-                            const uint64_t b_desc = make_mnmajor_desc(b_tap + (uint32_t)k * 8u * b_row, b_row, b_chunk);
-                            tc_mma_tf32(d_tmem, a_desc, b_desc, idesc, (uint32_t)((b | k) != 0));
+        // The whole warp runs the (warp-uniform) loop and one elected lane issues, so descriptors live in uniform registers
+        // and consecutive tcgen05.mma are a couple of integer adds apart: the issuing thread's own instruction stream is
+        // on the critical path of these small-N MMAs.
+        // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(p.mma_m >> 4) << 24);
+        const bool merged = p.reuse && p.b_groups == 1;
+        // merged mode: the three ky taps are ONE MMA with N = 96: the "channel chunk" stride (LBO) of the B descriptor is
+        // tw rows, chunk g IS tap ky = g, and the accumulator columns come out as [ky][ci].
+        const uint32_t idesc_m = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(96 >> 3) << 17);
+        // M is always 128 rows; when the tile has fewer channels the extra channel chunks alias chunk 0 (one chunk,
+        // LBO = 0) or read whatever follows in shared memory (two chunks): those accumulator rows are never stored
+        const uint32_t a_lbo = p.a_groups >= 2 ? a_chunk : 0u;
+        const uint32_t b_lbo = merged ? (uint32_t)p.tw * b_row : b_chunk;
+        // descriptor words: lo = start >> 4 | (LBO >> 4) << 16; hi = SBO >> 4 (4 rows) | version 1 (bit 46) | layout 1 (bit 61)
+        const uint32_t a_hi = ((4u * a_row) >> 4) | (1u << 14) | (1u << 29);
+        const uint32_t b_hi = ((4u * b_row) >> 4) | (1u << 14) | (1u << 29);
+        const uint32_t a_lo0 = ((smem_u32(a_base) >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t b_lo0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+        const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4;
+        const uint32_t a_k = (8u * a_row) >> 4, b_k = (8u * b_row) >> 4;        // one K step = 8 pixel rows
+        const uint32_t b_ky = ((uint32_t)p.tw * b_row) >> 4;                     // reuse mode: tap ky starts ky * tw rows further down
+        const int ksteps = (p.debug & 1) ? 0 : p.P / 8;
+        const int n_sub = merged ? 1 : nky;
+        const uint32_t id = merged ? idesc_m : idesc;
+        const uint32_t d_stride = merged ? 3u * (uint32_t)p.n_tile : (uint32_t)(nky * p.n_tile);
+        int s = 0; uint32_t ph = 0;
+        uint32_t a_lo = a_lo0, b_lo = b_lo0;
+        for (int b = 0; b < nblk; ++b) {
+            uint32_t d_tap = tmem_base;
+            for (int ti = 0; ti < ntaps; ++ti) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int ky = 0; ky < n_sub; ++ky) {
+                        const uint32_t d_tmem = d_tap + (uint32_t)(ky * p.n_tile);
+                        const uint32_t b_tap = b_lo + (uint32_t)ky * b_ky;
+                        if (ksteps == 8) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)k * a_k, a_hi, b_tap + (uint32_t)k * b_k, b_hi, id, (uint32_t)((b | k) != 0));
+                        } else {
+                            for (int k = 0; k < ksteps; ++k)
+                                tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)k * a_k, a_hi, b_tap + (uint32_t)k * b_k, b_hi, id, (uint32_t)((b | k) != 0));
                         }
                     }
                     tc_commit(&empty[s]);
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                d_tap += d_stride;
+                a_lo += a_stage; b_lo += b_stage;
+                if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
             }
-            tc_commit(tmem_full);
         }
+        if (elect_one()) tc_commit(tmem_full);
+        __syncwarp();
     } else if (nblk > 0 && warp >= 2) {
         const int lg = warp & 3;
         const int row = lg * 32 + lane;                  // accumulator row = output channel inside the tile
