@@ -111,6 +111,7 @@ extern "C" size_t chap_largest_cc_workspace_bytes(int32_t n, int32_t d, int32_t 
 
 extern "C" int chap_largest_cc(const int64_t* seg, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t n_classes,
                                float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    KernelTimer timer_("largest_cc", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(seg && out && workspace && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && n_classes >= 2,
                  CHAP_ERR_BAD_ARG, "largest_cc: bad argument");
     CHAP_REQUIRE(nd == 3 || d == 1, CHAP_ERR_BAD_ARG, "largest_cc: 2D needs d == 1");

@@ -48,6 +48,9 @@ struct KernelTimer {
     ~KernelTimer();
 };
 
+// family name, or (CHAP_TIMING_DETAIL set) family + shape, interned
+const char* timer_name(const char* family, int taps, int k, int n, int w, int h, int d, int64_t rows);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -90,7 +93,7 @@ inline int round_tf32_on() { return 0; }
 // streaming 128-bit load (read once) / store
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }

@@ -160,7 +160,7 @@ conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, con
 
 int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st) {
     const double rows_mac = (double)(op.up2 ? op.in_rows : op.out_rows);
-    KernelTimer timer(op.up2 ? "conv_simt_up2" : "conv_simt_gather", 2.0 * rows_mac * op.K * op.N * op.taps,
+    KernelTimer timer(timer_name(op.up2 ? "conv_simt_up2" : "conv_simt_gather", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * rows_mac * op.K * op.N * op.taps,
                       4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);
     const bool vec4 = (op.K % 4 == 0) && aligned16(in);
     const bool small = op.N <= 4;
@@ -329,7 +329,7 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
     const bool stem = op.K == 1 && op.N % 16 == 0;
     const bool head = op.N % 4 == 0 && op.K % 4 == 0 && op.K * op.N <= 1024 && aligned16(a);     // heads and other thin layers
     if (!op.up2 && op.ksz == 3 && op.stride == 1 && (stem || head) && aligned16(b)) {
-        KernelTimer timer("conv_thin_wgrad", 2.0 * (double)op.out_rows * op.K * op.N * op.taps,
+        KernelTimer timer(timer_name("conv_thin_wgrad", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * (double)op.out_rows * op.K * op.N * op.taps,
                           4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N), st);
         const int planes = op.nd == 3 ? 3 : 1;
         const int zdim = stem ? op.N / 16 : (op.K / 4) * (op.N / 4);
@@ -342,7 +342,7 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
         return launched("thin_wgrad_kernel");
     }
     const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
-    KernelTimer timer("conv_simt_wgrad", 2.0 * (double)rows * op.K * op.N * op.taps,
+    KernelTimer timer(timer_name("conv_simt_wgrad", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * (double)rows * op.K * op.N * op.taps,
                       4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);
     const int tiles = ((op.K + 15) / 16) * ((op.N + 15) / 16);
     int64_t want_splits = (kNumSMs * 4 + (int64_t)tiles * op.taps - 1) / ((int64_t)tiles * op.taps);

@@ -27,101 +27,111 @@
 
 namespace chap {
 
-// shared-memory matrix descriptor, K-major operand with 128B / 64B swizzle (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows) | [46,48) version=1 |
-//   [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
-    const uint64_t sbo = (8u * row_bytes) >> 4;
-    const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
 struct TcParams {
     int nd, ksz, pad, taps;
     int W, H, D;                  // spatial size (output == input for these kinds)
     int tw, th, td;               // spatial box of one M tile (tw*th*td <= 128)
-    int tiles_w, tiles_h, tiles_d;
+    int tiles_w, tiles_h, tiles_d, tiles_total;
     int kc, kchunks;              // channels per k chunk (32 or 16), chunks per tap
     int n_total, nt;              // output channels, channels per CTA
     int stages, tmem_cols;
+    int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
-    uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes;
-    float* out;
+    int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
+    uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
+    float* out;                   // channels [0, ca), row stride ca
+    float* out_b;                 // channels [ca, n_total), row stride n_total - ca (dgrad of a channel concat), or nullptr
+    int ca;
     const float* bias;
     double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
 };
 
 constexpr int kTcThreads = 192;
 
-// The single MMA-issuing thread.  Its own instruction stream is on the critical path (a runtime modulo per MMA cost 30 %
-// of the kernel), so the body is straight-line per stage: KSTEPS x NKY tcgen05.mma with descriptors formed by integer adds
-// on the lo word (+2 per 8 tf32 along K inside the swizzled row, + tw rows / one weight box per ky tap).
+// The MMA-issuing warp.  Its instruction stream is on the critical path of these small-N MMAs (a runtime modulo per MMA
+// cost 30 % of the kernel), so the whole warp runs the warp-uniform loop (descriptors live in uniform registers), one
+// elected lane issues, and the body is straight-line per stage: KSTEPS x NKY tcgen05.mma whose descriptors differ by
+// integer adds on the lo word (+2 per 8 tf32 along K inside the swizzled row, + tw rows / one weight box per ky tap).
 template <int KSTEPS, int NKY>
 __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
-                                           uint64_t* tmem_full, uint32_t tmem_base, int iters) {
+                                           uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base, int groups) {
     // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t row_bytes = KSTEPS * 32u;
     // descriptor hi word: SBO >> 4 (8 rows) | version 1 (bit 46) | layout (bit 61: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
     constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+    // descriptor lo word: start address >> 4 | LBO (= 1, unused for swizzled K-major) << 16
     const uint32_t a_lo0 = ((smem_u32(a_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4;
-    const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4, b_ky = p.b_box_bytes >> 4;
+    const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
+    const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4;
+    const uint32_t b_ky = p.b_resident ? 3u * (uint32_t)p.kchunks * b_box : b_box;     // resident layout is [tap][kchunk]
+    if (p.b_resident) mbar_wait(b_full, 0);
     int s = 0; uint32_t ph = 0;
-    uint32_t a_lo = a_lo0, b_lo = b_lo0, accum = 0;
-    for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full[s], ph);
+    uint32_t a_lo = a_lo0, b_lo_s = b_lo0;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
+        const int buf = p.n_buf == 2 ? (j & 1) : 0;
+        const uint32_t use = p.n_buf == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
+        mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
+        uint32_t accum = 0;
+        for (int grp = 0; grp < groups; ++grp) {
+            // reuse mode: grp = (kz, kx) and the stage serves taps ((kz * 3 + ky) * 3 + kx), ky = 0..2
+            const int tap0 = NKY == 3 ? (grp / 3) * 9 + (grp % 3) : grp;
+            for (int kci = 0; kci < p.kchunks; ++kci) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t b_lo = p.b_resident ? b_lo0 + (uint32_t)(tap0 * p.kchunks + kci) * b_box : b_lo_s;
+                if (elect_one()) {
 #pragma unroll
-            for (int ky = 0; ky < NKY; ++ky) {
+                    for (int ky = 0; ky < NKY; ++ky) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                    tc_mma_tf32_lh(tmem_base, a_lo + (uint32_t)ky * a_ky + 2u * k, hi, b_lo + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
-                                   (ky | k) == 0 ? accum : 1u);
+                        for (int k = 0; k < KSTEPS; ++k)
+                            tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)ky * a_ky + 2u * k, hi, b_lo + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
+                                           (ky | k) == 0 ? accum : 1u);
+                    }
+                    tc_commit(&empty[s]);
                 }
+                __syncwarp();
+                accum = 1;
+                a_lo += a_stage; b_lo_s += b_stage;
+                if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo_s = b_lo0; }
             }
-            tc_commit(&empty[s]);
         }
+        if (elect_one()) tc_commit(&tmem_full[buf]);
         __syncwarp();
-        accum = 1;
-        a_lo += a_stage; b_lo += b_stage;
-        if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
     }
-    if (elect_one()) tc_commit(tmem_full);
-    __syncwarp();
 }
 
+// Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
+// two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
+// tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_base = smem;
     uint8_t* b_base = smem + (size_t)p.stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.stages * p.b_stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (p.b_resident ? (size_t)p.b_area_bytes : (size_t)p.stages * p.b_stage_bytes));
     uint64_t* full = bars;
     uint64_t* empty = bars + p.stages;
-    uint64_t* tmem_full = bars + 2 * p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    uint64_t* tmem_full = bars + 2 * p.stages;          // [2]
+    uint64_t* tmem_empty = tmem_full + 2;               // [2]
+    uint64_t* b_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);          // [4 warps][2][nt] epilogue statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_w; t /= p.tiles_w;
-    const int ty = t % p.tiles_h; t /= p.tiles_h;
-    const int tz = t % p.tiles_d;
-    const int img = t / p.tiles_d;
-    const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
     const int n0 = blockIdx.y * p.nt;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -129,98 +139,140 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < 8 * p.nt; i += 128) red[i] = 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // reuse mode: one iteration = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
-    const int iters = (p.reuse ? p.taps / 3 : p.taps) * p.kchunks;
+    // reuse mode: one stage = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
+    const int groups = p.reuse ? p.taps / 3 : p.taps;
+    const int tiles_per_img = p.tiles_w * p.tiles_h * p.tiles_d;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                const int grp = it / p.kchunks, kci = it - grp * p.kchunks;
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
-                uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
-                if (p.reuse) {
-                    const int kx = grp % 3, kz = grp / 3;              // grp enumerates (kz, kx)
-                    mbar_expect_tx(&full[s], p.a_box_bytes + 3u * p.b_box_bytes);
-                    if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - 1, h0 - 1, img);
-                    else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - 1, h0 - 1, d0 + kz - 1, img);
-                    for (int ky = 0; ky < 3; ++ky)
-                        tma_load_2d(b_dst + (size_t)ky * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + ky) * 3 + kx) * p.n_total + n0);
-                } else {
-                    const int tap = grp;
-                    int kx, ky, kz;
-                    if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
-                    mbar_expect_tx(&full[s], p.a_box_bytes + p.b_box_bytes);
-                    if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                    else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
-                    tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, tap * p.n_total + n0);
+        // ------------------------------------------------------------------ TMA producer (warp-uniform, one elected lane issues)
+        if (p.b_resident) {
+            if (elect_one()) {
+                mbar_expect_tx(b_full, p.b_area_bytes);
+                for (int tap = 0; tap < p.taps; ++tap)
+                    for (int kci = 0; kci < p.kchunks; ++kci)
+                        tma_load_2d(b_base + (size_t)(tap * p.kchunks + kci) * p.b_box_bytes, &tmB, b_full, kci * p.kc, tap * p.n_total + n0);
+            }
+            __syncwarp();
+        }
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            const int img = tile / tiles_per_img;
+            int t = tile - img * tiles_per_img;
+            const int tx = t % p.tiles_w; t /= p.tiles_w;
+            const int ty = t % p.tiles_h;
+            const int tz = t / p.tiles_h;
+            const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
+            for (int grp = 0; grp < groups; ++grp) {
+                int kx, ky, kz;
+                if (p.reuse) { kx = grp % 3; kz = grp / 3; ky = 0; }                 // box origin one row above the tile
+                else if (p.ksz == 3) { kx = grp % 3; ky = (grp / 3) % 3; kz = grp / 9; }
+                else { kx = ky = kz = p.pad; }                                        // 1x1: pad = 0
+                for (int kci = 0; kci < p.kchunks; ++kci) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
+                        const uint32_t nb = p.b_resident ? 0u : (p.reuse ? 3u : 1u);
+                        mbar_expect_tx(&full[s], p.a_box_bytes + nb * p.b_box_bytes);
+                        if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                        else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
+                        if (!p.b_resident) {
+                            uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
+                            if (p.reuse) {
+                                for (int q = 0; q < 3; ++q)
+                                    tma_load_2d(b_dst + (size_t)q * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + q) * 3 + kx) * p.n_total + n0);
+                            } else {
+                                tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, grp * p.n_total + n0);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
-                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        // the whole warp runs the (uniform) loop, one elected lane issues: descriptors stay in uniform registers
-        if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters);
-                          else issue_mmas<4, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters); }
-        else            { if (p.reuse) issue_mmas<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters);
-                          else issue_mmas<2, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_base, iters); }
+        if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
+                          else issue_mmas<4, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
+        else            { if (p.reuse) issue_mmas<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
+                          else issue_mmas<2, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
         const int lg = warp & 3;
         const int m = lg * 32 + lane;                                  // accumulator row == position inside the box
         const int dx = m % p.tw, dy = (m / p.tw) % p.th, dz = m / (p.tw * p.th);
-        const int ow = w0 + dx, oh = h0 + dy, od = d0 + dz;
-        const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
-        float* dst = p.out + ((((int64_t)img * p.D + od) * p.H + oh) * p.W + ow) * (int64_t)p.n_total + n0;
         float* red_s = red + (size_t)(lg * 2 + 0) * p.nt;
         float* red_q = red + (size_t)(lg * 2 + 1) * p.nt;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        for (int c0 = 0; c0 < p.nt; c0 += 16) {
-            float v[16];
-            tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + n0 + c0 + j);
-            }
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.stats) {
-                // column sums over the 32 rows of this warp: butterfly reduce-scatter, 16 columns -> lanes 0..15
-                float s16[16], q16[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { float x = valid ? v[j] : 0.f; s16[j] = x; q16[j] = x * x; }
-#pragma unroll
-                for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-                    const bool upper = (lane & bit) != 0;
-#pragma unroll
-                    for (int j = 0; j < half; ++j) {
-                        float keep_s = upper ? s16[j + half] : s16[j], send_s = upper ? s16[j] : s16[j + half];
-                        float keep_q = upper ? q16[j + half] : q16[j], send_q = upper ? q16[j] : q16[j + half];
-                        s16[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                        q16[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-                    }
+        const int cb = p.n_total - p.ca;
+        int j = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
+            const int img = tile / tiles_per_img;
+            int t = tile - img * tiles_per_img;
+            const int tx = t % p.tiles_w; t /= p.tiles_w;
+            const int ty = t % p.tiles_h;
+            const int tz = t / p.tiles_h;
+            const int ow = tx * p.tw + dx, oh = ty * p.th + dy, od = tz * p.td + dz;
+            const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
+            const int64_t row = (((int64_t)img * p.D + od) * p.H + oh) * p.W + ow;
+            const int buf = p.n_buf == 2 ? (j & 1) : 0;
+            const uint32_t use = p.n_buf == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
+            mbar_wait(&tmem_full[buf], use & 1u);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * p.nt);
+            for (int c0 = 0; c0 < p.nt; c0 += 16) {
+                float v[16];
+                tc_ld16(t_addr + (uint32_t)c0, v);
+                if (c0 + 16 >= p.nt) {
+                    // every column of this warp's lanes is in registers: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
                 }
-                // lane l now holds column (bit-reversed assignment): col = 8*b4 + 4*b3 + 2*b2 + b1 of the lane, rows split by b0
-                float cs = s16[0] + __shfl_xor_sync(0xffffffffu, s16[0], 1);
-                float cq = q16[0] + __shfl_xor_sync(0xffffffffu, q16[0], 1);
-                if ((lane & 1) == 0) {
-                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    red_s[c0 + col] = cs; red_q[c0 + col] = cq;
+                if (p.bias) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + n0 + c0 + j4);
+                }
+                if (valid) {
+                    const int gc = n0 + c0;
+                    float* dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; j4 += 4)
+                        *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                }
+                if (p.stats) {
+                    // column sums over the 32 rows of this warp: butterfly reduce-scatter, 16 columns -> lanes 0..15
+                    float s16[16], q16[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4) { float x = valid ? v[j4] : 0.f; s16[j4] = x; q16[j4] = x * x; }
+#pragma unroll
+                    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+                        const bool upper = (lane & bit) != 0;
+#pragma unroll
+                        for (int j4 = 0; j4 < half; ++j4) {
+                            float keep_s = upper ? s16[j4 + half] : s16[j4], send_s = upper ? s16[j4] : s16[j4 + half];
+                            float keep_q = upper ? q16[j4 + half] : q16[j4], send_q = upper ? q16[j4] : q16[j4 + half];
+                            s16[j4] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                            q16[j4] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                        }
+                    }
+                    // lane l now holds column (bit-reversed assignment): col = 8*b4 + 4*b3 + 2*b2 + b1 of the lane, rows split by b0
+                    float cs = s16[0] + __shfl_xor_sync(0xffffffffu, s16[0], 1);
+                    float cq = q16[0] + __shfl_xor_sync(0xffffffffu, q16[0], 1);
+                    if ((lane & 1) == 0) {
+                        // per-warp running sums over this CTA's tiles (one owner lane per column: no race)
+                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        red_s[c0 + col] += cs; red_q[c0 + col] += cq;
+                    }
                 }
             }
         }
-        tc_fence_before();
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps only
             const int e = threadIdx.x - 64;
@@ -233,6 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 atomicAdd(slot + p.n_total + n0 + c, (double)b);
             }
         }
+        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -309,9 +362,9 @@ static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
 }
 
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
-            double* ch_sums, cudaStream_t st) {
+            double* ch_sums, cudaStream_t st, float* out_b, int ca) {
     if (!tc_supports(g, dgrad)) return 0;
-    if (thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
+    if (!out_b && thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
     CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
     int K, N;
     tc_channels(g, dgrad, K, N);
@@ -336,8 +389,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
     p.n_total = N; p.nt = N > 256 ? 256 : N;
-    p.tmem_cols = 32; while (p.tmem_cols < p.nt) p.tmem_cols *= 2;
+    p.tiles_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    p.n_buf = p.nt <= 128 ? 2 : 1;                                       // two accumulators while 2 CTAs/SM still fit in 512 columns
+    p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
+    p.b_area_bytes = (uint32_t)g.taps * p.kchunks * p.b_box_bytes;
+    p.b_resident = p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
     if (p.reuse) {
         p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
         p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
@@ -347,15 +404,22 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         p.a_box_bytes = (uint32_t)(p.tw * p.th * p.td) * p.kc * 4u;
         p.b_stage_bytes = (p.b_box_bytes + 1023u) & ~1023u;
     }
-    const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
-    int stages = (int)((96 * 1024) / stage);
+    const size_t stage = (size_t)p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    const size_t fixed = p.b_resident ? p.b_area_bytes : 0u;
+    int stages = (int)((96 * 1024 - fixed) / stage);
     const int iters = (p.reuse ? p.taps / 3 : p.taps) * p.kchunks;
+    const int ctas_per_sm = 2;
+    int grid_x = p.tiles_total < kNumSMs * ctas_per_sm ? p.tiles_total : kNumSMs * ctas_per_sm;
+    if (getenv("CHAP_NO_PERSIST")) grid_x = p.tiles_total;
+    const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
     if (stages > 6) stages = 6;
-    if (stages > iters) stages = iters;
-    if (stages < 2) stages = iters < 2 ? 1 : 2;
+    if (stages > stage_uses) stages = (int)stage_uses;
+    if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     p.stages = stages;
-    p.out = out; p.bias = bias; p.stats = ch_sums;
-    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 + (size_t)8 * p.nt * sizeof(float);
+    p.out = out; p.out_b = out_b; p.ca = out_b ? ca : N; p.bias = bias; p.stats = ch_sums;
+    CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
+                 "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
+    const size_t smem = 1024 + (size_t)stages * stage + fixed + (2 * stages + 5) * sizeof(uint64_t) + 16 + (size_t)8 * p.nt * sizeof(float);
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
@@ -382,9 +446,9 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * N * sizeof(double), st));
     const double rows = (double)g.out_rows;
-    KernelTimer timer(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", 2.0 * rows * K * N * g.taps,
+    KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * K * N * g.taps,
                       4.0 * (rows * K + rows * N + (double)g.taps * K * N), st);
-    dim3 grid((unsigned)(g.n * p.tiles_d * p.tiles_h * p.tiles_w), (unsigned)(N / p.nt));
+    dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
     conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("conv_tc_kernel"));
     return 1;

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restr
     });
 }
 
+constexpr int kEwUnroll = 4;
+__global__ void __launch_bounds__(256) channel_stats_fixed_kernel(const float* __restrict__ y, int64_t total_vec, int c, double* sums);
+
 int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_t st) {
     CHAP_REQUIRE(y && sums && rows > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_stats: bad argument");
     CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
@@ -66,7 +69,8 @@ int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "channel_stats: too many channels (%d)", c);
     const int rpb = 256 / cg;
     int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
-    if (v4) channel_stats_kernel<4><<<grid, 256, 0, st>>>(y, rows, c, sums);
+    if (v4 && 256 % cg == 0) channel_stats_fixed_kernel<<<grid_for(rows * cg, 256 * kEwUnroll * 2, kNumSMs * 8), 256, 0, st>>>(y, rows * cg, c, sums);
+    else if (v4) channel_stats_kernel<4><<<grid, 256, 0, st>>>(y, rows, c, sums);
     else channel_stats_kernel<1><<<grid, 256, 0, st>>>(y, rows, c, sums);
     return launched("channel_stats_kernel");
 }
@@ -221,6 +225,195 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
         for (int k = 0; k < VEC; ++k) o[k] = tf32_rn(o[k], rt);
         if (VEC == 4) reinterpret_cast<float4*>(dy)[i] = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
         else dy[i] = o[0];
+    }
+}
+
+// ------------------------------------------------------------------ fixed-channel-group variants (C % 4 == 0, C/4 | 256)
+// The grid stride is a multiple of 256 and C/4 divides 256, so a thread sees the SAME four channels in every iteration:
+// the per-channel constants live in registers, there is no division in the loop, and four independent 128-bit loads per
+// tensor are in flight per thread.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <bool EL, bool RES>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ ss, float slope,
+                        const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
+                        const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec, float* __restrict__ out) {
+    const int cg = c >> 2, g = threadIdx.x % cg;
+    const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g);
+    const int64_t per_sample = rows_per_sample * cg;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* e4 = reinterpret_cast<const float4*>(drop_el);
+    const float4* r4 = reinterpret_cast<const float4*>(res);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    auto act = [&](float v, float s, float h) { float z = fmaf(v, s, h); return z > 0.f ? z : slope * z; };
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+        float4 v[kEwUnroll], e[kEwUnroll], r[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total_vec) {
+                v[u] = ldg_stream(y4 + i);
+                if (EL) e[u] = ldg_stream(e4 + i);
+                if (RES) r[u] = ldg_stream(r4 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= total_vec) break;
+            float4 o = make_float4(act(v[u].x, sc.x, sh.x), act(v[u].y, sc.y, sh.y), act(v[u].z, sc.z, sh.z), act(v[u].w, sc.w, sh.w));
+            if (drop_nc) {
+                const float4 f = ld4(drop_nc + (i / per_sample) * c + 4 * g);
+                o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
+            }
+            if (EL) { o.x *= e[u].x; o.y *= e[u].y; o.z *= e[u].z; o.w *= e[u].w; }
+            if (RES) { o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w; }
+            o4[i] = o;
+        }
+    }
+}
+
+// block-level finish of a per-channel reduction: lanes of a warp that share a channel group are combined by shuffles,
+// warps / row lanes through shared memory, one double atomic per channel and block
+__device__ __forceinline__ void channel_reduce_finish(float4 s, float4 q, int c, int cg, int g, double* sums) {
+    __shared__ float4 part[2][256];
+    int lanes;                                    // partial sums per channel group left after the shuffle stage
+    if (cg < 32) {
+        for (int o = 16; o >= cg; o >>= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+            s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+            q.x += __shfl_xor_sync(0xffffffffu, q.x, o); q.y += __shfl_xor_sync(0xffffffffu, q.y, o);
+            q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
+        }
+        lanes = 8;
+        if ((threadIdx.x & 31) < cg) { part[0][(threadIdx.x >> 5) * cg + g] = s; part[1][(threadIdx.x >> 5) * cg + g] = q; }
+    } else {
+        lanes = 256 / cg;
+        part[0][threadIdx.x] = s; part[1][threadIdx.x] = q;        // thread t = lane * cg + g
+    }
+    __syncthreads();
+    // 2 * c (channel, statistic) outputs; thread t sums output t over the lanes in double
+    for (int t = threadIdx.x; t < 2 * c; t += 256) {
+        const int which = t / c, ch = t - which * c;
+        double a = 0.0;
+        for (int l = 0; l < lanes; ++l) a += (double)reinterpret_cast<const float*>(&part[which][l * cg + (ch >> 2)])[ch & 3];
+        atomicAdd(sums + t, a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+channel_stats_fixed_kernel(const float* __restrict__ y, int64_t total_vec, int c, double* sums) {
+    const int cg = c >> 2, g = threadIdx.x % cg;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+        float4 v[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            v[u] = i < total_vec ? ldg_stream(y4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+            q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y); q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+        }
+    }
+    channel_reduce_finish(s, q, c, cg, g, sums);
+}
+
+template <bool EL>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_fixed_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
+                               const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
+                               const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t total_vec, int c, double* sums) {
+    const int cg = c >> 2, g = threadIdx.x % cg;
+    const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g), mean = ld4(mi + 4 * g), istd = ld4(mi + c + 4 * g);
+    const int64_t per_sample = rows_per_sample * cg;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const float4* d4 = reinterpret_cast<const float4*>(dout);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* e4 = reinterpret_cast<const float4*>(drop_el);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+        float4 d[kEwUnroll], v[kEwUnroll], e[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total_vec) {
+                d[u] = ldg_stream(d4 + i); v[u] = ldg_stream(y4 + i);
+                if (EL) e[u] = ldg_stream(e4 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= total_vec) break;
+            float4 dd = d[u];
+            if (drop_nc) { const float4 f = ld4(drop_nc + (i / per_sample) * c + 4 * g); dd.x *= f.x; dd.y *= f.y; dd.z *= f.z; dd.w *= f.w; }
+            if (EL) { dd.x *= e[u].x; dd.y *= e[u].y; dd.z *= e[u].z; dd.w *= e[u].w; }
+            const float z0 = bn_dz(dd.x, v[u].x, sc.x, sh.x, slope), z1 = bn_dz(dd.y, v[u].y, sc.y, sh.y, slope);
+            const float z2 = bn_dz(dd.z, v[u].z, sc.z, sh.z, slope), z3 = bn_dz(dd.w, v[u].w, sc.w, sh.w, slope);
+            s.x += z0; s.y += z1; s.z += z2; s.w += z3;
+            q.x = fmaf(z0, (v[u].x - mean.x) * istd.x, q.x); q.y = fmaf(z1, (v[u].y - mean.y) * istd.y, q.y);
+            q.z = fmaf(z2, (v[u].z - mean.z) * istd.z, q.z); q.w = fmaf(z3, (v[u].w - mean.w) * istd.w, q.w);
+        }
+    }
+    channel_reduce_finish(s, q, c, cg, g, sums);
+}
+
+template <bool EL>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
+                              const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
+                              const float* __restrict__ drop_el, int64_t rows_per_sample, int c, int64_t total_vec, int train,
+                              double inv_count, const double* __restrict__ sums, float* __restrict__ dy,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int cg = c >> 2, g = threadIdx.x % cg;
+    if (blockIdx.x == 0 && dgamma) {
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) { dbeta[ch] = (float)sums[ch]; dgamma[ch] = (float)sums[c + ch]; }
+    }
+    const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g), mean = ld4(mi + 4 * g), istd = ld4(mi + c + 4 * g);
+    float4 mz = make_float4(0.f, 0.f, 0.f, 0.f), mzx = mz;            // batch means of dz and dz * xhat (0 in eval mode)
+    if (train) {
+        mz = make_float4((float)(sums[4 * g] * inv_count), (float)(sums[4 * g + 1] * inv_count),
+                         (float)(sums[4 * g + 2] * inv_count), (float)(sums[4 * g + 3] * inv_count));
+        mzx = make_float4((float)(sums[c + 4 * g] * inv_count), (float)(sums[c + 4 * g + 1] * inv_count),
+                          (float)(sums[c + 4 * g + 2] * inv_count), (float)(sums[c + 4 * g + 3] * inv_count));
+    }
+    const int64_t per_sample = rows_per_sample * cg;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const float4* d4 = reinterpret_cast<const float4*>(dout);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* e4 = reinterpret_cast<const float4*>(drop_el);
+    float4* o4 = reinterpret_cast<float4*>(dy);
+    auto one = [&](float dd, float yv, float s_, float h_, float m_, float is_, float mz_, float mzx_) {
+        const float dz = bn_dz(dd, yv, s_, h_, slope);
+        return train ? s_ * (dz - mz_ - (yv - m_) * is_ * mzx_) : s_ * dz;
+    };
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+        float4 d[kEwUnroll], v[kEwUnroll], e[kEwUnroll];
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total_vec) {
+                d[u] = ldg_stream(d4 + i); v[u] = ldg_stream(y4 + i);
+                if (EL) e[u] = ldg_stream(e4 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kEwUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= total_vec) break;
+            float4 dd = d[u];
+            if (EL) { dd.x *= e[u].x; dd.y *= e[u].y; dd.z *= e[u].z; dd.w *= e[u].w; }
+            if (drop_nc) { const float4 f = ld4(drop_nc + (i / per_sample) * c + 4 * g); dd.x *= f.x; dd.y *= f.y; dd.z *= f.z; dd.w *= f.w; }
+            o4[i] = make_float4(one(dd.x, v[u].x, sc.x, sh.x, mean.x, istd.x, mz.x, mzx.x), one(dd.y, v[u].y, sc.y, sh.y, mean.y, istd.y, mz.y, mzx.y),
+                                one(dd.z, v[u].z, sc.z, sh.z, mean.z, istd.z, mz.z, mzx.z), one(dd.w, v[u].w, sc.w, sh.w, mean.w, istd.w, mz.w, mzx.w));
+        }
     }
 }
 
@@ -436,7 +629,13 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     CHAP_REQUIRE(y && ss && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_fwd: bad argument");
     const int64_t total = (int64_t)n * rps * c;
     KernelTimer timer("bn_act_fwd", 0.0, 4.0 * total * (2 + (drop_el ? 1 : 0) + (residual ? 1 : 0)), S(stream));
-    if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
+    if (c % 4 == 0 && 256 % (c / 4) == 0 && all16({y, drop_el, residual, out, ss, drop_nc}) && round_tf32_on() == 0) {
+        const int grid = grid_for(total / 4, 256 * kEwUnroll);
+#define CHAP_FWD_FIXED(EL, RES) bn_act_fwd_fixed_kernel<EL, RES><<<grid, 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, out)
+        if (drop_el) { if (residual) CHAP_FWD_FIXED(true, true); else CHAP_FWD_FIXED(true, false); }
+        else         { if (residual) CHAP_FWD_FIXED(false, true); else CHAP_FWD_FIXED(false, false); }
+#undef CHAP_FWD_FIXED
+    } else if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
         bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, round_tf32_on(), out);
     } else {
         bn_act_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total, round_tf32_on(), out);
@@ -457,18 +656,31 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
     const bool v4 = c % 4 == 0 && all16({dout, y, drop_el, dy});
     const int cg = v4 ? c / 4 : c;
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);
+    const double inv_count = 1.0 / (double)rows;
+    if (v4 && 256 % cg == 0 && all16({ss, mi, drop_nc}) && round_tf32_on() == 0) {
+        if (train || dgamma) {
+            const int rgrid = grid_for(total / 4, 256 * kEwUnroll * 2, kNumSMs * 8);
+            if (drop_el) bn_act_bwd_reduce_fixed_kernel<true><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
+            else bn_act_bwd_reduce_fixed_kernel<false><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
+            CHAP_TRY(launched("bn_act_bwd_reduce_fixed_kernel"));
+        }
+        const int agrid = grid_for(total / 4, 256 * kEwUnroll);
+        if (drop_el) bn_act_bwd_apply_fixed_kernel<true><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
+        else bn_act_bwd_apply_fixed_kernel<false><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
+        return launched("bn_act_bwd_apply_fixed_kernel");
+    }
     const int rpb = 256 / cg;
     int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
     if (v4) bn_act_bwd_reduce_kernel<4><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
     else bn_act_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
     CHAP_TRY(launched("bn_act_bwd_reduce_kernel"));
-    const double inv_count = 1.0 / (double)rows;
     if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
     else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
     return launched("bn_act_bwd_apply_kernel");
 }
 
 extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, void* stream) {
+    KernelTimer timer_("maxpool2_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_fwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
     if (c % 4 == 0) maxpool2_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, h, w, c, total / 4, y);
@@ -477,6 +689,7 @@ extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w
 }
 
 extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int32_t h, int32_t w, int32_t c, float* dx, void* stream) {
+    KernelTimer timer_("maxpool2_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_bwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
     if (c % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, dy, h, w, c, total / 4, dx);
@@ -485,6 +698,7 @@ extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int
 }
 
 extern "C" int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* y, void* stream) {
+    KernelTimer timer_("upsample2x_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && y && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_fwd: bad argument");
     const int64_t total = (int64_t)n * (nd == 3 ? 2 * d : 1) * 2 * h * 2 * w * c;
     if (c % 4 == 0) upsample2x_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total / 4, round_tf32_on(), y);
@@ -493,6 +707,7 @@ extern "C" int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_
 }
 
 extern "C" int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, float* dx, void* stream) {
+    KernelTimer timer_("upsample2x_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(dy && dx && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_bwd: bad argument");
     const int64_t total = (int64_t)n * d * h * w * c;
     if (c % 4 == 0) upsample2x_bwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total / 4, round_tf32_on(), dx);
@@ -501,6 +716,7 @@ extern "C" int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32
 }
 
 extern "C" int chap_concat_channels(const float* a, const float* b, int64_t rows, int32_t ca, int32_t cb, float* out, void* stream) {
+    KernelTimer timer_("concat_channels", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && b && out && rows > 0 && ca > 0 && cb > 0, CHAP_ERR_BAD_ARG, "concat_channels: bad argument");
     const int64_t total = rows * (ca + cb);
     if (ca % 4 == 0 && cb % 4 == 0 && all16({a, b, out}))
@@ -511,12 +727,14 @@ extern "C" int chap_concat_channels(const float* a, const float* b, int64_t rows
 }
 
 extern "C" int chap_split_channels(const float* in, int64_t rows, int32_t ca, int32_t cb, float* a, float* b, void* stream) {
+    KernelTimer timer_("split_channels", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(in && rows > 0 && ca > 0 && cb > 0 && (a || b), CHAP_ERR_BAD_ARG, "split_channels: bad argument");
     split_kernel<<<grid_for(rows * (ca + cb), 256 * 4), 256, 0, S(stream)>>>(in, rows, ca, cb, a, b);
     return launched("split_kernel");
 }
 
 extern "C" int chap_channel_scale(const float* x, const float* s, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    KernelTimer timer_("channel_scale", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && s && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_scale: bad argument");
     const int64_t total = (int64_t)n * rps * c;
     channel_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(x, s, rps, c, total, out);
@@ -524,12 +742,14 @@ extern "C" int chap_channel_scale(const float* x, const float* s, int32_t n, int
 }
 
 extern "C" int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream) {
+    KernelTimer timer_("axpy", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && b && out && elems > 0, CHAP_ERR_BAD_ARG, "axpy: bad argument");
     axpy_kernel<<<grid_for(elems, 256 * 4), 256, 0, S(stream)>>>(a, b, alpha, elems, out);
     return launched("axpy_kernel");
 }
 
 extern "C" int chap_mask_mix(const float* a, const float* b, const int64_t* mask, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    KernelTimer timer_("mask_mix", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && b && mask && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "mask_mix: bad argument");
     const int64_t total = (int64_t)n * rps * c;
     mask_mix_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(a, b, mask, rps, c, total, out);

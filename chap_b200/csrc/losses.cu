@@ -311,6 +311,7 @@ static bool row_aligned(const void* p, int c) { return c == 4 ? aligned16(p) : (
 
 extern "C" int chap_pseudo_label(const float* pre1, const float* pre2, int64_t rows, int32_t c, float* soft1, float* soft2,
                                  int64_t* arg1, int64_t* arg2, float* knowledge, void* stream) {
+    KernelTimer timer_("pseudo_label", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(pre1 && pre2 && rows > 0, CHAP_ERR_BAD_ARG, "pseudo_label: bad argument");
     CHAP_REQUIRE(row_aligned(pre1, c) && row_aligned(pre2, c) && row_aligned(soft1, c) && row_aligned(soft2, c), CHAP_ERR_ALIGNMENT, "pseudo_label: misaligned");
     int grid = grid_for(rows, 256 * 2);
@@ -319,6 +320,7 @@ extern "C" int chap_pseudo_label(const float* pre1, const float* pre2, int64_t r
 }
 
 extern "C" int chap_softmax(const float* logits, int64_t rows, int32_t c, float* out, void* stream) {
+    KernelTimer timer_("softmax", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && out && rows > 0, CHAP_ERR_BAD_ARG, "softmax: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(out, c), CHAP_ERR_ALIGNMENT, "softmax: misaligned");
     int grid = grid_for(rows, 256 * 2);
@@ -327,6 +329,7 @@ extern "C" int chap_softmax(const float* logits, int64_t rows, int32_t c, float*
 }
 
 extern "C" int chap_argmax(const float* a, const float* b, int64_t rows, int32_t c, int64_t* out, void* stream) {
+    KernelTimer timer_("argmax", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && out && rows > 0, CHAP_ERR_BAD_ARG, "argmax: bad argument");
     CHAP_REQUIRE(row_aligned(a, c) && row_aligned(b, c), CHAP_ERR_ALIGNMENT, "argmax: misaligned");
     int grid = grid_for(rows, 256 * 2);
@@ -336,6 +339,7 @@ extern "C" int chap_argmax(const float* a, const float* b, int64_t rows, int32_t
 
 extern "C" int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t dtype, const int64_t* mask, int32_t invert,
                                 int32_t n, int64_t rps, int32_t c, double* sums, void* stream) {
+    KernelTimer timer_("dice_ce_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && labels && mask && sums && n > 0 && rps > 0, CHAP_ERR_BAD_ARG, "dice_ce_fwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c), CHAP_ERR_ALIGNMENT, "dice_ce_fwd: misaligned logits");
     CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)(3 * c + 2) * sizeof(double), S(stream)));
@@ -347,6 +351,7 @@ extern "C" int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t
 
 extern "C" int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t dtype, const int64_t* mask, int32_t invert,
                                 int32_t n, int64_t rps, int32_t c, const float* coef, int32_t accumulate, float* dlogits, void* stream) {
+    KernelTimer timer_("dice_ce_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && labels && mask && coef && dlogits && n > 0 && rps > 0, CHAP_ERR_BAD_ARG, "dice_ce_bwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(dlogits, c), CHAP_ERR_ALIGNMENT, "dice_ce_bwd: misaligned");
     const int64_t rows = (int64_t)n * rps;
@@ -357,6 +362,7 @@ extern "C" int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t
 
 extern "C" int chap_consistency_fwd(const float* logits, const float* target, const float* mask, int32_t dist, int64_t rows,
                                     int32_t c, double* sums, void* stream) {
+    KernelTimer timer_("consistency_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && target && sums && rows > 0 && (dist == CHAP_DIST_KL || dist == CHAP_DIST_DICE), CHAP_ERR_BAD_ARG, "consistency_fwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(target, c), CHAP_ERR_ALIGNMENT, "consistency_fwd: misaligned");
     CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)(3 * c + 1) * sizeof(double), S(stream)));
@@ -367,6 +373,7 @@ extern "C" int chap_consistency_fwd(const float* logits, const float* target, co
 
 extern "C" int chap_consistency_bwd(const float* logits, const float* target, const float* mask, int32_t dist, int64_t rows,
                                     int32_t c, const float* coef, float* dlogits, void* stream) {
+    KernelTimer timer_("consistency_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && target && coef && dlogits && rows > 0 && (dist == CHAP_DIST_KL || dist == CHAP_DIST_DICE), CHAP_ERR_BAD_ARG, "consistency_bwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(target, c) && row_aligned(dlogits, c), CHAP_ERR_ALIGNMENT, "consistency_bwd: misaligned");
     int grid = grid_for(rows, 256 * 2);
@@ -376,6 +383,7 @@ extern "C" int chap_consistency_bwd(const float* logits, const float* target, co
 
 extern "C" int chap_patch_score(const float* knowledge, const int64_t* arg1, const int64_t* arg2, int32_t nd, int32_t n,
                                 int32_t d, int32_t h, int32_t w, int32_t s, float* score, void* stream) {
+    KernelTimer timer_("patch_score", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(knowledge && arg1 && arg2 && score && (nd == 2 || nd == 3) && n > 0 && s > 0, CHAP_ERR_BAD_ARG, "patch_score: bad argument");
     CHAP_REQUIRE(h % s == 0 && w % s == 0 && (nd == 2 ? d == 1 : d % s == 0), CHAP_ERR_BAD_ARG, "patch_score: size not divisible by scale_factor");
     const int64_t total = (int64_t)n * (nd == 3 ? d / s : 1) * (h / s) * (w / s);
@@ -385,6 +393,7 @@ extern "C" int chap_patch_score(const float* knowledge, const int64_t* arg1, con
 
 extern "C" int chap_patch_mask(const float* score, const float* kth, int32_t nd, int32_t n, int32_t d, int32_t h, int32_t w,
                                int32_t s, float* mask, void* stream) {
+    KernelTimer timer_("patch_mask", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(score && kth && mask && (nd == 2 || nd == 3) && n > 0 && s > 0, CHAP_ERR_BAD_ARG, "patch_mask: bad argument");
     const int64_t total = (int64_t)n * d * h * w;
     patch_mask_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(score, kth, nd, d, h, w, s, total, mask);

@@ -1,6 +1,10 @@
 // Library state (errors, launch counter), fused SGD-momentum, sliding-window aggregation.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <string>
 
 namespace chap {
 thread_local char g_err[512] = "";
@@ -24,6 +28,19 @@ KernelTimer::KernelTimer(const char* name, double flops, double bytes, cudaStrea
     t.name = name; t.flops = flops; t.bytes = bytes;
     cudaEventRecord(t.a, st);
     slot = i;
+}
+// CHAP_TIMING_DETAIL=1: per-shape timer names ("conv_tc_fwd:k16n16:256x256x1"), interned for the life of the process
+const char* timer_name(const char* family, int taps, int k, int n, int w, int h, int d, int64_t rows) {
+    static const bool detail = getenv("CHAP_TIMING_DETAIL") != nullptr;
+    if (!detail || !g_timing_on.load(std::memory_order_relaxed)) return family;
+    static std::mutex mu;
+    static std::map<std::string, std::string*> names;
+    char buf[160];
+    snprintf(buf, sizeof buf, "%s:t%d:k%d:n%d:%dx%dx%d:r%lld", family, taps, k, n, w, h, d, (long long)rows);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = names.find(buf);
+    if (it == names.end()) it = names.emplace(buf, new std::string(buf)).first;
+    return it->second->c_str();
 }
 KernelTimer::~KernelTimer() {
     if (slot >= 0) cudaEventRecord(g_timed[slot].b, st);
@@ -165,13 +182,14 @@ extern "C" int chap_timing_report(char* buf, size_t cap) {
     int n = g_timed_n.load();
     if (n > kMaxTimed) n = kMaxTimed;
     struct Agg { const char* name; int count; double ms, flops, bytes; };
-    Agg agg[64]; int na = 0;
+    constexpr int kMaxAgg = 512;
+    static Agg agg[kMaxAgg]; int na = 0;
     for (int i = 0; i < n; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, g_timed[i].a, g_timed[i].b) != cudaSuccess) { cudaGetLastError(); continue; }
         int j = 0;
         for (; j < na; ++j) if (agg[j].name == g_timed[i].name || strcmp(agg[j].name, g_timed[i].name) == 0) break;
-        if (j == na) { if (na == 64) continue; agg[na++] = Agg{g_timed[i].name, 0, 0.0, 0.0, 0.0}; }
+        if (j == na) { if (na == kMaxAgg) continue; agg[na++] = Agg{g_timed[i].name, 0, 0.0, 0.0, 0.0}; }
         agg[j].count++; agg[j].ms += ms; agg[j].flops += g_timed[i].flops; agg[j].bytes += g_timed[i].bytes;
     }
     size_t off = 0;
@@ -195,6 +213,7 @@ extern "C" int chap_check_device(void) {
 
 extern "C" int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t elems, float lr, float momentum,
                                  float weight_decay, float grad_scale, int32_t first_step, void* stream) {
+    KernelTimer timer_("sgd_momentum", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(p && g && buf && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum: bad argument");
     CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum: buffers must be 16-byte aligned");
     sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, lr, nullptr, momentum, weight_decay, grad_scale, first_step);
@@ -203,6 +222,7 @@ extern "C" int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t e
 
 extern "C" int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int64_t elems, const float* lr_dev, float momentum,
                                        float weight_decay, float grad_scale, void* stream) {
+    KernelTimer timer_("sgd_momentum_lrdev", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(p && g && buf && lr_dev && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum_lrdev: bad argument");
     CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum_lrdev: buffers must be 16-byte aligned");
     sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, 0.f, lr_dev, momentum, weight_decay, grad_scale, 0);

@@ -224,6 +224,7 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
 
 extern "C" int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n, int64_t elems_per_sample,
                                     double* norms, float* out, void* stream) {
+    KernelTimer timer_("l2n_sample_axpy", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(d && norms && out && n > 0 && elems_per_sample > 0, CHAP_ERR_BAD_ARG, "l2n_sample_axpy: bad argument");
     cudaStream_t st = S(stream);
     CHAP_CUDA(cudaMemsetAsync(norms, 0, (size_t)n * sizeof(double), st));

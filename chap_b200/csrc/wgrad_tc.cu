@@ -333,7 +333,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
     CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * g.cin * g.cout * sizeof(float), st));
     const double rows = (double)g.out_rows;
-    KernelTimer timer("conv_tc_wgrad", 2.0 * rows * g.cin * g.cout * g.taps,
+    KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, g.cin, g.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * g.cin * g.cout * g.taps,
                       4.0 * (rows * g.cin + rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
     wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
