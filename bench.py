@@ -273,6 +273,7 @@ def run_gpu(args, w):
             roof["families_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
             roof["families_gbps"] = {k: round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) for k, v in fam.items()
                                      if v["bytes"] > 0 and v["flops"] == 0 and v["ms"] > 0}
+            roof["families_launches"] = {k: v["launches"] for k, v in fam.items()}
             roof["eager_ms_per_step"] = ms_eager
             roof["note"] = ("per-kernel CUDA-event timing taken in an eager re-issue of the same iteration right after the "
                             "timed graph replays; conv peak is the measured dense bf16 rate, TF32 runs at half of it by design")

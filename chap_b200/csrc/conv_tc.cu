@@ -37,6 +37,7 @@ struct TcParams {
     int stages, tmem_cols;
     int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
+    int debug;                    // CHAP_TC_DEBUG bit mask (profiling experiments): 1 no MMAs, 2 no A loads, 4 no stores/statistics
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
     uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
     float* out;                   // channels [0, ca), row stride ca
@@ -46,7 +47,50 @@ struct TcParams {
     double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;            // TMA warp, MMA warp, 2 x 4 epilogue warps
+#define TC_WAIT(bar, par) do { if (p.debug & 16) mbar_poll(bar, par); else mbar_wait(bar, par); } while (0)
+#define TC_COMMIT(bar) do { if (p.debug & 32) mbar_arrive(bar); else tc_commit(bar); } while (0)
+
+// Column sums (and sums of squares) of a 32-row x 16-column register tile (row = lane) through a warp-private padded
+// shared-memory scratch: 16 conflict-free stores and 16 conflict-free loads per lane instead of a 62-shuffle butterfly
+// (the epilogue is one latency-bound instruction stream per warp, so instruction count is what matters).  Lane l sums
+// column l % 16 over rows 16 * (l / 16) ..; the two halves meet in one shuffle and lanes 0..15 add into dst (one owner
+// per column and warp: no race).
+__device__ __forceinline__ void warp_column_sums(const float (&v)[16], const bool valid, const int lane, float* scratch,
+                                                 float* dst_s, float* dst_q) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) scratch[lane * 17 + j] = valid ? v[j] : 0.f;
+    __syncwarp();
+    const int col = lane & 15, r0 = (lane >> 4) * 16;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { const float x = scratch[(r0 + r) * 17 + col]; s += x; q = fmaf(x, x, q); }
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    q += __shfl_xor_sync(0xffffffffu, q, 16);
+    if (lane < 16) { dst_s[col] += s; dst_q[col] += q; }
+    __syncwarp();
+}
+
+// Walks tiles first, first + step, ... of the (w, h, d, image) tile grid without a division per tile: the step is
+// decomposed once into mixed-radix digits and added with carries.
+struct TileIter {
+    int tx, ty, tz, img, tile;
+    int sx, sy, sz, simg, step;
+    __device__ __forceinline__ void init(const int first, const int step_, const int tiles_w, const int tiles_h, const int tiles_d) {
+        tile = first; step = step_;
+        int t = first;
+        tx = t % tiles_w; t /= tiles_w; ty = t % tiles_h; t /= tiles_h; tz = t % tiles_d; img = t / tiles_d;
+        t = step_;
+        sx = t % tiles_w; t /= tiles_w; sy = t % tiles_h; t /= tiles_h; sz = t % tiles_d; simg = t / tiles_d;
+    }
+    __device__ __forceinline__ void next(const int tiles_w, const int tiles_h, const int tiles_d) {
+        tile += step;
+        tx += sx; int c = tx >= tiles_w; tx -= c ? tiles_w : 0;
+        ty += sy + c; c = ty >= tiles_h; ty -= c ? tiles_h : 0;
+        tz += sz + c; c = tz >= tiles_d; tz -= c ? tiles_d : 0;
+        img += simg + c;
+    }
+};
 
 // The MMA-issuing warp.  Its instruction stream is on the critical path of these small-N MMAs (a runtime modulo per MMA
 // cost 30 % of the kernel), so the whole warp runs the warp-uniform loop (descriptors live in uniform registers), one
@@ -66,14 +110,14 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
     const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
     const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4;
     const uint32_t b_ky = p.b_resident ? 3u * (uint32_t)p.kchunks * b_box : b_box;     // resident layout is [tap][kchunk]
-    if (p.b_resident) mbar_wait(b_full, 0);
+    if (p.b_resident) TC_WAIT(b_full, 0);
     int s = 0; uint32_t ph = 0;
     uint32_t a_lo = a_lo0, b_lo_s = b_lo0;
     int j = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
         const int buf = p.n_buf == 2 ? (j & 1) : 0;
         const uint32_t use = p.n_buf == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
-        mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
+        TC_WAIT(&tmem_empty[buf], (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
         uint32_t accum = 0;
@@ -81,18 +125,18 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
             // reuse mode: grp = (kz, kx) and the stage serves taps ((kz * 3 + ky) * 3 + kx), ky = 0..2
             const int tap0 = NKY == 3 ? (grp / 3) * 9 + (grp % 3) : grp;
             for (int kci = 0; kci < p.kchunks; ++kci) {
-                mbar_wait(&full[s], ph);
+                TC_WAIT(&full[s], ph);
                 tc_fence_after();
                 const uint32_t b_lo = p.b_resident ? b_lo0 + (uint32_t)(tap0 * p.kchunks + kci) * b_box : b_lo_s;
                 if (elect_one()) {
 #pragma unroll
-                    for (int ky = 0; ky < NKY; ++ky) {
+                    for (int ky = 0; ky < NKY && !(p.debug & 1); ++ky) {
 #pragma unroll
                         for (int k = 0; k < KSTEPS; ++k)
                             tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)ky * a_ky + 2u * k, hi, b_lo + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
                                            (ky | k) == 0 ? accum : 1u);
                     }
-                    tc_commit(&empty[s]);
+                    TC_COMMIT(&empty[s]);
                 }
                 __syncwarp();
                 accum = 1;
@@ -100,7 +144,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
                 if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo_s = b_lo0; }
             }
         }
-        if (elect_one()) tc_commit(&tmem_full[buf]);
+        if (elect_one()) TC_COMMIT(&tmem_full[buf]);
         __syncwarp();
     }
 }
@@ -121,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_empty = tmem_full + 2;               // [2]
     uint64_t* b_full = tmem_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);          // [4 warps][2][nt] epilogue statistics
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);          // [8 warps][2][nt] epilogue statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.nt;
@@ -130,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], p.n_buf == 2 ? 4 : 8); }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -140,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 8 * p.nt; i += 128) red[i] = 0.f;
+        for (int i = threadIdx.x - 64; i < 16 * p.nt; i += 256) red[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -148,7 +192,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
     // reuse mode: one stage = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
     const int groups = p.reuse ? p.taps / 3 : p.taps;
-    const int tiles_per_img = p.tiles_w * p.tiles_h * p.tiles_d;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (warp-uniform, one elected lane issues)
@@ -162,25 +205,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
         }
         int s = 0; uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-            const int img = tile / tiles_per_img;
-            int t = tile - img * tiles_per_img;
-            const int tx = t % p.tiles_w; t /= p.tiles_w;
-            const int ty = t % p.tiles_h;
-            const int tz = t / p.tiles_h;
-            const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
+        TileIter ti;
+        for (ti.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d); ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d)) {
+            const int img = ti.img;
+            const int w0 = ti.tx * p.tw, h0 = ti.ty * p.th, d0 = ti.tz * p.td;
             for (int grp = 0; grp < groups; ++grp) {
                 int kx, ky, kz;
                 if (p.reuse) { kx = grp % 3; kz = grp / 3; ky = 0; }                 // box origin one row above the tile
                 else if (p.ksz == 3) { kx = grp % 3; ky = (grp / 3) % 3; kz = grp / 9; }
                 else { kx = ky = kz = p.pad; }                                        // 1x1: pad = 0
                 for (int kci = 0; kci < p.kchunks; ++kci) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                    TC_WAIT(&empty[s], ph ^ 1);
                     if (elect_one()) {
                         uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
                         const uint32_t nb = p.b_resident ? 0u : (p.reuse ? 3u : 1u);
-                        mbar_expect_tx(&full[s], p.a_box_bytes + nb * p.b_box_bytes);
-                        if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                        mbar_expect_tx(&full[s], ((p.debug & 2) ? 0u : p.a_box_bytes) + nb * p.b_box_bytes);
+                        if (p.debug & 2) {}
+                        else if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
                         else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                         if (!p.b_resident) {
                             uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
@@ -204,83 +245,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else            { if (p.reuse) issue_mmas<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
                           else issue_mmas<2, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
-        const int lg = warp & 3;
+        // ------------------------------------------------------------------ epilogue: 2 groups of 4 warps
+        // The epilogue of one tile is a single latency-bound instruction stream per warp (measured: ~1.5 us per tile, the
+        // bottleneck of the thin layers), so two warp groups work concurrently: with two accumulators group e owns
+        // accumulator e (tiles j = e, e + 2, ...); with one accumulator (nt = 256) the groups split its columns.
+        const int eg = (warp - 2) >> 2;
+        const int lg = warp & 3;                                       // TMEM lane quarter this warp may read
         const int m = lg * 32 + lane;                                  // accumulator row == position inside the box
         const int dx = m % p.tw, dy = (m / p.tw) % p.th, dz = m / (p.tw * p.th);
-        float* red_s = red + (size_t)(lg * 2 + 0) * p.nt;
-        float* red_q = red + (size_t)(lg * 2 + 1) * p.nt;
+        float* red_s = red + (size_t)((warp - 2) * 2 + 0) * p.nt;
+        float* red_q = red + (size_t)((warp - 2) * 2 + 1) * p.nt;
         const int cb = p.n_total - p.ca;
-        int j = 0;
-        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
-            const int img = tile / tiles_per_img;
-            int t = tile - img * tiles_per_img;
-            const int tx = t % p.tiles_w; t /= p.tiles_w;
-            const int ty = t % p.tiles_h;
-            const int tz = t / p.tiles_h;
-            const int ow = tx * p.tw + dx, oh = ty * p.th + dy, od = tz * p.td + dz;
+        const bool alternate = p.n_buf == 2;
+        const int c_begin = alternate ? 0 : eg * (p.nt >> 1), c_end = alternate ? p.nt : c_begin + (p.nt >> 1);
+        const int buf = alternate ? eg : 0;
+        float* scratch = red + (size_t)16 * p.nt + (size_t)(warp - 2) * (32 * 17);   // warp-private transpose scratch
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;     // parameters may sit at any 4-byte offset of an arena
+        uint32_t use = 0;
+        TileIter ti;
+        for (ti.init(blockIdx.x + (alternate ? eg * (int)gridDim.x : 0), (alternate ? 2 : 1) * (int)gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d);
+             ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), ++use) {
+            const int ow = ti.tx * p.tw + dx, oh = ti.ty * p.th + dy, od = ti.tz * p.td + dz;
             const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
-            const int64_t row = (((int64_t)img * p.D + od) * p.H + oh) * p.W + ow;
-            const int buf = p.n_buf == 2 ? (j & 1) : 0;
-            const uint32_t use = p.n_buf == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
-            mbar_wait(&tmem_full[buf], use & 1u);
+            const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
+            TC_WAIT(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * p.nt);
-            for (int c0 = 0; c0 < p.nt; c0 += 16) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float v[16];
-                tc_ld16(t_addr + (uint32_t)c0, v);
-                if (c0 + 16 >= p.nt) {
+                if (!(p.debug & 8)) tc_ld16(t_addr + (uint32_t)c0, v);
+                else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4) v[j4] = 0.f;
+                }
+                if (c0 + 16 >= c_end) {
                     // every column of this warp's lanes is in registers: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
                 if (p.bias) {
+                    if (bias_vec) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
-                    for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + n0 + c0 + j4);
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 bb = __ldg(b4 + j4);
+                            v[4 * j4] += bb.x; v[4 * j4 + 1] += bb.y; v[4 * j4 + 2] += bb.z; v[4 * j4 + 3] += bb.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + n0 + c0 + j4);
+                    }
                 }
-                if (valid) {
+                if (valid && !(p.debug & 4)) {
                     const int gc = n0 + c0;
                     float* dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
 #pragma unroll
                     for (int j4 = 0; j4 < 16; j4 += 4)
                         *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
                 }
-                if (p.stats) {
-                    // column sums over the 32 rows of this warp: butterfly reduce-scatter, 16 columns -> lanes 0..15
-                    float s16[16], q16[16];
-#pragma unroll
-                    for (int j4 = 0; j4 < 16; ++j4) { float x = valid ? v[j4] : 0.f; s16[j4] = x; q16[j4] = x * x; }
-#pragma unroll
-                    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-                        const bool upper = (lane & bit) != 0;
-#pragma unroll
-                        for (int j4 = 0; j4 < half; ++j4) {
-                            float keep_s = upper ? s16[j4 + half] : s16[j4], send_s = upper ? s16[j4] : s16[j4 + half];
-                            float keep_q = upper ? q16[j4 + half] : q16[j4], send_q = upper ? q16[j4] : q16[j4 + half];
-                            s16[j4] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
-                            q16[j4] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
-                        }
-                    }
-                    // lane l now holds column (bit-reversed assignment): col = 8*b4 + 4*b3 + 2*b2 + b1 of the lane, rows split by b0
-                    float cs = s16[0] + __shfl_xor_sync(0xffffffffu, s16[0], 1);
-                    float cq = q16[0] + __shfl_xor_sync(0xffffffffu, q16[0], 1);
-                    if ((lane & 1) == 0) {
-                        // per-warp running sums over this CTA's tiles (one owner lane per column: no race)
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        red_s[c0 + col] += cs; red_q[c0 + col] += cq;
-                    }
-                }
+                if (p.stats && !(p.debug & 4)) warp_column_sums(v, valid, lane, scratch, red_s + c0, red_q + c0);
             }
         }
         if (p.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps only
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps only
             const int e = threadIdx.x - 64;
             double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * p.n_total;
-            for (int c = e; c < p.nt; c += 128) {
+            for (int c = e; c < p.nt; c += 256) {
                 float a = 0.f, b = 0.f;
 #pragma unroll
-                for (int w = 0; w < 4; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
+                for (int w = 0; w < 8; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
                 atomicAdd(slot + n0 + c, (double)a);
                 atomicAdd(slot + p.n_total + n0 + c, (double)b);
             }
@@ -411,15 +445,17 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     const int ctas_per_sm = 2;
     int grid_x = p.tiles_total < kNumSMs * ctas_per_sm ? p.tiles_total : kNumSMs * ctas_per_sm;
     if (getenv("CHAP_NO_PERSIST")) grid_x = p.tiles_total;
+    if (getenv("CHAP_TC_GRID")) grid_x = atoi(getenv("CHAP_TC_GRID")) < p.tiles_total ? atoi(getenv("CHAP_TC_GRID")) : p.tiles_total;
     const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
     if (stages > 6) stages = 6;
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     p.stages = stages;
+    p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : N; p.bias = bias; p.stats = ch_sums;
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
-    const size_t smem = 1024 + (size_t)stages * stage + fixed + (2 * stages + 5) * sizeof(uint64_t) + 16 + (size_t)8 * p.nt * sizeof(float);
+    const size_t smem = 1024 + (size_t)stages * stage + fixed + (2 * stages + 5) * sizeof(uint64_t) + 16 + ((size_t)16 * p.nt + 8 * 32 * 17) * sizeof(float);
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;

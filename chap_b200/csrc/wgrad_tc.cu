@@ -33,6 +33,8 @@ struct WgParams {
     int a_cpg, a_groups;            // channels per TMA chunk (32|16) and chunks per m_tile
     int b_cpg, b_groups;
     int tg;                         // taps per CTA (reuse mode: (kz, kx) pairs per CTA, each pair = 3 ky taps)
+    int swap;                       // 1 (reuse mode, cin <= 32): x is the M operand (M = 4 "ky" chunks x 32 ci, chunk stride tw rows), dy the N operand
+    int n_mma;                      // swap mode: MMA N = cout of this CTA rounded up to 16
     int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
     int b_rows;                     // rows (pixels) per x channel chunk in smem
     int debug;                      // CHAP_WG_DEBUG bit 0: skip the MMAs, bit 1: skip the TMA loads (timing experiments only)
@@ -141,14 +143,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(p.mma_m >> 4) << 24);
-        const bool merged = p.reuse && p.b_groups == 1;
-        // merged mode: the three ky taps are ONE MMA with N = 96: the "channel chunk" stride (LBO) of the B descriptor is
-        // tw rows, chunk g IS tap ky = g, and the accumulator columns come out as [ky][ci].
-        const uint32_t idesc_m = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(96 >> 3) << 17);
-        // M is always 128 rows; when the tile has fewer channels the extra channel chunks alias chunk 0 (one chunk,
-        // LBO = 0) or read whatever follows in shared memory (two chunks): those accumulator rows are never stored
+        // Swap mode (thin layers, cin <= 32): one tcgen05.mma costs time ~ N and M is 128 rows whatever is used, so x goes
+        // on the M side: the "channel chunk" stride (LBO) of its descriptor is tw rows of the h-haloed box, i.e. chunk g IS
+        // tap ky = g (chunk 3 is junk that is never stored), and dy is the N operand with N = cout.  One MMA per K step
+        // covers three taps at N = cout (16..128) instead of N = 3 * 32 with 16 of 128 rows in use.
+        const bool swap = p.swap != 0;
+        // the extra M chunks alias chunk 0 (one chunk, LBO = 0) or read whatever follows in shared memory: never stored
         const uint32_t a_lbo = p.a_groups >= 2 ? a_chunk : 0u;
-        const uint32_t b_lbo = merged ? (uint32_t)p.tw * b_row : b_chunk;
+        const uint32_t b_lbo = swap ? (uint32_t)p.tw * b_row : b_chunk;
         // descriptor words: lo = start >> 4 | (LBO >> 4) << 16; hi = SBO >> 4 (4 rows) | version 1 (bit 46) | layout 1 (bit 61)
         const uint32_t a_hi = ((4u * a_row) >> 4) | (1u << 14) | (1u << 29);
         const uint32_t b_hi = ((4u * b_row) >> 4) | (1u << 14) | (1u << 29);
@@ -158,9 +160,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t a_k = (8u * a_row) >> 4, b_k = (8u * b_row) >> 4;        // one K step = 8 pixel rows
         const uint32_t b_ky = ((uint32_t)p.tw * b_row) >> 4;                     // reuse mode: tap ky starts ky * tw rows further down
         const int ksteps = (p.debug & 1) ? 0 : p.P / 8;
-        const int n_sub = merged ? 1 : nky;
-        const uint32_t id = merged ? idesc_m : idesc;
-        const uint32_t d_stride = merged ? 3u * (uint32_t)p.n_tile : (uint32_t)(nky * p.n_tile);
+        const int n_sub = swap ? 1 : nky;
+        const uint32_t id = swap ? ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(p.n_mma >> 3) << 17)) : idesc;
+        const uint32_t d_stride = swap ? (uint32_t)p.n_mma : (uint32_t)(nky * p.n_tile);
         int s = 0; uint32_t ph = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0;
         for (int b = 0; b < nblk; ++b) {
@@ -172,13 +174,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int ky = 0; ky < n_sub; ++ky) {
                         const uint32_t d_tmem = d_tap + (uint32_t)(ky * p.n_tile);
                         const uint32_t b_tap = b_lo + (uint32_t)ky * b_ky;
-                        if (ksteps == 8) {
+                        // MMA operands: (dy, x) or, swapped, (x, dy)
+                        uint32_t m_d = swap ? b_tap : a_lo, n_d = swap ? a_lo : b_tap;
+                        const uint32_t m_hi = swap ? b_hi : a_hi, n_hi = swap ? a_hi : b_hi;
+                        const uint32_t m_k = swap ? b_k : a_k, n_k = swap ? a_k : b_k;
+                        if ((ksteps & 7) == 0) {
+                            for (int k0 = 0; k0 < ksteps; k0 += 8) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)k * a_k, a_hi, b_tap + (uint32_t)k * b_k, b_hi, id, (uint32_t)((b | k) != 0));
+                                for (int k = 0; k < 8; ++k)
+                                    tc_mma_tf32_lh(d_tmem, m_d + (uint32_t)k * m_k, m_hi, n_d + (uint32_t)k * n_k, n_hi, id, (uint32_t)((b | k0 | k) != 0));
+                                m_d += 8u * m_k; n_d += 8u * n_k;
+                            }
                         } else {
                             for (int k = 0; k < ksteps; ++k)
-                                tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)k * a_k, a_hi, b_tap + (uint32_t)k * b_k, b_hi, id, (uint32_t)((b | k) != 0));
+                                tc_mma_tf32_lh(d_tmem, m_d + (uint32_t)k * m_k, m_hi, n_d + (uint32_t)k * n_k, n_hi, id, (uint32_t)((b | k) != 0));
                         }
                     }
                     tc_commit(&empty[s]);
@@ -197,7 +206,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool valid = row < p.m_tile && row < p.mma_m;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (lg * 32 < p.mma_m) {                         // M = 64: lane groups 2,3 hold nothing
+        if (p.swap) {
+            // accumulator row = (ky = lane quarter, ci = lane); columns = [unit (kz, kx)][co]
+            const int ky = lg, ci = lane;
+            if (ky < 3) {
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    const int q = tap0 + ti;
+                    const int tap = ((q / 3) * 3 + ky) * 3 + (q % 3);
+                    float* dst = p.dw + (int64_t)ci * p.s_ci + tap;
+                    for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
+                        float v[16];
+                        tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * p.n_mma + c0), v);
+                        if (ci < p.cin) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.m_tile) atomicAdd(dst + (int64_t)(m0 + c0 + j) * p.s_co, v[j]);
+                        }
+                    }
+                }
+            }
+        } else if (lg * 32 < p.mma_m) {                  // M = 64: lane groups 2,3 hold nothing
             float* dst_row = p.dw + (int64_t)(m0 + row) * p.s_co;
             for (int ti = 0; ti < ntaps * nky; ++ti) {
                 int tap = tap0 + ti;
@@ -225,7 +253,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 bool tc_wgrad_supports(const Geom& g) {
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     auto ok = [](int c) { return c == 16 || (c % 32 == 0 && c <= 1024); };
-    return ok(g.cin) && ok(g.cout);
+    // swap mode (row-reuse geometry, cin <= 32) also takes the 4- / 8-channel heads: dy is the N operand, zero-filled to 16
+    const bool head = (g.cout == 4 || g.cout == 8) && g.kind == CHAP_CONV_K3 && (g.cin == 16 || g.cin == 32) && g.iW >= 8 && g.iH >= 10 &&
+                      getenv("CHAP_NO_ROW_REUSE") == nullptr && getenv("CHAP_WG_NO_SWAP") == nullptr;
+    return ok(g.cin) && (ok(g.cout) || head);
 }
 
 // spatial box inside the image (w <= W, h <= H, d <= D), at most 64 pixels, minimising the padded reduction length
@@ -255,6 +286,22 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.reuse = 0;
     if (g.kind == CHAP_CONV_K3 && n_tile_pre <= 128 && p.W >= 8 && p.H >= 10 && getenv("CHAP_NO_ROW_REUSE") == nullptr) {
         p.reuse = 1; p.tw = 8; p.th = 8; p.td = 1;
+        // The MMA-issuing warp pays a fixed ~0.4 us of scalar work per pipeline stage (measured), so large images use
+        // larger pixel blocks (16 x 8 or 16 x 16: 16 / 32 MMAs per stage instead of 8) as long as >= 3 stages still fit
+        // and there are enough blocks to fill the GPU.
+        const int m_tile_pre = g.cout > 128 ? 128 : g.cout;
+        const int force = getenv("CHAP_WG_BOX") ? atoi(getenv("CHAP_WG_BOX")) : 0;      // 64 / 128 / 256 pixels (experiments)
+        const int cand[2][2] = {{16, 16}, {16, 8}};
+        for (const auto& c : cand) {
+            const int tw = c[0], th = c[1], P = tw * th;
+            if (force && P != force) continue;
+            if (p.W < tw || p.H < th + 2) continue;
+            const size_t st_bytes = (size_t)((m_tile_pre + 31) / 32) * 32 * P * 4 + (size_t)n_tile_pre * tw * (th + 2) * 4;
+            const long blocks = (long)g.n * p.D * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th);
+            if (st_bytes * (force ? 2 : 3) > 198 * 1024 || blocks < 4 * kNumSMs) continue;
+            p.tw = tw; p.th = th;
+            break;
+        }
     }
     p.p_box = p.tw * p.th * p.td;
     p.P = (p.p_box + 7) / 8 * 8;
@@ -279,7 +326,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     // Two CTAs share an SM when a CTA needs <= 256 TMEM columns and <= 100 KB of smem.
     const long weights_pad = (long)g.cout * p.n_tile * n_tiles * g.taps;
     const int units = p.reuse ? g.taps / 3 : g.taps;          // what a CTA's tap group is made of
-    const int cols_per_unit = (p.reuse ? 3 : 1) * p.n_tile;
+    p.swap = p.reuse && p.b_groups == 1 && getenv("CHAP_WG_NO_SWAP") == nullptr;
+    p.n_mma = p.m_tile < 16 ? 16 : p.m_tile;
+    const int cols_per_unit = p.swap ? p.n_mma : (p.reuse ? 3 : 1) * p.n_tile;
     long max_splits = 4000000L / weights_pad;
     if (max_splits < 1) max_splits = 1;
     if (max_splits > p.blocks_total) max_splits = p.blocks_total;
@@ -330,7 +379,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 +
+                        (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
     CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * g.cin * g.cout * sizeof(float), st));
     const double rows = (double)g.out_rows;
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, g.cin, g.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * g.cin * g.cout * g.taps,

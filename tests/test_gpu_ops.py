@@ -90,6 +90,46 @@ def test_conv_fwd_dgrad_wgrad(case, force_simt):
     assert rel_err(sums[:cout], yd.sum(dims)) < 1e-4 + tol and rel_err(sums[cout:], (yd * yd).sum(dims)) < 1e-4 + tol, "fused BN statistics"
 
 
+LARGE_CONV_CASES = [
+    # many tiles per persistent CTA, ragged borders, several images; the big wgrad pixel blocks (16x16, 16x8)
+    ("k3", 2, 5, (144, 136), 16, 16), ("k3", 2, 12, (128, 128), 32, 32), ("k3", 2, 8, (128, 128), 64, 32),
+    ("k3", 2, 3, (200, 264), 16, 32), ("k3", 2, 6, (96, 96), 32, 16), ("k3", 3, 2, (24, 40, 48), 16, 16),
+    ("k1", 2, 9, (64, 64), 64, 32), ("k3", 2, 2, (72, 72), 128, 128), ("k3", 2, 4, (64, 80), 16, 4), ("k3", 2, 12, (128, 128), 32, 64),
+]
+
+
+@pytest.mark.parametrize("case", LARGE_CONV_CASES, ids=lambda c: "%s-%dd-n%d-%s-%d-%d" % (c[0], c[1], c[2], "x".join(map(str, c[3])), c[4], c[5]))
+def test_conv_large_shapes_tensor_core(case):
+    """Persistent multi-tile path: reference is torch fp64 on the GPU (same op, no TF32)."""
+    from chap_b200 import _lib
+    ops = _ops()
+    kind, nd, n, sp, cin, cout = case
+    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1}[kind]
+    k = {"k3": 3, "k1": 1}[kind]
+    g = torch.Generator().manual_seed(100 + LARGE_CONV_CASES.index(case))
+    x = torch.randn((n, cin) + sp, generator=g).to(DEV)
+    w = (torch.randn((cout, cin) + (k,) * nd, generator=g) / (cin * k ** nd) ** 0.5).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    y_ref = _torch_conv(kind, nd, xd, wd, bd)
+    gy = torch.randn(y_ref.shape, generator=g).to(DEV)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(y_ref, (xd, wd, bd), gy.double())
+    xg = ops.cl(x).requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    bg = b.clone().requires_grad_(True)
+    y, sums = ops.conv_stats(xg, wg, bg, kcode, True)
+    gx, gw, gb = torch.autograd.grad(y, (xg, wg, bg), ops.cl(gy))
+    torch.cuda.synchronize()
+    assert rel_err(y, y_ref) < CONV_TOL, "fwd"
+    assert rel_err(gx, gx_ref) < CONV_TOL, "dgrad"
+    assert rel_err(gw, gw_ref) < CONV_TOL, "wgrad"
+    assert rel_err(gb, gb_ref) < CONV_TOL, "dbias"
+    dims = (0,) + tuple(range(2, 2 + nd))
+    sums = sums.reshape(_lib.STAT_SLOTS, 2 * cout).sum(0)
+    yd = y.detach().double()
+    assert rel_err(sums[:cout], yd.sum(dims)) < 1e-4 and rel_err(sums[cout:], (yd * yd).sum(dims)) < 1e-4, "fused BN statistics"
+
+
 @pytest.mark.parametrize("nd,train,with_res,drop", list(itertools.product([2, 3], [True, False], [False, True], ["none", "nc", "el"])))
 def test_bn_act_fwd_bwd(nd, train, with_res, drop):
     ops = _ops()
