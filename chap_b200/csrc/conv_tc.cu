@@ -37,6 +37,9 @@ struct TcParams {
     int stages, tmem_cols;
     int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
+    int mode;                     // 0: stride-1 conv; 1: transposed k2 s2 forward (one GEMM, N = taps * Cout, scatter epilogue);
+                                  // 2: its 2D data gradient (4-tap gather of dy through the [2C, W, 2, H, N] view)
+    int up_c;                     // mode 1: Cout (columns per tap); mode 2: channels of dy
     int debug;                    // CHAP_TC_DEBUG bit mask (profiling experiments): 1 no MMAs, 2 no A loads, 4 no stores/statistics
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
     uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
@@ -221,6 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t nb = p.b_resident ? 0u : (p.reuse ? 3u : 1u);
                         mbar_expect_tx(&full[s], ((p.debug & 2) ? 0u : p.a_box_bytes) + nb * p.b_box_bytes);
                         if (p.debug & 2) {}
+                        else if (p.mode == 2) tma_load_5d(a_dst, &tmA, &full[s], (grp & 1) * p.up_c + kci * p.kc, w0, grp >> 1, h0, img);
                         else if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
                         else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                         if (!p.b_resident) {
@@ -284,9 +288,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
+                // channel of this chunk's first column: the taps of a transposed conv share the Cout channels
+                const int ch0 = p.mode == 1 ? (n0 + c0) % p.up_c : c0;          // statistics slot (CTA-relative)
+                const int bias0 = p.mode == 1 ? ch0 : n0 + c0;
                 if (p.bias) {
                     if (bias_vec) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias0);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 bb = __ldg(b4 + j4);
@@ -294,29 +301,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     } else {
 #pragma unroll
-                        for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + n0 + c0 + j4);
+                        for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + bias0 + j4);
                     }
                 }
                 if (valid && !(p.debug & 4)) {
                     const int gc = n0 + c0;
-                    float* dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
+                    float* dst;
+                    if (p.mode == 1) {
+                        // column = (tap, co); tap = ((kd * 2) + kh) * 2 + kw writes output pixel (2 d + kd, 2 h + kh, 2 w + kw)
+                        const int tap = gc / p.up_c, co = gc - tap * p.up_c;
+                        const int kw = tap & 1, kh = (tap >> 1) & 1, kd = tap >> 2;
+                        const int64_t orow = p.nd == 2 ? ((int64_t)ti.img * (2 * p.H) + 2 * oh + kh) * (2 * p.W) + 2 * ow + kw
+                                                       : (((int64_t)ti.img * (2 * p.D) + 2 * od + kd) * (2 * p.H) + 2 * oh + kh) * (2 * p.W) + 2 * ow + kw;
+                        dst = p.out + orow * p.up_c + co;
+                    } else {
+                        dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
+                    }
 #pragma unroll
                     for (int j4 = 0; j4 < 16; j4 += 4)
                         *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
                 }
-                if (p.stats && !(p.debug & 4)) warp_column_sums(v, valid, lane, scratch, red_s + c0, red_q + c0);
+                if (p.stats && !(p.debug & 4)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
             }
         }
         if (p.stats) {
             asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps only
             const int e = threadIdx.x - 64;
-            double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * p.n_total;
-            for (int c = e; c < p.nt; c += 256) {
+            const int n_ch = p.mode == 1 ? p.up_c : p.n_total, ch_base = p.mode == 1 ? 0 : n0, n_mine = p.mode == 1 ? p.up_c : p.nt;
+            double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * n_ch;
+            for (int c = e; c < n_mine; c += 256) {
                 float a = 0.f, b = 0.f;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
-                atomicAdd(slot + n0 + c, (double)a);
-                atomicAdd(slot + p.n_total + n0 + c, (double)b);
+                atomicAdd(slot + ch_base + c, (double)a);
+                atomicAdd(slot + n_ch + ch_base + c, (double)b);
             }
         }
         tc_fence_before();
@@ -372,6 +390,14 @@ static int tc_channels(const Geom& g, bool dgrad, int& K, int& N) {
 }
 
 bool tc_supports(const Geom& g, bool dgrad) {
+    if (g.kind == CHAP_CONV_UP2) {
+        // forward: one GEMM [pixels, Cin] x [Cin, taps * Cout] (2D and 3D); data gradient: 2D only (the gather needs a
+        // [2C, W, 2, H, N] view of dy, the 3D analogue would be 7-dimensional)
+        if (getenv("CHAP_NO_UP2_TC")) return false;
+        const bool chan_ok = (g.cin == 16 || g.cin % 32 == 0) && g.cout % 16 == 0 && g.cout >= 16 && g.cout <= 128 && g.cin <= 1024;
+        if (!dgrad) return chan_ok && ((g.taps * g.cout) <= 256 || (g.taps * g.cout) % 256 == 0);
+        return chan_ok && g.nd == 2 && (g.cout == 16 || g.cout % 32 == 0) && (g.cin <= 256 || g.cin % 256 == 0);
+    }
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     int K, N;
     tc_channels(g, dgrad, K, N);
@@ -405,6 +431,10 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     TcParams p{};
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD;
+    int w_taps = g.taps;                                  // taps in the packed weight operand [tap][N][K]
+    if (g.kind == CHAP_CONV_UP2 && !dgrad) { p.mode = 1; p.up_c = g.cout; N = g.taps * g.cout; p.taps = 1; w_taps = 1; }
+    if (g.kind == CHAP_CONV_UP2 && dgrad) { p.mode = 2; p.up_c = g.cout; p.ksz = 2; }
+    CHAP_REQUIRE(!(p.mode && out_b), CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for the transposed convolution");
     choose_box(p.W, p.H, p.D, p.tw, p.th, p.td);
     // Row-reuse mode for the activation-bound layers (few output channels): in-plane 128-pixel tile (tw x th, tw % 8 == 0)
     // and ONE TMA box with an h-halo (th + 2 rows) per (kz, kx); the three ky taps read it at row offsets ky * tw.
@@ -427,7 +457,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.n_buf = p.nt <= 128 ? 2 : 1;                                       // two accumulators while 2 CTAs/SM still fit in 512 columns
     p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
-    p.b_area_bytes = (uint32_t)g.taps * p.kchunks * p.b_box_bytes;
+    p.b_area_bytes = (uint32_t)p.taps * p.kchunks * p.b_box_bytes;
     p.b_resident = p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
     if (p.reuse) {
         p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
@@ -462,7 +492,13 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     {
         uint64_t dims[5], str[4]; uint32_t box[5];
         const uint64_t C = (uint64_t)K;
-        if (g.nd == 2) {
+        if (p.mode == 2) {
+            // dy [N, 2H, 2W, C] seen as [2C (kw, c), W, 2 (kh), H, N]: tap (kh, kw) of input pixel (h, w) is one box row
+            dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
+            str[0] = 2 * C * 4; str[1] = str[0] * p.W; str[2] = 2 * str[1]; str[3] = str[2] * p.H;
+            box[0] = p.kc; box[1] = p.tw; box[2] = 1; box[3] = p.th; box[4] = 1;
+            CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc));
+        } else if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
             box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = 1;
@@ -473,17 +509,18 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
             box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = p.td; box[4] = 1;
             CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc));
         }
-        uint64_t wd[2] = {(uint64_t)K, (uint64_t)g.taps * N};
+        uint64_t wd[2] = {(uint64_t)K, (uint64_t)w_taps * N};
         uint64_t ws[1] = {(uint64_t)K * 4};
         uint32_t wb[2] = {(uint32_t)p.kc, (uint32_t)p.nt};
         CHAP_TRY(make_tensor_map(&tmB, wp, 2, wd, ws, wb, p.kc));
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
-    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * N * sizeof(double), st));
-    const double rows = (double)g.out_rows;
-    KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * K * N * g.taps,
-                      4.0 * (rows * K + rows * N + (double)g.taps * K * N), st);
+    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : N) * sizeof(double), st));
+    const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
+    KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows),
+                      2.0 * rows * g.cin * g.cout * g.taps,
+                      4.0 * ((double)g.in_rows * g.cin + (double)g.out_rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
     conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("conv_tc_kernel"));

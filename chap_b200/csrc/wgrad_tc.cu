@@ -33,6 +33,7 @@ struct WgParams {
     int a_cpg, a_groups;            // channels per TMA chunk (32|16) and chunks per m_tile
     int b_cpg, b_groups;
     int tg;                         // taps per CTA (reuse mode: (kz, kx) pairs per CTA, each pair = 3 ky taps)
+    int up2;                        // 1: transposed k2 s2 conv (2D): the N operand is dy gathered per tap through its [2C, W, 2, H, N] view
     int swap;                       // 1 (reuse mode, cin <= 32): x is the M operand (M = 4 "ky" chunks x 32 ci, chunk stride tw rows), dy the N operand
     int n_mma;                      // swap mode: MMA N = cout of this CTA rounded up to 16
     int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
@@ -129,7 +130,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         else tma_load_5d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, d0, img);
                     }
                     for (int g = 0; g < p.b_groups; ++g) {
-                        if (p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                        if (p.up2) tma_load_5d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], (tap & 1) * p.cin + n0 + g * p.b_cpg, w0, tap >> 1, h0, img);
+                        else if (p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, img);
                         else tma_load_5d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -251,8 +253,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 bool tc_wgrad_supports(const Geom& g) {
-    if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     auto ok = [](int c) { return c == 16 || (c % 32 == 0 && c <= 1024); };
+    if (g.kind == CHAP_CONV_UP2) return g.nd == 2 && ok(g.cin) && ok(g.cout) && getenv("CHAP_NO_UP2_TC") == nullptr;
+    if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     // swap mode (row-reuse geometry, cin <= 32) also takes the 4- / 8-channel heads: dy is the N operand, zero-filled to 16
     const bool head = (g.cout == 4 || g.cout == 8) && g.kind == CHAP_CONV_K3 && (g.cin == 16 || g.cin == 32) && g.iW >= 8 && g.iH >= 10 &&
                       getenv("CHAP_NO_ROW_REUSE") == nullptr && getenv("CHAP_WG_NO_SWAP") == nullptr;
@@ -260,11 +263,11 @@ bool tc_wgrad_supports(const Geom& g) {
 }
 
 // spatial box inside the image (w <= W, h <= H, d <= D), at most 64 pixels, minimising the padded reduction length
-static void choose_box8(int W, int H, int D, int& tw, int& th, int& td) {
+static void choose_box8(int W, int H, int D, int& tw, int& th, int& td, int max_px = 64) {
     long best = -1;
-    for (int w = 1; w <= W && w <= 64; ++w)
-        for (int h = 1; h <= H && w * h <= 64; ++h)
-            for (int d = 1; d <= D && w * h * d <= 64; ++d) {
+    for (int w = 1; w <= W && w <= max_px; ++w)
+        for (int h = 1; h <= H && w * h <= max_px; ++h)
+            for (int d = 1; d <= D && w * h * d <= max_px; ++d) {
                 const int P = (w * h * d + 7) / 8 * 8;
                 long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
                 long score = tiles * P * 64 - w * h * d;    // least padded work, then the larger block
@@ -275,11 +278,29 @@ static void choose_box8(int W, int H, int D, int& tw, int& th, int& td) {
 int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st) {
     if (!tc_wgrad_supports(g)) return 0;
     CHAP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dw), CHAP_ERR_ALIGNMENT, "tc_wgrad: buffers must be 16-byte aligned");
+    // Transposed k2 s2 convolution (2D): dW[ci][co][kh][kw] = sum_p x[p, ci] * dy[2p + (kh, kw), co] is the same GEMM with the
+    // roles exchanged: the M operand is x (tap independent), the N operand is dy gathered per tap through its
+    // [2C, W, 2, H, N] view, and the gradient strides are those of the [ci][co][tap] layout.
+    const bool up2 = g.kind == CHAP_CONV_UP2;
+    Geom v = g;                                  // v.cout = channels of the M operand, v.cin = channels of the N operand
+    const float* m_src = dy; const float* n_src = x;
+    if (up2) { v.cin = g.cout; v.cout = g.cin; m_src = x; n_src = dy; }
     WgParams p{};
+    p.up2 = up2 ? 1 : 0;
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
     choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
-    const int n_tile_pre = g.cin > 256 ? 256 : (g.cin < 32 ? 32 : g.cin);
+    const int n_tile_pre = v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin);
+    {
+        // 128-pixel blocks (16 MMAs per pipeline stage instead of 8) when three stages still fit and the blocks fill the GPU
+        int tw, th, td;
+        choose_box8(p.W, p.H, p.D, tw, th, td, 128);
+        const int m_pre = v.cout > 128 ? 128 : v.cout;
+        const int P = (tw * th * td + 7) / 8 * 8;
+        const size_t st_bytes = (size_t)(((m_pre + 31) / 32) * 32 + n_tile_pre) * P * 4;
+        const long blocks = (long)g.n * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th) * ((p.D + td - 1) / td);
+        if (st_bytes * 3 <= 198 * 1024 && blocks >= 4 * kNumSMs && getenv("CHAP_WG_BOX") == nullptr) { p.tw = tw; p.th = th; p.td = td; }
+    }
     // Row-reuse mode (large images, <= 128 input channels per CTA): in-plane 8 x 8 pixel block; the x box is loaded once
     // per (kz, kx) with an h-halo of one row above and below and serves the three ky taps -> 3 (9) x-boxes of 10 rows
     // instead of 9 (27) boxes of 8 rows per block.
@@ -289,7 +310,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
         // The MMA-issuing warp pays a fixed ~0.4 us of scalar work per pipeline stage (measured), so large images use
         // larger pixel blocks (16 x 8 or 16 x 16: 16 / 32 MMAs per stage instead of 8) as long as >= 3 stages still fit
         // and there are enough blocks to fill the GPU.
-        const int m_tile_pre = g.cout > 128 ? 128 : g.cout;
+        const int m_tile_pre = v.cout > 128 ? 128 : v.cout;
         const int force = getenv("CHAP_WG_BOX") ? atoi(getenv("CHAP_WG_BOX")) : 0;      // 64 / 128 / 256 pixels (experiments)
         const int cand[2][2] = {{16, 16}, {16, 8}};
         for (const auto& c : cand) {
@@ -308,9 +329,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.b_rows = p.reuse ? p.tw * (p.th + 2) : p.P;
     p.debug = getenv("CHAP_WG_DEBUG") ? atoi(getenv("CHAP_WG_DEBUG")) : 0;
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
-    p.cout = g.cout; p.cin = g.cin;
-    p.m_tile = g.cout > 128 ? 128 : g.cout;
-    p.n_tile = g.cin > 256 ? 256 : (g.cin < 32 ? 32 : g.cin);     // 16-channel tensors: the TMA box is 32 wide, channels 16..31 zero-filled
+    p.cout = v.cout; p.cin = v.cin;
+    p.m_tile = v.cout > 128 ? 128 : v.cout;
+    p.n_tile = v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin);     // 16-channel tensors: the TMA box is 32 wide, channels 16..31 zero-filled
     p.mma_m = 128;           // M = 64 has a different TMEM lane mapping; M = 128 costs the same tensor time
     p.a_cpg = 32; p.a_groups = (p.m_tile + 31) / 32;
     p.b_cpg = 32; p.b_groups = p.n_tile / 32;
@@ -318,13 +339,13 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.b_stage_bytes = ((uint32_t)p.n_tile * p.b_rows * 4u + 1023u) & ~1023u;
     const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
     p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
-    const int n_tiles = g.cin > 256 ? g.cin / 256 : 1;
-    const int zdim = (g.cout / p.m_tile) * n_tiles;
+    const int n_tiles = v.cin > 256 ? v.cin / 256 : 1;
+    const int zdim = (v.cout / p.m_tile) * n_tiles;
     // Work split.  Parallelism comes from (channel tiles) x (tap groups) x (pixel splits).  Every pixel split adds one
     // fp32 atomic per (padded) weight element in the epilogue, so splits are capped by an atomic budget (measured: a
     // 256x256x9 layer with 24 splits spent >80% of its 106 us in 14 M atomics); tap groups are made smaller instead.
     // Two CTAs share an SM when a CTA needs <= 256 TMEM columns and <= 100 KB of smem.
-    const long weights_pad = (long)g.cout * p.n_tile * n_tiles * g.taps;
+    const long weights_pad = (long)v.cout * p.n_tile * n_tiles * g.taps;
     const int units = p.reuse ? g.taps / 3 : g.taps;          // what a CTA's tap group is made of
     p.swap = p.reuse && p.b_groups == 1 && getenv("CHAP_WG_NO_SWAP") == nullptr;
     p.n_mma = p.m_tile < 16 ? 16 : p.m_tile;
@@ -355,17 +376,22 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.stages = stages;
     p.blocks_per_cta = (p.blocks_total + splits - 1) / splits;
     splits = (p.blocks_total + p.blocks_per_cta - 1) / p.blocks_per_cta;
-    const PackSpec ps = fwd_pack(g);          // torch [co][ci][tap]: s_ci = T, s_co = Cin*T
-    p.s_ci = ps.sk; p.s_co = ps.sn;
+    const PackSpec ps = fwd_pack(g);          // torch [co][ci][tap]: s_ci = T, s_co = Cin*T; transposed [ci][co][tap]: M = ci
+    p.s_ci = up2 ? ps.sn : ps.sk; p.s_co = up2 ? ps.sk : ps.sn;
     p.dw = dw;
 
     CUtensorMap tmA, tmB;
     for (int which = 0; which < 2; ++which) {
-        const float* base = which == 0 ? dy : x;
-        const uint64_t C = which == 0 ? g.cout : g.cin;
+        const float* base = which == 0 ? m_src : n_src;
+        const uint64_t C = which == 0 ? v.cout : v.cin;
         const int cpg = which == 0 ? p.a_cpg : p.b_cpg;
         uint64_t dims[5], str[4]; uint32_t box[5];
-        if (g.nd == 2) {
+        if (up2 && which == 1) {
+            dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
+            str[0] = 2 * C * 4; str[1] = str[0] * p.W; str[2] = 2 * str[1]; str[3] = str[2] * p.H;
+            box[0] = cpg; box[1] = p.tw; box[2] = 1; box[3] = p.th; box[4] = 1;
+            CHAP_TRY(make_tensor_map(&tmB, base, 5, dims, str, box, cpg, true));
+        } else if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
             box[0] = cpg; box[1] = p.tw; box[2] = (which == 1 && p.reuse) ? p.th + 2 : p.th; box[3] = 1;
@@ -381,10 +407,10 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 +
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
-    CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * g.cin * g.cout * sizeof(float), st));
-    const double rows = (double)g.out_rows;
-    KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, g.cin, g.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * g.cin * g.cout * g.taps,
-                      4.0 * (rows * g.cin + rows * g.cout + (double)g.taps * g.cin * g.cout), st);
+    CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
+    const double rows = (double)(up2 ? g.in_rows : g.out_rows);
+    KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
+                      4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
     dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
     wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("wgrad_tc_kernel"));

@@ -95,6 +95,7 @@ LARGE_CONV_CASES = [
     ("k3", 2, 5, (144, 136), 16, 16), ("k3", 2, 12, (128, 128), 32, 32), ("k3", 2, 8, (128, 128), 64, 32),
     ("k3", 2, 3, (200, 264), 16, 32), ("k3", 2, 6, (96, 96), 32, 16), ("k3", 3, 2, (24, 40, 48), 16, 16),
     ("k1", 2, 9, (64, 64), 64, 32), ("k3", 2, 2, (72, 72), 128, 128), ("k3", 2, 4, (64, 80), 16, 4), ("k3", 2, 12, (128, 128), 32, 64),
+    ("up2", 2, 6, (64, 72), 32, 16), ("up2", 2, 3, (32, 32), 256, 128), ("up2", 3, 2, (12, 14, 10), 32, 16), ("up2", 2, 12, (128, 128), 32, 16),
 ]
 
 
@@ -104,11 +105,12 @@ def test_conv_large_shapes_tensor_core(case):
     from chap_b200 import _lib
     ops = _ops()
     kind, nd, n, sp, cin, cout = case
-    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1}[kind]
-    k = {"k3": 3, "k1": 1}[kind]
+    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1, "up2": _lib.CONV_UP2}[kind]
+    k = {"k3": 3, "k1": 1, "up2": 2}[kind]
     g = torch.Generator().manual_seed(100 + LARGE_CONV_CASES.index(case))
     x = torch.randn((n, cin) + sp, generator=g).to(DEV)
-    w = (torch.randn((cout, cin) + (k,) * nd, generator=g) / (cin * k ** nd) ** 0.5).to(DEV)
+    wshape = ((cin, cout) if kind == "up2" else (cout, cin)) + (k,) * nd
+    w = (torch.randn(wshape, generator=g) / (cin * k ** nd) ** 0.5).to(DEV)
     b = torch.randn(cout, generator=g).to(DEV)
     xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
     y_ref = _torch_conv(kind, nd, xd, wd, bd)
