@@ -51,6 +51,8 @@ SIGNATURES = {
     "chap_conv_pack_weights": (I, [_CD, P, P, P, P]),
     "chap_conv_fwd": (I, [_CD, P, P, P, P, P, P]),
     "chap_conv_dgrad": (I, [_CD, P, P, P, P]),
+    "chap_conv_dgrad_split_supported": (I, [_CD, I]),
+    "chap_conv_dgrad_split": (I, [_CD, P, P, P, I, P, P]),
     "chap_conv_wgrad_workspace_bytes": (c_size_t, [_CD]),
     "chap_conv_wgrad": (I, [_CD, P, P, P, P, P, c_size_t, P]),
     "chap_channel_stats": (I, [P, L, I, P, P]),

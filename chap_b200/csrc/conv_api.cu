@@ -60,6 +60,26 @@ extern "C" int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const f
     return simt_conv(dgrad_op(g), dy, w_dgrad, nullptr, dx, S(stream));
 }
 
+extern "C" int chap_conv_dgrad_split_supported(const chap_conv_desc* d, int32_t ca) {
+    Geom g{};
+    if (resolve(d, g) != CHAP_OK) return 0;
+    if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return 0;
+    return use_tc(g, true) && !thin_tc_supports(g, true) && ca > 0 && ca < g.cin && ca % 16 == 0 && (g.cin - ca) % 16 == 0 ? 1 : 0;
+}
+
+extern "C" int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx_a, int32_t ca,
+                                     float* dx_b, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(dy && w_dgrad && dx_a && dx_b, CHAP_ERR_BAD_ARG, "conv_dgrad_split: NULL pointer");
+    CHAP_REQUIRE(chap_conv_dgrad_split_supported(d, ca), CHAP_ERR_BAD_ARG,
+                 "conv_dgrad_split: shape not on the tensor-core split path (use chap_conv_dgrad + chap_split_channels)");
+    int rc = tc_conv(g, true, dy, w_dgrad, nullptr, dx_a, nullptr, S(stream), dx_b, ca);
+    if (rc < 0) return rc;
+    CHAP_REQUIRE(rc == 1, CHAP_ERR_BAD_ARG, "conv_dgrad_split: tensor-core path declined the shape");
+    return CHAP_OK;
+}
+
 extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
     Geom g{};
     if (resolve(d, g) != CHAP_OK) return 0;

@@ -38,11 +38,12 @@ class ConvBlock(nn.Module):
         self.conv_conv = nn.Sequential(*layers)
         self.dropout_p = dropout_p
 
-    def forward(self, x, drop_mask=None):
+    def forward(self, x, drop_mask=None, cat=None):
         """drop_mask: optional explicit (already 1/(1-p) scaled) dropout mask -- the parity-test
-        protocol; by default the mask is drawn like nn.Dropout would."""
+        protocol; by default the mask is drawn like nn.Dropout would.
+        cat: the block runs on torch.cat([x, cat], dim=1); the concat is fused into the first convolution."""
         c1, b1, _, _, c2, b2, _ = self.conv_conv
-        y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training)
+        y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training, cat=cat)
         if drop_mask is None:
             drop_mask = _elementwise_dropout_mask(y, self.dropout_p, self.training)
         a = ops.bn_act(y, b1, LEAKY_SLOPE, sums=sums, drop_el=drop_mask)
@@ -79,7 +80,7 @@ class UpBlock(nn.Module):
             x1 = ops.upsample2x(ops.conv(x1, self.conv1x1.weight, self.conv1x1.bias, CONV_K1))
         else:
             x1 = ops.conv(x1, self.up.weight, self.up.bias, CONV_UP2)
-        return self.conv(ops.concat_channels(x2, x1))
+        return self.conv(x2, cat=x1)
 
 
 class Encoder(nn.Module):

@@ -131,10 +131,21 @@ def _out_shape(kind, x, cout):
 
 
 class _Conv(Function):
+    """y = conv(cat(x, xb)) (xb optional).  With xb the channel concat of the U-Net skip connection is part of the op: the
+    backward's data gradient is written straight into the two parts by the tensor-core epilogue (no split pass)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False):
+    def forward(ctx, x, xb, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False):
         _require_cuda(x, weight, bias)
         x = cl(x)
+        ctx.split = None
+        if xb is not None:
+            xb = cl(xb)
+            ca, cb = x.shape[1], xb.shape[1]
+            cat = empty_cl([x.shape[0], ca + cb] + list(x.shape[2:]), x.device)
+            check(lib().chap_concat_channels(_p(x), _p(xb), x.numel() // ca, ca, cb, _p(cat), _stream()))
+            ctx.split = (ca, cb)
+            x = cat
         transposed = kind == _lib.CONV_UP2
         cin = weight.shape[0] if transposed else weight.shape[1]
         cout = weight.shape[1] if transposed else weight.shape[0]
@@ -148,7 +159,7 @@ class _Conv(Function):
         ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
         ctx.zero_bias_grad = zero_bias_grad
         ctx.wshape = tuple(weight.shape)
-        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None)
+        ctx.save_for_backward(x if ctx.needs_input_grad[2] else None)
         if want_stats:
             ctx.mark_non_differentiable(sums)
             return y, sums
@@ -159,36 +170,50 @@ class _Conv(Function):
         (x,) = ctx.saved_tensors
         desc = ctx.desc
         dy = cl(dy)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            nd = desc.nd
-            shape = [desc.n, desc.cin] + ([desc.in_h, desc.in_w] if nd == 2 else [desc.in_d, desc.in_h, desc.in_w])
-            dx = empty_cl(shape, dy.device)
+        dx = dxb = dw = db = None
+        nd = desc.nd
+        sp = [desc.in_h, desc.in_w] if nd == 2 else [desc.in_d, desc.in_h, desc.in_w]
+        if ctx.split is not None and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            ca, cb = ctx.split
+            dx, dxb = empty_cl([desc.n, ca] + sp, dy.device), empty_cl([desc.n, cb] + sp, dy.device)
+            if lib().chap_conv_dgrad_split_supported(ctypes.byref(desc), ca):
+                check(lib().chap_conv_dgrad_split(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(dx), ca, _p(dxb), _stream()))
+            else:
+                both = empty_cl([desc.n, ca + cb] + sp, dy.device)
+                check(lib().chap_conv_dgrad(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(both), _stream()))
+                check(lib().chap_split_channels(_p(both), both.numel() // (ca + cb), ca, cb, _p(dx), _p(dxb), _stream()))
+            if not ctx.needs_input_grad[0]:
+                dx = None
+            if not ctx.needs_input_grad[1]:
+                dxb = None
+        elif ctx.needs_input_grad[0]:
+            dx = empty_cl([desc.n, desc.cin] + sp, dy.device)
             check(lib().chap_conv_dgrad(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(dx), _stream()))
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2]:
             dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dy.device)
             # A bias that feeds a train-mode BatchNorm has an analytically ZERO gradient (BN subtracts the batch mean:
             # sum_r dy = scale * (sum dz - N mean(dz) - mean(dz xhat) * sum xhat) = 0); the reference computes rounding
             # noise there.  The gradient is returned as exact zeros (weight decay still applies in the optimiser).
-            want_b = ctx.has_bias and ctx.needs_input_grad[2] and not ctx.zero_bias_grad
+            want_b = ctx.has_bias and ctx.needs_input_grad[3] and not ctx.zero_bias_grad
             db = torch.empty(desc.cout, dtype=torch.float32, device=dy.device) if want_b else None
             ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
             check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
-            if ctx.has_bias and ctx.needs_input_grad[2] and ctx.zero_bias_grad:
+            if ctx.has_bias and ctx.needs_input_grad[3] and ctx.zero_bias_grad:
                 db = torch.zeros(desc.cout, dtype=torch.float32, device=dy.device)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dxb, dw, db, None, None, None, None, None
 
 
-def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False):
+def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat=None):
     """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted).
-    feeds_train_bn: y goes straight into a train-mode BatchNorm -> the bias gradient is exactly zero and is not computed."""
+    feeds_train_bn: y goes straight into a train-mode BatchNorm -> the bias gradient is exactly zero and is not computed.
+    cat: optional second input; the convolution runs on the channel concat (x, cat)  (U-Net skip connection)."""
     _require_cuda(x, weight)
     wf, wd = _packs(weight, kind, x.dim() - 2)
     if not _state["weight_grad"]:
         weight = weight.detach()
         bias = None if bias is None else bias.detach()
-    return _Conv.apply(x, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn))
+    return _Conv.apply(x, cat, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn))
 
 
 def conv(x, weight, bias, kind):

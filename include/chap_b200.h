@@ -91,6 +91,14 @@ int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, c
                   float* y, double* ch_sums, void* stream);
 /* dx = conv^T(dy) (data gradient), dx has the input shape */
 int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream);
+/* Data gradient of a convolution whose input was torch.cat([a, b], dim=1) (the U-Net skip connection, reference
+ * code/networks/unet.py:97-98): channels [0, ca) of dx go to dx_a (row stride ca), [ca, cin) to dx_b (row stride cin - ca),
+ * written by the tensor-core epilogue -- no separate split pass.  chap_conv_dgrad_split_supported() returns 1 when the
+ * shape takes that path (ca and cin - ca multiples of 16, tensor-core data gradient); otherwise the call fails with
+ * CHAP_ERR_BAD_ARG and the caller uses chap_conv_dgrad + chap_split_channels. */
+int chap_conv_dgrad_split_supported(const chap_conv_desc* d, int32_t ca);
+int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx_a, int32_t ca,
+                          float* dx_b, void* stream);
 /* dw (torch layout, overwritten) and dbias (nullable) from x and dy.
  * workspace: caller-owned scratch of chap_conv_wgrad_workspace_bytes(d) bytes (may be 0 -> NULL ok). */
 size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d);

@@ -68,15 +68,24 @@ def check(rec):
         name, a, kw, gout = e["name"], e["a"], e["kw"], e["gout"]
         if name == "conv_stats":
             x, w, b, kind = a[0], a[1], a[2], a[3]
+            cat = kw.get("cat")                                            # conv on the channel concat (x, cat)
             nd = x.dim() - 2
             xg = x.detach().clone().requires_grad_(x.dtype.is_floating_point)
             wg, bg = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
-            y = ops.conv_stats(xg, wg, bg, kind, False)[0]
-            gs = torch.autograd.grad(y, (xg, wg, bg), gout)
             xr, wr, br = d64(x).requires_grad_(True), d64(w).requires_grad_(True), d64(b).requires_grad_(True)
-            yr = _torch_conv(kind, nd, xr, wr, br)
-            gr = torch.autograd.grad(yr, (xr, wr, br), d64(gout))
-            berr = max(rel(u, v) for u, v in zip(gs[:2], gr[:2]))          # bias grads can be analytically ~0
+            if cat is None:
+                y = ops.conv_stats(xg, wg, bg, kind, False)[0]
+                gs = torch.autograd.grad(y, (xg, wg, bg), gout)
+                yr = _torch_conv(kind, nd, xr, wr, br)
+                gr = torch.autograd.grad(yr, (xr, wr, br), d64(gout))
+                berr = max(rel(u, v) for u, v in zip(gs[:2], gr[:2]))      # bias grads can be analytically ~0
+            else:
+                cg, cr = cat.detach().clone().requires_grad_(True), d64(cat).requires_grad_(True)
+                y = ops.conv_stats(xg, wg, bg, kind, False, cat=cg)[0]
+                gs = torch.autograd.grad(y, (xg, cg, wg), gout)
+                yr = _torch_conv(kind, nd, torch.cat([xr, cr], 1), wr, br)
+                gr = torch.autograd.grad(yr, (xr, cr, wr), d64(gout))
+                berr = max(rel(u, v) for u, v in zip(gs, gr))
             rows.append((i, "conv kind %d %s->%s" % (kind, tuple(x.shape), tuple(y.shape)), rel(y, yr), berr))
         elif name == "bn_act":
             y, bn, slope = a[0], a[1], a[2]

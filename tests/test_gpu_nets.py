@@ -155,7 +155,7 @@ def test_every_op_of_a_network_pass_matches_torch_fp64_on_identical_inputs(kind,
         rows = replay.check(replay.record(run))
     finally:
         ops.set_force_simt(False)
-    assert len(rows) > 70
+    assert len(rows) > 60          # (the skip-connection concats are part of the conv op)
     tol = 2e-5 if force_simt else 3e-3            # fp32 CUDA-core kernels / TF32 tensor-core kernels (one layer)
     bad = [r for r in rows if r[2] > tol or r[3] > tol]
     assert len(bad) <= 1, bad[:5]

@@ -132,6 +132,31 @@ def test_conv_large_shapes_tensor_core(case):
     assert rel_err(sums[:cout], yd.sum(dims)) < 1e-4 and rel_err(sums[cout:], (yd * yd).sum(dims)) < 1e-4, "fused BN statistics"
 
 
+@pytest.mark.parametrize("case", [(2, 3, (40, 56), 16, 16, 16), (2, 12, (128, 128), 32, 32, 32), (2, 2, (16, 16), 128, 128, 128),
+                                  (2, 2, (12, 12), 16, 8, 16)])
+def test_conv_on_channel_concat_fused_split(case):
+    """conv(cat(a, b)): forward and the two data gradients written by the split epilogue (or the fallback split pass)."""
+    from chap_b200 import _lib
+    ops = _ops()
+    nd, n, sp, ca, cb, cout = case
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn((n, ca) + sp, generator=g).to(DEV)
+    b = torch.randn((n, cb) + sp, generator=g).to(DEV)
+    w = (torch.randn((cout, ca + cb, 3, 3), generator=g) / (9 * (ca + cb)) ** 0.5).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    ad, bd, wd, biasd = (t.double().requires_grad_(True) for t in (a, b, w, bias))
+    y_ref = F.conv2d(torch.cat([ad, bd], 1), wd, biasd, padding=1)
+    gy = torch.randn(y_ref.shape, generator=g).to(DEV)
+    refs = torch.autograd.grad(y_ref, (ad, bd, wd), gy.double())
+    ag, bg, wg = ops.cl(a).requires_grad_(True), ops.cl(b).requires_grad_(True), w.clone().requires_grad_(True)
+    y, _ = ops.conv_stats(ag, wg, bias, _lib.CONV_K3, True, cat=bg)
+    outs = torch.autograd.grad(y, (ag, bg, wg), ops.cl(gy))
+    torch.cuda.synchronize()
+    assert rel_err(y, y_ref) < CONV_TOL
+    for name, o, r in zip(("d/da", "d/db", "d/dw"), outs, refs):
+        assert o.shape == r.shape and rel_err(o, r) < CONV_TOL, name
+
+
 @pytest.mark.parametrize("nd,train,with_res,drop", list(itertools.product([2, 3], [True, False], [False, True], ["none", "nc", "el"])))
 def test_bn_act_fwd_bwd(nd, train, with_res, drop):
     ops = _ops()
