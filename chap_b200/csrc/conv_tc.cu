@@ -40,9 +40,11 @@ struct TcParams {
     int mode;                     // 0: stride-1 conv; 1: transposed k2 s2 forward (one GEMM, N = taps * Cout, scatter epilogue);
                                   // 2: its 2D data gradient (4-tap gather of dy through the [2C, W, 2, H, N] view)
     int up_c;                     // mode 1: Cout (columns per tap); mode 2: channels of dy
-    int debug;                    // CHAP_TC_DEBUG bit mask (profiling experiments): 1 no MMAs, 2 no A loads, 4 no stores/statistics
+    int epi_groups;               // 1 or 2 groups of 4 epilogue warps (blockDim = 64 + 128 * groups)
+    int cps;                      // k chunks per pipeline stage (1, 2 or 4): fewer, fatter stages for the deep layers
+    int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
-    uint32_t a_stage_bytes, b_stage_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
+    uint32_t a_stage_bytes, b_stage_bytes, a_chunk_bytes, b_chunk_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
     float* out;                   // channels [0, ca), row stride ca
     float* out_b;                 // channels [ca, n_total), row stride n_total - ca (dgrad of a channel concat), or nullptr
     int ca;
@@ -50,9 +52,19 @@ struct TcParams {
     double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
 };
 
-constexpr int kTcThreads = 320;            // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kTcThreadsMax = 320;         // TMA warp, MMA warp, 1 or 2 groups of 4 epilogue warps
+// Profiling experiments (CHAP_TC_DEBUG bit mask: 1 no MMAs, 2 no A loads, 4 no stores / statistics, 8 no tcgen05.ld,
+// 16 polling waits, 32 plain arrives instead of commits) are compiled in only with -DCHAP_TC_DEBUG_HOOKS: the
+// single-warp issue loops are latency-bound and every extra branch costs.
+#ifdef CHAP_TC_DEBUG_HOOKS
+#define TC_DBG(bit) (p.debug & (bit))
 #define TC_WAIT(bar, par) do { if (p.debug & 16) mbar_poll(bar, par); else mbar_wait(bar, par); } while (0)
 #define TC_COMMIT(bar) do { if (p.debug & 32) mbar_arrive(bar); else tc_commit(bar); } while (0)
+#else
+#define TC_DBG(bit) false
+#define TC_WAIT(bar, par) mbar_wait(bar, par)
+#define TC_COMMIT(bar) tc_commit(bar)
+#endif
 
 // Column sums (and sums of squares) of a 32-row x 16-column register tile (row = lane) through a warp-private padded
 // shared-memory scratch: 16 conflict-free stores and 16 conflict-free loads per lane instead of a 62-shuffle butterfly
@@ -111,8 +123,11 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
     const uint32_t a_lo0 = ((smem_u32(a_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t b_lo0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
+    const uint32_t a_chunk = p.a_chunk_bytes >> 4, b_chunk = p.b_chunk_bytes >> 4;   // one k chunk inside a stage
     const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4;
     const uint32_t b_ky = p.b_resident ? 3u * (uint32_t)p.kchunks * b_box : b_box;     // resident layout is [tap][kchunk]
+    const uint32_t b_step = p.b_resident ? b_box : b_chunk;                            // next k chunk of the same tap
+    const int stage_iters = p.kchunks / p.cps;
     if (p.b_resident) TC_WAIT(b_full, 0);
     int s = 0; uint32_t ph = 0;
     uint32_t a_lo = a_lo0, b_lo_s = b_lo0;
@@ -127,22 +142,28 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
         for (int grp = 0; grp < groups; ++grp) {
             // reuse mode: grp = (kz, kx) and the stage serves taps ((kz * 3 + ky) * 3 + kx), ky = 0..2
             const int tap0 = NKY == 3 ? (grp / 3) * 9 + (grp % 3) : grp;
-            for (int kci = 0; kci < p.kchunks; ++kci) {
+            uint32_t b_res = b_lo0 + (uint32_t)(tap0 * p.kchunks) * b_box;             // resident weights of this tap, k chunk 0
+            for (int it = 0; it < stage_iters; ++it) {
                 TC_WAIT(&full[s], ph);
                 tc_fence_after();
-                const uint32_t b_lo = p.b_resident ? b_lo0 + (uint32_t)(tap0 * p.kchunks + kci) * b_box : b_lo_s;
                 if (elect_one()) {
+                    uint32_t a_c = a_lo, b_c = p.b_resident ? b_res : b_lo_s;
+                    for (int c = 0; c < p.cps && !TC_DBG(1); ++c) {
 #pragma unroll
-                    for (int ky = 0; ky < NKY && !(p.debug & 1); ++ky) {
+                        for (int ky = 0; ky < NKY; ++ky) {
 #pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k)
-                            tc_mma_tf32_lh(d_tmem, a_lo + (uint32_t)ky * a_ky + 2u * k, hi, b_lo + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
-                                           (ky | k) == 0 ? accum : 1u);
+                            for (int k = 0; k < KSTEPS; ++k)
+                                tc_mma_tf32_lh(d_tmem, a_c + (uint32_t)ky * a_ky + 2u * k, hi, b_c + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
+                                               (ky | k) == 0 ? accum : 1u);
+                        }
+                        accum = 1;
+                        a_c += a_chunk; b_c += b_step;
                     }
                     TC_COMMIT(&empty[s]);
                 }
                 __syncwarp();
                 accum = 1;
+                b_res += (uint32_t)p.cps * b_box;
                 a_lo += a_stage; b_lo_s += b_stage;
                 if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo_s = b_lo0; }
             }
@@ -155,7 +176,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
 // two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
 // tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreadsMax)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -177,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], p.n_buf == 2 ? 4 : 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.n_buf == 2 || p.epi_groups == 1) ? 4 : 8); }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -187,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 16 * p.nt; i += 256) red[i] = 0.f;
+        for (int i = threadIdx.x - 64; i < p.epi_groups * 8 * p.nt; i += p.epi_groups * 128) red[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -217,23 +238,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.reuse) { kx = grp % 3; kz = grp / 3; ky = 0; }                 // box origin one row above the tile
                 else if (p.ksz == 3) { kx = grp % 3; ky = (grp / 3) % 3; kz = grp / 9; }
                 else { kx = ky = kz = p.pad; }                                        // 1x1: pad = 0
-                for (int kci = 0; kci < p.kchunks; ++kci) {
+                for (int kc0 = 0; kc0 < p.kchunks; kc0 += p.cps) {
                     TC_WAIT(&empty[s], ph ^ 1);
                     if (elect_one()) {
-                        uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
                         const uint32_t nb = p.b_resident ? 0u : (p.reuse ? 3u : 1u);
-                        mbar_expect_tx(&full[s], ((p.debug & 2) ? 0u : p.a_box_bytes) + nb * p.b_box_bytes);
-                        if (p.debug & 2) {}
-                        else if (p.mode == 2) tma_load_5d(a_dst, &tmA, &full[s], (grp & 1) * p.up_c + kci * p.kc, w0, grp >> 1, h0, img);
-                        else if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
-                        else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
-                        if (!p.b_resident) {
-                            uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
-                            if (p.reuse) {
-                                for (int q = 0; q < 3; ++q)
-                                    tma_load_2d(b_dst + (size_t)q * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + q) * 3 + kx) * p.n_total + n0);
-                            } else {
-                                tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, grp * p.n_total + n0);
+                        mbar_expect_tx(&full[s], (uint32_t)p.cps * ((TC_DBG(2) ? 0u : p.a_box_bytes) + nb * p.b_box_bytes));
+                        for (int c = 0; c < p.cps; ++c) {
+                            const int kci = kc0 + c;
+                            uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes + (size_t)c * p.a_chunk_bytes;
+                            if (TC_DBG(2)) {}
+                            else if (p.mode == 2) tma_load_5d(a_dst, &tmA, &full[s], (grp & 1) * p.up_c + kci * p.kc, w0, grp >> 1, h0, img);
+                            else if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
+                            else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
+                            if (!p.b_resident) {
+                                uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes + (size_t)c * p.b_chunk_bytes;
+                                if (p.reuse) {
+                                    for (int q = 0; q < 3; ++q)
+                                        tma_load_2d(b_dst + (size_t)q * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + q) * 3 + kx) * p.n_total + n0);
+                                } else {
+                                    tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, grp * p.n_total + n0);
+                                }
                             }
                         }
                     }
@@ -260,15 +284,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* red_s = red + (size_t)((warp - 2) * 2 + 0) * p.nt;
         float* red_q = red + (size_t)((warp - 2) * 2 + 1) * p.nt;
         const int cb = p.n_total - p.ca;
-        const bool alternate = p.n_buf == 2;
-        const int c_begin = alternate ? 0 : eg * (p.nt >> 1), c_end = alternate ? p.nt : c_begin + (p.nt >> 1);
-        const int buf = alternate ? eg : 0;
-        float* scratch = red + (size_t)16 * p.nt + (size_t)(warp - 2) * (32 * 17);   // warp-private transpose scratch
+        // two groups: with two accumulators group e owns accumulator e (tiles j = e, e + 2, ...), with one they split its columns;
+        // one group: all tiles, accumulators alternating
+        const bool two = p.epi_groups == 2;
+        const bool alternate = two && p.n_buf == 2;
+        const bool colsplit = two && p.n_buf == 1;
+        const int c_begin = colsplit ? eg * (p.nt >> 1) : 0, c_end = colsplit ? c_begin + (p.nt >> 1) : p.nt;
+        float* scratch = red + (size_t)p.epi_groups * 8 * p.nt + (size_t)(warp - 2) * (32 * 17);   // warp-private transpose scratch
         const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;     // parameters may sit at any 4-byte offset of an arena
-        uint32_t use = 0;
+        int jj = alternate ? eg : 0;                                   // index of the tile among this CTA's tiles
         TileIter ti;
         for (ti.init(blockIdx.x + (alternate ? eg * (int)gridDim.x : 0), (alternate ? 2 : 1) * (int)gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d);
-             ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), ++use) {
+             ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), jj += alternate ? 2 : 1) {
+            const int buf = p.n_buf == 2 ? (jj & 1) : 0;
+            const uint32_t use = p.n_buf == 2 ? (uint32_t)(jj >> 1) : (uint32_t)jj;
             const int ow = ti.tx * p.tw + dx, oh = ti.ty * p.th + dy, od = ti.tz * p.td + dz;
             const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
             const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
@@ -277,7 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * p.nt);
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float v[16];
-                if (!(p.debug & 8)) tc_ld16(t_addr + (uint32_t)c0, v);
+                if (!TC_DBG(8)) tc_ld16(t_addr + (uint32_t)c0, v);
                 else {
 #pragma unroll
                     for (int j4 = 0; j4 < 16; ++j4) v[j4] = 0.f;
@@ -304,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + bias0 + j4);
                     }
                 }
-                if (valid && !(p.debug & 4)) {
+                if (valid && !TC_DBG(4)) {
                     const int gc = n0 + c0;
                     float* dst;
                     if (p.mode == 1) {
@@ -321,18 +350,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j4 = 0; j4 < 16; j4 += 4)
                         *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
                 }
-                if (p.stats && !(p.debug & 4)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
+                if (p.stats && !TC_DBG(4)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
             }
         }
         if (p.stats) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps only
+            asm volatile("bar.sync 1, %0;" ::"r"(p.epi_groups * 128) : "memory");   // the epilogue warps only
             const int e = threadIdx.x - 64;
             const int n_ch = p.mode == 1 ? p.up_c : p.n_total, ch_base = p.mode == 1 ? 0 : n0, n_mine = p.mode == 1 ? p.up_c : p.nt;
             double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * n_ch;
-            for (int c = e; c < n_mine; c += 256) {
+            for (int c = e; c < n_mine; c += p.epi_groups * 128) {
                 float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
+                for (int w = 0; w < p.epi_groups * 4; ++w) { a += red[(size_t)(w * 2) * p.nt + c]; b += red[(size_t)(w * 2 + 1) * p.nt + c]; }
                 atomicAdd(slot + ch_base + c, (double)a);
                 atomicAdd(slot + n_ch + ch_base + c, (double)b);
             }
@@ -461,21 +489,49 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.b_resident = p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
     if (p.reuse) {
         p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
-        p.a_stage_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
-        p.b_stage_bytes = 3u * p.b_box_bytes;
+        p.a_chunk_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
+        p.b_chunk_bytes = 3u * p.b_box_bytes;
     } else {
-        p.a_stage_bytes = 128u * p.kc * 4u;                              // always room for 128 rows
+        p.a_chunk_bytes = 128u * p.kc * 4u;                              // always room for 128 rows
         p.a_box_bytes = (uint32_t)(p.tw * p.th * p.td) * p.kc * 4u;
-        p.b_stage_bytes = (p.b_box_bytes + 1023u) & ~1023u;
+        p.b_chunk_bytes = (p.b_box_bytes + 1023u) & ~1023u;
     }
-    const size_t stage = (size_t)p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    // CTAs per SM.  Measured (16 -> 16 @ 256^2, b12): 2 CTAs x 6 stages 45 us, 3 CTAs 50 us, 4 CTAs x 3 stages 61 us -- a tile costs
+    // ~1 us of scalar work in the MMA warp AND ~2 us of load -> MMA -> commit round trip per ring slot, so more CTAs with
+    // shallower rings gain nothing.  CHAP_TC_CTAS / CHAP_TC_EPI override for experiments.
+    int ctas_per_sm = 2;
+    if (getenv("CHAP_TC_CTAS")) ctas_per_sm = atoi(getenv("CHAP_TC_CTAS"));
+    if (ctas_per_sm > 2 && p.nt > 64) ctas_per_sm = 2;
     const size_t fixed = p.b_resident ? p.b_area_bytes : 0u;
-    int stages = (int)((96 * 1024 - fixed) / stage);
-    const int iters = (p.reuse ? p.taps / 3 : p.taps) * p.kchunks;
-    const int ctas_per_sm = 2;
-    int grid_x = p.tiles_total < kNumSMs * ctas_per_sm ? p.tiles_total : kNumSMs * ctas_per_sm;
-    if (getenv("CHAP_NO_PERSIST")) grid_x = p.tiles_total;
-    if (getenv("CHAP_TC_GRID")) grid_x = atoi(getenv("CHAP_TC_GRID")) < p.tiles_total ? atoi(getenv("CHAP_TC_GRID")) : p.tiles_total;
+    const size_t chunk_bytes = (size_t)p.a_chunk_bytes + (p.b_resident ? 0u : p.b_chunk_bytes);
+    int grid_x = 0;
+    size_t extras = 0, budget = 0;
+    for (;; --ctas_per_sm) {
+        p.epi_groups = ctas_per_sm > 2 ? 1 : 2;
+        if (getenv("CHAP_TC_EPI")) p.epi_groups = atoi(getenv("CHAP_TC_EPI")) == 1 ? 1 : 2;
+        if (ctas_per_sm > 3 && p.epi_groups == 2) ctas_per_sm = 3;      // register file: 3 x 320 threads x 64 registers
+        grid_x = p.tiles_total < kNumSMs * ctas_per_sm ? p.tiles_total : kNumSMs * ctas_per_sm;
+        if (getenv("CHAP_NO_PERSIST")) grid_x = p.tiles_total;
+        if (getenv("CHAP_TC_GRID")) grid_x = atoi(getenv("CHAP_TC_GRID")) < p.tiles_total ? atoi(getenv("CHAP_TC_GRID")) : p.tiles_total;
+        extras = 1024 + 256 + (size_t)p.epi_groups * (8 * p.nt + 4 * 32 * 17) * sizeof(float);   // alignment slack, barriers, epilogue scratch
+        // with <= 148 CTAs in the grid a CTA may use a whole SM's shared memory
+        const size_t per_cta = (long)grid_x * (N / p.nt) <= kNumSMs ? 224 * 1024 : (size_t)(226 * 1024) / ctas_per_sm;
+        budget = per_cta > extras + fixed ? per_cta - extras - fixed : 0;
+        if (budget >= 3 * chunk_bytes || ctas_per_sm <= 2) break;       // at least three pipeline stages, else fewer CTAs per SM
+    }
+    CHAP_REQUIRE(budget >= chunk_bytes, CHAP_ERR_BAD_ARG, "tc_conv: tile does not fit shared memory");
+    // k chunks per pipeline stage.  The MMA warp pays ~0.4 us of scalar work per stage (measured), which dominates the deep
+    // layers (K = 9 x 256 in 32-channel chunks = 72 stages of 4 MMAs per tile): fuse 2 or 4 chunks into one stage when at
+    // least three such stages fit.
+    p.cps = 1;
+    const int cps_max = getenv("CHAP_TC_CPS") ? atoi(getenv("CHAP_TC_CPS")) : 4;
+    for (int c : {4, 2}) {
+        if (c <= cps_max && p.kchunks % c == 0 && 3 * c * chunk_bytes <= budget) { p.cps = c; break; }
+    }
+    p.a_stage_bytes = p.cps * p.a_chunk_bytes; p.b_stage_bytes = p.cps * p.b_chunk_bytes;
+    const size_t stage = p.cps * chunk_bytes;
+    int stages = (int)(budget / stage);
+    const int iters = (p.reuse ? p.taps / 3 : p.taps) * (p.kchunks / p.cps);
     const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
     if (stages > 6) stages = 6;
     if (stages > stage_uses) stages = (int)stage_uses;
@@ -485,7 +541,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : N; p.bias = bias; p.stats = ch_sums;
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
-    const size_t smem = 1024 + (size_t)stages * stage + fixed + (2 * stages + 5) * sizeof(uint64_t) + 16 + ((size_t)16 * p.nt + 8 * 32 * 17) * sizeof(float);
+    const size_t smem = (size_t)stages * stage + fixed + extras;
+    static_assert(2 * 6 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
@@ -515,14 +572,14 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         CHAP_TRY(make_tensor_map(&tmB, wp, 2, wd, ws, wb, p.kc));
     }
     static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : N) * sizeof(double), st));
     const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows),
                       2.0 * rows * g.cin * g.cout * g.taps,
                       4.0 * ((double)g.in_rows * g.cin + (double)g.out_rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
-    conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+    conv_tc_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("conv_tc_kernel"));
     return 1;
 }
