@@ -5,8 +5,8 @@
 // 2D, 26 in 3D); among components of equal size the one labelled first wins (np.argmax over np.bincount), i.e. the
 // component whose first voxel comes first in scan order.  The reference does this on the host with one D2H/H2D
 // round trip and 72 skimage calls per iteration; here it is a lock-free union-find on the label map itself:
-//   1. parent[v] = v
-//   2. every voxel unites with its "forward" neighbours of the SAME class (4 of 8 in 2D, 13 of 26 in 3D);
+//   1. parent[v] = first voxel of v's horizontal run inside its warp (ballot, no atomics)
+//   2. run boundaries unite with the SAME-class neighbours of the previous row / plane (and across warp boundaries);
 //      roots are always linked towards the smaller index, so a component's root is its first voxel in scan order
 //   3. size[root] += 1 for every foreground voxel; best[n][c] = max over roots of (size << 32 | ~root)
 //      -> largest size, ties to the smallest root = first labelled component
@@ -37,30 +37,68 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(256) cc_init_kernel(int* parent, int* size, unsigned long long* best, int64_t total, int nbest) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        parent[i] = (int)i; size[i] = 0;
-        if (i < nbest) best[i] = 0ull;
+// Step 1+: parent[v] = first voxel of v's run inside its warp (32 consecutive voxels of a row): horizontal connectivity is
+// resolved by a ballot instead of atomics, so the union phase only touches run boundaries.
+__global__ void __launch_bounds__(256)
+cc_init_kernel(const int64_t* __restrict__ seg, int* parent, int* size, unsigned long long* best, int W, int64_t total, int nbest) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (total + stride - 1) / stride;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = 0; r < rounds; ++r, i += stride) {            // whole warps iterate together (ballot)
+        const bool in = i < total;
+        const int64_t c = in ? seg[i] : 0;
+        const bool left_same = in && c != 0 && lane > 0 && (i % W) != 0 && seg[i - 1] == c;
+        const unsigned conn = __ballot_sync(0xffffffffu, left_same);
+        if (in) {
+            const unsigned starts = ~conn & (0xffffffffu >> (31 - lane));      // run starts at or before this lane (bit 0 always set)
+            const int s = 31 - __clz(starts);
+            parent[i] = (int)i - (lane - s);
+            size[i] = 0;
+            if (i < nbest) best[i] = 0ull;
+        }
     }
 }
 
+// Step 2: unions with the previous row / plane, only where the connection is not already implied by a horizontal neighbour:
+//   * up (x, y-1) unless the left voxel is in my run AND up-left is the same class (then the left voxel carries the link);
+//   * the diagonals only when up is a different class, and only from the end of the run that touches them.
 __global__ void __launch_bounds__(256)
 cc_unite_kernel(const int64_t* __restrict__ seg, int* parent, int nd, int D, int H, int W, int64_t total) {
     const int64_t vol = (int64_t)D * H * W;
+    const int lane = threadIdx.x & 31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = seg[i];
         if (c == 0) continue;
         const int64_t r = i % vol;
         const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((int64_t)W * H));
-        // forward half of the neighbourhood: (dz, dy, dx) lexicographically > (0, 0, 0)
-        for (int dz = 0; dz <= (nd == 3 ? 1 : 0); ++dz)
-            for (int dy = (dz == 0 ? 0 : -1); dy <= 1; ++dy)
-                for (int dx = ((dz == 0 && dy == 0) ? 1 : -1); dx <= 1; ++dx) {
-                    const int xx = x + dx, yy = y + dy, zz = z + dz;
-                    if (xx < 0 || xx >= W || yy < 0 || yy >= H || zz >= D) continue;
-                    const int64_t j = i + ((int64_t)dz * H + dy) * W + dx;
-                    if (seg[j] == c) uf_unite(parent, (int)i, (int)j);
-                }
+        const bool left_same = x > 0 && seg[i - 1] == c;
+        const bool right_same = x < W - 1 && seg[i + 1] == c;
+        if (left_same && lane == 0) uf_unite(parent, (int)i, (int)(i - 1));      // runs that continue across a warp boundary
+        if (y > 0) {
+            const int64_t u = i - W;
+            const bool up = seg[u] == c, ul = x > 0 && seg[u - 1] == c, ur = x < W - 1 && seg[u + 1] == c;
+            if (up) { if (!(left_same && ul)) uf_unite(parent, (int)i, (int)u); }
+            else {
+                if (ul && !left_same) uf_unite(parent, (int)i, (int)(u - 1));
+                if (ur && !right_same) uf_unite(parent, (int)i, (int)(u + 1));
+            }
+        }
+        if (nd == 3 && z > 0) {
+            const int64_t b = i - (int64_t)W * H;
+            const bool below = seg[b] == c;
+            if (below) { if (!(left_same && seg[b - 1] == c)) uf_unite(parent, (int)i, (int)b); }
+            else {
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dx == 0 && dy == 0) continue;
+                        const int xx = x + dx, yy = y + dy;
+                        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+                        const int64_t j = b + (int64_t)dy * W + dx;
+                        if (seg[j] == c) uf_unite(parent, (int)i, (int)j);
+                    }
+            }
+        }
     }
 }
 
@@ -123,7 +161,7 @@ extern "C" int chap_largest_cc(const int64_t* seg, int32_t nd, int32_t n, int32_
     int* size = parent + total;
     cudaStream_t st = S(stream);
     const int grid = grid_for(total, 256 * 2);
-    cc_init_kernel<<<grid, 256, 0, st>>>(parent, size, best, total, n * n_classes);
+    cc_init_kernel<<<grid, 256, 0, st>>>(seg, parent, size, best, w, total, n * n_classes);
     CHAP_TRY(launched("cc_init_kernel"));
     cc_unite_kernel<<<grid, 256, 0, st>>>(seg, parent, nd, d, h, w, total);
     CHAP_TRY(launched("cc_unite_kernel"));

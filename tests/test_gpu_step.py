@@ -154,6 +154,9 @@ def test_largest_cc_kernel_matches_host_oracle():
         assert got.dtype == torch.float32 and torch.equal(got, want), shape
     _, lab = _batch2d(6, 48)
     assert torch.equal(ops.largest_cc(lab.to(DEV), 4).cpu(), L.largest_cc_labels(lab, 4))
+    _, lab = _batch2d(4, 256)                                            # large blobs: long runs, heavy root contention
+    lab[0, 100:103, :] = 2                                               # a full-width bar crossing every warp boundary
+    assert torch.equal(ops.largest_cc(lab.to(DEV), 4).cpu(), L.largest_cc_labels(lab, 4))
 
 
 def test_cuda_graph_trainer_equals_eager_trainer():
