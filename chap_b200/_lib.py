@@ -74,6 +74,8 @@ SIGNATURES = {
     "chap_argmax": (I, [P, P, L, I, P, P]),
     "chap_dice_ce_fwd": (I, [P, P, I, P, I, I, L, I, P, P]),
     "chap_dice_ce_bwd": (I, [P, P, I, P, I, I, L, I, P, I, P, P]),
+    "chap_mix_loss_finalize": (I, [P, P, I, F, F, P, P]),
+    "chap_mix_loss_coef": (I, [P, P, I, F, F, P, P, P, P]),
     "chap_consistency_fwd": (I, [P, P, P, I, L, I, P, P]),
     "chap_consistency_bwd": (I, [P, P, P, I, L, I, P, P, P]),
     "chap_patch_score": (I, [P, P, P, I, I, I, I, I, I, P, P]),

@@ -360,6 +360,60 @@ extern "C" int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t
     return launched("dice_ce_bwd_kernel");
 }
 
+// ------------------------------------------------------------------ mix_loss scalar tail (code/train_ours_2D.py:198-216)
+// One thread block turns the two sets of masked sums into (loss_image, loss_patch, total); a second tiny kernel turns the
+// upstream gradient of those three scalars into the coefficient vectors of chap_dice_ce_bwd.  Replaces ~85 scalar torch
+// kernels per mix_loss call (each a ~2 us graph node).
+namespace chap {
+__device__ __forceinline__ void dice_ce_from_sums(const double* s, int c, double& dice, double& ce) {
+    double acc = 0.0;
+    for (int k = 0; k < c; ++k) acc += 1.0 - (2.0 * s[k] + 1e-10) / (s[c + k] + s[2 * c + k] + 1e-10);
+    dice = acc / c;
+    ce = s[3 * c] / (s[3 * c + 1] + 1e-16);
+}
+__global__ void mix_loss_finalize_kernel(const double* s_img, const double* s_patch, int c, float w_img, float w_patch, float* out3) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double d1, c1, d2, c2;
+    dice_ce_from_sums(s_img, c, d1, c1);
+    dice_ce_from_sums(s_patch, c, d2, c2);
+    d1 *= w_img; c1 *= w_img; d2 *= w_patch; c2 *= w_patch;
+    out3[0] = (float)((d1 + c1) / 2.0);
+    out3[1] = (float)((d2 + c2) / 2.0);
+    out3[2] = (float)(((d1 + d2) + (c1 + c2)) / 2.0);
+}
+// coef = (d loss / d inter[c], d loss / d (sum s^2 m)[c], d loss / d (sum CE m)) for one pass, given dL/d(dice) = dL/d(ce) = up
+__device__ __forceinline__ void dice_ce_coef(const double* s, int c, double up, float* coef, int k) {
+    if (k < c) {
+        const double den = s[c + k] + s[2 * c + k] + 1e-10;
+        coef[k] = (float)(up * (-2.0 / (c * den)));
+        coef[c + k] = (float)(up * ((2.0 * s[k] + 1e-10) / (c * den * den)));
+    }
+    if (k == 0) coef[2 * c] = (float)(up / (s[3 * c + 1] + 1e-16));
+}
+__global__ void mix_loss_coef_kernel(const double* s_img, const double* s_patch, int c, float w_img, float w_patch,
+                                     const float* g3, float* coef_img, float* coef_patch) {
+    const int k = threadIdx.x;
+    // loss_image = w_img (dice1 + ce1) / 2, loss_patch = w_patch (dice2 + ce2) / 2, total = their sum
+    dice_ce_coef(s_img, c, 0.5 * w_img * ((double)g3[0] + (double)g3[2]), coef_img, k);
+    dice_ce_coef(s_patch, c, 0.5 * w_patch * ((double)g3[1] + (double)g3[2]), coef_patch, k);
+}
+}  // namespace chap
+
+extern "C" int chap_mix_loss_finalize(const double* sums_img, const double* sums_patch, int32_t c, float w_img, float w_patch,
+                                      float* out3, void* stream) {
+    CHAP_REQUIRE(sums_img && sums_patch && out3 && c > 0 && c <= 64, CHAP_ERR_BAD_ARG, "mix_loss_finalize: bad argument");
+    mix_loss_finalize_kernel<<<1, 32, 0, S(stream)>>>(sums_img, sums_patch, c, w_img, w_patch, out3);
+    return launched("mix_loss_finalize_kernel");
+}
+
+extern "C" int chap_mix_loss_coef(const double* sums_img, const double* sums_patch, int32_t c, float w_img, float w_patch,
+                                  const float* grad_out3, float* coef_img, float* coef_patch, void* stream) {
+    CHAP_REQUIRE(sums_img && sums_patch && grad_out3 && coef_img && coef_patch && c > 0 && c <= 64, CHAP_ERR_BAD_ARG,
+                 "mix_loss_coef: bad argument");
+    mix_loss_coef_kernel<<<1, 64, 0, S(stream)>>>(sums_img, sums_patch, c, w_img, w_patch, grad_out3, coef_img, coef_patch);
+    return launched("mix_loss_coef_kernel");
+}
+
 extern "C" int chap_consistency_fwd(const float* logits, const float* target, const float* mask, int32_t dist, int64_t rows,
                                     int32_t c, double* sums, void* stream) {
     KernelTimer timer_("consistency_fwd", 0.0, 0.0, S(stream));

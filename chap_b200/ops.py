@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ConvDesc, check
 
-_state = {"epoch": 0, "bn_tracking": True, "weight_grad": True}
+_state = {"epoch": 0, "bn_tracking": True, "weight_grad": True, "bias_grad_none": False}
 
 
 def lib():
@@ -82,6 +82,19 @@ def no_weight_grad():
         yield
     finally:
         _state["weight_grad"] = old
+
+
+@contextlib.contextmanager
+def zero_bias_grad_as_none(flag=True):
+    """Inside: the analytically-zero gradient of a bias that feeds a train-mode BatchNorm is returned as None (autograd's
+    zero) instead of a zeros tensor -- saves a fill and an accumulate kernel per layer for optimisers that treat a missing
+    .grad as zero (FlatSGD)."""
+    old = _state["bias_grad_none"]
+    _state["bias_grad_none"] = bool(flag)
+    try:
+        yield
+    finally:
+        _state["bias_grad_none"] = old
 
 
 def set_force_simt(flag):
@@ -485,6 +498,48 @@ class _DiceCeSums(Function):
 def dice_ce_sums(logits, labels, mask, invert=False):
     """float64[3C+2]: inter[C], sum(s^2 m)[C], sum(t m)[C], sum(CE m), sum(m); differentiable in logits."""
     return _DiceCeSums.apply(logits, labels, mask, 1 if invert else 0)
+
+
+class _MixLoss(Function):
+    """mix_loss (code/train_ours_2D.py:198-216) as ONE autograd node: two fused masked Dice + CE passes over the logits, a
+    one-block kernel for the scalar tail, and in the backward one coefficient kernel + two passes accumulating into dlogits."""
+
+    @staticmethod
+    def forward(ctx, logits, img_l, patch_l, mask, w_img, w_patch):
+        _require_cuda(logits, img_l, patch_l, mask)
+        x = cl(logits)
+        n, c = x.shape[0], x.shape[1]
+        rps = x.numel() // (n * c)
+        lab1, dt1 = _label_arg(img_l)
+        lab2, dt2 = _label_arg(patch_l)
+        m = mask.to(torch.int64).contiguous()
+        if m.numel() != rps:
+            raise RuntimeError("mix_loss: mask must have one entry per spatial position")
+        sums = torch.empty(2, 3 * c + 2, dtype=torch.float64, device=x.device)
+        check(lib().chap_dice_ce_fwd(_p(x), _p(lab1), dt1, _p(m), 0, n, rps, c, _p(sums[0]), _stream()))
+        check(lib().chap_dice_ce_fwd(_p(x), _p(lab2), dt2, _p(m), 1, n, rps, c, _p(sums[1]), _stream()))
+        out = torch.empty(3, dtype=torch.float32, device=x.device)
+        check(lib().chap_mix_loss_finalize(_p(sums[0]), _p(sums[1]), c, w_img, w_patch, _p(out), _stream()))
+        ctx.save_for_backward(x, lab1, lab2, m, sums)
+        ctx.cfg = (dt1, dt2, n, rps, c, w_img, w_patch)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, lab1, lab2, m, sums = ctx.saved_tensors
+        dt1, dt2, n, rps, c, w_img, w_patch = ctx.cfg
+        g = dout.float().contiguous()
+        coef = torch.empty(2, 2 * c + 1, dtype=torch.float32, device=x.device)
+        check(lib().chap_mix_loss_coef(_p(sums[0]), _p(sums[1]), c, w_img, w_patch, _p(g), _p(coef[0]), _p(coef[1]), _stream()))
+        dl = torch.empty_like(x)
+        check(lib().chap_dice_ce_bwd(_p(x), _p(lab1), dt1, _p(m), 0, n, rps, c, _p(coef[0]), 0, _p(dl), _stream()))
+        check(lib().chap_dice_ce_bwd(_p(x), _p(lab2), dt2, _p(m), 1, n, rps, c, _p(coef[1]), 1, _p(dl), _stream()))
+        return dl, None, None, None, None, None
+
+
+def mix_loss_fused(logits, img_l, patch_l, mask, w_img, w_patch):
+    """float32[3] = (loss_image, loss_patch, total); see _MixLoss."""
+    return _MixLoss.apply(logits, img_l, patch_l, mask, float(w_img), float(w_patch))
 
 
 class _ConsistencySums(Function):

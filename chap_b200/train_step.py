@@ -201,7 +201,8 @@ class ChapTrainer:
                                         rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace,
                                         img_mask=img_mask, cw=cw)
         self.opt.zero_grad()                                                            # :381
-        loss.backward()                                                                 # :382
+        with ops.zero_bias_grad_as_none():
+            loss.backward()                                                             # :382
         self.opt.step(self.grad_scale)                                                  # :383
         aux["loss"] = loss.detach()
         return aux

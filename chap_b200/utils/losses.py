@@ -40,13 +40,8 @@ def mix_loss(output, img_l, patch_l, mask, l_weight=1.0, u_weight=0.5, unlab=Fal
     """code/train_ours_2D.py:198-216.  Returns (loss_image, loss_patch, (dice + ce) / 2) as fp32 scalars."""
     image_weight, patch_weight = (u_weight, l_weight) if unlab else (l_weight, u_weight)
     m = _spatial_mask(mask, output)
-    d1, c1 = masked_dice_ce(output, img_l, m, invert=False)
-    d2, c2 = masked_dice_ce(output, patch_l, m, invert=True)
-    d1, c1, d2, c2 = d1 * image_weight, c1 * image_weight, d2 * patch_weight, c2 * patch_weight
-    loss_image = (d1 + c1) / 2.0
-    loss_patch = (d2 + c2) / 2.0
-    total = ((d1 + d2) + (c1 + c2)) / 2.0
-    return loss_image.float(), loss_patch.float(), total.float()
+    out = ops.mix_loss_fused(output, img_l, patch_l, m, image_weight, patch_weight)      # one autograd node, two tiny scalar kernels
+    return out[0], out[1], out[2]
 
 
 class DiceLoss_bcp:

@@ -185,6 +185,13 @@ int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t label_dtyp
 int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t label_dtype, const int64_t* mask,
                      int32_t invert, int32_t n, int64_t rows_per_sample, int32_t c, const float* coef,
                      int32_t accumulate, float* dlogits, void* stream);
+/* Scalar tail of mix_loss (code/train_ours_2D.py:198-216) from the two chap_dice_ce_fwd results (image pass with mask m,
+ * patch pass with 1 - m): out3 = (loss_image, loss_patch, total) with loss_x = w_x (dice_x + ce_x) / 2, total = their sum.
+ * chap_mix_loss_coef turns the upstream gradient of out3 (float[3], device) into the two coef vectors of chap_dice_ce_bwd. */
+int chap_mix_loss_finalize(const double* sums_img, const double* sums_patch, int32_t c, float w_img, float w_patch,
+                           float* out3, void* stream);
+int chap_mix_loss_coef(const double* sums_img, const double* sums_patch, int32_t c, float w_img, float w_patch,
+                       const float* grad_out3, float* coef_img, float* coef_patch, void* stream);
 
 #define CHAP_DIST_KL 0
 #define CHAP_DIST_DICE 1

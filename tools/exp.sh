@@ -1,3 +1,3 @@
-timeout -k 5 300 python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "large or conv_fwd or concat" 2>&1 | tail -3
-L="'k3 16 16 12 256 256' 'k3 32 16 12 256 256' 'k3 32 32 12 128 128' 'k3 64 32 12 128 128' 'k3 64 64 12 64 64' 'k3 16 32 12 256 256'"
-for C in 2 3 4; do for E in 1 2; do echo "CTAS=$C EPI=$E"; eval CHAP_TC_CTAS=$C CHAP_TC_EPI=$E timeout -k 5 120 python tools/conv_bench.py $L; done; done
+timeout -k 5 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-timing > gpurun_out/b_plain.json 2> gpurun_out/b_plain.err || exit 1
+timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_r01_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-timing > gpurun_out/ncu_launch.log 2>&1
+tail -2 gpurun_out/ncu_launch.log; wc -l gpurun_out/launches_r01_final.csv
