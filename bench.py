@@ -18,6 +18,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("CHAP_TIMING_DETAIL", "1")          # per-shape kernel timer names (read by libchap_b200 at first use)
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -255,28 +256,48 @@ def run_gpu(args, w):
         d2h = 2 * n_unl * vox * 8 + 8                                   # two argmax maps (i64) for the host CC filter + the loss
         roof = None
         if fam:
-            top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-            name, f = top
+            # fam holds per-shape entries ("family:t9:k16:n16:256x256x1:r786432", CHAP_TIMING_DETAIL); families = their sums
+            families = {}
+            for k, v in fam.items():
+                f = families.setdefault(k.split(":")[0], dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+                for key in f:
+                    f[key] += v[key]
+            top_family = max(families.items(), key=lambda kv: kv[1]["ms"])[0]    # dominant kernel family of the step ...
+            name, f = max(((k, v) for k, v in fam.items() if k.split(":")[0] == top_family), key=lambda kv: kv[1]["ms"])   # ... its costliest layer shape
             per_launch_s = f["ms"] / 1e3 / max(f["launches"], 1)
-            tensor_bound = f["flops"] > 0 and name.startswith("conv")
+            tf32_peak = peaks["tensor"] / 2.0                                     # kind::tf32 runs at half the dense bf16 rate
+            intensity = f["flops"] / f["bytes"] if f["bytes"] > 0 else float("inf")
+            tensor_bound = f["flops"] > 0 and intensity > tf32_peak * 1e12 / (peaks["hbm"] * 1e9)
             if tensor_bound:
                 achieved = f["flops"] / f["launches"] / per_launch_s / 1e12
-                roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["tensor"], "traffic": None}
+                roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tf32_peak}
             else:
                 achieved = f["bytes"] / f["launches"] / per_launch_s / 1e9
                 roof = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm"], "traffic": None}
-            roof["peak_source"] = peaks["source"]
+                        "frac": achieved / peaks["hbm"]}
+            traffic_table = {}
+            tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+            if os.path.isfile(tpath):
+                traffic_table = json.load(open(tpath)).get("dram_bytes_per_launch", {})
+            roof["traffic"] = traffic_table.get(name)                              # ncu --set full: dram read + write bytes, per launch
+            roof["algorithmic_per_launch"] = {"flops": f["flops"] / f["launches"], "bytes": f["bytes"] / f["launches"],
+                                              "flop_per_byte": intensity}
+            roof["us_per_launch"] = per_launch_s * 1e6
+            roof["peak_source"] = peaks["source"] + ("; tensor peak = measured dense bf16 / 2 (tf32)" if tensor_bound else "")
+            roof["family"] = top_family
+            roof["family_share_of_step"] = families[top_family]["ms"] / (ms / args.steps)
             roof["launches_per_step"] = f["launches"]
             roof["share_of_step"] = f["ms"] / (ms / args.steps)
-            roof["families_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-            roof["families_gbps"] = {k: round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) for k, v in fam.items()
+            roof["families_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(families.items(), key=lambda kv: -kv[1]["ms"])}
+            roof["families_gbps"] = {k: round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) for k, v in families.items()
                                      if v["bytes"] > 0 and v["flops"] == 0 and v["ms"] > 0}
-            roof["families_launches"] = {k: v["launches"] for k, v in fam.items()}
+            roof["top_kernels_us"] = {k: [v["launches"], round(1e3 * v["ms"] / v["launches"], 1)]
+                                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:12]}
             roof["eager_ms_per_step"] = ms_eager
-            roof["note"] = ("per-kernel CUDA-event timing taken in an eager re-issue of the same iteration right after the "
-                            "timed graph replays; conv peak is the measured dense bf16 rate, TF32 runs at half of it by design")
+            roof["note"] = ("per-kernel CUDA-event timing on the launching stream, taken in an eager re-issue of the same iteration "
+                            "right after the timed graph replays; the dominant kernel is one layer shape of one kernel family; "
+                            "bound chosen by its algorithmic FLOP/byte against the measured machine balance")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
