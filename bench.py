@@ -337,7 +337,7 @@ def run_gpu(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="chap_b200", choices=["chap_b200", "reference"])
     ap.add_argument("--workload", default="unet2d", choices=sorted(WORKLOADS))
