@@ -12,7 +12,7 @@ static bool use_tc(const Geom& g, bool dgrad) {
 extern "C" size_t chap_conv_packed_elems(const chap_conv_desc* d) {
     Geom g{};
     if (resolve(d, g) != CHAP_OK) return 0;
-    return (size_t)g.taps * g.cin * g.cout;
+    return (size_t)g.taps * tc_pad16(g.cin) * tc_pad16(g.cout);      // room for the zero-padded tensor-core operand of thin heads
 }
 
 extern "C" int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream) {
@@ -21,11 +21,13 @@ extern "C" int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, f
     CHAP_REQUIRE(w != nullptr, CHAP_ERR_BAD_ARG, "pack_weights: w is NULL");
     if (w_fwd) {
         PackSpec p = fwd_pack(g);
-        CHAP_TRY(launch_pack(w, w_fwd, p.taps, p.K, p.N, p.sk, p.sn, p.flip, use_tc(g, false) ? 0 : 1, S(stream)));
+        const bool tc = use_tc(g, false);
+        CHAP_TRY(launch_pack(w, w_fwd, p.taps, p.K, p.N, p.sk, p.sn, p.flip, tc ? 0 : 1, S(stream), tc ? tc_pad16(p.K) : 0, tc ? tc_pad16(p.N) : 0));
     }
     if (w_dgrad) {
         PackSpec p = dgrad_pack(g);
-        CHAP_TRY(launch_pack(w, w_dgrad, p.taps, p.K, p.N, p.sk, p.sn, p.flip, use_tc(g, true) ? 0 : 1, S(stream)));
+        const bool tc = use_tc(g, true);
+        CHAP_TRY(launch_pack(w, w_dgrad, p.taps, p.K, p.N, p.sk, p.sn, p.flip, tc ? 0 : 1, S(stream), tc ? tc_pad16(p.K) : 0, tc ? tc_pad16(p.N) : 0));
     }
     return CHAP_OK;
 }

@@ -56,7 +56,9 @@ inline PackSpec dgrad_pack(const Geom& g) {
 }
 
 int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, int64_t sn, int flip,
-                int kn_order, cudaStream_t st);
+                int kn_order, cudaStream_t st, int Kp = 0, int Np = 0);
+// tensor-core operands need K, N >= 16: the 4- / 8-channel heads are zero-padded in the packed weight
+inline int tc_pad16(int c) { return c < 16 ? 16 : c; }
 int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st);
 int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
                int64_t sk, int64_t sn, cudaStream_t st);

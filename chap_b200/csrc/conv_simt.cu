@@ -18,24 +18,27 @@ __device__ __forceinline__ void decode_row(int64_t m, int D, int H, int W, int& 
 }
 
 // ---------------------------------------------------------------- weight packing
-// out[t][k][n] (kn_order = 1) or out[t][n][k] (kn_order = 0) = w[k*sk + n*sn + tmap(t)]
+// out[t][k][n] (kn_order = 1) or out[t][n][k] (kn_order = 0) = w[k*sk + n*sn + tmap(t)]; the packed operand may be
+// zero-padded to Kp x Np (tensor-core path of the 4- / 8-channel heads: the MMA needs K, N >= 16)
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out,
-                                    int taps, int K, int N, int64_t sk, int64_t sn, int flip, int kn_order) {
-    int64_t total = (int64_t)taps * K * N;
+                                    int taps, int K, int N, int Kp, int Np, int64_t sk, int64_t sn, int flip, int kn_order) {
+    int64_t total = (int64_t)taps * Kp * Np;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int t = (int)(i / ((int64_t)K * N));
-        int r = (int)(i % ((int64_t)K * N));
+        int t = (int)(i / ((int64_t)Kp * Np));
+        int r = (int)(i % ((int64_t)Kp * Np));
         int k, n;
-        if (kn_order) { k = r / N; n = r % N; } else { n = r / K; k = r % K; }
+        if (kn_order) { k = r / Np; n = r % Np; } else { n = r / Kp; k = r % Kp; }
         int ts = flip ? (taps - 1 - t) : t;
-        out[i] = w[k * sk + n * sn + ts];
+        out[i] = (k < K && n < N) ? w[k * sk + n * sn + ts] : 0.f;
     }
 }
 
 int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, int64_t sn, int flip,
-                int kn_order, cudaStream_t st) {
-    int64_t total = (int64_t)taps * K * N;
-    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, sk, sn, flip, kn_order);
+                int kn_order, cudaStream_t st, int Kp, int Np) {
+    if (Kp < K) Kp = K;
+    if (Np < N) Np = N;
+    int64_t total = (int64_t)taps * Kp * Np;
+    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, Kp, Np, sk, sn, flip, kn_order);
     return launched("pack_weights_kernel");
 }
 

@@ -37,6 +37,7 @@ struct TcParams {
     int stages, tmem_cols;
     int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
+    int n_real;                   // output channels that exist (< nt = 16 for the zero-padded 4- / 8-channel heads)
     int mode;                     // 0: stride-1 conv; 1: transposed k2 s2 forward (one GEMM, N = taps * Cout, scatter epilogue);
                                   // 2: its 2D data gradient (4-tap gather of dy through the [2C, W, 2, H, N] view)
     int up_c;                     // mode 1: Cout (columns per tap); mode 2: channels of dy
@@ -321,7 +322,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int ch0 = p.mode == 1 ? (n0 + c0) % p.up_c : c0;          // statistics slot (CTA-relative)
                 const int bias0 = p.mode == 1 ? ch0 : n0 + c0;
                 if (p.bias) {
-                    if (bias_vec) {
+                    if (p.n_real < 16) {                                // padded head: only n_real bias entries exist
+#pragma unroll
+                        for (int j4 = 0; j4 < 16; ++j4) if (j4 < p.n_real) v[j4] += __ldg(p.bias + j4);
+                    } else if (bias_vec) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + bias0);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -348,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int j4 = 0; j4 < 16; j4 += 4)
-                        *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                        if (j4 < p.n_real) *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
                 }
                 if (p.stats && !TC_DBG(4)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
             }
@@ -356,7 +360,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.stats) {
             asm volatile("bar.sync 1, %0;" ::"r"(p.epi_groups * 128) : "memory");   // the epilogue warps only
             const int e = threadIdx.x - 64;
-            const int n_ch = p.mode == 1 ? p.up_c : p.n_total, ch_base = p.mode == 1 ? 0 : n0, n_mine = p.mode == 1 ? p.up_c : p.nt;
+            const int n_ch = p.mode == 1 ? p.up_c : (p.n_real < p.n_total ? p.n_real : p.n_total), ch_base = p.mode == 1 ? 0 : n0;
+            const int n_mine = p.mode == 1 ? p.up_c : (p.n_real < p.nt ? p.n_real : p.nt);
             double* slot = p.stats + (size_t)(blockIdx.x % CHAP_STAT_SLOTS) * 2 * n_ch;
             for (int c = e; c < n_mine; c += p.epi_groups * 128) {
                 float a = 0.f, b = 0.f;
@@ -429,6 +434,11 @@ bool tc_supports(const Geom& g, bool dgrad) {
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     int K, N;
     tc_channels(g, dgrad, K, N);
+    // thin heads (Cout = 4 / 8), forward only: N zero-padded to 16 in the packed weight, 4 / 8 columns stored (16 -> 4 @ 12x256^2:
+    // 45 us vs 93 us on the CUDA cores).  The data gradient (K = 4 padded to 16: 16-byte TMA rows) measured 84 us vs 77 us on
+    // the CUDA cores and stays there.
+    static const bool no_heads = getenv("CHAP_NO_HEAD_TC") != nullptr;
+    if (g.kind == CHAP_CONV_K3 && !dgrad && !no_heads && (g.cout == 4 || g.cout == 8) && (g.cin == 16 || (g.cin % 32 == 0 && g.cin <= 256))) return true;
     if (!(K == 16 || K % 32 == 0)) return false;
     if (N < 16 || N % 16 != 0) return false;
     if (N > 256 && N % 256 != 0) return false;
@@ -459,10 +469,14 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     TcParams p{};
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD;
+    const int k_real = K, n_real = N;                    // thin heads: the MMA runs on operands zero-padded to 16
+    K = tc_pad16(K); N = tc_pad16(N);
     int w_taps = g.taps;                                  // taps in the packed weight operand [tap][N][K]
     if (g.kind == CHAP_CONV_UP2 && !dgrad) { p.mode = 1; p.up_c = g.cout; N = g.taps * g.cout; p.taps = 1; w_taps = 1; }
     if (g.kind == CHAP_CONV_UP2 && dgrad) { p.mode = 2; p.up_c = g.cout; p.ksz = 2; }
     CHAP_REQUIRE(!(p.mode && out_b), CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for the transposed convolution");
+    p.n_real = p.mode == 1 ? N : n_real;
+    CHAP_REQUIRE(p.n_real == N || !out_b, CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for padded heads");
     choose_box(p.W, p.H, p.D, p.tw, p.th, p.td);
     // Row-reuse mode for the activation-bound layers (few output channels): in-plane 128-pixel tile (tw x th, tw % 8 == 0)
     // and ONE TMA box with an h-halo (th + 2 rows) per (kz, kx); the three ky taps read it at row offsets ky * tw.
@@ -538,7 +552,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     p.stages = stages;
     p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
-    p.out = out; p.out_b = out_b; p.ca = out_b ? ca : N; p.bias = bias; p.stats = ch_sums;
+    p.out = out; p.out_b = out_b; p.ca = out_b ? ca : p.n_real; p.bias = bias; p.stats = ch_sums;
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
     const size_t smem = (size_t)stages * stage + fixed + extras;
@@ -548,7 +562,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[5], str[4]; uint32_t box[5];
-        const uint64_t C = (uint64_t)K;
+        const uint64_t C = (uint64_t)k_real;                 // a box wider than the tensor zero-fills (padded heads)
         if (p.mode == 2) {
             // dy [N, 2H, 2W, C] seen as [2C (kw, c), W, 2 (kh), H, N]: tap (kh, kw) of input pixel (h, w) is one box row
             dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
@@ -573,7 +587,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : N) * sizeof(double), st));
+    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real) * sizeof(double), st));
     const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows),
                       2.0 * rows * g.cin * g.cout * g.taps,
