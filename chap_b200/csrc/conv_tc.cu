@@ -177,7 +177,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
 // two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
 // tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
-__global__ void __launch_bounds__(kTcThreadsMax)
+__global__ void __launch_bounds__(kTcThreadsMax, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
