@@ -85,7 +85,9 @@ extern "C" int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, c
 extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
     Geom g{};
     if (resolve(d, g) != CHAP_OK) return 0;
-    return (size_t)2 * g.cout * sizeof(double);
+    // [2 * cout doubles for the bias gradient][pad to 256][taps * cin * cout floats: the tensor-core kernel accumulates the
+    // gradient in a [tap][M][N] layout with vector reductions, then a small kernel writes the torch layout]
+    return (((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255) + (size_t)g.taps * g.cin * g.cout * sizeof(float);
 }
 
 extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
@@ -101,7 +103,10 @@ extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const fl
     static const int thin_max = getenv("CHAP_THIN_MAX") ? atoi(getenv("CHAP_THIN_MAX")) : 0;
     const bool thin = g.kind == CHAP_CONV_K3 && g.cin % 4 == 0 && g.cout % 4 == 0 && g.cin * g.cout <= thin_max;
     if (g_force_simt.load() == 0 && tc_wgrad_supports(g) && !thin) {
-        handled = tc_wgrad(g, x, dy, dw, S(stream));
+        const size_t off = ((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255;
+        float* acc_ws = (workspace && workspace_bytes >= off + (size_t)g.taps * g.cin * g.cout * sizeof(float))
+                            ? reinterpret_cast<float*>(static_cast<char*>(workspace) + off) : nullptr;
+        handled = tc_wgrad(g, x, dy, dw, S(stream), acc_ws);
         if (handled < 0) return handled;
     }
     if (!handled) CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream)));

@@ -74,7 +74,9 @@ int thin_tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, co
                  double* ch_sums, cudaStream_t st);
 bool thin_tc_supports(const Geom& g, bool dgrad);
 // tensor-core weight gradient (wgrad_tc.cu): 1 handled, 0 unsupported shape, <0 error.  dw is overwritten.
-int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st);
+// acc_ws (nullable): taps * cin * cout floats of scratch; when given, the (non-swap) kernel reduces into a [tap][M][N] layout
+// with 128-bit vector reductions and a small kernel writes the torch layout afterwards.
+int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st, float* acc_ws = nullptr);
 bool tc_wgrad_supports(const Geom& g);
 
 int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_t st);

@@ -35,6 +35,7 @@ struct WgParams {
     int tg;                         // taps per CTA (reuse mode: (kz, kx) pairs per CTA, each pair = 3 ky taps)
     int up2;                        // 1: transposed k2 s2 conv (2D): the N operand is dy gathered per tap through its [2C, W, 2, H, N] view
     int swap;                       // 1 (reuse mode, cin <= 32): x is the M operand (M = 4 "ky" chunks x 32 ci, chunk stride tw rows), dy the N operand
+    int acc2;                       // experiment (CHAP_WG_ACC2): alternate K steps between two TMEM accumulators, summed in the epilogue
     int n_mma;                      // swap mode: MMA N = cout of this CTA rounded up to 16
     int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
     int b_rows;                     // rows (pixels) per x channel chunk in smem
@@ -44,7 +45,26 @@ struct WgParams {
     uint32_t a_stage_bytes, b_stage_bytes;
     int64_t s_co, s_ci;             // gradient strides in floats (torch layout), tap stride is 1
     float* dw;
+    float* acc;                     // nullable: [tap][cout (M)][cin (N)] accumulation scratch for 128-bit vector reductions
 };
+
+// red.global.add.v4.f32 (sm_90+): one L2 reduction for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// acc [tap][M][N] -> torch-layout gradient dw[m * s_co + n * s_ci + tap]
+__global__ void __launch_bounds__(256)
+wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dw, int taps, int M, int N, int64_t s_co, int64_t s_ci) {
+    const int64_t total = (int64_t)taps * M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // consecutive threads walk the torch layout's fastest index (tap) so that the writes coalesce
+        const int t = (int)(i % taps);
+        const int64_t r = i / taps;
+        const int n = (int)(r % N), m = (int)(r / N);
+        dw[(int64_t)m * s_co + (int64_t)n * s_ci + t] = acc[((int64_t)t * M + m) * N + n];
+    }
+}
 
 constexpr int kWgThreads = 192;
 
@@ -180,7 +200,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint32_t m_d = swap ? b_tap : a_lo, n_d = swap ? a_lo : b_tap;
                         const uint32_t m_hi = swap ? b_hi : a_hi, n_hi = swap ? a_hi : b_hi;
                         const uint32_t m_k = swap ? b_k : a_k, n_k = swap ? a_k : b_k;
-                        if ((ksteps & 7) == 0) {
+                        if ((ksteps & 7) == 0 && p.acc2) {
+                            const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;
+                            for (int k0 = 0; k0 < ksteps; k0 += 8) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    tc_mma_tf32_lh(d_tmem + ((k & 1) ? acc_stride : 0u), m_d + (uint32_t)k * m_k, m_hi, n_d + (uint32_t)k * n_k, n_hi, id,
+                                                   (uint32_t)((b | k0 | (k >> 1)) != 0));
+                                m_d += 8u * m_k; n_d += 8u * n_k;
+                            }
+                        } else if ((ksteps & 7) == 0) {
                             for (int k0 = 0; k0 < ksteps; k0 += 8) {
 #pragma unroll
                                 for (int k = 0; k < 8; ++k)
@@ -219,6 +248,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
                         float v[16];
                         tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * p.n_mma + c0), v);
+                        if (p.acc2) {
+                            float u[16];
+                            tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((p.tmem_cols >> 1) + ti * p.n_mma + c0), u);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += u[j];
+                        }
                         if (ci < p.cin) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
@@ -236,9 +271,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     float v[16];
                     tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ti * p.n_tile + c0), v);
                     if (valid && n0 + c0 < p.cin) {                 // columns beyond cin are the zero-filled channels
+                        if (p.acc) {
+                            float* a = p.acc + ((int64_t)tap * p.cout + m0 + row) * p.cin + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            atomicAdd(dst_row + (int64_t)(n0 + c0 + j) * p.s_ci + tap, v[j]);
+                            for (int j = 0; j < 16; j += 4) red_add_v4(a + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                atomicAdd(dst_row + (int64_t)(n0 + c0 + j) * p.s_ci + tap, v[j]);
+                        }
                     }
                 }
             }
@@ -275,7 +316,7 @@ static void choose_box8(int W, int H, int D, int& tw, int& th, int& td, int max_
             }
 }
 
-int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st) {
+int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st, float* acc_ws) {
     if (!tc_wgrad_supports(g)) return 0;
     CHAP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dw), CHAP_ERR_ALIGNMENT, "tc_wgrad: buffers must be 16-byte aligned");
     // Transposed k2 s2 convolution (2D): dW[ci][co][kh][kw] = sum_p x[p, ci] * dy[2p + (kh, kw), co] is the same GEMM with the
@@ -350,7 +391,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.swap = p.reuse && p.b_groups == 1 && getenv("CHAP_WG_NO_SWAP") == nullptr;
     p.n_mma = p.m_tile < 16 ? 16 : p.m_tile;
     const int cols_per_unit = p.swap ? p.n_mma : (p.reuse ? 3 : 1) * p.n_tile;
-    long max_splits = 4000000L / weights_pad;
+    // (measured with the 128-bit reduction path: 4 M elements is still the best budget, 8 M / 16 M are 5-15 % slower)
+    const long budget = getenv("CHAP_WG_BUDGET") ? atol(getenv("CHAP_WG_BUDGET")) : 4000000L;
+    long max_splits = budget / weights_pad;
     if (max_splits < 1) max_splits = 1;
     if (max_splits > p.blocks_total) max_splits = p.blocks_total;
     int best_tg = 1, best_ctas = -1, best_splits = 1, best_groups = units;
@@ -369,6 +412,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     int splits = best_splits;
     p.tg = tg;
     p.tmem_cols = 32; while (p.tmem_cols < tg * cols_per_unit) p.tmem_cols *= 2;
+    p.acc2 = p.swap && p.P % 64 == 0 && p.tmem_cols <= 256 && getenv("CHAP_WG_ACC2") != nullptr;
+    if (p.acc2) p.tmem_cols *= 2;
     const bool two_per_sm = p.tmem_cols <= 256 && 3 * stage <= 100 * 1024;
     int stages = (int)(((two_per_sm ? 100 : 200) * 1024 - 2048) / stage);
     if (stages > 8) stages = 8;
@@ -407,13 +452,20 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 +
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
-    CHAP_CUDA(cudaMemsetAsync(dw, 0, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
+    // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
+    p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
+    CHAP_CUDA(cudaMemsetAsync(p.acc ? p.acc : dw, 0, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
     const double rows = (double)(up2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
                       4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
     dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
     wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("wgrad_tc_kernel"));
+    if (p.acc) {
+        const int64_t total = (int64_t)g.taps * v.cin * v.cout;
+        wgrad_unpack_kernel<<<grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st>>>(p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci);
+        CHAP_TRY(launched("wgrad_unpack_kernel"));
+    }
     return 1;
 }
 
