@@ -81,7 +81,8 @@ typedef struct {
  * buffers (fewer colliding atomics); layout double[CHAP_STAT_SLOTS][2*cout], summed by chap_bn_finalize. */
 #define CHAP_STAT_SLOTS 16
 
-/* number of floats in one packed weight buffer (same for the fwd and the dgrad packing) */
+/* number of floats in one packed weight buffer (same for the fwd and the dgrad packing): taps * max(cin, 16) * max(cout, 16)
+ * -- channel counts below 16 are zero-padded for the tensor-core operands of the thin heads */
 size_t chap_conv_packed_elems(const chap_conv_desc* d);
 /* torch-layout weight -> packed forward operand and packed data-gradient operand (either may be NULL) */
 int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream);

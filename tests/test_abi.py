@@ -39,7 +39,8 @@ def test_bad_arguments_fail_loudly_without_touching_the_gpu():
     assert rc == -1
     assert b"nd must be 2 or 3" in lib.chap_last_error()
     assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(0, 3, 2, 4, 4, 4, 16, 32))) == 27 * 16 * 32
-    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(3, 2, 2, 1, 4, 4, 16, 8))) == 4 * 16 * 8
+    # channel counts below 16 are zero-padded to 16 in the packed operand (tensor-core path of the 4- / 8-channel heads)
+    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(3, 2, 2, 1, 4, 4, 16, 8))) == 4 * 16 * 16
 
 
 def test_ops_refuse_cpu_tensors():
