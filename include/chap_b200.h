@@ -101,7 +101,9 @@ int chap_conv_dgrad_split_supported(const chap_conv_desc* d, int32_t ca);
 int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx_a, int32_t ca,
                           float* dx_b, void* stream);
 /* dw (torch layout, overwritten) and dbias (nullable) from x and dy.
- * workspace: caller-owned scratch of chap_conv_wgrad_workspace_bytes(d) bytes (may be 0 -> NULL ok). */
+ * workspace: caller-owned scratch of chap_conv_wgrad_workspace_bytes(d) bytes: 2*cout doubles for the bias gradient plus
+ * taps*cin*cout floats in which the tensor-core kernel accumulates with 128-bit reductions before a small kernel writes the
+ * torch layout.  NULL / a smaller buffer is accepted when dbias is NULL (the kernel then reduces with scalar atomics). */
 size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d);
 int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                     void* workspace, size_t workspace_bytes, void* stream);
