@@ -42,6 +42,7 @@ struct TcParams {
                                   // 2: its 2D data gradient (4-tap gather of dy through the [2C, W, 2, H, N] view)
     int up_c;                     // mode 1: Cout (columns per tap); mode 2: channels of dy
     int epi_groups;               // 1 or 2 groups of 4 epilogue warps (blockDim = 64 + 128 * groups)
+    int colsplit;                 // two groups: 1 = both work on every tile, half the columns each; 0 = they alternate tiles
     int cps;                      // k chunks per pipeline stage (1, 2 or 4): fewer, fatter stages for the deep layers
     int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
@@ -58,10 +59,15 @@ constexpr int kTcThreadsMax = 320;         // TMA warp, MMA warp, 1 or 2 groups 
 // 16 polling waits, 32 plain arrives instead of commits) are compiled in only with -DCHAP_TC_DEBUG_HOOKS: the
 // single-warp issue loops are latency-bound and every extra branch costs.
 #ifdef CHAP_TC_DEBUG_HOOKS
+// timeline of CTA 0 (SM clock): 0 entry, 1 prologue done, 2 first smem stage full, 3 first accumulator full, 4 first tile stored,
+// 5 last tile stored, 6 statistics written, 7 before exit; read back with chap_debug_tc_trace()
+__device__ long long g_tc_trace[8];
+#define TC_TRACE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_tc_trace[i] = clock64(); } while (0)
 #define TC_DBG(bit) (p.debug & (bit))
 #define TC_WAIT(bar, par) do { if (p.debug & 16) mbar_poll(bar, par); else mbar_wait(bar, par); } while (0)
 #define TC_COMMIT(bar) do { if (p.debug & 32) mbar_arrive(bar); else tc_commit(bar); } while (0)
 #else
+#define TC_TRACE(i) do { } while (0)
 #define TC_DBG(bit) false
 #define TC_WAIT(bar, par) mbar_wait(bar, par)
 #define TC_COMMIT(bar) tc_commit(bar)
@@ -146,6 +152,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
             uint32_t b_res = b_lo0 + (uint32_t)(tap0 * p.kchunks) * b_box;             // resident weights of this tap, k chunk 0
             for (int it = 0; it < stage_iters; ++it) {
                 TC_WAIT(&full[s], ph);
+                if (j == 0 && grp == 0 && it == 0 && (threadIdx.x & 31) == 0) TC_TRACE(2);
                 tc_fence_after();
                 if (elect_one()) {
                     uint32_t a_c = a_lo, b_c = p.b_resident ? b_res : b_lo_s;
@@ -194,12 +201,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.nt;
+    if (threadIdx.x == 0) TC_TRACE(0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.n_buf == 2 || p.epi_groups == 1) ? 4 : 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.epi_groups == 2 && p.colsplit) ? 8 : 4); }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -215,6 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_TRACE(1);
     // reuse mode: one stage = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
     const int groups = p.reuse ? p.taps / 3 : p.taps;
 
@@ -288,8 +297,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // two groups: with two accumulators group e owns accumulator e (tiles j = e, e + 2, ...), with one they split its columns;
         // one group: all tiles, accumulators alternating
         const bool two = p.epi_groups == 2;
-        const bool alternate = two && p.n_buf == 2;
-        const bool colsplit = two && p.n_buf == 1;
+        // column split whenever the halves are whole 16-column chunks: both groups work on EVERY tile, which halves the
+        // epilogue latency of a tile (measured 0.9 us per 16-column chunk and warp: 7.2 us for nt = 128, on the critical path
+        // of the deep layers that have one tile per CTA); nt = 16 alternates tiles between the groups instead
+        const bool colsplit = two && p.colsplit;
+        const bool alternate = two && !colsplit;
         const int c_begin = colsplit ? eg * (p.nt >> 1) : 0, c_end = colsplit ? c_begin + (p.nt >> 1) : p.nt;
         float* scratch = red + (size_t)p.epi_groups * 8 * p.nt + (size_t)(warp - 2) * (32 * 17);   // warp-private transpose scratch
         const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;     // parameters may sit at any 4-byte offset of an arena
@@ -303,21 +315,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
             const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
             TC_WAIT(&tmem_full[buf], use & 1u);
+            if (jj == 0 && threadIdx.x == 64) TC_TRACE(3);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * p.nt);
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            // one 16-column chunk: +bias, store, BatchNorm statistics
+            auto process = [&](const uint32_t (&raw)[16], const int c0) {
                 float v[16];
-                if (!TC_DBG(8)) tc_ld16(t_addr + (uint32_t)c0, v);
-                else {
 #pragma unroll
-                    for (int j4 = 0; j4 < 16; ++j4) v[j4] = 0.f;
-                }
-                if (c0 + 16 >= c_end) {
-                    // every column of this warp's lanes is in registers: hand the accumulator back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-                }
+                for (int j4 = 0; j4 < 16; ++j4) v[j4] = TC_DBG(8) ? 0.f : __uint_as_float(raw[j4]);
                 // channel of this chunk's first column: the taps of a transposed conv share the Cout channels
                 const int ch0 = p.mode == 1 ? (n0 + c0) % p.up_c : c0;          // statistics slot (CTA-relative)
                 const int bias0 = p.mode == 1 ? ch0 : n0 + c0;
@@ -337,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + bias0 + j4);
                     }
                 }
-                if (valid && !TC_DBG(4)) {
+                if (valid && !TC_DBG(4) && !TC_DBG(128)) {
                     const int gc = n0 + c0;
                     float* dst;
                     if (p.mode == 1) {
@@ -354,8 +359,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j4 = 0; j4 < 16; j4 += 4)
                         if (j4 < p.n_real) *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
                 }
-                if (p.stats && !TC_DBG(4)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
+                if (p.stats && !TC_DBG(4) && !TC_DBG(64)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
+            };
+            // ping-pong: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed; after the fence of the last
+            // chunk every column of this warp's lanes is in registers and the accumulator goes back to the MMA warp
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            };
+            uint32_t ra[16], rb[16];
+            int c0 = c_begin;
+            tc_ld16_issue(t_addr + (uint32_t)c0, ra);
+            while (true) {
+                tc_ld16_fence(ra);
+                if (c0 + 16 < c_end) tc_ld16_issue(t_addr + (uint32_t)(c0 + 16), rb); else release();
+                process(ra, c0);
+                c0 += 16;
+                if (c0 >= c_end) break;
+                tc_ld16_fence(rb);
+                if (c0 + 16 < c_end) tc_ld16_issue(t_addr + (uint32_t)(c0 + 16), ra); else release();
+                process(rb, c0);
+                c0 += 16;
+                if (c0 >= c_end) break;
             }
+            if (threadIdx.x == 64) { if (jj == 0) TC_TRACE(4); TC_TRACE(5); }
         }
         if (p.stats) {
             asm volatile("bar.sync 1, %0;" ::"r"(p.epi_groups * 128) : "memory");   // the epilogue warps only
@@ -370,9 +398,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 atomicAdd(slot + n_ch + ch_base + c, (double)b);
             }
         }
+        if (threadIdx.x == 64) TC_TRACE(6);
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(7);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -534,6 +564,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         if (budget >= 3 * chunk_bytes || ctas_per_sm <= 2) break;       // at least three pipeline stages, else fewer CTAs per SM
     }
     CHAP_REQUIRE(budget >= chunk_bytes, CHAP_ERR_BAD_ARG, "tc_conv: tile does not fit shared memory");
+    p.colsplit = (p.nt >= 32 || p.n_buf == 1) && getenv("CHAP_TC_ALTERNATE") == nullptr ? 1 : 0;
+    if (p.n_buf == 1) p.colsplit = 1;
     // k chunks per pipeline stage.  The MMA warp pays ~0.4 us of scalar work per stage (measured), which dominates the deep
     // layers (K = 9 x 256 in 32-channel chunks = 72 stages of 4 MMAs per tile): fuse 2 or 4 chunks into one stage when at
     // least three such stages fit.
@@ -599,3 +631,10 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
 }
 
 }  // namespace chap
+
+#ifdef CHAP_TC_DEBUG_HOOKS
+extern "C" int chap_debug_tc_trace(long long* out8) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out8, chap::g_tc_trace, 8 * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
