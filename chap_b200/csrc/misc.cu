@@ -253,6 +253,10 @@ extern "C" int chap_sw_aggregate(const chap_sw_desc* d, const float* win, int32_
     CHAP_TRY(check_sw(d));
     CHAP_REQUIRE(win && label, CHAP_ERR_BAD_ARG, "sw_aggregate: NULL pointer");
     const int64_t nvox = (int64_t)d->vol[0] * d->vol[1] * d->vol[2];
+    const double n_win = (double)d->nwin[0] * d->nwin[1] * d->nwin[2];
+    // algorithmic bytes: every window's logits once + score (C floats), cnt, label (8 B) per voxel once
+    KernelTimer timer_("sw_aggregate", 0.0, 4.0 * n_win * d->patch[0] * d->patch[1] * d->patch[2] * d->c +
+                                                (double)nvox * ((score ? 4.0 * d->c : 0.0) + (cnt ? 4.0 : 0.0) + 8.0), S(stream));
     int grid = grid_for(nvox, 256);
     switch (d->c) {
         case 2: CHAP_REQUIRE(((uintptr_t)win & 7u) == 0, CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
