@@ -355,9 +355,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else {
                         dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
                     }
+                    if (p.n_real >= 16 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+                        // two 256-bit stores (STG.256, sm_100) per 16-column chunk
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                                     "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]),
+                                     "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+                    } else {
 #pragma unroll
-                    for (int j4 = 0; j4 < 16; j4 += 4)
-                        if (j4 < p.n_real) *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                        for (int j4 = 0; j4 < 16; j4 += 4)
+                            if (j4 < p.n_real) *reinterpret_cast<float4*>(dst + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                    }
                 }
                 if (p.stats && !TC_DBG(4) && !TC_DBG(64)) warp_column_sums(v, valid, lane, scratch, red_s + ch0, red_q + ch0);
             };
