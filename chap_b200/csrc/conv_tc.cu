@@ -11,12 +11,18 @@
 // [tap][n][k] (K-major).  Operands are fp32 in memory, converted to TF32 (round-to-nearest) by the TMA unit
 // (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32) and multiplied by tcgen05.mma.kind::tf32 with fp32 accumulation in TMEM.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (one elected lane) + TMEM allocator, warps 2..5 epilogue
-// (tcgen05.ld -> +bias -> 128-bit stores, and the per-channel sum / sum-of-squares of the BatchNorm that follows,
-// reduced warp-shuffle -> smem -> one double atomic per CTA and channel into one of CHAP_STAT_SLOTS slots).
-// smem ring of `stages` {A, B} buffers with full/empty mbarriers; the accumulator is handed to the epilogue through a
-// tcgen05.commit on a third mbarrier.  Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's main loop.
+// Also: the transposed k2 s2 convolution forward (one GEMM with N = taps * Cout and a scatter epilogue, 2D and 3D) and its 2D
+// data gradient (4-tap gather of dy through a [2C, W, 2, H, N] tensor map); forward of the 4- / 8-channel heads (N zero-padded
+// to 16 in the packed weight); the data gradient of conv(cat(a, b)) with the two parts written by the epilogue.
+//
+// Persistent CTA (<= 2 per SM) = 10 warps: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator (both run their loops
+// warp-uniformly, one elect.sync lane issues), two groups of 4 epilogue warps (tcgen05.ld pipelined against the processing of
+// the previous 16-column chunk -> +bias -> 256-bit stores; per-channel sum / sum-of-squares of the following BatchNorm through
+// a padded shared-memory transpose, accumulated per CTA and added with one double atomic per channel into one of
+// CHAP_STAT_SLOTS slots).  The smem ring of {A, B} stages (full/empty mbarriers; 1, 2 or 4 k-chunks per stage) and TWO TMEM
+// accumulators (tmem_full / tmem_empty mbarriers) run across tile boundaries: loads and MMAs of tile j + 1 overlap the
+// epilogue of tile j.  Weights stay resident in shared memory when they fit (<= 40 KB).  Row-reuse mode (N <= 64, k3): one
+// h-haloed A box per (kz, kx) serves the three ky taps through descriptor row offsets.
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>

@@ -1,17 +1,22 @@
-// tcgen05 weight-gradient kernel for the stride-1 convolutions (k=3 pad 1, k=1; 2D and 3D).
+// tcgen05 weight-gradient kernel: stride-1 convolutions (k=3 pad 1, k=1; 2D and 3D) and the 2D transposed k2 s2 convolution.
 //
 //     dW[tap][co][ci] = sum_p dy[p, co] * x[p + tap, ci]
-// is, per tap, a GEMM whose reduction dimension is the pixel index p.  Both operands are channels-last, i.e. the
-// M (= co) and N (= ci) dimensions are the contiguous ones: "MN-major" UMMA operands.  A spatial box of P pixels
-// (P % 8 == 0, P <= 64) is one K block: the dy box [co-chunk x P] and, per tap, the x box shifted by the tap offset
-// [ci-chunk x P] are fetched by tiled TMA loads (out-of-bounds pixels are zero-filled = the conv padding), 32 channels
-// (128 B rows, SWIZZLE_128B) or 16 channels (64 B rows, SWIZZLE_64B) per load.  In smem a load is P rows of one
-// swizzle-atom width: exactly the canonical MN-major layout ((atom,n),(8,k)) with SBO = 8 rows, LBO = the distance
-// between channel chunks; one tcgen05.mma.kind::tf32 (K = 8) consumes one 8-row group.
+// is, per tap, a GEMM whose reduction dimension is the pixel index p.  Both operands are channels-last, i.e. the M and N
+// dimensions are the contiguous ones: "MN-major" UMMA operands.  A spatial box of P pixels (64 / 128 / 256) is one K block:
+// the dy box [channel chunk x P] and the x box shifted by the tap offset are fetched by tiled TMA loads (out-of-bounds pixels
+// zero-filled = the conv padding) as rows of 32 channels (128 B, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B = UMMA layout type 1, the
+// only layout tcgen05 accepts for MN-major 32-bit operands; 16- and 4-channel tensors are zero-filled to 32).  K atom = 4 rows
+// (SBO = 512 B), LBO = distance between 32-channel chunks; one tcgen05.mma.kind::tf32 (K = 8) consumes 8 pixel rows.
 //
-// Work split: blockIdx.z = (co tile, ci tile), blockIdx.y = tap group (as many taps as fit 512 TMEM columns),
-// blockIdx.x = slice of the pixel blocks.  Each CTA accumulates its slice in TMEM (fp32) and adds it to the
-// torch-layout gradient with red.global.add.f32 (the gradient buffer is zeroed first).
+// Modes (chosen on the host, tc_wgrad):
+//   * row reuse (k3, <= 128 input channels per CTA): the x box carries an h-halo and serves the three ky taps at row offsets;
+//   * swap (row reuse and cin <= 32): x is the M operand, its LBO is tw rows so that chunk g IS tap ky = g (one MMA = 3 taps),
+//     dy is the N operand with N = cout (>= 16; the 4-channel heads are zero-filled);
+//   * transposed conv: M = x (tap independent), N = dy gathered per tap through its [2C, W, 2, H, N] view.
+// Work split: blockIdx.z = (M tile, N tile), blockIdx.y = tap group (as many taps as fit the TMEM columns), blockIdx.x = slice
+// of the pixel blocks.  Each CTA accumulates its slice in TMEM (fp32) and adds it either straight into the torch-layout
+// gradient with red.global.add.f32 (thin layers) or, with 128-bit red.global.add.v4.f32, into a [tap][M][N] scratch that a
+// small kernel transposes into the torch layout (deep layers: the scalar reductions were ~50 % of their time).
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
