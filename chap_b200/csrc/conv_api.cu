@@ -44,7 +44,7 @@ extern "C" int chap_conv_fwd(const chap_conv_desc* d, const float* x, const floa
     }
     CHAP_TRY(simt_conv(fwd_op(g), x, w_fwd, bias, y, S(stream)));
     if (ch_sums) {      // CUDA-core path: statistics by a separate pass into slot 0, the other slots stay zero
-        CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * g.cout * sizeof(double), S(stream)));
+        CHAP_TRY(zero_async(ch_sums, (size_t)CHAP_STAT_SLOTS * 2 * g.cout * sizeof(double), S(stream)));
         CHAP_TRY(channel_stats(y, g.out_rows, g.cout, ch_sums, S(stream)));
     }
     return CHAP_OK;

@@ -328,7 +328,7 @@ thin_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restric
 
 int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
                int64_t sk, int64_t sn, cudaStream_t st) {
-    CHAP_CUDA(cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), st));
+    CHAP_TRY(zero_async(dw, dw_elems * sizeof(float), st));
     const bool stem = op.K == 1 && op.N % 16 == 0;
     const bool head = op.N % 4 == 0 && op.K % 4 == 0 && op.K * op.N <= 1024 && aligned16(a);     // heads and other thin layers
     if (!op.up2 && op.ksz == 3 && op.stride == 1 && (stem || head) && aligned16(b)) {

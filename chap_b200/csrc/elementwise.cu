@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) channel_stats_fixed_kernel(const float* _
 
 int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_t st) {
     CHAP_REQUIRE(y && sums && rows > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_stats: bad argument");
-    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));
     KernelTimer timer("channel_stats", 0.0, 4.0 * (double)rows * c, st);
     const bool v4 = (c % 4 == 0) && aligned16(y);
     const int cg = v4 ? c / 4 : c;
@@ -651,7 +651,7 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
     CHAP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), CHAP_ERR_BAD_ARG, "bn_act_bwd: dgamma/dbeta must both be set or both NULL");
     const int64_t rows = (int64_t)n * rps, total = rows * c;
     cudaStream_t st = S(stream);
-    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * c * sizeof(double), st));
+    CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));
     KernelTimer timer("bn_act_bwd", 0.0, 4.0 * total * (3 + (drop_el ? 1 : 0)), st);   // algorithmic: read dout, y; write dy
     const bool v4 = c % 4 == 0 && all16({dout, y, drop_el, dy});
     const int cg = v4 ? c / 4 : c;

@@ -342,7 +342,7 @@ extern "C" int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t
     KernelTimer timer_("dice_ce_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && labels && mask && sums && n > 0 && rps > 0, CHAP_ERR_BAD_ARG, "dice_ce_fwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c), CHAP_ERR_ALIGNMENT, "dice_ce_fwd: misaligned logits");
-    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)(3 * c + 2) * sizeof(double), S(stream)));
+    CHAP_TRY(zero_async(sums, (size_t)(3 * c + 2) * sizeof(double), S(stream)));
     const int64_t rows = (int64_t)n * rps;
     int grid = grid_for(rows, 256 * 4, kNumSMs * 4);
     DISPATCH_C(c, (dice_ce_fwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, labels, dtype, mask, invert, rps, rows, sums)));
@@ -419,7 +419,7 @@ extern "C" int chap_consistency_fwd(const float* logits, const float* target, co
     KernelTimer timer_("consistency_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(logits && target && sums && rows > 0 && (dist == CHAP_DIST_KL || dist == CHAP_DIST_DICE), CHAP_ERR_BAD_ARG, "consistency_fwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(target, c), CHAP_ERR_ALIGNMENT, "consistency_fwd: misaligned");
-    CHAP_CUDA(cudaMemsetAsync(sums, 0, (size_t)(3 * c + 1) * sizeof(double), S(stream)));
+    CHAP_TRY(zero_async(sums, (size_t)(3 * c + 1) * sizeof(double), S(stream)));
     int grid = grid_for(rows, 256 * 4, kNumSMs * 4);
     DISPATCH_C(c, (consistency_fwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, target, mask, dist, rows, sums)));
     return launched("consistency_fwd_kernel");

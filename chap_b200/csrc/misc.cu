@@ -46,6 +46,24 @@ KernelTimer::~KernelTimer() {
     if (slot >= 0) cudaEventRecord(g_timed[slot].b, st);
 }
 
+// ------------------------------------------------------------------ zero fill
+__global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, int64_t n4, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < n4; i += stride) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = n4 * 4 + i0; i < n; i += stride) p[i] = 0u;
+}
+int zero_async(void* ptr, size_t bytes, cudaStream_t st) {
+    static const bool use_memset = getenv("CHAP_ZERO_MEMSET") != nullptr;
+    if (bytes == 0) return CHAP_OK;
+    if (use_memset || (bytes & 3u) || (reinterpret_cast<uintptr_t>(ptr) & 3u)) { CHAP_CUDA(cudaMemsetAsync(ptr, 0, bytes, st)); return CHAP_OK; }
+    const int64_t n = (int64_t)(bytes >> 2);
+    const bool vec = (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
+    const int64_t n4 = vec ? n / 4 : 0;
+    zero_kernel<<<grid_for(vec ? n4 + 1 : n, 256 * 4, kNumSMs * 4), 256, 0, st>>>(reinterpret_cast<uint32_t*>(ptr), n4, n);
+    return launched("zero_kernel");
+}
+
 // ------------------------------------------------------------------ SGD momentum on a flat arena
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n4, int64_t n,

@@ -201,7 +201,7 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
     CHAP_REQUIRE(mode >= CHAP_PERTURB_SAMPLE && mode <= CHAP_PERTURB_CHANNEL_SPATIAL, CHAP_ERR_BAD_ARG, "perturb_fwd: unknown mode %d", mode);
     CHAP_REQUIRE(ws_elems >= chap_perturb_workspace_elems(levels, n_levels, n), CHAP_ERR_WORKSPACE, "perturb_fwd: workspace too small");
     cudaStream_t st = S(stream);
-    CHAP_CUDA(cudaMemsetAsync(workspace, 0, chap_perturb_workspace_elems(levels, n_levels, n) * sizeof(double), st));
+    CHAP_TRY(zero_async(workspace, chap_perturb_workspace_elems(levels, n_levels, n) * sizeof(double), st));
     double* ws = workspace;
     for (int l = 0; l < n_levels; ++l) {
         const chap_level& L = levels[l];
@@ -227,7 +227,7 @@ extern "C" int chap_l2n_sample_axpy(const float* d, const float* base, float xi,
     KernelTimer timer_("l2n_sample_axpy", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(d && norms && out && n > 0 && elems_per_sample > 0, CHAP_ERR_BAD_ARG, "l2n_sample_axpy: bad argument");
     cudaStream_t st = S(stream);
-    CHAP_CUDA(cudaMemsetAsync(norms, 0, (size_t)n * sizeof(double), st));
+    CHAP_TRY(zero_async(norms, (size_t)n * sizeof(double), st));
     int bps = (int)((elems_per_sample + 256 * 8 - 1) / (256 * 8));
     int cap = (kNumSMs * 8 + n - 1) / n;
     if (bps > cap) bps = cap;

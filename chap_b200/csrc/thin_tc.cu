@@ -285,7 +285,7 @@ int thin_tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, co
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_thin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-    if (ch_sums) CHAP_CUDA(cudaMemsetAsync(ch_sums, 0, (size_t)CHAP_STAT_SLOTS * 2 * N * sizeof(double), st));
+    if (ch_sums) CHAP_TRY(zero_async(ch_sums, (size_t)CHAP_STAT_SLOTS * 2 * N * sizeof(double), st));
     const double rows = (double)g.out_rows;
     KernelTimer timer(dgrad ? "conv_thin_tc_dgrad" : "conv_thin_tc_fwd", 2.0 * rows * K * N * g.taps,
                       4.0 * (rows * K + rows * N + (double)g.taps * K * N), st);

@@ -459,7 +459,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
     // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
     p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
-    CHAP_CUDA(cudaMemsetAsync(p.acc ? p.acc : dw, 0, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
+    CHAP_TRY(zero_async(p.acc ? p.acc : dw, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
     const double rows = (double)(up2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
                       4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
