@@ -11,6 +11,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CHAP_B200_LIB", os.path.join(_HERE, "lib", "libchap_b200.so"))   # override: developer builds (debug hooks)
 
 
+class BnTrainArgs(ctypes.Structure):          # chap_bn_train_args
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("momentum", c_float),
+                ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
+                ("mean_invstd", c_void_p), ("scale_shift", c_void_p)]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("nd", c_int32), ("n", c_int32), ("in_d", c_int32), ("in_h", c_int32),
                 ("in_w", c_int32), ("cin", c_int32), ("cout", c_int32)]
@@ -50,6 +56,7 @@ SIGNATURES = {
     "chap_conv_packed_elems": (c_size_t, [_CD]),
     "chap_conv_pack_weights": (I, [_CD, P, P, P, P]),
     "chap_conv_fwd": (I, [_CD, P, P, P, P, P, P]),
+    "chap_conv_bn_fwd": (I, [_CD, P, P, P, P, P, P, P]),
     "chap_conv_dgrad": (I, [_CD, P, P, P, P]),
     "chap_conv_dgrad_split_supported": (I, [_CD, I]),
     "chap_conv_dgrad_split": (I, [_CD, P, P, P, I, P, P]),

@@ -50,6 +50,25 @@ extern "C" int chap_conv_fwd(const chap_conv_desc* d, const float* x, const floa
     return CHAP_OK;
 }
 
+extern "C" int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias, float* y,
+                                double* ch_sums, const chap_bn_train_args* bn, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(x && w_fwd && y && ch_sums && bn && bn->gamma && bn->beta && bn->mean_invstd && bn->scale_shift, CHAP_ERR_BAD_ARG,
+                 "conv_bn_fwd: NULL pointer");
+    CHAP_REQUIRE((bn->running_mean == nullptr) == (bn->running_var == nullptr), CHAP_ERR_BAD_ARG, "conv_bn_fwd: running_mean / running_var must both be set or both NULL");
+    if (use_tc(g, false) && getenv("CHAP_NO_BN_FOLD") == nullptr) {
+        BnFold f{bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean, bn->running_var,
+                 reinterpret_cast<long long*>(bn->num_batches_tracked), bn->mean_invstd, bn->scale_shift, 0.0, nullptr};
+        int rc = tc_conv(g, false, x, w_fwd, bias, y, ch_sums, S(stream), nullptr, 0, &f);
+        if (rc < 0) return rc;
+        if (rc == 1) return CHAP_OK;
+    }
+    CHAP_TRY(chap_conv_fwd(d, x, w_fwd, bias, y, ch_sums, stream));
+    return chap_bn_finalize(ch_sums, CHAP_STAT_SLOTS, g.out_rows, bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean,
+                            bn->running_var, bn->num_batches_tracked, bn->mean_invstd, bn->scale_shift, g.cout, stream);
+}
+
 extern "C" int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream) {
     Geom g{};
     CHAP_TRY(resolve(d, g));

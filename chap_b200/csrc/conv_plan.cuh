@@ -65,9 +65,17 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
 
 // tensor-core path (conv_tc.cu): returns 1 if it handled the op, 0 if the shape is not supported
 // (caller falls through to the CUDA-core kernels), <0 on error.
+// BatchNorm finalize folded into the convolution kernel (done by its last thread block); mi == nullptr: not requested
+struct BnFold {
+    const float* gamma; const float* beta; float eps, momentum;
+    float* rmean; float* rvar; long long* nbt;
+    float* mi; float* ss;
+    double count;                // elements per channel (N * spatial of the output)
+    unsigned* counter;           // zero-initialised ticket counter (the double after the statistics slots)
+};
 // out_b != nullptr: output channels [0, ca) go to `out` (row stride ca), [ca, N) to `out_b` (row stride N - ca)
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
-            double* ch_sums, cudaStream_t st, float* out_b = nullptr, int ca = 0);
+            double* ch_sums, cudaStream_t st, float* out_b = nullptr, int ca = 0, const BnFold* bn = nullptr);
 bool tc_supports(const Geom& g, bool dgrad);
 // thin-layer tensor-core path (thin_tc.cu): taps in the N dimension + shift-add epilogue, Cin/Cout in {16, 32}
 int thin_tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,

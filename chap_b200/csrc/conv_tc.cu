@@ -58,6 +58,7 @@ struct TcParams {
     int ca;
     const float* bias;
     double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
+    BnFold bn;                    // bn.mi != nullptr: the last CTA turns the statistics into BatchNorm scale / shift
 };
 
 constexpr int kTcThreadsMax = 320;         // TMA warp, MMA warp, 1 or 2 groups of 4 epilogue warps
@@ -411,6 +412,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 atomicAdd(slot + ch_base + c, (double)a);
                 atomicAdd(slot + n_ch + ch_base + c, (double)b);
             }
+            if (p.bn.mi) {
+                // BatchNorm finalize by the last CTA of the grid: ticket counter after the statistics slots
+                __threadfence();                                                  // this thread's atomics are visible device-wide
+                asm volatile("bar.sync 1, %0;" ::"r"(p.epi_groups * 128) : "memory");
+                if (e == 0) {
+                    const unsigned ticket = atomicAdd(p.bn.counter, 1u);
+                    tmem_slot[1] = ticket == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(p.epi_groups * 128) : "memory");
+                if (tmem_slot[1]) {
+                    __threadfence();
+                    for (int c = e; c < n_ch; c += p.epi_groups * 128) {
+                        double s1 = 0.0, s2 = 0.0;
+                        for (int sl = 0; sl < CHAP_STAT_SLOTS; ++sl) {
+                            s1 += __ldcg(p.stats + (size_t)sl * 2 * n_ch + c);
+                            s2 += __ldcg(p.stats + (size_t)sl * 2 * n_ch + n_ch + c);
+                        }
+                        const double mean = s1 / p.bn.count;
+                        double var = s2 / p.bn.count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const float invstd = (float)(1.0 / sqrt(var + (double)p.bn.eps));
+                        const float sc = p.bn.gamma[c] * invstd;
+                        p.bn.mi[c] = (float)mean; p.bn.mi[n_ch + c] = invstd;
+                        p.bn.ss[c] = sc; p.bn.ss[n_ch + c] = p.bn.beta[c] - (float)mean * sc;
+                        if (p.bn.rmean) {
+                            const double unbiased = p.bn.count > 1.0 ? var * p.bn.count / (p.bn.count - 1.0) : var;
+                            p.bn.rmean[c] = (1.f - p.bn.momentum) * p.bn.rmean[c] + p.bn.momentum * (float)mean;
+                            p.bn.rvar[c] = (1.f - p.bn.momentum) * p.bn.rvar[c] + p.bn.momentum * (float)unbiased;
+                        }
+                    }
+                    if (e == 0 && p.bn.nbt) *p.bn.nbt += 1;
+                }
+            }
         }
         if (threadIdx.x == 64) TC_TRACE(6);
         tc_fence_before();
@@ -504,9 +538,9 @@ static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
 }
 
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
-            double* ch_sums, cudaStream_t st, float* out_b, int ca) {
+            double* ch_sums, cudaStream_t st, float* out_b, int ca, const BnFold* bn) {
     if (!tc_supports(g, dgrad)) return 0;
-    if (!out_b && thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
+    if (!out_b && !bn && thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
     CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
     int K, N;
     tc_channels(g, dgrad, K, N);
@@ -633,7 +667,14 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-    if (ch_sums) CHAP_TRY(zero_async(ch_sums, (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real) * sizeof(double), st));
+    const size_t stat_doubles = (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real);
+    if (bn) {
+        CHAP_REQUIRE(ch_sums != nullptr, CHAP_ERR_BAD_ARG, "tc_conv: the folded BatchNorm finalize needs the statistics buffer");
+        p.bn = *bn;
+        p.bn.count = (double)g.out_rows;
+        p.bn.counter = reinterpret_cast<unsigned*>(ch_sums + stat_doubles);
+    }
+    if (ch_sums) CHAP_TRY(zero_async(ch_sums, (stat_doubles + (bn ? 1 : 0)) * sizeof(double), st));
     const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows),
                       2.0 * rows * g.cin * g.cout * g.taps,

@@ -43,11 +43,11 @@ class ConvBlock(nn.Module):
         protocol; by default the mask is drawn like nn.Dropout would.
         cat: the block runs on torch.cat([x, cat], dim=1); the concat is fused into the first convolution."""
         c1, b1, _, _, c2, b2, _ = self.conv_conv
-        y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training, cat=cat)
+        y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training, cat=cat, bn=b1)
         if drop_mask is None:
             drop_mask = _elementwise_dropout_mask(y, self.dropout_p, self.training)
         a = ops.bn_act(y, b1, LEAKY_SLOPE, sums=sums, drop_el=drop_mask)
-        y, sums = ops.conv_stats(a, c2.weight, c2.bias, CONV_K3, b2.training, feeds_train_bn=b2.training)
+        y, sums = ops.conv_stats(a, c2.weight, c2.bias, CONV_K3, b2.training, feeds_train_bn=b2.training, bn=b2)
         return ops.bn_act(y, b2, LEAKY_SLOPE, sums=sums)
 
 

@@ -21,7 +21,7 @@ def _check_norm(normalization):
 
 
 def _conv_bn_relu(x, conv, bn, kind, residual=None, drop_nc=None):
-    y, sums = ops.conv_stats(x, conv.weight, conv.bias, kind, bn.training, feeds_train_bn=bn.training)
+    y, sums = ops.conv_stats(x, conv.weight, conv.bias, kind, bn.training, feeds_train_bn=bn.training, bn=bn)
     return ops.bn_act(y, bn, 0.0, sums=sums, residual=residual, drop_nc=drop_nc)
 
 

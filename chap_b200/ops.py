@@ -148,7 +148,7 @@ class _Conv(Function):
     backward's data gradient is written straight into the two parts by the tensor-core epilogue (no split pass)."""
 
     @staticmethod
-    def forward(ctx, x, xb, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False):
+    def forward(ctx, x, xb, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False, bn=None):
         _require_cuda(x, weight, bias)
         x = cl(x)
         ctx.split = None
@@ -166,20 +166,33 @@ class _Conv(Function):
             raise RuntimeError("conv: input has %d channels, weight expects %d" % (x.shape[1], cin))
         desc = _conv_desc(kind, x, cin, cout)
         y = empty_cl(_out_shape(kind, x, cout), x.device)
-        sums = torch.empty(_lib.STAT_SLOTS * 2 * cout, dtype=torch.float64, device=x.device) if want_stats else None
+        fold = bn is not None and want_stats                      # +1 double: the kernel's block ticket counter
+        sums = torch.empty(_lib.STAT_SLOTS * 2 * cout + (1 if fold else 0), dtype=torch.float64, device=x.device) if want_stats else None
         b = None if bias is None else bias.detach()
-        check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
+        mi = ss = None
+        if fold:
+            # train-mode BatchNorm follows: its finalize step (scale / shift, running statistics) runs inside the conv kernel
+            gamma, beta, eps, momentum, rm, rv, nbt = bn
+            mi = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+            ss = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
+            args = _lib.BnTrainArgs(_p(gamma.detach()), _p(beta.detach()), eps, momentum, _p(rm), _p(rv), _p(nbt), _p(mi), _p(ss))
+            check(lib().chap_conv_bn_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), ctypes.byref(args), _stream()))
+        else:
+            check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
         ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
         ctx.zero_bias_grad = zero_bias_grad
         ctx.wshape = tuple(weight.shape)
         ctx.save_for_backward(x if ctx.needs_input_grad[2] else None)
         if want_stats:
+            if mi is not None:
+                ctx.mark_non_differentiable(sums, mi, ss)
+                return y, sums, mi, ss
             ctx.mark_non_differentiable(sums)
-            return y, sums
-        return y, None
+            return y, sums, None, None
+        return y, None, None, None
 
     @staticmethod
-    def backward(ctx, dy, _dsums):
+    def backward(ctx, dy, _dsums, _dmi, _dss):
         (x,) = ctx.saved_tensors
         desc = ctx.desc
         dy = cl(dy)
@@ -214,10 +227,14 @@ class _Conv(Function):
             check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
             if ctx.has_bias and ctx.needs_input_grad[3] and ctx.zero_bias_grad:
                 db = torch.zeros(desc.cout, dtype=torch.float32, device=dy.device)
-        return dx, dxb, dw, db, None, None, None, None, None
+        return dx, dxb, dw, db, None, None, None, None, None, None
 
 
-def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat=None):
+class BnStats(tuple):
+    """(sums, mean_invstd, scale_shift) of a convolution whose BatchNorm finalize already ran inside the conv kernel."""
+
+
+def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat=None, bn=None):
     """(y, sums): sums = per-channel sum / sum-of-squares of y as float64[2*Cout] (None if not wanted).
     feeds_train_bn: y goes straight into a train-mode BatchNorm -> the bias gradient is exactly zero and is not computed.
     cat: optional second input; the convolution runs on the channel concat (x, cat)  (U-Net skip connection)."""
@@ -226,7 +243,17 @@ def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat
     if not _state["weight_grad"]:
         weight = weight.detach()
         bias = None if bias is None else bias.detach()
-    return _Conv.apply(x, cat, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn))
+    pack = None
+    if bn is not None and want_stats and bn.training:
+        # bn: the nn.BatchNormNd holder that consumes y -> (y, BnStats) and bn_act skips its own finalize launch
+        update = bn.track_running_stats and _state["bn_tracking"]
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        pack = (bn.weight, bn.bias, float(bn.eps), float(momentum),
+                bn.running_mean if update else None, bn.running_var if update else None, bn.num_batches_tracked if update else None)
+    y, sums, mi, ss = _Conv.apply(x, cat, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn), pack)
+    if mi is not None:
+        return y, BnStats((sums, mi, ss))
+    return y, sums
 
 
 def conv(x, weight, bias, kind):
@@ -236,16 +263,21 @@ def conv(x, weight, bias, kind):
 # ----------------------------------------------------------------------------- BN + activation
 class _BnAct(Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, residual, sums, running, train, update, slope, eps, momentum, drop_nc, drop_el):
+    def forward(ctx, y, gamma, beta, residual, sums, running, train, update, slope, eps, momentum, drop_nc, drop_el, pre=None):
         _require_cuda(y, gamma, beta)
         y = cl(y)
         n, c = y.shape[0], y.shape[1]
         rps = y.numel() // (n * c)
         dev = y.device
-        mi = torch.empty(2 * c, dtype=torch.float32, device=dev)
-        ss = torch.empty(2 * c, dtype=torch.float32, device=dev)
         g, b = gamma.detach(), beta.detach()
-        if train:
+        if pre is not None:
+            mi, ss = pre                      # finalize (and the running-statistics update) already done by the conv kernel
+        else:
+            mi = torch.empty(2 * c, dtype=torch.float32, device=dev)
+            ss = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        if pre is not None:
+            pass
+        elif train:
             slots = _lib.STAT_SLOTS
             if sums is None:
                 slots = 1
@@ -281,7 +313,7 @@ class _BnAct(Function):
         check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,
                                     1 if train else 0, _p(sums), _p(dy), _p(dgamma), _p(dbeta), _stream()))
         dres = dout if (has_res and ctx.needs_input_grad[3]) else None
-        return (dy, dgamma, dbeta, dres) + (None,) * 9
+        return (dy, dgamma, dbeta, dres) + (None,) * 10
 
 
 def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
@@ -291,8 +323,11 @@ def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
     running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else None
     update = bn.training and bn.track_running_stats and _state["bn_tracking"]
     momentum = 0.1 if bn.momentum is None else bn.momentum
+    pre = None
+    if isinstance(sums, BnStats):
+        sums, pre = sums[0], (sums[1], sums[2])
     return _BnAct.apply(y, bn.weight, bn.bias, residual, sums, running, train, update, float(slope), float(bn.eps),
-                        float(momentum), drop_nc, drop_el)
+                        float(momentum), drop_nc, drop_el, pre)
 
 
 # ----------------------------------------------------------------------------- pooling / upsampling / concat

@@ -90,6 +90,23 @@ int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd
  * sum(y), sum(y*y) (zeroed by the call) -- the BatchNorm batch statistics of the following layer. */
 int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
                   float* y, double* ch_sums, void* stream);
+/* Convolution followed by a train-mode BatchNorm (reference: nn.ConvNd -> nn.BatchNormNd, code/networks/unet.py:50-51,
+ * vnet.py:19-21): y = conv(x) + bias, batch statistics in the epilogue, and the BatchNorm "finalize" step of chap_bn_finalize
+ * (mean / invstd / scale / shift, running statistics update) done by the LAST thread block of the same kernel -- no separate
+ * launch between the convolution and chap_bn_act_fwd.  ch_sums must hold CHAP_STAT_SLOTS*2*cout + 1 doubles (the extra one is
+ * the block ticket counter).  Shapes the tensor-core kernel does not take run conv + statistics + finalize as three launches. */
+typedef struct chap_bn_train_args {
+    const float* gamma;
+    const float* beta;
+    float eps, momentum;
+    float* running_mean;             /* nullable trio: running statistics are updated when given */
+    float* running_var;
+    int64_t* num_batches_tracked;
+    float* mean_invstd;              /* out: float[2*cout] */
+    float* scale_shift;              /* out: float[2*cout] */
+} chap_bn_train_args;
+int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias, float* y,
+                     double* ch_sums, const chap_bn_train_args* bn, void* stream);
 /* dx = conv^T(dy) (data gradient), dx has the input shape */
 int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream);
 /* Data gradient of a convolution whose input was torch.cat([a, b], dim=1) (the U-Net skip connection, reference
