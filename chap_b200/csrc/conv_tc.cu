@@ -44,9 +44,11 @@ struct TcParams {
     int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
     int n_real;                   // output channels that exist (< nt = 16 for the zero-padded 4- / 8-channel heads)
-    int mode;                     // 0: stride-1 conv; 1: transposed k2 s2 forward (one GEMM, N = taps * Cout, scatter epilogue);
-                                  // 2: its 2D data gradient (4-tap gather of dy through the [2C, W, 2, H, N] view)
-    int up_c;                     // mode 1: Cout (columns per tap); mode 2: channels of dy
+    int mode;                     // 0: stride-1 conv; 1: k2 s2 scatter (transposed conv forward, strided conv data gradient): one GEMM over
+                                  // the low-resolution grid, N = taps * C_big, scatter epilogue; 2: 2D k2 s2 gather through the
+                                  // [2C, W, 2, H, N] view (transposed conv data gradient); 3: k2 s2 gather with one tensor map per tap
+                                  // (strided conv forward 2D / 3D, transposed conv data gradient 3D).  W, H, D = low-resolution grid.
+    int up_c;                     // mode 1: channels of the high-resolution tensor (columns per tap); mode 2: channels of dy
     int epi_groups;               // 1 or 2 groups of 4 epilogue warps (blockDim = 64 + 128 * groups)
     int colsplit;                 // two groups: 1 = both work on every tile, half the columns each; 0 = they alternate tiles
     int cps;                      // k chunks per pipeline stage (1, 2 or 4): fewer, fatter stages for the deep layers
@@ -191,8 +193,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
 // two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
 // tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
-__global__ void __launch_bounds__(kTcThreadsMax, 2)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+__device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmTaps* tmTp, const TcParams& p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_base = smem;
@@ -265,6 +266,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes + (size_t)c * p.a_chunk_bytes;
                             if (TC_DBG(2)) {}
                             else if (p.mode == 2) tma_load_5d(a_dst, &tmA, &full[s], (grp & 1) * p.up_c + kci * p.kc, w0, grp >> 1, h0, img);
+                            else if (p.mode == 3 && p.nd == 2) tma_load_4d(a_dst, &tmTp->m[grp], &full[s], kci * p.kc, w0, h0, img);
+                            else if (p.mode == 3) tma_load_5d(a_dst, &tmTp->m[grp], &full[s], kci * p.kc, w0, h0, d0, img);
                             else if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, img);
                             else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                             if (!p.b_resident) {
@@ -457,6 +460,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// Two entry points: the per-tap tensor maps (1 KB of kernel parameters) are only passed for the k2 s2 gathers.
+__global__ void __launch_bounds__(kTcThreadsMax, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    conv_tc_kernel_body(tmA, tmB, nullptr, p);
+}
+__global__ void __launch_bounds__(kTcThreadsMax, 2)
+conv_tc_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
+                    const TcParams p) {
+    conv_tc_kernel_body(tmA, tmB, &tmT, p);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -501,13 +515,20 @@ static int tc_channels(const Geom& g, bool dgrad, int& K, int& N) {
 }
 
 bool tc_supports(const Geom& g, bool dgrad) {
+    if (g.kind == CHAP_CONV_DOWN2) {
+        // forward: 4- / 8-tap gather (one tensor map per tap); data gradient: one GEMM with N = taps * Cin and a scatter epilogue
+        if (getenv("CHAP_NO_UP2_TC")) return false;
+        const bool chan_ok = (g.cin == 16 || g.cin % 32 == 0) && (g.cout == 16 || g.cout % 32 == 0) && g.cin <= 1024 && g.cout <= 1024;
+        if (!dgrad) return chan_ok && (g.cout <= 256 || g.cout % 256 == 0);
+        return chan_ok && ((g.taps * g.cin) <= 256 || (g.taps * g.cin) % 256 == 0);
+    }
     if (g.kind == CHAP_CONV_UP2) {
-        // forward: one GEMM [pixels, Cin] x [Cin, taps * Cout] (2D and 3D); data gradient: 2D only (the gather needs a
-        // [2C, W, 2, H, N] view of dy, the 3D analogue would be 7-dimensional)
+        // forward: one GEMM [pixels, Cin] x [Cin, taps * Cout] (2D and 3D); data gradient: gather of dy, 2D through its
+        // [2C, W, 2, H, N] view, 3D with one tensor map per tap
         if (getenv("CHAP_NO_UP2_TC")) return false;
         const bool chan_ok = (g.cin == 16 || g.cin % 32 == 0) && g.cout % 16 == 0 && g.cout >= 16 && g.cout <= 128 && g.cin <= 1024;
         if (!dgrad) return chan_ok && ((g.taps * g.cout) <= 256 || (g.taps * g.cout) % 256 == 0);
-        return chan_ok && g.nd == 2 && (g.cout == 16 || g.cout % 32 == 0) && (g.cin <= 256 || g.cin % 256 == 0);
+        return chan_ok && (g.cout == 16 || g.cout % 32 == 0) && (g.cin <= 256 || g.cin % 256 == 0);
     }
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     int K, N;
@@ -547,12 +568,15 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     TcParams p{};
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD;
+    if (g.kind == CHAP_CONV_DOWN2) { p.W = g.oW; p.H = g.oH; p.D = g.oD; }      // the k2 s2 modes tile the LOW-resolution grid
     const int k_real = K, n_real = N;                    // thin heads: the MMA runs on operands zero-padded to 16
     K = tc_pad16(K); N = tc_pad16(N);
     int w_taps = g.taps;                                  // taps in the packed weight operand [tap][N][K]
     if (g.kind == CHAP_CONV_UP2 && !dgrad) { p.mode = 1; p.up_c = g.cout; N = g.taps * g.cout; p.taps = 1; w_taps = 1; }
-    if (g.kind == CHAP_CONV_UP2 && dgrad) { p.mode = 2; p.up_c = g.cout; p.ksz = 2; }
-    CHAP_REQUIRE(!(p.mode && out_b), CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for the transposed convolution");
+    if (g.kind == CHAP_CONV_UP2 && dgrad) { p.mode = g.nd == 2 ? 2 : 3; p.up_c = g.cout; p.ksz = 2; }
+    if (g.kind == CHAP_CONV_DOWN2 && !dgrad) { p.mode = 3; p.up_c = g.cin; p.ksz = 2; }
+    if (g.kind == CHAP_CONV_DOWN2 && dgrad) { p.mode = 1; p.up_c = g.cin; N = g.taps * g.cin; p.taps = 1; w_taps = 1; }
+    CHAP_REQUIRE(!(p.mode && out_b), CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for the k2 s2 convolutions");
     p.n_real = p.mode == 1 ? N : n_real;
     CHAP_REQUIRE(p.n_real == N || !out_b, CHAP_ERR_BAD_ARG, "tc_conv: split output is not available for padded heads");
     choose_box(p.W, p.H, p.D, p.tw, p.th, p.td);
@@ -640,10 +664,31 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
+    static thread_local TmTaps tmT;                     // only filled (and read by the kernel) in mode 3
     {
         uint64_t dims[5], str[4]; uint32_t box[5];
         const uint64_t C = (uint64_t)k_real;                 // a box wider than the tensor zero-fills (padded heads)
-        if (p.mode == 2) {
+        if (p.mode == 3) {
+            // high-resolution tensor [N, 2D, 2H, 2W, C]: tap (kd, kh, kw) of low-resolution position (d, h, w) is element
+            // (2d + kd, 2h + kh, 2w + kw) -> per tap a map with the base moved by the tap and every spatial stride doubled
+            const uint64_t bw = 2 * (uint64_t)p.W, bh = 2 * (uint64_t)p.H;
+            for (int t = 0; t < g.taps; ++t) {
+                const int kw = t & 1, kh = (t >> 1) & 1, kd = t >> 2;
+                const float* base = in + (((uint64_t)kd * bh + kh) * bw + kw) * C;
+                if (g.nd == 2) {
+                    dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
+                    str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = bh * bw * C * 4;
+                    box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 4, dims, str, box, p.kc));
+                } else {
+                    dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
+                    str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = 2 * bh * bw * C * 4; str[3] = 2 * (uint64_t)p.D * bh * bw * C * 4;
+                    box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 5, dims, str, box, p.kc));
+                }
+            }
+            tmA = tmT.m[0];
+        } else if (p.mode == 2) {
             // dy [N, 2H, 2W, C] seen as [2C (kw, c), W, 2 (kh), H, N]: tap (kh, kw) of input pixel (h, w) is one box row
             dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
             str[0] = 2 * C * 4; str[1] = str[0] * p.W; str[2] = 2 * str[1]; str[3] = str[2] * p.H;
@@ -666,7 +711,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         CHAP_TRY(make_tensor_map(&tmB, wp, 2, wd, ws, wb, p.kc));
     }
     static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     const size_t stat_doubles = (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real);
     if (bn) {
         CHAP_REQUIRE(ch_sums != nullptr, CHAP_ERR_BAD_ARG, "tc_conv: the folded BatchNorm finalize needs the statistics buffer");
@@ -680,7 +726,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
                       2.0 * rows * g.cin * g.cout * g.taps,
                       4.0 * ((double)g.in_rows * g.cin + (double)g.out_rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
-    conv_tc_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, p);
+    if (p.mode == 3) conv_tc_kernel_taps<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, tmT, p);
+    else conv_tc_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("conv_tc_kernel"));
     return 1;
 }

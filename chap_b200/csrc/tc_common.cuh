@@ -5,6 +5,9 @@
 
 namespace chap {
 
+// one tensor map per tap of a k2 s2 gather: base pointer moved by the tap, every spatial stride doubled (kernel parameter)
+struct TmTaps { CUtensorMap m[8]; };
+
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -38,7 +38,8 @@ struct WgParams {
     int a_cpg, a_groups;            // channels per TMA chunk (32|16) and chunks per m_tile
     int b_cpg, b_groups;
     int tg;                         // taps per CTA (reuse mode: (kz, kx) pairs per CTA, each pair = 3 ky taps)
-    int up2;                        // 1: transposed k2 s2 conv (2D): the N operand is dy gathered per tap through its [2C, W, 2, H, N] view
+    int k2s2;                       // 1: k2 s2 convolution (strided or transposed): the N operand is the high-resolution tensor gathered per
+                                    // tap through one tensor map per tap; the pixel blocks tile the LOW-resolution grid
     int swap;                       // 1 (reuse mode, cin <= 32): x is the M operand (M = 4 "ky" chunks x 32 ci, chunk stride tw rows), dy the N operand
     int acc2;                       // experiment (CHAP_WG_ACC2): alternate K steps between two TMEM accumulators, summed in the epilogue
     int n_mma;                      // swap mode: MMA N = cout of this CTA rounded up to 16
@@ -82,8 +83,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t r
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-__global__ void __launch_bounds__(kWgThreads)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+__device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmTaps* tmTp, const WgParams& p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_base = smem;
@@ -155,7 +155,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         else tma_load_5d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, d0, img);
                     }
                     for (int g = 0; g < p.b_groups; ++g) {
-                        if (p.up2) tma_load_5d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], (tap & 1) * p.cin + n0 + g * p.b_cpg, w0, tap >> 1, h0, img);
+                        if (p.k2s2 && p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmTp->m[tap], &full[s], n0 + g * p.b_cpg, w0, h0, img);
+                        else if (p.k2s2) tma_load_5d(b_dst + (size_t)g * b_chunk, &tmTp->m[tap], &full[s], n0 + g * p.b_cpg, w0, h0, d0, img);
                         else if (p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, img);
                         else tma_load_5d(b_dst + (size_t)g * b_chunk, &tmB, &full[s], n0 + g * p.b_cpg, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                     }
@@ -298,9 +299,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// Two entry points: the per-tap tensor maps (1 KB of kernel parameters) are only passed for the k2 s2 gathers.
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+    wgrad_tc_kernel_body(tmA, tmB, nullptr, p);
+}
+__global__ void __launch_bounds__(kWgThreads)
+wgrad_tc_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
+                     const WgParams p) {
+    wgrad_tc_kernel_body(tmA, tmB, &tmT, p);
+}
+
 bool tc_wgrad_supports(const Geom& g) {
     auto ok = [](int c) { return c == 16 || (c % 32 == 0 && c <= 1024); };
-    if (g.kind == CHAP_CONV_UP2) return g.nd == 2 && ok(g.cin) && ok(g.cout) && getenv("CHAP_NO_UP2_TC") == nullptr;
+    if (g.kind == CHAP_CONV_UP2 || g.kind == CHAP_CONV_DOWN2) return ok(g.cin) && ok(g.cout) && getenv("CHAP_NO_UP2_TC") == nullptr;
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return false;
     // swap mode (row-reuse geometry, cin <= 32) also takes the 4- / 8-channel heads: dy is the N operand, zero-filled to 16
     const bool head = (g.cout == 4 || g.cout == 8) && g.kind == CHAP_CONV_K3 && (g.cin == 16 || g.cin == 32) && g.iW >= 8 && g.iH >= 10 &&
@@ -324,17 +336,18 @@ static void choose_box8(int W, int H, int D, int& tw, int& th, int& td, int max_
 int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st, float* acc_ws) {
     if (!tc_wgrad_supports(g)) return 0;
     CHAP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dw), CHAP_ERR_ALIGNMENT, "tc_wgrad: buffers must be 16-byte aligned");
-    // Transposed k2 s2 convolution (2D): dW[ci][co][kh][kw] = sum_p x[p, ci] * dy[2p + (kh, kw), co] is the same GEMM with the
-    // roles exchanged: the M operand is x (tap independent), the N operand is dy gathered per tap through its
-    // [2C, W, 2, H, N] view, and the gradient strides are those of the [ci][co][tap] layout.
-    const bool up2 = g.kind == CHAP_CONV_UP2;
+    // k2 s2 convolutions: dW = sum_p S[p, .] * B[2p + tap, .] with S the low-resolution tensor (tap independent: the M operand) and
+    // B the high-resolution one gathered per tap (the N operand).  Strided conv: S = dy, B = x (the usual orientation);
+    // transposed conv: S = x, B = dy, i.e. the roles exchanged and the gradient strides those of the [ci][co][tap] layout.
+    const bool up2 = g.kind == CHAP_CONV_UP2, down2 = g.kind == CHAP_CONV_DOWN2, k2 = up2 || down2;
     Geom v = g;                                  // v.cout = channels of the M operand, v.cin = channels of the N operand
     const float* m_src = dy; const float* n_src = x;
     if (up2) { v.cin = g.cout; v.cout = g.cin; m_src = x; n_src = dy; }
     WgParams p{};
-    p.up2 = up2 ? 1 : 0;
+    p.k2s2 = k2 ? 1 : 0;
     p.nd = g.nd; p.ksz = g.kind == CHAP_CONV_K3 ? 3 : 1; p.pad = g.kind == CHAP_CONV_K3 ? 1 : 0; p.taps = g.taps;
     p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
+    if (down2) { p.W = g.oW; p.H = g.oH; p.D = g.oD; }
     choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
     const int n_tile_pre = v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin);
     {
@@ -431,16 +444,30 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.dw = dw;
 
     CUtensorMap tmA, tmB;
+    static thread_local TmTaps tmT;                 // filled (and read by the kernel) only for the k2 s2 convolutions
     for (int which = 0; which < 2; ++which) {
         const float* base = which == 0 ? m_src : n_src;
         const uint64_t C = which == 0 ? v.cout : v.cin;
         const int cpg = which == 0 ? p.a_cpg : p.b_cpg;
         uint64_t dims[5], str[4]; uint32_t box[5];
-        if (up2 && which == 1) {
-            dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
-            str[0] = 2 * C * 4; str[1] = str[0] * p.W; str[2] = 2 * str[1]; str[3] = str[2] * p.H;
-            box[0] = cpg; box[1] = p.tw; box[2] = 1; box[3] = p.th; box[4] = 1;
-            CHAP_TRY(make_tensor_map(&tmB, base, 5, dims, str, box, cpg, true));
+        if (k2 && which == 1) {
+            const uint64_t bw = 2 * (uint64_t)p.W, bh = 2 * (uint64_t)p.H;
+            for (int t = 0; t < g.taps; ++t) {
+                const int kw = t & 1, kh = (t >> 1) & 1, kd = t >> 2;
+                const float* tb = base + (((uint64_t)kd * bh + kh) * bw + kw) * C;
+                if (g.nd == 2) {
+                    dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
+                    str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = bh * bw * C * 4;
+                    box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = 1;
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], tb, 4, dims, str, box, cpg, true));
+                } else {
+                    dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
+                    str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = 2 * bh * bw * C * 4; str[3] = 2 * (uint64_t)p.D * bh * bw * C * 4;
+                    box[0] = cpg; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], tb, 5, dims, str, box, cpg, true));
+                }
+            }
+            tmB = tmT.m[0];
         } else if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
@@ -454,17 +481,19 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
         }
     }
     static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(wgrad_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 +
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
     // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
     p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
     CHAP_TRY(zero_async(p.acc ? p.acc : dw, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
-    const double rows = (double)(up2 ? g.in_rows : g.out_rows);
+    const double rows = (double)(up2 ? g.in_rows : g.out_rows);     // = pixels of the low-resolution grid for the k2 s2 kinds
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
                       4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
     dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
-    wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
+    if (p.k2s2) wgrad_tc_kernel_taps<<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmT, p);
+    else wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
     CHAP_TRY(launched("wgrad_tc_kernel"));
     if (p.acc) {
         const int64_t total = (int64_t)g.taps * v.cin * v.cout;

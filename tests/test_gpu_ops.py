@@ -96,6 +96,7 @@ LARGE_CONV_CASES = [
     ("k3", 2, 3, (200, 264), 16, 32), ("k3", 2, 6, (96, 96), 32, 16), ("k3", 3, 2, (24, 40, 48), 16, 16),
     ("k1", 2, 9, (64, 64), 64, 32), ("k3", 2, 2, (72, 72), 128, 128), ("k3", 2, 4, (64, 80), 16, 4), ("k3", 2, 12, (128, 128), 32, 64),
     ("up2", 2, 6, (64, 72), 32, 16), ("up2", 2, 3, (32, 32), 256, 128), ("up2", 3, 2, (12, 14, 10), 32, 16), ("up2", 2, 12, (128, 128), 32, 16),
+    ("down2", 3, 2, (24, 40, 48), 16, 32), ("down2", 2, 6, (64, 72), 32, 64), ("down2", 3, 2, (8, 12, 10), 128, 256), ("up2", 3, 1, (14, 14, 10), 128, 64),
 ]
 
 
@@ -105,8 +106,8 @@ def test_conv_large_shapes_tensor_core(case):
     from chap_b200 import _lib
     ops = _ops()
     kind, nd, n, sp, cin, cout = case
-    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1, "up2": _lib.CONV_UP2}[kind]
-    k = {"k3": 3, "k1": 1, "up2": 2}[kind]
+    kcode = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1, "up2": _lib.CONV_UP2, "down2": _lib.CONV_DOWN2}[kind]
+    k = {"k3": 3, "k1": 1, "up2": 2, "down2": 2}[kind]
     g = torch.Generator().manual_seed(100 + LARGE_CONV_CASES.index(case))
     x = torch.randn((n, cin) + sp, generator=g).to(DEV)
     wshape = ((cin, cout) if kind == "up2" else (cout, cin)) + (k,) * nd
