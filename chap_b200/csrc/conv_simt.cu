@@ -107,6 +107,18 @@ conv_gather_kernel(SimtOp op, int all_w, const float* __restrict__ in, const flo
             }
     if (!live) return;
     float* dst = out + m * op.N + n0;
+    if (CO_T % 4 == 0 && op.N % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        // 128-bit stores: a thread's CO_T outputs are contiguous (scalar stores at a 4 * N byte lane stride wasted 7/8 of every sector)
+#pragma unroll
+        for (int j = 0; j < CO_T; j += 4) {
+            if (n0 + j < op.N) {
+                float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                if (bias) { o.x += bias[n0 + j]; o.y += bias[n0 + j + 1]; o.z += bias[n0 + j + 2]; o.w += bias[n0 + j + 3]; }
+                *reinterpret_cast<float4*>(dst + j) = o;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < CO_T; ++j)
         if (n0 + j < op.N) dst[j] = acc[j] + (bias ? bias[n0 + j] : 0.f);
@@ -161,10 +173,78 @@ conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, con
         if (n0 + j < op.N) dst[j] = acc[j] + (bias ? bias[n0 + j] : 0.f);
 }
 
+// ---------------------------------------------------------------- Cin = 1 stems (k3, pad 1, 16 output channels)
+// One thread computes PX consecutive pixels of a row x 16 channels: the PX + 2 inputs of a (kz, ky) line are loaded once and every
+// weight read from shared memory feeds PX FMAs (the generic gather kernel is bound by its one shared-memory read per FMA:
+// 432 per voxel in 3D).  Output: PX x 64 contiguous bytes per thread.
+template <int PX>
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(SimtOp op, const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ out) {
+    __shared__ float ws[27 * 16];
+    for (int i = threadIdx.x; i < op.taps * 16; i += 128) ws[i] = wp[i];            // packed [tap][K = 1][N = 16]
+    __syncthreads();
+    const int wq = (op.oW + PX - 1) / PX;                                            // thread columns per row
+    const int64_t total = (int64_t)op.out_rows / op.oW * wq;
+    const int64_t id = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (id >= total) return;
+    const int q = (int)(id % wq);
+    int64_t r = id / wq;                                                             // (n, d, h) row index
+    const int oh = (int)(r % op.oH); r /= op.oH;
+    const int od = (int)(r % op.oD); const int bn = (int)(r / op.oD);
+    const int w0 = q * PX;
+    float acc[PX][16];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
+    const int kd_n = op.nd == 3 ? 3 : 1;
+    for (int kz = 0; kz < kd_n; ++kz) {
+        const int iz = od + kz - (op.nd == 3 ? 1 : 0);
+        if (iz < 0 || iz >= op.iD) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oh + ky - 1;
+            if (iy < 0 || iy >= op.iH) continue;
+            const float* row = in + (((int64_t)bn * op.iD + iz) * op.iH + iy) * op.iW;
+            float xv[PX + 2];
+#pragma unroll
+            for (int p = 0; p < PX + 2; ++p) {
+                const int ix = w0 + p - 1;
+                xv[p] = (ix >= 0 && ix < op.iW) ? __ldg(row + ix) : 0.f;
+            }
+            const float* wt = ws + ((kz * 3 + ky) * 3) * 16;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float wv = wt[kx * 16 + j];
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) acc[p][j] = fmaf(xv[p + kx], wv, acc[p][j]);
+                }
+        }
+    }
+    float b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = bias ? bias[j] : 0.f;
+    float* dst = out + ((((int64_t)bn * op.oD + od) * op.oH + oh) * op.oW + w0) * 16;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        if (w0 + p >= op.oW) break;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + p * 16 + j) = make_float4(acc[p][j] + b[j], acc[p][j + 1] + b[j + 1], acc[p][j + 2] + b[j + 2], acc[p][j + 3] + b[j + 3]);
+    }
+}
+
 int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* bias, float* out, cudaStream_t st) {
     const double rows_mac = (double)(op.up2 ? op.in_rows : op.out_rows);
     KernelTimer timer(timer_name(op.up2 ? "conv_simt_up2" : "conv_simt_gather", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * rows_mac * op.K * op.N * op.taps,
                       4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N + (double)op.taps * op.K * op.N), st);
+    if (!op.up2 && op.K == 1 && op.N == 16 && op.ksz == 3 && op.stride == 1 && op.pad == 1 && aligned16(out)) {
+        constexpr int PX = 4;
+        const int64_t threads = op.out_rows / op.oW * ((op.oW + PX - 1) / PX);
+        stem_conv_kernel<PX><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(op, in, wp, bias, out);
+        return launched("stem_conv_kernel");
+    }
     const bool vec4 = (op.K % 4 == 0) && aligned16(in);
     const bool small = op.N <= 4;
     const int co_t = small ? 4 : 16;

@@ -22,7 +22,7 @@ from chap_b200 import _lib, ops  # noqa: E402
 KINDS = {"k3": _lib.CONV_K3, "k1": _lib.CONV_K1, "down2": _lib.CONV_DOWN2, "up2": _lib.CONV_UP2}
 
 
-def run_layer(spec, reps, bufs):
+def run_layer(spec, reps, bufs, dgrad=True):
     f = spec.split()
     kind, cin, cout, n, h, w = f[0], int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5])
     d = int(f[6]) if len(f) > 6 else None
@@ -31,7 +31,7 @@ def run_layer(spec, reps, bufs):
     dev = torch.device("cuda:0")
     fmt = torch.channels_last_3d if nd == 3 else torch.channels_last
     shape = (n, cin, d, h, w) if d else (n, cin, h, w)
-    xs = [torch.randn(shape, device=dev).contiguous(memory_format=fmt).requires_grad_(True) for _ in range(bufs)]
+    xs = [torch.randn(shape, device=dev).contiguous(memory_format=fmt).requires_grad_(dgrad) for _ in range(bufs)]
     wshape = ((cin, cout) if kind == "up2" else (cout, cin)) + (k,) * nd
     weight = torch.nn.Parameter(torch.randn(wshape, device=dev) * 0.05)
     bias = torch.nn.Parameter(torch.zeros(cout, device=dev))
@@ -60,13 +60,14 @@ def main():
     ap.add_argument("layers", nargs="+")
     ap.add_argument("--reps", type=int, default=12)
     ap.add_argument("--bufs", type=int, default=3)
+    ap.add_argument("--no-dgrad", action="store_true", help="the input needs no gradient (network stems)")
     ap.add_argument("--env", action="append", default=[], help="NAME=VALUE set before the run (repeatable)")
     args = ap.parse_args()
     for kv in args.env:
         k, v = kv.split("=", 1)
         os.environ[k] = v
     for spec in args.layers:
-        run_layer(spec, args.reps, args.bufs)
+        run_layer(spec, args.reps, args.bufs, not args.no_dgrad)
 
 
 if __name__ == "__main__":
