@@ -5,7 +5,7 @@ fails, a RuntimeError is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CHAP_B200_LIB", os.path.join(_HERE, "lib", "libchap_b200.so"))   # override: developer builds (debug hooks)
