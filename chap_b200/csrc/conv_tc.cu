@@ -651,7 +651,9 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     int stages = (int)(budget / stage);
     const int iters = (p.reuse ? p.taps / 3 : p.taps) * (p.kchunks / p.cps);
     const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
-    if (stages > 6) stages = 6;
+    const int stage_cap = getenv("CHAP_TC_STAGES") ? atoi(getenv("CHAP_TC_STAGES")) : 6;
+    if (stages > stage_cap) stages = stage_cap;
+    if (stages > 12) stages = 12;
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     p.stages = stages;
@@ -660,7 +662,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
     const size_t smem = (size_t)stages * stage + fixed + extras;
-    static_assert(2 * 6 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
+    static_assert(2 * 12 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
