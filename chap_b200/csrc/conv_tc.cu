@@ -733,10 +733,11 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     if (stages > 12) stages = 12;
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
-    p.stages = stages;
-    // statically addressed loops for the thin 2D layers (see issue_mmas_thin2d)
+    // statically addressed loops for the thin 2D layers (see issue_mmas_thin2d): ring of one or two slot triples
     p.thin2d = (p.mode == 0 && g.nd == 2 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 &&
-                (stages == 3 || stages == 6) && TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
+                stages >= 3 && TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
+    if (p.thin2d) stages = stages >= 6 ? 6 : 3;
+    p.stages = stages;
     p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : p.n_real; p.bias = bias; p.stats = ch_sums;
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
