@@ -52,8 +52,7 @@ struct TcParams {
     int epi_groups;               // 1 or 2 groups of 4 epilogue warps (blockDim = 64 + 128 * groups)
     int colsplit;                 // two groups: 1 = both work on every tile, half the columns each; 0 = they alternate tiles
     int cps;                      // k chunks per pipeline stage (1, 2 or 4): fewer, fatter stages for the deep layers
-    int thin2d;                   // 1: 2D row-reuse layer with one k chunk, resident weights and 3 or 6 ring slots -> the statically
-                                  // addressed issue / producer loops (a tile = the 3 kx slots {0,1,2} or {3,4,5})
+    int thin2d;                   // 1: row-reuse layer (2D or 3D) with one k chunk and resident weights -> the lean issue / producer loops
     int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
     uint32_t a_stage_bytes, b_stage_bytes, a_chunk_bytes, b_chunk_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
@@ -131,13 +130,14 @@ struct TileIter {
 // cost 30 % of the kernel), so the whole warp runs the warp-uniform loop (descriptors live in uniform registers), one
 // elected lane issues, and the body is straight-line per stage: KSTEPS x NKY tcgen05.mma whose descriptors differ by
 // integer adds on the lo word (+2 per 8 tf32 along K inside the swizzled row, + tw rows / one weight box per ky tap).
-// Thin 2D layers (K = 16 / 32 in one chunk, weights resident, 3 kx ring slots per tile): the generic loop spends ~90 SASS
-// instructions per ring slot on index arithmetic, and that scalar stream of the single issuing warp IS the bound of these layers.
-// Here a tile always occupies ring slots {0,1,2} or {3,4,5}, so every shared-memory address, barrier and descriptor word is a
-// per-tile constant plus compile-time offsets: per slot only wait / fence / elect / 3 x KSTEPS MMAs / commit remain.
-template <int KSTEPS>
-__device__ __forceinline__ void issue_mmas_thin2d(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
-                                                  uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base) {
+// Thin layers (row-reuse mode, K = 16 / 32 in one chunk, weights resident; NG = 3 (kx) ring slots per tile in 2D, 9 (kz, kx) in
+// 3D): the generic loop spends ~90 SASS instructions per ring slot on index arithmetic, and that scalar stream of the single
+// issuing warp IS the bound of these layers.  Here the tap structure is compile time (unrolled over the NG slots of a tile), the
+// weight descriptors are constants and only the ring position (slot, phase, A address) is carried: per slot wait / fence /
+// elect / 3 x KSTEPS MMAs / commit.
+template <int KSTEPS, int NG>
+__device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
+                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t row_bytes = KSTEPS * 32u;
     constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
@@ -145,33 +145,33 @@ __device__ __forceinline__ void issue_mmas_thin2d(const TcParams& p, uint8_t* a_
     const uint32_t b0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t a_stage = p.a_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
     const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4;
-    const bool six = p.stages == 6;
     mbar_wait(b_full, 0);
+    int s = 0; uint32_t ph = 0, a_s = a0;
     int j = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
         const int buf = j & 1;
         mbar_wait(&tmem_empty[buf], (uint32_t)((j >> 1) & 1) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
-        const int sbase = six ? (j & 1) * 3 : 0;
-        const uint32_t ph = six ? (uint32_t)((j >> 1) & 1) : (uint32_t)(j & 1);
-        const uint32_t a_tile = a0 + (uint32_t)sbase * a_stage;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            mbar_wait(&full[sbase + kx], ph);
+        for (int g = 0; g < NG; ++g) {
+            constexpr int dummy = 0; (void)dummy;
+            const int kx = g % 3, kz = g / 3;                               // compile time after unrolling
+            mbar_wait(&full[s], ph);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t a_s = a_tile + (uint32_t)kx * a_stage;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k)
-                        tc_mma_tf32_lh(d_tmem, a_s + (uint32_t)ky * a_ky + 2u * k, hi, b0 + (uint32_t)(ky * 3 + kx) * b_box + 2u * k, hi, idesc,
-                                       (kx | ky | k) == 0 ? 0u : 1u);
+                        tc_mma_tf32_lh(d_tmem, a_s + (uint32_t)ky * a_ky + 2u * k, hi, b0 + (uint32_t)((kz * 3 + ky) * 3 + kx) * b_box + 2u * k, hi, idesc,
+                                       (g | ky | k) == 0 ? 0u : 1u);
                 }
-                tc_commit(&empty[sbase + kx]);
+                tc_commit(&empty[s]);
             }
             __syncwarp();
+            a_s += a_stage;
+            if (++s == p.stages) { s = 0; ph ^= 1u; a_s = a0; }
         }
         if (elect_one()) tc_commit(&tmem_full[buf]);
         __syncwarp();
@@ -298,23 +298,24 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             __syncwarp();
         }
         if (p.thin2d) {
-            // statically addressed twin of issue_mmas_thin2d: slot kx of the tile's slot triple, one 4D box per slot
-            const bool six = p.stages == 6;
-            int j = 0;
+            // twin of issue_mmas_thin: one haloed box per (kz, kx) slot, only the ring position is carried
+            int s = 0; uint32_t ph = 0;
+            uint8_t* a_dst = a_base;
+            const int ng = p.nd == 2 ? 3 : 9;
             TileIter tj;
-            for (tj.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d); tj.tile < p.tiles_total; tj.next(p.tiles_w, p.tiles_h, p.tiles_d), ++j) {
-                const int sbase = six ? (j & 1) * 3 : 0;
-                const uint32_t ph = six ? (uint32_t)((j >> 1) & 1) : (uint32_t)(j & 1);
-                const int w0 = tj.tx * p.tw - 1, h0 = tj.ty * p.th - 1;
-                uint8_t* a_tile = a_base + (size_t)sbase * p.a_stage_bytes;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    mbar_wait(&empty[sbase + kx], ph ^ 1u);
+            for (tj.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d); tj.tile < p.tiles_total; tj.next(p.tiles_w, p.tiles_h, p.tiles_d)) {
+                const int w0 = tj.tx * p.tw - 1, h0 = tj.ty * p.th - 1, d0 = tj.tz * p.td - 1;
+                for (int g = 0; g < ng; ++g) {
+                    const int kx = g % 3, kz = g / 3;
+                    mbar_wait(&empty[s], ph ^ 1u);
                     if (elect_one()) {
-                        mbar_expect_tx(&full[sbase + kx], p.a_box_bytes);
-                        tma_load_4d(a_tile + (size_t)kx * p.a_stage_bytes, &tmA, &full[sbase + kx], 0, w0 + kx, h0, tj.img);
+                        mbar_expect_tx(&full[s], p.a_box_bytes);
+                        if (p.nd == 2) tma_load_4d(a_dst, &tmA, &full[s], 0, w0 + kx, h0, tj.img);
+                        else tma_load_5d(a_dst, &tmA, &full[s], 0, w0 + kx, h0, d0 + kz, tj.img);
                     }
                     __syncwarp();
+                    a_dst += p.a_stage_bytes;
+                    if (++s == p.stages) { s = 0; ph ^= 1u; a_dst = a_base; }
                 }
             }
         } else {
@@ -362,8 +363,10 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (p.thin2d) {
-            if (p.kc == 32) issue_mmas_thin2d<4>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
-            else issue_mmas_thin2d<2>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
+            if (p.nd == 2) { if (p.kc == 32) issue_mmas_thin<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base); }
+            else           { if (p.kc == 32) issue_mmas_thin<4, 9>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 9>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base); }
         } else
         if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
                           else issue_mmas<4, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
@@ -733,10 +736,9 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     if (stages > 12) stages = 12;
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
-    // statically addressed loops for the thin 2D layers (see issue_mmas_thin2d): ring of one or two slot triples
-    p.thin2d = (p.mode == 0 && g.nd == 2 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 &&
-                stages >= 3 && TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
-    if (p.thin2d) stages = stages >= 6 ? 6 : 3;
+    // lean issue / producer loops for the thin row-reuse layers (see issue_mmas_thin)
+    p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 && stages >= 2 &&
+                TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
     p.stages = stages;
     p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : p.n_real; p.bias = bias; p.stats = ch_sums;
