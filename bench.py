@@ -250,10 +250,11 @@ def run_gpu(args, w):
     ms, ms_e2e = float(ms), float(ms_e2e)
     if rank == 0:
         peaks = measured_peaks()
-        n_unl = w["batch"] - w["labeled"]
         vox = float(np.prod(w["shape"]))
-        h2d = w["batch"] * vox * (4 + 8) + 2 * n_unl * vox * 4         # volume f32 + label i64 + largest-CC labels back up (f32)
-        d2h = 2 * n_unl * vox * 8 + 8                                   # two argmax maps (i64) for the host CC filter + the loss
+        # per step: volume f32 + label i64, plus the trainer's own small uploads (copy-paste mask i64 [*spatial], lr and
+        # consistency-weight scalars); the CC filter runs on the device, nothing else crosses the bus
+        h2d = w["batch"] * vox * (4 + 8) + vox * 8 + 8
+        d2h = 4                                                         # the loss (f32 scalar) read back every step
         roof = None
         if fam:
             # fam holds per-shape entries ("family:t9:k16:n16:256x256x1:r786432", CHAP_TIMING_DETAIL); families = their sums

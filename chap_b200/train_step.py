@@ -6,9 +6,9 @@ not part of this step).  The reference has no 3D trainer; the 3D 
 procedure on DualDecoder3d with a cubic copy-paste mask (frozen in oracle/train_step.py).
 
 Device work: conv/BN/activation stacks, pseudo-label block, mix losses, patch mask, the perturbation
-generator, consistency losses and the fused SGD-momentum update are all libchap_b200 kernels.  The
-largest-connected-component filter of get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144) runs on
-the host like the reference (skimage there, scipy.ndimage here; one D2H/H2D round trip per step).
+generator, consistency losses, the largest-connected-component filter of get_ACDC_2DLargestCC
+(code/train_ours_2D.py:123-144; a union-find kernel, no host round trip) and the fused SGD-momentum update are all
+libchap_b200 kernels.  There is no CPU path: everything here raises if the library or a CUDA device is missing.
 """
 import numpy as np
 import torch
@@ -32,21 +32,6 @@ def largest_cc_labels(seg, n_classes):
     """get_ACDC_2DLargestCC (code/train_ours_2D.py:123-144): keep the largest connected component of every
     foreground class per sample (full connectivity, first component wins ties) -- union-find kernel, no host sync."""
     return ops.largest_cc(seg, n_classes)
-
-
-def largest_cc_labels_host(seg, n_classes):
-    """Same filter on the host with scipy (what the reference does with skimage: one D2H/H2D round trip)."""
-    from scipy import ndimage
-    seg_np = seg.detach().cpu().numpy()
-    structure = np.ones((3,) * (seg_np.ndim - 1), dtype=bool)
-    out = np.zeros(seg_np.shape, dtype=np.float32)
-    for i in range(seg_np.shape[0]):
-        for c in range(1, n_classes):
-            labels, n = ndimage.label(seg_np[i] == c, structure=structure)
-            if n != 0:
-                keep = labels == (np.argmax(np.bincount(labels.ravel())[1:]) + 1)
-                out[i] += keep.astype(np.float32) * c
-    return torch.from_numpy(out).to(seg.device, non_blocking=True)
 
 
 def get_masks(output, n_classes, nms=1):

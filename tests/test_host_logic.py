@@ -33,11 +33,10 @@ def test_generate_mask_matches_reference_semantics():
 
 def test_host_largest_cc_and_metrics():
     from chap_b200.test_3D_util import asd, cal_dice, dice_coefficient, hd95, jc
-    from chap_b200.train_step import largest_cc_labels_host
     seg = torch.zeros(1, 8, 8, dtype=torch.int64)
     seg[0, 0:2, 0:2] = 1; seg[0, 4:7, 4:7] = 1; seg[0, 0, 7] = 2
-    out = largest_cc_labels_host(seg, 3)
-    assert torch.equal(out, L.largest_cc_labels(seg, 3)) and out.sum() == 9 + 2 and out[0, 0, 0] == 0
+    out = L.largest_cc_labels(seg, 3)               # the oracle's filter (the product's is the device kernel: tests/test_gpu_step.py)
+    assert out.sum() == 9 + 2 and out[0, 0, 0] == 0 and out[0, 5, 5] == 1 and out[0, 0, 7] == 2
     a = np.zeros((8, 8, 8), bool); a[2:6, 2:6, 2:6] = True
     b = np.zeros((8, 8, 8), bool); b[3:7, 2:6, 2:6] = True
     assert abs(dice_coefficient(a, b) - 0.75) < 1e-12 and abs(jc(a, b) - 0.6) < 1e-12
