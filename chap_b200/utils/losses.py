@@ -63,12 +63,20 @@ class DiceLoss_bcp:
         return self.from_logits(torch.log(soft.clamp_min(1e-30)), target, mask)
 
 
-def consistency_distance(logits, target_soft, mask, losstype):
-    """'kl': sum(mask * KL(target || softmax(logits))) / N;  'dice': masked soft Dice, mean over classes."""
+KL_REDUCTIONS = ("mean", "batchmean")
+
+
+def consistency_distance(logits, target_soft, mask, losstype, reduction="mean"):
+    """'kl': sum(mask * KL(target || softmax(logits))) / (N * positions) ('mean', the frozen default) or / N
+    ('batchmean', the classic-VAT scaling that made the round-1 step diverge -- see oracle/chap_losses.py
+    kl_consistency);  'dice': masked soft Dice, mean over classes (scale free)."""
     c = logits.shape[1]
     if losstype == "kl":
+        if reduction not in KL_REDUCTIONS:
+            raise ValueError("reduction must be one of %r" % (KL_REDUCTIONS,))
         s = ops.consistency_sums(logits, target_soft, mask, DIST_KL)
-        return (s[0] / logits.shape[0]).float()
+        denom = logits.shape[0] if reduction == "batchmean" else logits.numel() // c
+        return (s[0] / denom).float()
     if losstype == "dice":
         s = ops.consistency_sums(logits, target_soft, mask, DIST_DICE)
         return _dice_from_sums(s[:c], s[c:2 * c], s[2 * c:3 * c]).float()
@@ -84,11 +92,14 @@ class VAT2d:
     decoders on f + xi*l2n(d) recording data gradients only; the fused perturbation generator
     (channel-wise + spatial-wise L2 normalisation, eps scaling, injection) for all levels in one
     library call; decoder re-forward on f + r with gradients flowing to encoder and decoders.
-    BatchNorm running statistics are not updated inside VAT.
+    BatchNorm running statistics are not updated inside VAT.  reduction: scaling of the returned 'kl' loss
+    ('mean' per pixel, default; 'batchmean' per sample).
     """
 
-    def __init__(self, xi=10.0, epi=6.0, num_classes=4, mode="channel_spatial"):
-        self.xi, self.epi, self.num_classes, self.mode = xi, epi, num_classes, mode
+    def __init__(self, xi=10.0, epi=6.0, num_classes=4, mode="channel_spatial", reduction="mean"):
+        if reduction not in KL_REDUCTIONS:
+            raise ValueError("reduction must be one of %r" % (KL_REDUCTIONS,))
+        self.xi, self.epi, self.num_classes, self.mode, self.reduction = xi, epi, num_classes, mode, reduction
 
     def __call__(self, model, x, soft1, soft2, mask=None, losstype="kl", d_init=None, trace=None):
         x_u = x[x.shape[0] - soft1.shape[0]:]
@@ -98,13 +109,14 @@ class VAT2d:
                 d_init = [torch.rand_like(f) - 0.5 for f in feats]
             hat = [ops.l2n_sample_axpy(d, f, self.xi).requires_grad_(True) for d, f in zip(d_init, feats)]
             with ops.no_weight_grad():
-                dist = consistency_distance(model.decoder1(hat), soft2, mask, losstype) + \
-                    consistency_distance(model.decoder2(hat), soft1, mask, losstype)
+                # the probe distance is always 'batchmean' (direction only; keeps |g| far above the 1e-8 of the norms)
+                dist = consistency_distance(model.decoder1(hat), soft2, mask, losstype, "batchmean") + \
+                    consistency_distance(model.decoder2(hat), soft1, mask, losstype, "batchmean")
             g = torch.autograd.grad(dist, hat)
             adv_values = ops.perturb(g, feats, self.epi, self.mode, g_scale=self.xi)
             adv = [ops.attach_identity_grad(f, v) for f, v in zip(feats, adv_values)]
-            loss = consistency_distance(model.decoder1(adv), soft2, mask, losstype) + \
-                consistency_distance(model.decoder2(adv), soft1, mask, losstype)
+            loss = consistency_distance(model.decoder1(adv), soft2, mask, losstype, self.reduction) + \
+                consistency_distance(model.decoder2(adv), soft1, mask, losstype, self.reduction)
         if trace is not None:
             trace.update(feats=feats, g=g, adv=adv_values, dist=dist)
         return loss

@@ -163,14 +163,26 @@ def perturbation(g, eps, mode="channel_spatial"):
     return eps * l2n_sample(0.5 * (l2n_channel(g) + l2n_spatial(g)))
 
 
-def kl_consistency(logits, target_soft, mask=None):
+KL_REDUCTIONS = ("mean", "batchmean")
+
+
+def kl_consistency(logits, target_soft, mask=None, reduction="mean"):
     """'kl': sum_c t (log t - log_softmax(logits)) per position (0 log 0 = 0), optionally
-    multiplied by mask[N,*spatial], summed and divided by the batch size ('batchmean')."""
+    multiplied by mask[N,*spatial], summed and divided by
+      reduction='mean'       N * positions  -- a PER-PIXEL mean, the frozen default: the loss stays O(1) and
+                             comparable to bcp_loss, which is also a per-pixel mean (code/train_ours_2D.py:208-209)
+      reduction='batchmean'  N              -- F.kl_div(..., reduction='batchmean') of the classic VAT lineage;
+                             for a segmentation map this is H*W (*D) times the per-pixel loss.  Round 1 froze this
+                             and the CHAP step diverged (vat_loss 1.8e3 -> 5e5 within 25 iterations at 256^2,
+                             1e15 / NaN in 3D) because cw * vat_loss swamped bcp_loss; kept selectable only.
+    The VAT2d source is absent from the reference, so the scaling is a frozen CHOICE ("parity unpinned")."""
+    assert reduction in KL_REDUCTIONS
     logp = F.log_softmax(logits, dim=1)
     kl = (torch.xlogy(target_soft, target_soft) - target_soft * logp).sum(dim=1)
     if mask is not None:
         kl = kl * mask.to(kl.dtype)
-    return kl.sum() / logits.shape[0]
+    denom = logits.shape[0] if reduction == "batchmean" else kl.numel()
+    return kl.sum() / denom
 
 
 def dice_consistency(logits, target_soft, mask=None):
@@ -185,9 +197,10 @@ def dice_consistency(logits, target_soft, mask=None):
     return loss / p.shape[1]
 
 
-def consistency_distance(logits, target_soft, mask, losstype):
+def consistency_distance(logits, target_soft, mask, losstype, reduction="mean"):
+    """`reduction` only concerns 'kl' (the soft Dice is a ratio of sums, scale free)."""
     if losstype == "kl":
-        return kl_consistency(logits, target_soft, mask)
+        return kl_consistency(logits, target_soft, mask, reduction)
     assert losstype == "dice"
     return dice_consistency(logits, target_soft, mask)
 
@@ -223,13 +236,18 @@ class VAT:
              g_l = d dist / d d_l                                     (decoder data-grad only)
       3      r_l = epi * normalise(g_l)   (perturbation(), channel+spatial)
       4      o1, o2 = decoder1/2([f_l + r_l]); loss = D(o1, soft2) + D(o2, soft1)
+    Reduction of the 'kl' distance: the returned loss (step 4) uses `reduction` (default 'mean', a per-pixel mean;
+    see kl_consistency).  The PROBE distance of step 2 always uses 'batchmean': the direction normalise(g) is
+    invariant to a positive rescaling of dist except through the absolute 1e-8 in the norms, and a per-pixel mean
+    would shrink |g| by H*W*D (1e6 in 3D) down to that epsilon.
     BatchNorm uses batch statistics in all VAT passes when the model is in train mode, and
     running statistics are NOT updated inside VAT (`model.bn_tracking(False)`).
     `model` must offer encoder(x), decoder1(feats), decoder2(feats), bn_tracking(flag) ctx.
     """
 
-    def __init__(self, xi=10.0, epi=6.0, num_classes=4, mode="channel_spatial"):
-        self.xi, self.epi, self.num_classes, self.mode = xi, epi, num_classes, mode
+    def __init__(self, xi=10.0, epi=6.0, num_classes=4, mode="channel_spatial", reduction="mean"):
+        assert reduction in KL_REDUCTIONS
+        self.xi, self.epi, self.num_classes, self.mode, self.reduction = xi, epi, num_classes, mode, reduction
 
     def __call__(self, model, x, soft1, soft2, mask=None, losstype="kl", d_init=None, trace=None):
         x_u = x[x.shape[0] - soft1.shape[0]:]
@@ -239,13 +257,13 @@ class VAT:
                 d_init = [torch.rand_like(f) - 0.5 for f in feats]
             d = [l2n_sample(t).detach().requires_grad_(True) for t in d_init]
             hat = [f.detach() + self.xi * di for f, di in zip(feats, d)]
-            dist = consistency_distance(model.decoder1(hat), soft2, mask, losstype) + \
-                consistency_distance(model.decoder2(hat), soft1, mask, losstype)
+            dist = consistency_distance(model.decoder1(hat), soft2, mask, losstype, "batchmean") + \
+                consistency_distance(model.decoder2(hat), soft1, mask, losstype, "batchmean")
             g = torch.autograd.grad(dist, d)
             r = [perturbation(gi.detach(), self.epi, self.mode) for gi in g]
             adv = [f + ri for f, ri in zip(feats, r)]
-            loss = consistency_distance(model.decoder1(adv), soft2, mask, losstype) + \
-                consistency_distance(model.decoder2(adv), soft1, mask, losstype)
+            loss = consistency_distance(model.decoder1(adv), soft2, mask, losstype, self.reduction) + \
+                consistency_distance(model.decoder2(adv), soft1, mask, losstype, self.reduction)
         if trace is not None:
             trace.update(feats=feats, d=d, g=g, r=r, dist=dist)
         return loss

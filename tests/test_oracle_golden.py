@@ -103,6 +103,10 @@ def test_frozen_losses_have_not_drifted():
     dm = L.create_mask_v1(ps1, ps2, know, 4, 0.25)
     assert np.array_equal(dm.numpy(), g["diff_mask"])
     np.testing.assert_allclose([L.kl_consistency(logits, soft2, dm).item(), L.kl_consistency(logits, soft2, None).item()], g["kl"], rtol=1e-6)
+    np.testing.assert_allclose([L.kl_consistency(logits, soft2, dm, "batchmean").item(),
+                                L.kl_consistency(logits, soft2, None, "batchmean").item()], g["kl_batchmean"], rtol=1e-6)
+    # the two reductions differ by exactly the number of positions per sample
+    np.testing.assert_allclose(g["kl_batchmean"], g["kl"] * 16 * 16, rtol=1e-6)
     np.testing.assert_allclose([L.dice_consistency(logits, soft2, dm).item(), L.dice_consistency(logits, soft2, None).item()], g["dice"], rtol=1e-6)
     gf = torch.from_numpy(g["gfield"])
     for key, mode in (("r_cs", "channel_spatial"), ("r_c", "channel"), ("r_s", "spatial"), ("r_n", "sample")):
