@@ -346,6 +346,8 @@ def main():
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--force-simt", action="store_true", help="debug: fp32 CUDA-core convolutions only")
+    ap.add_argument("--conv-precision", type=int, default=None,
+                    help="split-operand 3xTF32 tensor-core convolutions for layers with max(Cin, Cout) <= this (0: plain TF32)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -354,6 +356,9 @@ def main():
     if args.force_simt:
         from chap_b200 import ops
         ops.set_force_simt(True)
+    if args.conv_precision is not None:
+        from chap_b200 import ops
+        ops.set_conv_precision(args.conv_precision)
     run_gpu(args, w)
 
 

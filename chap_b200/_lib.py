@@ -53,6 +53,8 @@ SIGNATURES = {
     "chap_timing_report": (I, [ctypes.c_char_p, c_size_t]),
     "chap_set_force_simt": (None, [I]),
     "chap_get_force_simt": (I, []),
+    "chap_set_conv_precision": (None, [I]),
+    "chap_get_conv_precision": (I, []),
     "chap_conv_packed_elems": (c_size_t, [_CD]),
     "chap_conv_pack_weights": (I, [_CD, P, P, P, P]),
     "chap_conv_fwd": (I, [_CD, P, P, P, P, P, P]),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "chap_l2n_sample_axpy": (I, [P, P, F, I, L, P, P, P]),
     "chap_sgd_momentum_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
     "chap_sgd_momentum": (I, [P, P, P, L, F, F, F, F, I, P]),
+    "chap_schedule_step": (I, [P, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, L, P, P, P]),
     "chap_sw_extract": (I, [_SW, P, I, I, P, P]),
     "chap_sw_aggregate": (I, [_SW, P, I, P, P, P, P]),
 }

@@ -12,6 +12,7 @@ namespace chap {
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_force_simt;
+extern std::atomic<int> g_precise_max_c;  // 3xTF32 split-operand convolutions for layers with max(K, N) <= this (0: plain TF32)
 
 inline int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -79,20 +80,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Round-to-nearest conversion to TF32 (kept in an fp32 container, low 13 mantissa bits zero).  tcgen05.mma
-// kind::tf32 IGNORES the low 13 bits of its fp32 operands (truncation, biased); producers of tensors that feed a
-// tensor-core convolution therefore round on store when the tensor-core path is active (`on`), which is what
-// cuDNN's TF32 path does with cvt.rna and halves the rounding error (measured, DESIGN.md "precision").
+// Round-to-nearest (ties away) conversion to TF32, kept in an fp32 container (low 13 mantissa bits zero).
+//
+// What the tensor-core path does with fp32 operands -- MEASURED on B200 (tools/tf32_probe.py, profiles/r02_tf32_probe.md):
+// one convolution layer run with raw / host-pre-rounded (cvt.rna emulation) / host-truncated operands gives bit-identical
+// results for "raw" and "pre-rounded" on BOTH operands and matches an exact-arithmetic evaluation of rna(x) * rna(w) (and
+// cuDNN's TF32 kernels) to 1e-7, while pre-truncated operands show the -3.5e-4 per-operand shrink that truncation must give.
+// So operands loaded through CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 tensor maps ARE rounded to nearest (round 1's comment here
+// claimed truncation; that was wrong), producer-side rounding changes nothing (`rt` below stays 0), and a TF32 layer of
+// this library has exactly cuDNN-TF32's error.  The network-level gap to torch-eager "TF32" (1.8x in 2D) comes from cuDNN
+// silently running its fp32 kernels on the 16-channel layers (layer c16: cuDNN allow_tf32 error 2e-7); the answer to that
+// is the split-operand ("3xTF32") mode of conv_tc.cu, not a rounding switch.
 __device__ __forceinline__ float tf32_rn(float x, int on) {
     if (!on) return x;
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
-// Measured on B200 (round 1): rounding the producers' outputs to TF32 did NOT change the network-level error of the
-// tensor-core path (2D logits 1.49e-3 with, 1.46e-3 without, vs the fp32 oracle) -- the CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
-// tensor maps / the MMA unit already round -- while it costs the fp32 precision of tensors that are also consumed
-// elementwise (the perturbed features f + r lose r below TF32 resolution).  Producer-side rounding is therefore OFF.
 inline int round_tf32_on() { return 0; }
 
 // streaming 128-bit load (read once) / store

@@ -12,7 +12,8 @@ static bool use_tc(const Geom& g, bool dgrad) {
 extern "C" size_t chap_conv_packed_elems(const chap_conv_desc* d) {
     Geom g{};
     if (resolve(d, g) != CHAP_OK) return 0;
-    return (size_t)g.taps * tc_pad16(g.cin) * tc_pad16(g.cout);      // room for the zero-padded tensor-core operand of thin heads
+    // room for the zero-padded tensor-core operand of thin heads, twice: TF32 hi half, then lo half (split-operand mode)
+    return 2 * (size_t)g.taps * tc_pad16(g.cin) * tc_pad16(g.cout);
 }
 
 extern "C" int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream) {
@@ -85,7 +86,7 @@ extern "C" int chap_conv_dgrad_split_supported(const chap_conv_desc* d, int32_t 
     Geom g{};
     if (resolve(d, g) != CHAP_OK) return 0;
     if (g.kind != CHAP_CONV_K3 && g.kind != CHAP_CONV_K1) return 0;
-    return use_tc(g, true) && !thin_tc_supports(g, true) && ca > 0 && ca < g.cin && ca % 16 == 0 && (g.cin - ca) % 16 == 0 ? 1 : 0;
+    return use_tc(g, true) && ca > 0 && ca < g.cin && ca % 16 == 0 && (g.cin - ca) % 16 == 0 ? 1 : 0;
 }
 
 extern "C" int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx_a, int32_t ca,

@@ -77,10 +77,6 @@ struct BnFold {
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
             double* ch_sums, cudaStream_t st, float* out_b = nullptr, int ca = 0, const BnFold* bn = nullptr);
 bool tc_supports(const Geom& g, bool dgrad);
-// thin-layer tensor-core path (thin_tc.cu): taps in the N dimension + shift-add epilogue, Cin/Cout in {16, 32}
-int thin_tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
-                 double* ch_sums, cudaStream_t st);
-bool thin_tc_supports(const Geom& g, bool dgrad);
 // tensor-core weight gradient (wgrad_tc.cu): 1 handled, 0 unsupported shape, <0 error.  dw is overwritten.
 // acc_ws (nullable): taps * cin * cout floats of scratch; when given, the (non-swap) kernel reduces into a [tap][M][N] layout
 // with 128-bit vector reductions and a small kernel writes the torch layout afterwards.

@@ -21,7 +21,7 @@ __device__ __forceinline__ void decode_row(int64_t m, int D, int H, int W, int& 
 // out[t][k][n] (kn_order = 1) or out[t][n][k] (kn_order = 0) = w[k*sk + n*sn + tmap(t)]; the packed operand may be
 // zero-padded to Kp x Np (tensor-core path of the 4- / 8-channel heads: the MMA needs K, N >= 16)
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out,
-                                    int taps, int K, int N, int Kp, int Np, int64_t sk, int64_t sn, int flip, int kn_order) {
+                                    int taps, int K, int N, int Kp, int Np, int64_t sk, int64_t sn, int flip, int kn_order, int rt) {
     int64_t total = (int64_t)taps * Kp * Np;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int t = (int)(i / ((int64_t)Kp * Np));
@@ -29,7 +29,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
         int k, n;
         if (kn_order) { k = r / Np; n = r % Np; } else { n = r / Kp; k = r % Kp; }
         int ts = flip ? (taps - 1 - t) : t;
-        out[i] = (k < K && n < N) ? w[k * sk + n * sn + ts] : 0.f;
+        const float v = (k < K && n < N) ? w[k * sk + n * sn + ts] : 0.f;
+        if (rt) {       // tensor-core operand: TF32 halves w = hi + lo for the split-operand mode (plain TF32 reads hi only)
+            const float hi = tf32_rn(v, 1);
+            out[i] = hi;
+            out[total + i] = tf32_rn(v - hi, 1);
+        } else {
+            out[i] = v;
+        }
     }
 }
 
@@ -38,7 +45,8 @@ int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, 
     if (Kp < K) Kp = K;
     if (Np < N) Np = N;
     int64_t total = (int64_t)taps * Kp * Np;
-    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, Kp, Np, sk, sn, flip, kn_order);
+    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, Kp, Np, sk, sn, flip, kn_order,
+                                                                    kn_order == 0 ? 1 : 0);   // kn_order 0 = tensor-core operand
     return launched("pack_weights_kernel");
 }
 

@@ -55,6 +55,9 @@ struct TcParams {
     int thin2d;                   // 1: row-reuse layer (2D or 3D) with one k chunk and resident weights -> the lean issue / producer loops
     int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
+    int precise;                  // 1: split-operand 3xTF32 (kernel template PRECISE): 4 extra warps split every A stage into TF32 hi / lo halves
+    int b_lo_rows;                // precise: row offset of the lo half inside the weight tensor map
+    uint32_t a_lo_off, b_lo_off;  // precise: byte offsets of the lo copies of the A ring / the B area (or B ring) in shared memory
     uint32_t a_stage_bytes, b_stage_bytes, a_chunk_bytes, b_chunk_bytes, a_box_bytes, b_box_bytes, b_area_bytes;
     float* out;                   // channels [0, ca), row stride ca
     float* out_b;                 // channels [ca, n_total), row stride n_total - ca (dgrad of a channel concat), or nullptr
@@ -65,6 +68,7 @@ struct TcParams {
 };
 
 constexpr int kTcThreadsMax = 320;         // TMA warp, MMA warp, 1 or 2 groups of 4 epilogue warps
+constexpr int kTcThreadsPrecise = 448;     // + 4 operand-splitting warps (split-operand 3xTF32 mode)
 // Profiling experiments (CHAP_TC_DEBUG bit mask: 1 no MMAs, 2 no A loads, 4 no stores / statistics, 8 no tcgen05.ld,
 // 16 polling waits, 32 plain arrives instead of commits) are compiled in only with -DCHAP_TC_DEBUG_HOOKS: the
 // single-warp issue loops are latency-bound and every extra branch costs.
@@ -135,12 +139,26 @@ struct TileIter {
 // issuing warp IS the bound of these layers.  Here the tap structure is compile time (unrolled over the NG slots of a tile), the
 // weight descriptors are constants and only the ring position (slot, phase, A address) is carried: per slot wait / fence /
 // elect / 3 x KSTEPS MMAs / commit.
-template <int KSTEPS, int NG>
+// One product term of the implicit GEMM.  PRECISE: x = x_hi + x_lo, w = w_hi + w_lo (TF32 halves; the x halves are written by
+// the splitter warps, the w halves come packed from global memory) and x_hi w_hi + x_lo w_hi + x_hi w_lo goes into the same
+// fp32 accumulator (the dropped x_lo w_lo term is 2^-22 relative).
+template <bool PRECISE>
+__device__ __forceinline__ void mma_term(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t a_lo_off, uint32_t b_lo_off) {
+    tc_mma_tf32_lh(d_tmem, a_lo, hi, b_lo, hi, idesc, accumulate);
+    if (PRECISE) {
+        tc_mma_tf32_lh(d_tmem, a_lo + a_lo_off, hi, b_lo, hi, idesc, 1u);
+        tc_mma_tf32_lh(d_tmem, a_lo, hi, b_lo + b_lo_off, hi, idesc, 1u);
+    }
+}
+
+template <int KSTEPS, int NG, bool PRECISE>
 __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
                                                 uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t row_bytes = KSTEPS * 32u;
     constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+    const uint32_t a_lo_off = p.a_lo_off >> 4, b_lo_off = p.b_lo_off >> 4;
     const uint32_t a0 = ((smem_u32(a_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t b0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t a_stage = p.a_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
@@ -164,8 +182,8 @@ __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_ba
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k)
-                        tc_mma_tf32_lh(d_tmem, a_s + (uint32_t)ky * a_ky + 2u * k, hi, b0 + (uint32_t)((kz * 3 + ky) * 3 + kx) * b_box + 2u * k, hi, idesc,
-                                       (g | ky | k) == 0 ? 0u : 1u);
+                        mma_term<PRECISE>(d_tmem, a_s + (uint32_t)ky * a_ky + 2u * k, b0 + (uint32_t)((kz * 3 + ky) * 3 + kx) * b_box + 2u * k, hi, idesc,
+                                          (g | ky | k) == 0 ? 0u : 1u, a_lo_off, b_lo_off);
                 }
                 tc_commit(&empty[s]);
             }
@@ -178,7 +196,7 @@ __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_ba
     }
 }
 
-template <int KSTEPS, int NKY>
+template <int KSTEPS, int NKY, bool PRECISE>
 __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
                                            uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base, int groups) {
     // instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at 17, M >> 4 at 24
@@ -191,6 +209,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
     const uint32_t b_lo0 = ((smem_u32(b_base) >> 4) & 0x3FFFu) | (1u << 16);
     const uint32_t a_stage = p.a_stage_bytes >> 4, b_stage = p.b_stage_bytes >> 4, b_box = p.b_box_bytes >> 4;
     const uint32_t a_chunk = p.a_chunk_bytes >> 4, b_chunk = p.b_chunk_bytes >> 4;   // one k chunk inside a stage
+    const uint32_t a_lo_off = p.a_lo_off >> 4, b_lo_off = p.b_lo_off >> 4;
     const uint32_t a_ky = ((uint32_t)p.tw * row_bytes) >> 4;
     const uint32_t b_ky = p.b_resident ? 3u * (uint32_t)p.kchunks * b_box : b_box;     // resident layout is [tap][kchunk]
     const uint32_t b_step = p.b_resident ? b_box : b_chunk;                            // next k chunk of the same tap
@@ -221,8 +240,8 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
                         for (int ky = 0; ky < NKY; ++ky) {
 #pragma unroll
                             for (int k = 0; k < KSTEPS; ++k)
-                                tc_mma_tf32_lh(d_tmem, a_c + (uint32_t)ky * a_ky + 2u * k, hi, b_c + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
-                                               (ky | k) == 0 ? accum : 1u);
+                                mma_term<PRECISE>(d_tmem, a_c + (uint32_t)ky * a_ky + 2u * k, b_c + (uint32_t)ky * b_ky + 2u * k, hi, idesc,
+                                                  (ky | k) == 0 ? accum : 1u, a_lo_off, b_lo_off);
                         }
                         accum = 1;
                         a_c += a_chunk; b_c += b_step;
@@ -244,18 +263,23 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
 // two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
 // tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
+template <bool PRECISE>
 __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmTaps* tmTp, const TcParams& p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_base = smem;
-    uint8_t* b_base = smem + (size_t)p.stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (p.b_resident ? (size_t)p.b_area_bytes : (size_t)p.stages * p.b_stage_bytes));
-    uint64_t* full = bars;
+    // precise: [A hi ring][A lo ring][B hi][B lo]; the lo copies sit at constant offsets (p.a_lo_off, p.b_lo_off)
+    const int dup = PRECISE ? 2 : 1;
+    uint8_t* b_base = smem + (size_t)dup * p.stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)dup * (p.b_resident ? (size_t)p.b_area_bytes : (size_t)p.stages * p.b_stage_bytes));
+    uint64_t* full = bars;                              // TMA bytes of a ring slot have landed
     uint64_t* empty = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;          // [2]
     uint64_t* tmem_empty = tmem_full + 2;               // [2]
     uint64_t* b_full = tmem_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+    uint64_t* split = b_full + 1;                       // [stages] precise: the slot's A data has been split into hi / lo
+    uint64_t* ready = PRECISE ? split : full;           // what the MMA warp waits for
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split + (PRECISE ? p.stages : 0));
     float* red = reinterpret_cast<float*>(tmem_slot + 2);          // [8 warps][2][nt] epilogue statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,7 +289,7 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); if (PRECISE) mbar_init(&split[s], 4); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.epi_groups == 2 && p.colsplit) ? 8 : 4); }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -290,10 +314,12 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
         // ------------------------------------------------------------------ TMA producer (warp-uniform, one elected lane issues)
         if (p.b_resident) {
             if (elect_one()) {
-                mbar_expect_tx(b_full, p.b_area_bytes);
-                for (int tap = 0; tap < p.taps; ++tap)
-                    for (int kci = 0; kci < p.kchunks; ++kci)
-                        tma_load_2d(b_base + (size_t)(tap * p.kchunks + kci) * p.b_box_bytes, &tmB, b_full, kci * p.kc, tap * p.n_total + n0);
+                mbar_expect_tx(b_full, (uint32_t)dup * p.b_area_bytes);
+                for (int half = 0; half < dup; ++half)
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        for (int kci = 0; kci < p.kchunks; ++kci)
+                            tma_load_2d(b_base + (size_t)half * p.b_lo_off + (size_t)(tap * p.kchunks + kci) * p.b_box_bytes, &tmB, b_full,
+                                        kci * p.kc, half * p.b_lo_rows + tap * p.n_total + n0);
             }
             __syncwarp();
         }
@@ -333,7 +359,7 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
                     TC_WAIT(&empty[s], ph ^ 1);
                     if (elect_one()) {
                         const uint32_t nb = p.b_resident ? 0u : (p.reuse ? 3u : 1u);
-                        mbar_expect_tx(&full[s], (uint32_t)p.cps * ((TC_DBG(2) ? 0u : p.a_box_bytes) + nb * p.b_box_bytes));
+                        mbar_expect_tx(&full[s], (uint32_t)p.cps * ((TC_DBG(2) ? 0u : p.a_box_bytes) + (uint32_t)dup * nb * p.b_box_bytes));
                         for (int c = 0; c < p.cps; ++c) {
                             const int kci = kc0 + c;
                             uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes + (size_t)c * p.a_chunk_bytes;
@@ -345,11 +371,15 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
                             else tma_load_5d(a_dst, &tmA, &full[s], kci * p.kc, w0 + kx - p.pad, h0 + ky - p.pad, d0 + kz - p.pad, img);
                             if (!p.b_resident) {
                                 uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes + (size_t)c * p.b_chunk_bytes;
-                                if (p.reuse) {
-                                    for (int q = 0; q < 3; ++q)
-                                        tma_load_2d(b_dst + (size_t)q * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + q) * 3 + kx) * p.n_total + n0);
-                                } else {
-                                    tma_load_2d(b_dst, &tmB, &full[s], kci * p.kc, grp * p.n_total + n0);
+                                for (int half = 0; half < dup; ++half) {
+                                    uint8_t* bd = b_dst + (size_t)half * p.b_lo_off;
+                                    const int r0 = half * p.b_lo_rows + n0;
+                                    if (p.reuse) {
+                                        for (int q = 0; q < 3; ++q)
+                                            tma_load_2d(bd + (size_t)q * p.b_box_bytes, &tmB, &full[s], kci * p.kc, ((kz * 3 + q) * 3 + kx) * p.n_total + r0);
+                                    } else {
+                                        tma_load_2d(bd, &tmB, &full[s], kci * p.kc, grp * p.n_total + r0);
+                                    }
                                 }
                             }
                         }
@@ -363,15 +393,42 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (p.thin2d) {
-            if (p.nd == 2) { if (p.kc == 32) issue_mmas_thin<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
-                             else issue_mmas_thin<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base); }
-            else           { if (p.kc == 32) issue_mmas_thin<4, 9>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base);
-                             else issue_mmas_thin<2, 9>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base); }
+            if (p.nd == 2) { if (p.kc == 32) issue_mmas_thin<4, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base); }
+            else           { if (p.kc == 32) issue_mmas_thin<4, 9, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 9, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base); }
         } else
-        if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
-                          else issue_mmas<4, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
-        else            { if (p.reuse) issue_mmas<2, 3>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
-                          else issue_mmas<2, 1>(p, a_base, b_base, full, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
+        if (p.kc == 32) { if (p.reuse) issue_mmas<4, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
+                          else issue_mmas<4, 1, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
+        else            { if (p.reuse) issue_mmas<2, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base, groups);
+                          else issue_mmas<2, 1, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base, groups); }
+    } else if (PRECISE && warp >= 2 + 4 * p.epi_groups) {
+        // ------------------------------------------------------------------ operand splitter (precise mode): 4 warps
+        // Every ring slot, once its TMA bytes have landed (fp32, NOT rounded: the A tensor maps of this mode are FLOAT32):
+        // hi = rna_tf32(x) in place, lo = x - hi (exact in fp32) into the lo ring at the same swizzled offset.  Elementwise, so
+        // the swizzle is irrelevant.  Generic-proxy writes -> fence.proxy.async -> the MMA warp's tcgen05.mma may read them.
+        const int t = (int)threadIdx.x - (64 + 128 * p.epi_groups);
+        const int slot_uses = groups * (p.kchunks / p.cps);
+        const uint32_t n16 = p.a_stage_bytes >> 4;
+        int s = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            for (int u = 0; u < slot_uses; ++u) {
+                mbar_wait(&full[s], ph);
+                float4* hi4 = reinterpret_cast<float4*>(a_base + (size_t)s * p.a_stage_bytes);
+                float4* lo4 = reinterpret_cast<float4*>(a_base + p.a_lo_off + (size_t)s * p.a_stage_bytes);
+                for (uint32_t i = (uint32_t)t; i < n16; i += 128u) {
+                    const float4 x = hi4[i];
+                    float4 h, l;
+                    h.x = tf32_rn(x.x, 1); h.y = tf32_rn(x.y, 1); h.z = tf32_rn(x.z, 1); h.w = tf32_rn(x.w, 1);
+                    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+                    hi4[i] = h; lo4[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+        }
     } else {
         // ------------------------------------------------------------------ epilogue: 2 groups of 4 warps
         // The epilogue of one tile is a single latency-bound instruction stream per warp (measured: ~1.5 us per tile, the
@@ -543,12 +600,22 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
 // Two entry points: the per-tap tensor maps (1 KB of kernel parameters) are only passed for the k2 s2 gathers.
 __global__ void __launch_bounds__(kTcThreadsMax, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    conv_tc_kernel_body(tmA, tmB, nullptr, p);
+    conv_tc_kernel_body<false>(tmA, tmB, nullptr, p);
 }
 __global__ void __launch_bounds__(kTcThreadsMax, 2)
 conv_tc_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
                     const TcParams p) {
-    conv_tc_kernel_body(tmA, tmB, &tmT, p);
+    conv_tc_kernel_body<false>(tmA, tmB, &tmT, p);
+}
+// split-operand 3xTF32 variants (chap_set_conv_precision): + 4 splitter warps
+__global__ void __launch_bounds__(kTcThreadsPrecise, 2)
+conv_tc_precise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    conv_tc_kernel_body<true>(tmA, tmB, nullptr, p);
+}
+__global__ void __launch_bounds__(kTcThreadsPrecise, 2)
+conv_tc_precise_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
+                            const TcParams p) {
+    conv_tc_kernel_body<true>(tmA, tmB, &tmT, p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -570,7 +637,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int kc, bool mn_major_tf32) {
+                    const uint32_t* box, int kc, bool mn_major_tf32, bool plain_f32) {
     // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current in this thread.  autograd's
     // backward thread may not have touched the runtime yet -> bind it once per thread with a no-op runtime call.
     static thread_local bool ctx_bound = false;
@@ -580,7 +647,9 @@ int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t
     cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+    // TFLOAT32: the TMA unit rounds the fp32 data to nearest TF32 on the way into shared memory (measured, common.cuh);
+    // FLOAT32 (split-operand mode): bits arrive untouched and the splitter warps make the TF32 hi / lo halves
+    CUresult r = fn(map, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     mn_major_tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -641,7 +710,6 @@ static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
             double* ch_sums, cudaStream_t st, float* out_b, int ca, const BnFold* bn) {
     if (!tc_supports(g, dgrad)) return 0;
-    if (!out_b && !bn && thin_tc_supports(g, dgrad)) return thin_tc_conv(g, dgrad, in, wp, bias, out, ch_sums, st);
     CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
     int K, N;
     tc_channels(g, dgrad, K, N);
@@ -682,7 +750,11 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
     p.b_area_bytes = (uint32_t)p.taps * p.kchunks * p.b_box_bytes;
-    p.b_resident = p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
+    // split-operand 3xTF32 (chap_set_conv_precision): every A stage and every weight box exists twice (hi / lo halves)
+    const int pmc = g_precise_max_c.load(std::memory_order_relaxed);
+    p.precise = (pmc > 0 && (g.cin > g.cout ? g.cin : g.cout) <= pmc) ? 1 : 0;
+    const uint32_t dup = p.precise ? 2u : 1u;
+    p.b_resident = dup * p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
     if (p.reuse) {
         p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
         p.a_chunk_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
@@ -698,8 +770,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     int ctas_per_sm = 2;
     if (getenv("CHAP_TC_CTAS")) ctas_per_sm = atoi(getenv("CHAP_TC_CTAS"));
     if (ctas_per_sm > 2 && p.nt > 64) ctas_per_sm = 2;
-    const size_t fixed = p.b_resident ? p.b_area_bytes : 0u;
-    const size_t chunk_bytes = (size_t)p.a_chunk_bytes + (p.b_resident ? 0u : p.b_chunk_bytes);
+    const size_t fixed = p.b_resident ? dup * p.b_area_bytes : 0u;
+    const size_t chunk_bytes = dup * ((size_t)p.a_chunk_bytes + (p.b_resident ? 0u : p.b_chunk_bytes));
     int grid_x = 0;
     size_t extras = 0, budget = 0;
     for (;; --ctas_per_sm) {
@@ -733,19 +805,21 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
     const int stage_cap = getenv("CHAP_TC_STAGES") ? atoi(getenv("CHAP_TC_STAGES")) : 6;
     if (stages > stage_cap) stages = stage_cap;
-    if (stages > 12) stages = 12;
+    if (stages > (p.precise ? 8 : 12)) stages = p.precise ? 8 : 12;          // barrier block: 3 (2) barriers per stage + 5 in 256 bytes
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     // lean issue / producer loops for the thin row-reuse layers (see issue_mmas_thin)
     p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 && stages >= 2 &&
                 TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
     p.stages = stages;
+    p.a_lo_off = (uint32_t)stages * p.a_stage_bytes;
+    p.b_lo_off = p.b_resident ? p.b_area_bytes : (uint32_t)stages * p.b_stage_bytes;
     p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : p.n_real; p.bias = bias; p.stats = ch_sums;
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
     const size_t smem = (size_t)stages * stage + fixed + extras;
-    static_assert(2 * 12 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
+    static_assert(2 * 12 + 5 <= 256 / 8 - 2 && 3 * 8 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
@@ -764,12 +838,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
                     dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
                     str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = bh * bw * C * 4;
                     box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = 1;
-                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 4, dims, str, box, p.kc));
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 4, dims, str, box, p.kc, false, p.precise));
                 } else {
                     dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
                     str[0] = 2 * C * 4; str[1] = 2 * bw * C * 4; str[2] = 2 * bh * bw * C * 4; str[3] = 2 * (uint64_t)p.D * bh * bw * C * 4;
                     box[0] = p.kc; box[1] = p.tw; box[2] = p.th; box[3] = p.td; box[4] = 1;
-                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 5, dims, str, box, p.kc));
+                    CHAP_TRY(make_tensor_map(&tmT.m[t], base, 5, dims, str, box, p.kc, false, p.precise));
                 }
             }
             tmA = tmT.m[0];
@@ -778,26 +852,30 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
             dims[0] = 2 * C; dims[1] = p.W; dims[2] = 2; dims[3] = p.H; dims[4] = g.n;
             str[0] = 2 * C * 4; str[1] = str[0] * p.W; str[2] = 2 * str[1]; str[3] = str[2] * p.H;
             box[0] = p.kc; box[1] = p.tw; box[2] = 1; box[3] = p.th; box[4] = 1;
-            CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc));
+            CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc, false, p.precise));
         } else if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
             box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = 1;
-            CHAP_TRY(make_tensor_map(&tmA, in, 4, dims, str, box, p.kc));
+            CHAP_TRY(make_tensor_map(&tmA, in, 4, dims, str, box, p.kc, false, p.precise));
         } else {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
             box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = p.td; box[4] = 1;
-            CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc));
+            CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc, false, p.precise));
         }
-        uint64_t wd[2] = {(uint64_t)K, (uint64_t)w_taps * N};
+        // packed weights: [hi half | lo half], each [w_taps * N rows][K]; the plain TF32 kernel only ever addresses the hi rows
+        p.b_lo_rows = w_taps * N;
+        uint64_t wd[2] = {(uint64_t)K, 2 * (uint64_t)w_taps * N};
         uint64_t ws[1] = {(uint64_t)K * 4};
         uint32_t wb[2] = {(uint32_t)p.kc, (uint32_t)p.nt};
         CHAP_TRY(make_tensor_map(&tmB, wp, 2, wd, ws, wb, p.kc));
     }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+        cudaFuncSetAttribute(conv_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_precise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_precise_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     const size_t stat_doubles = (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real);
     if (bn) {
         CHAP_REQUIRE(ch_sums != nullptr, CHAP_ERR_BAD_ARG, "tc_conv: the folded BatchNorm finalize needs the statistics buffer");
@@ -807,12 +885,19 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     }
     if (ch_sums) CHAP_TRY(zero_async(ch_sums, (stat_doubles + (bn ? 1 : 0)) * sizeof(double), st));
     const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
-    KernelTimer timer(timer_name(dgrad ? "conv_tc_dgrad" : "conv_tc_fwd", g.taps, K, N, g.iW, g.iH, g.iD, g.in_rows),
+    KernelTimer timer(timer_name(p.precise ? (dgrad ? "conv_tc3x_dgrad" : "conv_tc3x_fwd") : (dgrad ? "conv_tc_dgrad" : "conv_tc_fwd"), g.taps,
+                                 dgrad ? g.cout : g.cin, dgrad ? g.cin : g.cout, g.iW, g.iH, g.iD, g.in_rows),       // real channel counts
                       2.0 * rows * g.cin * g.cout * g.taps,
                       4.0 * ((double)g.in_rows * g.cin + (double)g.out_rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
-    if (p.mode == 3) conv_tc_kernel_taps<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, tmT, p);
-    else conv_tc_kernel<<<grid, 64 + 128 * p.epi_groups, smem, st>>>(tmA, tmB, p);
+    const unsigned threads = 64 + 128 * p.epi_groups + (p.precise ? 128 : 0);
+    if (p.precise) {
+        if (p.mode == 3) conv_tc_precise_kernel_taps<<<grid, threads, smem, st>>>(tmA, tmB, tmT, p);
+        else conv_tc_precise_kernel<<<grid, threads, smem, st>>>(tmA, tmB, p);
+    } else {
+        if (p.mode == 3) conv_tc_kernel_taps<<<grid, threads, smem, st>>>(tmA, tmB, tmT, p);
+        else conv_tc_kernel<<<grid, threads, smem, st>>>(tmA, tmB, p);
+    }
     CHAP_TRY(launched("conv_tc_kernel"));
     return 1;
 }

@@ -10,6 +10,7 @@ namespace chap {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_force_simt{0};
+std::atomic<int> g_precise_max_c{getenv("CHAP_PRECISE_MAX_C") ? atoi(getenv("CHAP_PRECISE_MAX_C")) : 0};
 
 // ------------------------------------------------------------------ live kernel timing
 namespace {
@@ -87,6 +88,27 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
         float b = first ? gg : fmaf(mom, buf[i], gg);
         buf[i] = b; p[i] -= lr * b;
     }
+}
+
+// ------------------------------------------------------------------ per-iteration schedule on the device
+// Poly learning rate (code/train_ours_2D.py:387) and consistency weight (:34-36,356) from an iteration counter that lives in
+// device memory and is advanced here: nothing per-iteration is written from the host, so a replayed CUDA graph cannot race
+// with a host that runs iterations ahead.  One thread; double math (the host oracle computes these in Python floats).
+__global__ void schedule_kernel(long long* iter, double base_lr, double max_it, double consistency, double rampup, long long ramp_div,
+                                float* lr, float* cw) {
+    const long long it = *iter;
+    double frac = 1.0 - (double)it / max_it;
+    if (frac < 0.0) frac = 0.0;
+    *lr = (float)(base_lr * pow(frac, 0.9));
+    double w = 1.0;
+    if (rampup != 0.0) {
+        double cur = (double)(it / ramp_div);
+        cur = cur < 0.0 ? 0.0 : (cur > rampup ? rampup : cur);
+        const double ph = 1.0 - cur / rampup;
+        w = exp(-5.0 * ph * ph);
+    }
+    *cw = (float)(consistency * w);
+    *iter = it + 1;
 }
 
 // ------------------------------------------------------------------ sliding window
@@ -183,6 +205,8 @@ extern "C" uint64_t chap_launch_count(void) { return g_launches.load(); }
 extern "C" void chap_reset_launch_count(void) { g_launches.store(0); }
 extern "C" void chap_set_force_simt(int flag) { g_force_simt.store(flag ? 1 : 0); }
 extern "C" int chap_get_force_simt(void) { return g_force_simt.load(); }
+extern "C" void chap_set_conv_precision(int max_channels) { g_precise_max_c.store(max_channels < 0 ? 0 : max_channels); }
+extern "C" int chap_get_conv_precision(void) { return g_precise_max_c.load(); }
 
 extern "C" void chap_timing_enable(int on) {
     if (on && !g_timed) g_timed = new TimedLaunch[kMaxTimed]();
@@ -247,6 +271,14 @@ extern "C" int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int
     return launched("sgd_kernel");
 }
 
+extern "C" int chap_schedule_step(int64_t* iter_dev, double base_lr, double max_iterations, double consistency, double rampup,
+                                  int64_t ramp_div, float* lr_dev, float* cw_dev, void* stream) {
+    CHAP_REQUIRE(iter_dev && lr_dev && cw_dev && max_iterations > 0 && ramp_div > 0, CHAP_ERR_BAD_ARG, "schedule_step: bad argument");
+    schedule_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<long long*>(iter_dev), base_lr, max_iterations, consistency, rampup,
+                                            (long long)ramp_div, lr_dev, cw_dev);
+    return launched("schedule_kernel");
+}
+
 static int check_sw(const chap_sw_desc* d) {
     CHAP_REQUIRE(d != nullptr, CHAP_ERR_BAD_ARG, "sliding window desc is NULL");
     for (int a = 0; a < 3; ++a) {
@@ -277,6 +309,7 @@ extern "C" int chap_sw_aggregate(const chap_sw_desc* d, const float* win, int32_
                                                 (double)nvox * ((score ? 4.0 * d->c : 0.0) + (cnt ? 4.0 : 0.0) + 8.0), S(stream));
     int grid = grid_for(nvox, 256);
     switch (d->c) {
+        case 1: sw_aggregate_kernel<1><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;   // the reference's default num_classes=1
         case 2: CHAP_REQUIRE(((uintptr_t)win & 7u) == 0, CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
                 sw_aggregate_kernel<2><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
         case 3: sw_aggregate_kernel<3><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;

@@ -111,6 +111,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 // 64B for 16-channel boxes.  MN-major TF32 operands (weight gradient): the only layout the tensor core accepts is
 // "128B swizzle with 32B atoms" (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type SWIZZLE_128B_BASE32B).
 int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int kc, bool mn_major_tf32 = false);
+                    const uint32_t* box, int kc, bool mn_major_tf32 = false, bool plain_f32 = false);
 
 }  // namespace chap

@@ -102,6 +102,15 @@ def set_force_simt(flag):
     invalidate_weight_cache()
 
 
+def set_conv_precision(max_channels):
+    """0: plain TF32 tensor-core convolutions; c > 0: split-operand 3xTF32 for layers with max(Cin, Cout) <= c
+    (>= 1024: every layer, the "precise mode"); see chap_set_conv_precision in include/chap_b200.h."""
+    lib().chap_set_conv_precision(int(max_channels))
+
+
+PRECISE_ALL = 1 << 20
+
+
 # ----------------------------------------------------------------------------- convolution
 def _conv_desc(kind, x, cin, cout):
     nd, d, h, w = _spatial3(x)
@@ -704,6 +713,14 @@ def sgd_momentum_lrdev_(flat_p, flat_g, flat_buf, lr_dev, momentum, weight_decay
     check(lib().chap_sgd_momentum_lrdev(_p(flat_p), _p(flat_g), _p(flat_buf), flat_p.numel(), _p(lr_dev), float(momentum),
                                         float(weight_decay), float(grad_scale), _stream()))
     invalidate_weight_cache()
+
+
+def schedule_step(iter_dev, base_lr, max_iterations, consistency, rampup, lr_dev, cw_dev, ramp_div=150):
+    """lr_dev <- poly LR, cw_dev <- consistency weight for the iteration held in iter_dev (int64, device), then
+    iter_dev += 1 -- all on the device (code/train_ours_2D.py:356,387)."""
+    _require_cuda(iter_dev, lr_dev, cw_dev)
+    check(lib().chap_schedule_step(_p(iter_dev), float(base_lr), float(max_iterations), float(consistency), float(rampup),
+                                   int(ramp_div), _p(lr_dev), _p(cw_dev), _stream()))
 
 
 # ----------------------------------------------------------------------------- sliding window

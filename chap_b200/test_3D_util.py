@@ -121,6 +121,7 @@ def jc(pred, gt):
 
 def cal_metric(gt, pred):
     """code/test_3D_util.py:82-88 / code/val_3D.py:82-88: [dice, hd95] or zeros."""
+    gt, pred = np.asarray(gt), np.asarray(pred)
     if pred.sum() > 0 and gt.sum() > 0:
         return np.array([dice_coefficient(pred, gt), hd95(pred, gt)])
     return np.zeros(2)
@@ -135,25 +136,93 @@ def cal_dice(prediction, label, num=2):
     return total_dice
 
 
+def ravd(pred, gt):
+    """medpy.metric.binary.ravd: (|pred| - |gt|) / |gt| (raises on an empty reference like medpy does)."""
+    pred, gt = np.asarray(pred).astype(bool), np.asarray(gt).astype(bool)
+    v2 = np.count_nonzero(gt)
+    if v2 == 0:
+        raise RuntimeError("ravd is undefined for an empty reference mask")
+    return (np.count_nonzero(pred) - v2) / float(v2)
+
+
 def calculate_metric_percase(pred, gt):
-    """code/test_3D_util.py:147-152: dice, jaccard, hd95, asd."""
-    return dice_coefficient(pred, gt), jc(pred, gt), hd95(pred, gt), asd(pred, gt)
+    """code/test_3D_util.py:147-152: np.array([dice, |ravd|, hd95, asd]) (medpy restated on numpy / scipy).
+    The reference lets medpy raise when a mask is empty; here an empty prediction or label gives the all-zero row
+    (the convention of cal_metric, :82-88) instead of an exception in the middle of an evaluation run."""
+    pred, gt = np.asarray(pred).astype(bool), np.asarray(gt).astype(bool)
+    if not pred.any() or not gt.any():
+        return np.zeros(4)
+    return np.array([dice_coefficient(pred, gt), abs(ravd(pred, gt)), hd95(pred, gt), asd(pred, gt)])
 
 
-def test_all_case(net, image_list, num_classes=2, patch_size=(112, 112, 80), stride_xy=18, stride_z=4,
-                  batch_windows=4, rank=0, world_size=1):
-    """Evaluate a list of (image, label) numpy volumes; cases are sharded round-robin over ranks
-    (replicas only, no collective -- SURVEY.md section 8e).  Returns the per-case metric rows
-    [dice, jc, hd95, asd] of this rank's cases and their indices."""
-    rows, idx = [], []
-    for i, (image, label) in enumerate(image_list):
+def read_case(image_path):
+    """(image, label) of one case.  The reference reads HDF5 datasets 'image' / 'label' (code/test_3D_util.py:101-103);
+    h5py is used when it is installed, otherwise an `.npz` / `.npy` pair with the same stem is accepted (the on-disk
+    layout is the same two arrays).  I/O only -- no device work."""
+    stem = image_path[:-3] if image_path.endswith(".h5") else image_path
+    import os
+    if os.path.isfile(stem + ".h5"):
+        try:
+            import h5py
+        except ImportError as e:                                   # pragma: no cover - depends on the image
+            raise RuntimeError("%s.h5 exists but h5py is not installed; convert the case to %s.npz" % (stem, stem)) from e
+        with h5py.File(stem + ".h5", "r") as f:
+            return f["image"][:], f["label"][:]
+    if os.path.isfile(stem + ".npz"):
+        z = np.load(stem + ".npz")
+        return z["image"], z["label"]
+    raise FileNotFoundError("no case file %s.h5 / %s.npz" % (stem, stem))
+
+
+def read_case_list(base_dir, test_list):
+    """code/test_3D_util.py:92-95: one case id per line (text before the first comma) -> base_dir/data/<id>.h5"""
+    with open(base_dir + '/{}'.format(test_list), 'r') as f:
+        lines = f.readlines()
+    return [base_dir + "/data/{}.h5".format(item.replace('\n', '').split(",")[0]) for item in lines if item.strip()]
+
+
+def _sum_over_ranks(total, world_size):
+    if world_size <= 1:
+        return total
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return total                                   # caller combines the partial means itself
+    from .parallel import gather_rows
+    return np.sum(np.stack(gather_rows(total, world_size)), axis=0)
+
+
+def test_all_case(net, base_dir, method="unet_3D", test_list="full_test.list", num_classes=4, patch_size=(48, 160, 160),
+                  stride_xy=32, stride_z=24, test_save_path=None, cases=None, batch_windows=4, rank=0, world_size=1):
+    """code/test_3D_util.py:91-129, same positional signature and return value: total_metric / n_cases with
+    total_metric [num_classes - 1, 4] holding [dice, |ravd|, hd95, asd] of class 1 in row 0 (the reference only fills
+    row 0, :105-106).  Per-case lines go to `test_save_path/<method>.txt` like the reference; predictions are saved as
+    `<id>_pred.npy` (the reference writes NIfTI through SimpleITK, which is I/O outside the hot path).
+    Extensions (keyword only in practice): `cases` = in-memory list of (image, label) or (id, image, label) used instead
+    of base_dir / test_list; `rank` / `world_size` shard the cases round-robin (replicas only) -- with an
+    initialised process group the totals are summed over ranks, so every rank returns the global mean."""
+    if cases is None:
+        paths = read_case_list(base_dir, test_list)
+        items = [(pth.split("/")[-1].replace(".h5", ""), pth) for pth in paths]
+    else:
+        items = [(c[0], c[1:]) if len(c) == 3 else ("case%d" % i, c) for i, c in enumerate(cases)]
+    total_metric = np.zeros((num_classes - 1, 4))
+    lines = []
+    for i, (ids, src) in enumerate(items):
         if i % world_size != rank:
             continue
-        pred = test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes, batch_windows)
-        if pred.sum() == 0 or (label > 0).sum() == 0:
-            rows.append((0.0, 0.0, 0.0, 0.0))
-        else:
-            rows.append(calculate_metric_percase(pred == 1, label == 1) if num_classes == 2 else
-                        tuple(np.mean([calculate_metric_percase(pred == c, label == c) for c in range(1, num_classes)], axis=0)))
-        idx.append(i)
-    return np.array(rows, dtype=np.float64).reshape(-1, 4), idx
+        image, label = read_case(src) if isinstance(src, str) else src
+        prediction = test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=num_classes,
+                                      batch_windows=batch_windows)
+        metric = calculate_metric_percase(prediction == 1, label == 1)
+        total_metric[0, :] += metric
+        lines.append("{},{},{},{},{}\n".format(ids, metric[0], metric[1], metric[2], metric[3]))
+        if test_save_path is not None:
+            np.save(test_save_path + "/{}_pred.npy".format(ids), prediction.astype(np.uint8))
+    total_metric = _sum_over_ranks(total_metric, world_size)
+    n = max(len(items), 1)
+    if test_save_path is not None:
+        suffix = "" if world_size == 1 else ".rank%d" % rank
+        with open(test_save_path + "/{}{}.txt".format(method, suffix), "a") as f:
+            f.writelines(lines)
+            f.writelines("Mean metrics,{},{},{},{}".format(*(total_metric[0] / n)))
+    return total_metric / n

@@ -116,7 +116,7 @@ class FlatSGD:
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_buf = torch.zeros(total, dtype=torch.float32, device=dev)     # zeros: first step gives buf = g
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
-        self._lr_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        self._lr = float(lr)
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
                 view = self.flat_p[off:off + p.numel()].view_as(p)
@@ -127,12 +127,14 @@ class FlatSGD:
 
     @property
     def lr(self):
-        return float(self._lr_host[0])
+        return self._lr
 
     @lr.setter
     def lr(self, value):
-        self._lr_host[0] = float(value)
-        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+        """Eager-mode setter: a stream-ordered fill of the device scalar (no pinned staging buffer that a host running
+        ahead could overwrite).  The CUDA-graph trainer never calls this -- its schedule is computed on the device."""
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)
 
     def zero_grad(self):
         for p in self.params:
@@ -152,6 +154,30 @@ class FlatSGD:
         if self.grad_hook is not None:
             self.grad_hook(self.flat_g)
         ops.sgd_momentum_lrdev_(self.flat_p, self.flat_g, self.flat_buf, self.lr_dev, self.momentum, self.weight_decay, grad_scale)
+
+    # -- optimizer-state save / resume.  The reference only saves model.state_dict() (code/train_ours_2D.py:428-435) and has no
+    #    resume logic; the layout below is torch.optim.SGD's own (`state[i]['momentum_buffer']`, param_groups), so a checkpoint
+    #    written here loads into a torch.optim.SGD over the same parameter list and vice versa.
+    def state_dict(self):
+        state = {i: {"momentum_buffer": self.flat_buf[off:off + p.numel()].view_as(p).detach().clone()}
+                 for i, (p, off) in enumerate(zip(self.params, self.offsets))}
+        group = {"lr": self._lr, "momentum": self.momentum, "dampening": 0, "weight_decay": self.weight_decay, "nesterov": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FlatSGD.load_state_dict: expected one param group with %d parameters" % len(self.params))
+        g = groups[0]
+        self.momentum, self.weight_decay = float(g["momentum"]), float(g["weight_decay"])
+        self.lr = float(g["lr"])
+        with torch.no_grad():
+            self.flat_buf.zero_()                                  # torch creates momentum buffers lazily: missing == zeros here
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+                st = sd["state"].get(i)
+                if st is not None and st.get("momentum_buffer") is not None:
+                    self.flat_buf[off:off + p.numel()].view_as(p).copy_(st["momentum_buffer"])
 
 
 class ChapTrainer:
@@ -196,36 +222,71 @@ class ChapTrainer:
         return self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9        # set at :387-389 of the previous iteration
 
     def step(self, volume, label, mask_offsets=None, d_init=None, trace=None):
-        self.opt.lr = self._poly_lr()
-        eager = (not self.use_graph) or d_init is not None or trace is not None
+        """One iteration.  d_init: optional explicit VAT probing noise (list of 5 tensors; the parity protocol) -- in graph
+        mode it is copied into static buffers that the captured graph reads; without it the noise is drawn inside the graph."""
+        eager = (not self.use_graph) or trace is not None
         if eager or self.iter_num < self.graph_warmup:
+            self.opt.lr = self._poly_lr()
             aux = self._iteration(volume, label, mask_offsets=mask_offsets, d_init=d_init, trace=trace)
             self.iter_num += 1                                                          # :385
             return aux
         if self.graph is None:
-            self._capture(volume, label)
+            self._capture(volume, label, d_init)
         st = self.static
+        if (d_init is not None) != (st["d_init"] is not None):
+            raise RuntimeError("ChapTrainer: the graph was captured %s explicit d_init; keep passing it the same way"
+                               % ("with" if st["d_init"] is not None else "without"))
+        # per-iteration host work: stream-ordered copies into the static inputs; lr / consistency weight / iteration counter
+        # live on the device and are advanced by a kernel inside the graph (no pinned scalars a fast host could overwrite)
         st["volume"].copy_(volume, non_blocking=True)
         st["label"].copy_(label, non_blocking=True)
         mask, _ = generate_mask(volume[:1], mask_offsets)
         st["mask"].copy_(mask, non_blocking=True)
-        st["cw_host"].fill_(consistency_weight(self.iter_num, self.consistency, self.rampup))
-        st["cw"].copy_(st["cw_host"], non_blocking=True)
+        if d_init is not None:
+            for dst, src in zip(st["d_init"], d_init):
+                dst.copy_(src, non_blocking=True)
+        if st["next_iter"] != self.iter_num:   # eager iterations ran in between: resynchronise the device counter
+            st["iter"].fill_(self.iter_num)
         self.graph.replay()
         ops.invalidate_weight_cache()          # the replay updated the weights behind the Python-side pack cache
         self.iter_num += 1
+        st["next_iter"] = self.iter_num
+        self.opt._lr = self._poly_lr()         # host mirror of the device schedule (what the NEXT eager step / a checkpoint sees)
         return st["aux"]
 
-    def _capture(self, volume, label):
+    def _capture(self, volume, label, d_init=None):
         dev = volume.device
         st = dict(volume=torch.empty_like(volume), label=torch.empty_like(label),
                   mask=torch.ones(tuple(volume.shape[2:]), dtype=torch.int64, device=dev),
-                  cw=torch.zeros((), dtype=torch.float32, device=dev), cw_host=torch.zeros(()).pin_memory())
+                  cw=torch.zeros(1, dtype=torch.float32, device=dev),
+                  iter=torch.full((1,), self.iter_num, dtype=torch.int64, device=dev),
+                  d_init=None if d_init is None else [ops.cl(d.to(dev)).clone() for d in d_init], next_iter=self.iter_num)
         st["volume"].copy_(volume)
         st["label"].copy_(label)
         ops.invalidate_weight_cache()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"])
+            ops.schedule_step(st["iter"], self.base_lr, self.max_iterations, self.consistency, self.rampup, self.opt.lr_dev, st["cw"])
+            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"][0], d_init=st["d_init"])
         self.static = st
+
+    def close(self):
+        """Drop the captured graph (and its static buffers).  Call before tearing down an NCCL process group whose
+        all-reduce was captured: destroying the communicator while a graph still references it hangs."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph = None
+            self.static = None
+
+    # -- checkpoint: model.state_dict() is the reference's own artefact (:428-435); optimizer + iteration make it resumable
+    def state_dict(self):
+        return {"model": self.model.state_dict(), "optimizer": self.opt.state_dict(), "iter_num": self.iter_num}
+
+    def load_state_dict(self, sd):
+        if self.graph is not None:
+            self.close()
+        self.model.load_state_dict(sd["model"])           # copies INTO the flat-arena views
+        self.opt.load_state_dict(sd["optimizer"])
+        self.iter_num = int(sd["iter_num"])
+        ops.invalidate_weight_cache()

@@ -55,6 +55,16 @@ void chap_timing_enable(int on);
 int chap_timing_report(char* buf, size_t cap);
 void chap_set_force_simt(int flag);
 int chap_get_force_simt(void);
+/* Arithmetic of the tensor-core convolutions (forward and data gradient).
+ *   0 (default): plain TF32 -- operands rounded to nearest by the TMA unit, fp32 accumulation in TMEM; per layer this is
+ *       exactly cuDNN's TF32 arithmetic (reference default: torch.backends.cudnn.allow_tf32, code/train_ours_2D.py:542-547).
+ *   c > 0: layers with max(Cin, Cout) <= c run the split-operand "3xTF32" mode: x = x_hi + x_lo and w = w_hi + w_lo with
+ *       TF32 halves, x_hi*w_hi + x_lo*w_hi + x_hi*w_lo accumulated in fp32 (relative error ~2^-21 per product instead of
+ *       2^-11).  c >= 1024 covers every layer ("precise mode", logits within 1e-3 of an fp32 evaluation); c = 32 covers
+ *       the thin, HBM-bound layers that cuDNN itself runs in fp32 even when TF32 is allowed.
+ * The weight gradient always uses plain TF32.  Env CHAP_PRECISE_MAX_C sets the initial value. */
+void chap_set_conv_precision(int max_channels);
+int chap_get_conv_precision(void);
 
 /* ------------------------------------------------------------------ convolutions
  * Replaces nn.Conv2d/Conv3d/ConvTranspose2d/ConvTranspose3d forward + backward inside
@@ -273,6 +283,12 @@ int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n,
  * step give buf = g'): the launch can be captured once in a CUDA graph and replayed with a changing learning rate */
 int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int64_t elems, const float* lr_dev, float momentum,
                             float weight_decay, float grad_scale, void* stream);
+/* The per-iteration scalars of code/train_ours_2D.py computed on the device from an iteration counter in device memory
+ * (read, then incremented): lr = base_lr * (1 - it / max_iterations)^0.9 (:387) and
+ * cw = consistency * sigmoid_rampup(it / ramp_div, rampup) (:34-36 with the call at :356, ramp_div = 150).
+ * Lets a replayed CUDA graph run without any per-iteration host write. */
+int chap_schedule_step(int64_t* iter_dev, double base_lr, double max_iterations, double consistency, double rampup,
+                       int64_t ramp_div, float* lr_dev, float* cw_dev, void* stream);
 int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t elems, float lr, float momentum,
                       float weight_decay, float grad_scale, int32_t first_step, void* stream);
 

@@ -28,6 +28,9 @@ def test_library_loads_and_reports_version():
     lib = _lib.load()
     assert lib.chap_abi_version() == 1
     assert lib.chap_get_force_simt() in (0, 1)
+    lib.chap_set_conv_precision(32)
+    assert lib.chap_get_conv_precision() == 32
+    lib.chap_set_conv_precision(0)
     assert isinstance(_lib.launch_count(), int)
 
 
@@ -38,9 +41,9 @@ def test_bad_arguments_fail_loudly_without_touching_the_gpu():
     rc = lib.chap_conv_fwd(ctypes.byref(d), None, None, None, None, None, None)
     assert rc == -1
     assert b"nd must be 2 or 3" in lib.chap_last_error()
-    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(0, 3, 2, 4, 4, 4, 16, 32))) == 27 * 16 * 32
+    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(0, 3, 2, 4, 4, 4, 16, 32))) == 2 * 27 * 16 * 32      # TF32 hi half + lo half
     # channel counts below 16 are zero-padded to 16 in the packed operand (tensor-core path of the 4- / 8-channel heads)
-    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(3, 2, 2, 1, 4, 4, 16, 8))) == 4 * 16 * 16
+    assert lib.chap_conv_packed_elems(ctypes.byref(_lib.ConvDesc(3, 2, 2, 1, 4, 4, 16, 8))) == 2 * 4 * 16 * 16
 
 
 def test_ops_refuse_cpu_tensors():
