@@ -785,7 +785,9 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         // with <= 148 CTAs in the grid a CTA may use a whole SM's shared memory
         const size_t per_cta = (long)grid_x * (N / p.nt) <= kNumSMs ? 224 * 1024 : (size_t)(226 * 1024) / ctas_per_sm;
         budget = per_cta > extras + fixed ? per_cta - extras - fixed : 0;
-        if (budget >= 3 * chunk_bytes || ctas_per_sm <= 2) break;       // at least three pipeline stages, else fewer CTAs per SM
+        // at least three pipeline stages, else fewer CTAs per SM; one CTA per SM only when two cannot hold two stages each
+        // (split-operand mode of the wide layers: every stage exists twice)
+        if (budget >= 3 * chunk_bytes || (ctas_per_sm == 2 && budget >= 2 * chunk_bytes) || ctas_per_sm <= 1) break;
     }
     CHAP_REQUIRE(budget >= chunk_bytes, CHAP_ERR_BAD_ARG, "tc_conv: tile does not fit shared memory");
     p.colsplit = (p.nt >= 32 || p.n_buf == 1) && getenv("CHAP_TC_ALTERNATE") == nullptr ? 1 : 0;
