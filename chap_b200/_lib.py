@@ -76,6 +76,8 @@ SIGNATURES = {
     "chap_concat_channels": (I, [P, P, L, I, I, P, P]),
     "chap_split_channels": (I, [P, L, I, I, P, P, P]),
     "chap_channel_scale": (I, [P, P, I, L, I, P, P]),
+    "chap_feature_dropout_fwd": (I, [P, P, P, I, I, L, I, P, P, P]),
+    "chap_feature_dropout_bwd": (I, [P, P, P, P, I, I, L, I, P, P]),
     "chap_axpy": (I, [P, P, F, L, P, P]),
     "chap_mask_mix": (I, [P, P, P, I, L, I, P, P]),
     "chap_pseudo_label": (I, [P, P, L, I, P, P, P, P, P, P]),

@@ -579,6 +579,75 @@ channel_scale_kernel(const float* __restrict__ x, const float* __restrict__ s, i
         out[i] = x[i] * s[n * c + ch];
     }
 }
+// perform_dropout (code/networks/FilterDropout.py:45-89) for one pyramid level in ONE pass: feat [N, rps, C] is read once and
+// both decoder inputs out1 / out2 [N + nu, rps, C] = cat(feat, feat[nl:] * m{1,2}[nu, C]) are written (nl = N - nu labelled rows).
+// The reference makes two masked copies and two concatenations (4 passes, 8N moved); this moves 4N.  m == nullptr: factor 1.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+feature_dropout_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ m1, const float* __restrict__ m2,
+                           int n, int nu, int64_t rps, int c, float* __restrict__ out1, float* __restrict__ out2) {
+    const int cv = c / VEC;
+    const int64_t per_sample = rps * cv, total = (int64_t)n * per_sample;
+    const int nl = n - nu;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i / per_sample;
+        const int ch = (int)(i % cv) * VEC;
+        float v[VEC];
+        if (VEC == 4) { const float4 t = ldg_stream(reinterpret_cast<const float4*>(feat) + i); v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w; }
+        else v[0] = feat[i];
+        if (VEC == 4) {
+            reinterpret_cast<float4*>(out1)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+            reinterpret_cast<float4*>(out2)[i] = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        } else { out1[i] = v[0]; out2[i] = v[0]; }
+        if (s >= nl) {
+            const int64_t u = s - nl;
+            const int64_t o = i + (int64_t)nu * per_sample;                 // row N + u of the outputs
+            float a[VEC], b[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                a[k] = m1 ? v[k] * m1[u * c + ch + k] : v[k];
+                b[k] = m2 ? v[k] * m2[u * c + ch + k] : v[k];
+            }
+            if (VEC == 4) {
+                reinterpret_cast<float4*>(out1)[o] = make_float4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]);
+                reinterpret_cast<float4*>(out2)[o] = make_float4(b[0], b[1 % VEC], b[2 % VEC], b[3 % VEC]);
+            } else { out1[o] = a[0]; out2[o] = b[0]; }
+        }
+    }
+}
+// backward: dfeat[s] = d1[s] + d2[s] (+ d1[N + u] * m1[u] + d2[N + u] * m2[u] for the unlabelled rows s = nl + u); d1 / d2 nullable
+template <int VEC>
+__global__ void __launch_bounds__(256)
+feature_dropout_bwd_kernel(const float* __restrict__ d1, const float* __restrict__ d2, const float* __restrict__ m1, const float* __restrict__ m2,
+                           int n, int nu, int64_t rps, int c, float* __restrict__ dfeat) {
+    const int cv = c / VEC;
+    const int64_t per_sample = rps * cv, total = (int64_t)n * per_sample;
+    const int nl = n - nu;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i / per_sample;
+        const int ch = (int)(i % cv) * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+        auto add = [&](const float* src, int64_t idx, const float* m, int64_t u) {
+            float v[VEC];
+            if (VEC == 4) { const float4 t = ldg_stream(reinterpret_cast<const float4*>(src) + idx); v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w; }
+            else v[0] = src[idx];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] += m ? v[k] * m[u * c + ch + k] : v[k];
+        };
+        if (d1) add(d1, i, nullptr, 0);
+        if (d2) add(d2, i, nullptr, 0);
+        if (s >= nl) {
+            const int64_t u = s - nl, o = i + (int64_t)nu * per_sample;
+            if (d1) add(d1, o, m1, u);
+            if (d2) add(d2, o, m2, u);
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(dfeat)[i] = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        else dfeat[i] = acc[0];
+    }
+}
+
 __global__ void __launch_bounds__(256)
 axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, int64_t total, float* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
@@ -739,6 +808,30 @@ extern "C" int chap_channel_scale(const float* x, const float* s, int32_t n, int
     const int64_t total = (int64_t)n * rps * c;
     channel_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(x, s, rps, c, total, out);
     return launched("channel_scale_kernel");
+}
+
+extern "C" int chap_feature_dropout_fwd(const float* feat, const float* m1, const float* m2, int32_t n, int32_t nu, int64_t rps, int32_t c,
+                                        float* out1, float* out2, void* stream) {
+    CHAP_REQUIRE(feat && out1 && out2 && n > 0 && nu >= 0 && nu <= n && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "feature_dropout_fwd: bad argument");
+    const double elems = (double)n * rps * c, extra = (double)nu * rps * c;
+    KernelTimer timer_("feature_dropout_fwd", 0.0, 4.0 * (elems + 2.0 * (elems + extra)), S(stream));       // read feat once, write both outputs
+    const bool v4 = c % 4 == 0 && aligned16(feat) && aligned16(out1) && aligned16(out2);
+    const int64_t total = (int64_t)n * rps * c;
+    if (v4) feature_dropout_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(feat, m1, m2, n, nu, rps, c, out1, out2);
+    else feature_dropout_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(feat, m1, m2, n, nu, rps, c, out1, out2);
+    return launched("feature_dropout_fwd_kernel");
+}
+
+extern "C" int chap_feature_dropout_bwd(const float* d1, const float* d2, const float* m1, const float* m2, int32_t n, int32_t nu, int64_t rps,
+                                        int32_t c, float* dfeat, void* stream) {
+    CHAP_REQUIRE((d1 || d2) && dfeat && n > 0 && nu >= 0 && nu <= n && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "feature_dropout_bwd: bad argument");
+    const double elems = (double)n * rps * c, extra = (double)nu * rps * c;
+    KernelTimer timer_("feature_dropout_bwd", 0.0, 4.0 * (elems + ((d1 ? 1.0 : 0.0) + (d2 ? 1.0 : 0.0)) * (elems + extra)), S(stream));
+    const bool v4 = c % 4 == 0 && aligned16(dfeat) && (!d1 || aligned16(d1)) && (!d2 || aligned16(d2));
+    const int64_t total = (int64_t)n * rps * c;
+    if (v4) feature_dropout_bwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(d1, d2, m1, m2, n, nu, rps, c, dfeat);
+    else feature_dropout_bwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(d1, d2, m1, m2, n, nu, rps, c, dfeat);
+    return launched("feature_dropout_bwd_kernel");
 }
 
 extern "C" int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream) {

@@ -4,8 +4,8 @@ Same entry points and argument meaning as the reference's code/networks/FilterDr
 (`perform_dropout` :45-89, `scores_dropoutV2` :116-138, `drop_based_on_prob` :140-160): for every
 pyramid level the unlabelled half of the batch gets two channel-masked copies that are appended
 to the batch (one list per decoder).  The [N, C] masks are tiny host-side bookkeeping drawn with
-torch's generator (like the reference); applying them to the feature maps is the
-`chap_channel_scale` kernel.
+torch's generator (like the reference); applying them AND building the two concatenated decoder
+inputs is one fused kernel per level (`chap_feature_dropout_fwd`).
 """
 import random
 
@@ -47,34 +47,50 @@ def scores_dropoutV2(grad_sim, activation, if_comp, type):
 
 
 def _dropout2d_mask(n, c, device):
-    """nn.Dropout2d(0.5) as an [n, c] factor."""
-    return torch.empty(n, c, device=device).bernoulli_(0.5).mul_(2.0)
+    """The factor nn.Dropout2d(0.5) applies, as [n, c]: F.dropout2d on a ones tensor [n, c, 1, 1] consumes the generator
+    exactly like the reference's `nn.Dropout2d(0.5)(unlab_feat)` (the noise tensor is [n, c, 1, 1] whatever the spatial size)."""
+    return torch.nn.functional.dropout2d(torch.ones(n, c, 1, 1, device=device), 0.5, True).reshape(n, c)
 
 
-def perform_dropout(x, level=None, scores=None, comp_drop=False):
-    """Returns (features_for_decoder1, features_for_decoder2); each level is cat(feat, perturbed
-    unlabelled half) along the batch (reference :45-89)."""
-    feature_fp1, feature_fp2 = [], []
+def draw_dropout_masks(x, level=None, scores=None, comp_drop=False):
+    """The mask draws of perform_dropout (reference :54-80), level by level and in the reference's order of generator calls:
+    returns a list with None (level not perturbed) or (m1, m2) [nu, C] per level.  Pure torch on tiny tensors."""
+    out = []
     for idx, feat in enumerate(x):
         bs, dim = feat.shape[0], feat.shape[1]
         labeled_bs = bs // 2
-        unlab = feat[labeled_bs:]
-        nu = unlab.shape[0]
-        if level is not None and idx in level:
-            if scores is None:
-                if comp_drop:
-                    m1 = torch.empty(nu, dim, device=feat.device).bernoulli_(0.5).mul_(2.0)
-                    m2 = 2.0 - m1
-                else:
-                    m1, m2 = _dropout2d_mask(nu, dim, feat.device), _dropout2d_mask(nu, dim, feat.device)
-            elif torch.all(scores[idx].eq(0)):
-                m1, m2 = _dropout2d_mask(nu, dim, feat.device), _dropout2d_mask(nu, dim, feat.device)
+        nu = bs - labeled_bs
+        if level is None or idx not in level:
+            out.append(None)
+        elif scores is None:
+            if comp_drop:
+                binomial = torch.distributions.binomial.Binomial(probs=0.5)           # sampled on the host like the reference (:47,58)
+                m1 = binomial.sample((labeled_bs, dim)).to(feat.device) * 2.0
+                out.append((m1, 2.0 - m1))
             else:
-                activation = unlab.detach().mean(dim=tuple(range(2, unlab.dim())))
-                m1, m2 = scores_dropoutV2(scores[idx], activation, comp_drop, 'sigmoid')
-            p1, p2 = ops.channel_scale(unlab, m1), ops.channel_scale(unlab, m2)
+                out.append((_dropout2d_mask(nu, dim, feat.device), _dropout2d_mask(nu, dim, feat.device)))
+        elif torch.all(scores[idx].eq(0)):
+            out.append((_dropout2d_mask(nu, dim, feat.device), _dropout2d_mask(nu, dim, feat.device)))
         else:
-            p1 = p2 = unlab
-        feature_fp1.append(torch.cat((feat, p1)))
-        feature_fp2.append(torch.cat((feat, p2)))
+            activation = feat[labeled_bs:].detach().mean(dim=tuple(range(2, feat.dim())))     # adaptive_avg_pool2d(.., (1, 1))
+            out.append(scores_dropoutV2(scores[idx], activation, comp_drop, 'sigmoid'))
+    return out
+
+
+def perform_dropout(x, level=None, scores=None, comp_drop=False, masks=None):
+    """Returns (features_for_decoder1, features_for_decoder2); each level is cat(feat, perturbed
+    unlabelled half) along the batch (reference :45-89).  Mask draws follow the reference branch by branch
+    (draw_dropout_masks); applying them and building the two concatenated tensors is ONE fused kernel per level
+    (`chap_feature_dropout_fwd`).
+    masks (extension, the parity-test / CUDA-graph protocol): explicit list with, per level, None or a pair (m1, m2) of
+    per-(sample, channel) factors [nu, C] used instead of drawing."""
+    if masks is None:
+        masks = draw_dropout_masks(x, level, scores, comp_drop)
+    feature_fp1, feature_fp2 = [], []
+    for feat, m in zip(x, masks):
+        nu = feat.shape[0] - feat.shape[0] // 2
+        m1, m2 = (None, None) if m is None else m
+        p1, p2 = ops.feature_dropout(feat, m1, m2, nu)
+        feature_fp1.append(p1)
+        feature_fp2.append(p2)
     return feature_fp1, feature_fp2

@@ -162,10 +162,12 @@ class DualDecoder(nn.Module):
             raise NotImplementedError("decoder_type %r is outside the CHAP hot path (use 'mcnet' or 'same')"
                                       % (self.decoder_type,))
 
-    def forward(self, x, with_feat=False, dropout=False, dropout_level=None, scores=None, comp_dropout=False):
+    def forward(self, x, with_feat=False, dropout=False, dropout_level=None, scores=None, comp_dropout=False, dropout_masks=None):
+        """Reference signature (unet.py:277); `dropout_masks` is a trailing extension: explicit per-level channel factors for
+        perform_dropout (the parity-test protocol), ignored unless dropout=True."""
         feature = self.encoder(x)
         if dropout:
-            feature1, feature2 = perform_dropout(feature, dropout_level, scores, comp_dropout)
+            feature1, feature2 = perform_dropout(feature, dropout_level, scores, comp_dropout, masks=dropout_masks)
             output1 = self.decoder1(feature1)
             output2 = self.decoder2(feature2)
         else:

@@ -446,6 +446,39 @@ def channel_scale(x, scale_nc):
     return _ChannelScale.apply(x, scale_nc)
 
 
+class _FeatureDropout(Function):
+    @staticmethod
+    def forward(ctx, feat, m1, m2, nu):
+        _require_cuda(feat, m1, m2)
+        feat = cl(feat)
+        n, c = feat.shape[0], feat.shape[1]
+        rps = feat.numel() // (n * c)
+        m1 = None if m1 is None else m1.detach().reshape(nu, c).float().contiguous()
+        m2 = None if m2 is None else m2.detach().reshape(nu, c).float().contiguous()
+        shape = [n + nu, c] + list(feat.shape[2:])
+        out1, out2 = empty_cl(shape, feat.device), empty_cl(shape, feat.device)
+        check(lib().chap_feature_dropout_fwd(_p(feat), _p(m1), _p(m2), n, nu, rps, c, _p(out1), _p(out2), _stream()))
+        ctx.save_for_backward(m1, m2)
+        ctx.cfg = (n, nu, rps, c, tuple(feat.shape))
+        return out1, out2
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        m1, m2 = ctx.saved_tensors
+        n, nu, rps, c, shape = ctx.cfg
+        d1 = None if d1 is None else cl(d1)
+        d2 = None if d2 is None else cl(d2)
+        dev = (d1 if d1 is not None else d2).device
+        dfeat = empty_cl(list(shape), dev)
+        check(lib().chap_feature_dropout_bwd(_p(d1), _p(d2), _p(m1), _p(m2), n, nu, rps, c, _p(dfeat), _stream()))
+        return dfeat, None, None, None
+
+
+def feature_dropout(feat, m1, m2, nu):
+    """(cat(feat, feat[-nu:] * m1), cat(feat, feat[-nu:] * m2)) along the batch, m [nu, C] or None (= 1), in one fused pass."""
+    return _FeatureDropout.apply(feat, m1, m2, int(nu))
+
+
 def axpy(a, b, alpha):
     """a + alpha * b (flat, no autograd)."""
     _require_cuda(a, b)

@@ -34,26 +34,19 @@ def _net_logits(net, patches, output_index=0):
     return y
 
 
-def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, batch_windows=4,
-                     device=None, return_maps=False, window_logits_hook=None):
-    """image: numpy [W, H, D] float; returns label_map int64 numpy [W, H, D] (and, with
-    return_maps, score_map [C, W, H, D] and cnt [W, H, D] float32) -- code/test_3D_util.py:14-79."""
-    if device is None:
-        device = next(net.parameters()).device
-    w, h, d = image.shape
-    pads = _pad_amounts(image.shape, patch_size)
-    add_pad = any(a + b > 0 for a, b in pads)
-    if add_pad:
-        image = np.pad(image, pads, mode='constant', constant_values=0)
-    ww, hh, dd = image.shape
+def sliding_window_device(net, vol, stride_xy, stride_z, patch_size, num_classes, batch_windows=4, return_maps=False,
+                          window_logits_hook=None):
+    """Device-resident core of test_single_case: `vol` is a float32 CUDA tensor [W, H, D] already padded to at least the
+    patch size; returns the int64 label volume on the device (and score [C, W, H, D] / count [W, H, D] with return_maps).
+    Window loop, clamped last window and accumulation order follow code/test_3D_util.py:42-72."""
+    ww, hh, dd = vol.shape
     sx = math.ceil((ww - patch_size[0]) / stride_xy) + 1
     sy = math.ceil((hh - patch_size[1]) / stride_xy) + 1
     sz = math.ceil((dd - patch_size[2]) / stride_z) + 1
     desc = ops.sw_desc((ww, hh, dd), patch_size, (sx, sy, sz), (stride_xy, stride_xy, stride_z), num_classes)
-    vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(device)
     n_win = sx * sy * sz
     pw, ph, pd = patch_size
-    win = torch.empty((n_win, pw, ph, pd, num_classes), dtype=torch.float32, device=device)   # channels-last logits
+    win = torch.empty((n_win, pw, ph, pd, num_classes), dtype=torch.float32, device=vol.device)   # channels-last logits
     was_training = net.training
     net.eval()
     with torch.no_grad():
@@ -67,6 +60,23 @@ def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1,
         out = ops.sw_aggregate(desc, win, is_prob=False, want_maps=return_maps)
     if was_training:
         net.train()
+    return out
+
+
+def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, batch_windows=4,
+                     device=None, return_maps=False, window_logits_hook=None):
+    """image: numpy [W, H, D] float; returns label_map int64 numpy [W, H, D] (and, with
+    return_maps, score_map [C, W, H, D] and cnt [W, H, D] float32) -- code/test_3D_util.py:14-79."""
+    if device is None:
+        device = next(net.parameters()).device
+    w, h, d = image.shape
+    pads = _pad_amounts(image.shape, patch_size)
+    add_pad = any(a + b > 0 for a, b in pads)
+    if add_pad:
+        image = np.pad(image, pads, mode='constant', constant_values=0)
+    vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(device)
+    out = sliding_window_device(net, vol, stride_xy, stride_z, patch_size, num_classes, batch_windows, return_maps,
+                                window_logits_hook)
     if return_maps:
         label, score, cnt = out
         label_map, score_map, cnt_map = label.cpu().numpy(), score.cpu().numpy(), cnt.cpu().numpy()

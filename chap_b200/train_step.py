@@ -45,9 +45,23 @@ def consistency_weight(iter_num, consistency=1.0, rampup=50.0):
     return consistency * ramps.sigmoid_rampup(iter_num // 150, rampup)
 
 
+def feature_dropout_loss(model, uimg_ab, ps1, ps2, sim_score=None, comp_drop=False, dropout_masks=None):
+    """The --dropout branch, code/train_ours_2D.py:359-364: model(uimg_ab, False, True, [0,1,2,3,4], sim_score, False), then
+    cross-entropy of each decoder's output against the other decoder's pseudo-labels.  As shipped the reference passes
+    [1.5 N] logits and [N] targets to F.cross_entropy (:362-363), which raises; the frozen fix (oracle/train_step.py) is
+    target = cat(pseudo, pseudo[N/2:]) -- the appended rows are perturbed copies of samples N/2...  The mean CE over all
+    rows and pixels comes from the fused Dice/CE kernel with an all-ones mask."""
+    o1, o2 = model(uimg_ab, False, True, [0, 1, 2, 3, 4], sim_score, comp_drop, dropout_masks=dropout_masks)
+    half = ps1.shape[0] // 2
+    t1, t2 = torch.cat((ps1, ps1[half:])), torch.cat((ps2, ps2[half:]))
+    ones = torch.ones(tuple(ps1.shape[1:]), dtype=torch.int64, device=ps1.device)
+    return (losses.masked_dice_ce(o1, t2, ones)[1] + losses.masked_dice_ce(o2, t1, ones)[1]).float()
+
+
 def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, vat=None, adv_losstype="kl",
                         topk=0.1, use_diff_mask=True, consistency=1.0, rampup=50.0, mask_offsets=None,
-                        d_init=None, trace=None, img_mask=None, cw=None):
+                        d_init=None, trace=None, img_mask=None, cw=None, dropout=False, comp_drop=False, sim_score=None,
+                        dropout_masks=None):
     """Forward part of the iteration; returns (loss, aux).  Line numbers: code/train_ours_2D.py.
     img_mask (int64 [*spatial]) / cw (float or 0-dim device tensor) may be supplied by the caller (the CUDA-graph
     trainer keeps them in static device buffers); otherwise they are drawn / computed here like the reference does."""
@@ -85,13 +99,17 @@ def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, v
     if cw is None:
         cw = consistency_weight(iter_num, consistency, rampup)                          # :356
 
+    if dropout:                                                                         # :359-365 (GradSim is absent: sim_score is an input)
+        fp_loss = feature_dropout_loss(model, uimg_ab, ps1, ps2, sim_score, comp_drop, dropout_masks)
+    else:
+        fp_loss = torch.zeros((), device=volume.device)
     if vat is not None:                                                                 # :369-372
         diff_mask = patch.create_maskV1(ps1, ps2, knowledge, scale_factor=4, topk=topk) if use_diff_mask else None
         vat_loss = vat(model, volume, soft1, soft2, diff_mask, adv_losstype, d_init=d_init, trace=trace)
     else:
         vat_loss = torch.zeros((), device=volume.device)
-    loss = bcp_loss + cw * vat_loss                                                     # :378
-    aux = dict(bcp_loss=bcp_loss.detach(), vat_loss=vat_loss.detach(), loss_l=loss_l.detach(),
+    loss = bcp_loss + cw * (fp_loss + vat_loss)                                         # :378
+    aux = dict(bcp_loss=bcp_loss.detach(), vat_loss=vat_loss.detach(), fp_loss=fp_loss.detach(), loss_l=loss_l.detach(),
                loss_u=loss_u.detach(), cw=cw, soft1=soft1, soft2=soft2, knowledge=knowledge,
                plab=(plab_a1, plab_b1, plab_a2, plab_b2), out_mix=(out1.detach(), out2.detach()))
     return loss, aux
@@ -191,8 +209,16 @@ class ChapTrainer:
 
     def __init__(self, model, n_classes, labeled_bs, base_lr=0.01, max_iterations=30000, adv_noise=True,
                  adv_losstype="kl", noise_mag=10.0, epi=6.0, topk=0.1, consistency=1.0, consistency_rampup=50.0,
-                 use_diff_mask=True, grad_hook=None, grad_scale=1.0, use_graph=False, graph_warmup=3):
+                 use_diff_mask=True, grad_hook=None, grad_scale=1.0, use_graph=False, graph_warmup=3,
+                 dropout=False, comp_drop=False, sim_score=None):
+        """dropout / comp_drop / sim_score: the --dropout feature-perturbation branch (code/train_ours_2D.py:359-365, 2D nets only:
+        the reference's DualDecoder3d.forward has no such branch); sim_score stands in for the absent GradSim.get_sim()."""
         self.model, self.n_classes, self.labeled_bs = model, n_classes, labeled_bs
+        self.dropout, self.comp_drop, self.sim_score = dropout, comp_drop, sim_score
+        if dropout and not hasattr(model.encoder, "ft_chns"):
+            raise NotImplementedError("--dropout: only the 2D DualDecoder has the perform_dropout branch (code/networks/unet.py:280-284)")
+        if dropout and use_graph and sim_score is not None:
+            raise NotImplementedError("score-driven feature dropout draws its masks from the activations; use use_graph=False")
         self.base_lr, self.max_iterations = base_lr, max_iterations
         self.vat = losses.VAT2d(xi=noise_mag, epi=epi, num_classes=n_classes) if adv_noise else None
         self.adv_losstype, self.topk, self.use_diff_mask = adv_losstype, topk, use_diff_mask
@@ -205,12 +231,20 @@ class ChapTrainer:
         model.train()
 
     # ------------------------------------------------------------------ one iteration on given device tensors
-    def _iteration(self, volume, label, img_mask=None, cw=None, mask_offsets=None, d_init=None, trace=None):
+    def _draw_dropout_masks(self, n_unlab, device):
+        """Host-side draw of the perform_dropout masks for the n_unlab-row batch uimg_ab (its second half is perturbed) (scores None: the masks do not
+        depend on the activations) -- placeholders stand in for the features, draw_dropout_masks only reads their shapes."""
+        from .networks.FilterDropout import draw_dropout_masks
+        fake = [torch.empty(n_unlab, c, 1, 1, device=device) for c in self.model.encoder.ft_chns]
+        return draw_dropout_masks(fake, [0, 1, 2, 3, 4], None, self.comp_drop)
+
+    def _iteration(self, volume, label, img_mask=None, cw=None, mask_offsets=None, d_init=None, trace=None, dropout_masks=None):
         loss, aux = chap_losses_forward(self.model, volume, label, self.labeled_bs, self.n_classes, self.iter_num,
                                         vat=self.vat, adv_losstype=self.adv_losstype, topk=self.topk,
                                         use_diff_mask=self.use_diff_mask, consistency=self.consistency,
                                         rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace,
-                                        img_mask=img_mask, cw=cw)
+                                        img_mask=img_mask, cw=cw, dropout=self.dropout, comp_drop=self.comp_drop,
+                                        sim_score=self.sim_score, dropout_masks=dropout_masks)
         self.opt.zero_grad()                                                            # :381
         with ops.zero_bias_grad_as_none():
             loss.backward()                                                             # :382
@@ -221,13 +255,15 @@ class ChapTrainer:
     def _poly_lr(self):
         return self.base_lr * (1.0 - self.iter_num / self.max_iterations) ** 0.9        # set at :387-389 of the previous iteration
 
-    def step(self, volume, label, mask_offsets=None, d_init=None, trace=None):
+    def step(self, volume, label, mask_offsets=None, d_init=None, trace=None, dropout_masks=None):
         """One iteration.  d_init: optional explicit VAT probing noise (list of 5 tensors; the parity protocol) -- in graph
-        mode it is copied into static buffers that the captured graph reads; without it the noise is drawn inside the graph."""
+        mode it is copied into static buffers that the captured graph reads; without it the noise is drawn inside the graph.
+        dropout_masks: optional explicit perform_dropout masks (list of 5: None or (m1, m2) [n_unlab / 2, C]); drawn like the
+        reference when omitted."""
         eager = (not self.use_graph) or trace is not None
         if eager or self.iter_num < self.graph_warmup:
             self.opt.lr = self._poly_lr()
-            aux = self._iteration(volume, label, mask_offsets=mask_offsets, d_init=d_init, trace=trace)
+            aux = self._iteration(volume, label, mask_offsets=mask_offsets, d_init=d_init, trace=trace, dropout_masks=dropout_masks)
             self.iter_num += 1                                                          # :385
             return aux
         if self.graph is None:
@@ -245,6 +281,12 @@ class ChapTrainer:
         if d_init is not None:
             for dst, src in zip(st["d_init"], d_init):
                 dst.copy_(src, non_blocking=True)
+        if self.dropout:                       # the masks are drawn outside the graph (host generator, like the reference) ...
+            if dropout_masks is None:
+                dropout_masks = self._draw_dropout_masks(volume.shape[0] - self.labeled_bs, volume.device)
+            for dst, src in zip(st["drop"], dropout_masks):
+                dst[0].copy_(src[0], non_blocking=True)             # ... and copied into the static buffers the graph reads
+                dst[1].copy_(src[1], non_blocking=True)
         if st["next_iter"] != self.iter_num:   # eager iterations ran in between: resynchronise the device counter
             st["iter"].fill_(self.iter_num)
         self.graph.replay()
@@ -260,7 +302,8 @@ class ChapTrainer:
                   mask=torch.ones(tuple(volume.shape[2:]), dtype=torch.int64, device=dev),
                   cw=torch.zeros(1, dtype=torch.float32, device=dev),
                   iter=torch.full((1,), self.iter_num, dtype=torch.int64, device=dev),
-                  d_init=None if d_init is None else [ops.cl(d.to(dev)).clone() for d in d_init], next_iter=self.iter_num)
+                  d_init=None if d_init is None else [ops.cl(d.to(dev)).clone() for d in d_init], next_iter=self.iter_num,
+                  drop=self._draw_dropout_masks(volume.shape[0] - self.labeled_bs, dev) if self.dropout else None)
         st["volume"].copy_(volume)
         st["label"].copy_(label)
         ops.invalidate_weight_cache()
@@ -268,7 +311,8 @@ class ChapTrainer:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             ops.schedule_step(st["iter"], self.base_lr, self.max_iterations, self.consistency, self.rampup, self.opt.lr_dev, st["cw"])
-            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"][0], d_init=st["d_init"])
+            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"][0], d_init=st["d_init"],
+                                        dropout_masks=st["drop"])
         self.static = st
 
     def close(self):

@@ -182,6 +182,14 @@ int chap_split_channels(const float* in, int64_t rows, int32_t ca, int32_t cb, f
  * code/networks/FilterDropout.py:45-89, and unet.UNet.perform_dropout unet.py:532-552) */
 int chap_channel_scale(const float* x, const float* scale_nc, int32_t n, int64_t rows_per_sample, int32_t c, float* out, void* stream);
 /* out = a + alpha*b (flat) */
+/* perform_dropout of code/networks/FilterDropout.py:45-89 for one pyramid level, fused: feat [N, rps, C] -> the two decoder
+ * inputs out{1,2} [N + nu, rps, C] = cat(feat, feat[N - nu:] * m{1,2}) with per-(sample, channel) factors m{1,2} [nu, C]
+ * (NULL = 1: level not perturbed).  One pass: feat read once, both outputs written.  bwd: dfeat from the two output gradients
+ * (either may be NULL). */
+int chap_feature_dropout_fwd(const float* feat, const float* m1, const float* m2, int32_t n, int32_t nu, int64_t rows_per_sample,
+                             int32_t c, float* out1, float* out2, void* stream);
+int chap_feature_dropout_bwd(const float* d1, const float* d2, const float* m1, const float* m2, int32_t n, int32_t nu,
+                             int64_t rows_per_sample, int32_t c, float* dfeat, void* stream);
 int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream);
 /* out = a*m + b*(1-m), m int64/broadcast spatial mask [rows_per_sample] (copy-paste mixing,
  * code/train_ours_2D.py:335-336) */

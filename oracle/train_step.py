@@ -15,6 +15,7 @@ import contextlib
 import torch
 
 from . import chap_losses as L
+from . import filter_dropout
 from . import nets
 
 
@@ -97,9 +98,25 @@ class ModuleModel:
         return self.m.decoder2(feats)
 
 
+def feature_dropout_loss(model, uimg_ab, ps1, ps2, dropout_masks):
+    """The --dropout branch, code/train_ours_2D.py:359-364: model(uimg_ab, False, True, [0..4], sim_score, False) -- encoder,
+    perform_dropout (FilterDropout.py:45-89: the second half of uimg_ab gets a channel-masked copy appended per decoder), both
+    decoders -- then CE against the other decoder's pseudo-labels.
+    FROZEN FIX: as shipped the reference calls F.cross_entropy(outputs1_fp [1.5 N], pseudo_outputs2 [N]) (:362-363), which
+    raises on the batch-size mismatch; the appended rows are perturbed copies of samples N/2.., so their targets are the
+    pseudo-labels of those samples: target = cat(pseudo, pseudo[N/2:])."""
+    import torch.nn.functional as F
+    feats = model.encoder(uimg_ab)
+    f1, f2 = filter_dropout.perform_dropout(feats, dropout_masks)
+    o1, o2 = model.decoder1(f1), model.decoder2(f2)
+    half = ps1.shape[0] // 2
+    t1, t2 = torch.cat((ps1, ps1[half:])), torch.cat((ps2, ps2[half:]))
+    return F.cross_entropy(o1, t2.long()) + F.cross_entropy(o2, t1.long())           # :362-364
+
+
 def chap_losses_forward(model, volume, label, labeled_bs, n_classes, mask_offsets, iter_num,
                         vat=None, adv_losstype="kl", topk=0.1, use_diff_mask=True,
-                        consistency=1.0, rampup=50.0, d_init=None, trace=None):
+                        consistency=1.0, rampup=50.0, d_init=None, trace=None, dropout_masks=None):
     """Forward part of one iteration: returns (loss, aux dict).  Lines refer to
     code/train_ours_2D.py."""
     n = volume.shape[0]
@@ -137,13 +154,15 @@ def chap_losses_forward(model, volume, label, labeled_bs, n_classes, mask_offset
     loss_u = lu_i1 + lu_i2 + lu_o1 + lu_o2                                      # :354
     cw = L.consistency_weight(iter_num, consistency, rampup)                   # :356
 
+    # :359-367 -- dropout_masks given <=> args["dropout"]; explicit masks (list of 5: None or (m1, m2)) replace the RNG draws
+    fp_loss = feature_dropout_loss(model, uimg_ab, ps1, ps2, dropout_masks) if dropout_masks is not None else torch.zeros((), device=volume.device)
     if vat is not None:                                                         # :369-372
         diff_mask = L.create_mask_v1(ps1, ps2, knowledge, 4, topk) if use_diff_mask else None
         vat_loss = vat(model, volume, soft1, soft2, diff_mask, adv_losstype, d_init=d_init, trace=trace)
     else:
-        vat_loss = torch.zeros(())
-    loss = bcp_loss + cw * vat_loss                                             # :378 (fp_loss = 0 without --dropout)
-    aux = dict(bcp_loss=bcp_loss.detach(), vat_loss=vat_loss.detach(), loss_l=loss_l.detach(),
+        vat_loss = torch.zeros((), device=volume.device)
+    loss = bcp_loss + cw * (fp_loss + vat_loss)                                 # :378
+    aux = dict(bcp_loss=bcp_loss.detach(), vat_loss=vat_loss.detach(), fp_loss=fp_loss.detach(), loss_l=loss_l.detach(),
                loss_u=loss_u.detach(), cw=cw, soft1=soft1, soft2=soft2, knowledge=knowledge,
                plab=(plab_a1, plab_b1, plab_a2, plab_b2), out_mix=(out1.detach(), out2.detach()))
     return loss, aux

@@ -3,12 +3,12 @@ fixtures (generated from the unmodified reference) and through the functional or
 inputs.
 
 Tolerances (relative L2 against the fp32 CPU oracle / fixture), BASELINE.json north_star asks <= 1e-3 on logits:
-  * fp32 CUDA-core mode (ops.set_force_simt(True)):       logits <= 1e-4 (measured ~1e-6)
-  * TF32 tensor-core mode (default, = the reference's default cuDNN setting `allow_tf32=True`):
-        2D logits <= 3e-3 (measured 1.5e-3; torch-eager + cuDNN TF32 on the same box: 0.8e-3)
-        3D logits <= 3e-2 (measured 1.5e-2; torch-eager + cuDNN TF32 on the same box: 2.9e-2)
-    i.e. the 1e-3 bar is met in fp32 mode and is not attainable by ANY TF32 execution of the V-Net, the
-    reference's own included (numbers in DESIGN.md "precision").
+  * fp32 CUDA-core mode (ops.set_force_simt(True)):                       logits <= 1e-4 (measured ~1e-6)
+  * 3xTF32 tensor-core mode (ops.set_conv_precision(ops.PRECISE_ALL)):    logits <= 1e-3 (measured ~5e-6 2D, ~2e-4 3D)
+  * TF32 tensor-core mode (default, = the reference's default cuDNN setting `allow_tf32=True`): no constant --
+        <= 1.25x the deviation of the IDEAL TF32 evaluation of the same network (tests/tf32_emul.py: float64 arithmetic,
+        conv operands rounded to TF32).  Measured at BASELINE shapes (tests/test_gpu_baseline_shapes.py): product 1.684e-3
+        = ideal 1.684e-3 (2D), 1.49e-2 vs 1.47e-2 (3D); torch-eager + cuDNN allow_tf32 on the same box: 2.2e-3 / 1.5e-2.
 """
 import numpy as np
 import pytest
@@ -16,62 +16,84 @@ import torch
 
 from conftest import golden, max_err, rel_err, seeded_model, weights_checksum
 from oracle import nets
+from tf32_emul import ideal_tf32
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+MODES = ["fp32-cuda-core", "tf32-tensor-core", "3xtf32-tensor-core"]
 
 
-def logit_tol(simt, nd):
-    return 1e-4 if simt else (3e-3 if nd == 2 else 3e-2)
-
-
-def grad_tol(simt, nd):
-    return (2e-4 if nd == 2 else 5e-2) if simt else None      # TF32 mode: calibrated live, see cudnn_tf32_grad_dev
-
-
-def cudnn_tf32_grad_dev(kind, state_dict, x, loss_fn, names, want):
-    """How far the REFERENCE's own default GPU execution (torch eager + cuDNN, allow_tf32=True) lands from the fp32
-    fixture gradients `want` -- the yardstick for the TF32 tensor-core mode: a 1e-3 forward perturbation flips the
-    derivative of ~1e-3 of the (Leaky)ReLU units, which shows up as percent-level gradient differences in ANY TF32
-    execution.  Test infrastructure only (runs the functional oracle on the GPU through torch/cuDNN)."""
+def _oracle64(kind, state_dict, x, loss_fn=None, names=None, emulate=False, drop=None, update_running=False):
+    """float64 evaluation of the oracle on the GPU (optionally as ideal TF32): (o1, o2), grads of loss_fn w.r.t. `names`."""
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in nets.clone_state_dict(state_dict, device=DEV).items()}
+    for n in names or []:
+        sd[n].requires_grad_(True)
     old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = False
     try:
-        sd = {k: v.to(DEV) for k, v in nets.clone_state_dict(state_dict).items()}
-        for n in names:
-            sd[n].requires_grad_(True)
-        if kind == "3d":
-            o1, o2 = nets.dualdecoder3d_forward(sd, x.to(DEV), True, False, False)
-        else:
-            o1, o2 = nets.dualdecoder2d_forward(sd, x.to(DEV), True, False, None)
-        grads = torch.autograd.grad(loss_fn(o1, o2), [sd[n] for n in names])
+        ctx = ideal_tf32() if emulate else torch.enable_grad()
+        with ctx:
+            if kind == "3d":
+                o1, o2 = nets.dualdecoder3d_forward(sd, x.to(DEV).double(), True, update_running, drop is not None, drop)
+            else:
+                o1, o2 = nets.dualdecoder2d_forward(sd, x.to(DEV).double(), True, update_running, drop)
+            grads = torch.autograd.grad(loss_fn(o1, o2), [sd[n] for n in names]) if names else None
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    return [rel_err(g_, w_) for g_, w_ in zip(grads, want)]
+    return (o1.detach(), o2.detach()), grads
 
 
-def assert_grads(simt, nd, mine, want, dev_ref, floor=2e-2):
-    """fp32 mode: fixed tolerance; TF32 mode: no worse than 3x the cuDNN-TF32 deviation (+ floor)."""
+def ideal_tf32_devs(kind, state_dict, x, loss_fn=None, names=None, drop=None):
+    """Deviation of the ideal-TF32 evaluation from the unrounded float64 one: (logit deviation, [per-tensor gradient deviation])."""
+    if drop is not None:
+        drop = {k: v.to(DEV).double() for k, v in drop.items()}
+    o, g = _oracle64(kind, state_dict, x, loss_fn, names, False, drop)
+    oi, gi = _oracle64(kind, state_dict, x, loss_fn, names, True, drop)
+    return max(rel_err(a, b) for a, b in zip(oi, o)), ([rel_err(a, b) for a, b in zip(gi, g)] if names else None)
+
+
+def logit_tol(mode, kind, state_dict=None, x=None, drop=None):
+    if mode == "fp32-cuda-core":
+        return 1e-4
+    if mode == "3xtf32-tensor-core":
+        return 1e-3
+    return 1.25 * ideal_tf32_devs(kind, state_dict, x, drop=drop)[0] + 1e-5
+
+
+@pytest.fixture(params=MODES)
+def mode(request):
+    from chap_b200 import ops
+    ops.set_force_simt(request.param == "fp32-cuda-core")
+    ops.set_conv_precision(ops.PRECISE_ALL if request.param == "3xtf32-tensor-core" else 0)
+    yield request.param
+    ops.set_force_simt(False)
+    ops.set_conv_precision(0)
+
+
+def assert_grads(mode, kind, mine, want, ideal_dev):
+    """fp32 mode: fixed tolerance; 3xTF32: every conv op is at 1e-6 forward and data gradient (tools/_diag / replay), the
+    weight-gradient GEMM is one TF32 rounding deep (3e-4), and a handful of (Leaky)ReLU units whose pre-activation lies within
+    the 5e-6 forward error of zero flip their derivative -- each flip moves a small tensor like the 16x1x3x3 stem gradient by
+    ~1e-3 (DESIGN.md "conditioning"); TF32: no worse than 2x the ideal-TF32 deviation of that tensor (+ a small floor)."""
     for i, (a, b) in enumerate(zip(mine, want)):
-        lim = grad_tol(simt, nd) if simt else 3.0 * dev_ref[i] + floor
+        if mode == "fp32-cuda-core":
+            lim = 2e-4 if kind == "2d" else 5e-2
+        elif mode == "3xtf32-tensor-core":
+            lim = 1e-2 if kind == "2d" else 5e-2
+        else:
+            lim = 2.0 * ideal_dev[i] + 2e-3
         assert rel_err(a, b) < lim, (i, rel_err(a, b), lim)
 
 
-@pytest.fixture(params=[True, False], ids=["fp32-cuda-core", "tf32-tensor-core"])
-def simt(request):
-    from chap_b200 import ops
-    ops.set_force_simt(request.param)
-    yield request.param
-    ops.set_force_simt(False)
-
-
-def test_dualdecoder2d_matches_reference_fixture(simt):
+def test_dualdecoder2d_matches_reference_fixture(mode):
     g = golden("unet2d.npz")
     m = seeded_model("dualdecoder2d")
     assert abs(weights_checksum(m.state_dict()) - float(g["weights_checksum"])) < 1e-6
+    sd0 = seeded_model("dualdecoder2d").state_dict()
     m = m.to(DEV).train()
     x = torch.from_numpy(g["x"]).to(DEV)
-    tol = logit_tol(simt, 2)
+    simt = mode == "fp32-cuda-core"
+    tol = logit_tol(mode, "2d", sd0, x)
     o1, o2, feats = m(x, with_feat=True)
     assert o1.shape == (2, 4, 48, 48)
     assert rel_err(o1, g["o1"]) < tol and rel_err(o2, g["o2"]) < tol
@@ -83,12 +105,19 @@ def test_dualdecoder2d_matches_reference_fixture(simt):
     grads = torch.autograd.grad(loss, [params[n] for n in names])
     sel = ["encoder.in_conv.conv_conv.0.weight", "decoder1.out_conv.weight", "decoder2.up4.up.weight"]
     want = [g["grad_in_conv"], g["grad_out1"], g["grad_up4_t"]]
-    lin = lambda a, b: (a * w).sum() + (b * w.flip(0)).sum()      # noqa: E731
-    dev = None if simt else cudnn_tf32_grad_dev("2d", seeded_model("dualdecoder2d").state_dict(), x, lin, sel, want)
-    assert_grads(simt, 2, [grads[names.index(n)] for n in sel], want, dev)
+    lin = lambda a, b: (a * w.double()).sum() + (b * w.double().flip(0)).sum()      # noqa: E731
+    dev = ideal_tf32_devs("2d", sd0, x, lin, sel)[1] if mode == "tf32-tensor-core" else None
+    assert_grads(mode, "2d", [grads[names.index(n)] for n in sel], want, dev)
     norms = np.array([t.double().norm().item() for t in grads])
     big = g["grad_norms"] > 1.0                      # pre-BN conv biases have analytically zero gradient
-    np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1e-3 if simt else 0.2)
+    if mode == "tf32-tensor-core":                   # norms of ALL parameter gradients: as close as the ideal TF32 evaluation (x1.5)
+        all_names = [n for n in names if big[names.index(n)]]
+        (_, g64) = _oracle64("2d", sd0, x, lin, all_names)
+        (_, gid) = _oracle64("2d", sd0, x, lin, all_names, emulate=True)
+        ideal_norm_dev = max(abs(float(a.norm()) / float(b.norm()) - 1.0) for a, b in zip(gid, g64))
+        np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1.5 * ideal_norm_dev + 1e-3)
+    else:
+        np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1e-3 if simt else 3e-3)
     assert rel_err(m.encoder.in_conv.conv_conv[1].running_mean, g["running_mean0"]) < 1e-4
     assert rel_err(m.encoder.in_conv.conv_conv[1].running_var, g["running_var0"]) < 1e-4
     m.eval()
@@ -100,11 +129,12 @@ def test_dualdecoder2d_matches_reference_fixture(simt):
     assert rel_err(uo, g["unet_o"]) < tol and uf.shape == (2, 16, 48, 48)
 
 
-def test_dualdecoder3d_and_vnet_match_reference_fixture(simt):
+def test_dualdecoder3d_and_vnet_match_reference_fixture(mode):
     g = golden("vnet3d.npz")
+    sd0 = seeded_model("dualdecoder3d").state_dict()
     m = seeded_model("dualdecoder3d").to(DEV).train()
     x = torch.from_numpy(g["x"]).to(DEV)
-    tol = logit_tol(simt, 3)
+    tol = logit_tol(mode, "3d", sd0, x)
     o1, o2 = m(x)
     assert rel_err(o1, g["o1"]) < tol and rel_err(o2, g["o2"]) < tol
     w = torch.linspace(-1.0, 1.0, o1.numel()).reshape(o1.shape).to(DEV)
@@ -117,13 +147,15 @@ def test_dualdecoder3d_and_vnet_match_reference_fixture(simt):
     # per-op replay test below.
     sel = ["encoder.block_one.conv.0.weight", "encoder.block_one_dw.conv.0.weight", "decoder2.block_eight_up.conv.0.weight"]
     want = [g["grad_block_one"], g["grad_dw"], g["grad_up_t"]]
-    lin = lambda a, b: (a * w).sum() + (b * w.flip(0)).sum()      # noqa: E731
-    dev = None if simt else cudnn_tf32_grad_dev("3d", seeded_model("dualdecoder3d").state_dict(), x, lin, sel, want)
-    assert_grads(simt, 3, [grads[names.index(n)] for n in sel], want, dev, floor=5e-2)
+    lin = lambda a, b: (a * w.double()).sum() + (b * w.double().flip(0)).sum()      # noqa: E731
+    dev = ideal_tf32_devs("3d", sd0, x, lin, sel)[1] if mode == "tf32-tensor-core" else None
+    if dev is not None:
+        dev = [d + 2.5e-2 for d in dev]               # the fp32 fixture itself is 1.7e-2 from an fp64 evaluation (see above)
+    assert_grads(mode, "3d", [grads[names.index(n)] for n in sel], want, dev)
     v = seeded_model("vnet").to(DEV).eval()
     with torch.no_grad():
         out = v(x)
-    assert rel_err(out, g["vnet_eval"]) < tol
+    assert rel_err(out, g["vnet_eval"]) < tol                        # eval-mode BN: better conditioned than the train-mode yardstick
 
 
 def _oracle_grads(kind, sd_src, x, dtype, loss_fn):
@@ -188,7 +220,7 @@ def test_end_to_end_gradients_vs_fp64_oracle(kind):
     assert e_gpu.max() < 5e-2, e_gpu.max()
 
 
-def test_dualdecoder2d_vs_oracle_with_dropout_masks_and_odd_batch(simt):
+def test_dualdecoder2d_vs_oracle_with_dropout_masks_and_odd_batch(mode):
     """same weights / inputs / explicit dropout masks on both sides, batch 3, 64x64."""
     torch.manual_seed(5)
     m = seeded_model("dualdecoder2d", seed=21).to(DEV).train()
@@ -201,17 +233,29 @@ def test_dualdecoder2d_vs_oracle_with_dropout_masks_and_odd_batch(simt):
     o1r, o2r = nets.dualdecoder2d_forward(sd, x, True, True, dict(zip(keys, masks)))
     feats = m.encoder(x.to(DEV), [t.to(DEV) for t in masks])
     o1, o2 = m.decoder1(feats), m.decoder2(feats)
-    tol = logit_tol(simt, 2)
-    assert rel_err(o1, o1r) < tol and rel_err(o2, o2r) < tol
+    sd0 = {k: v.detach() for k, v in sd.items()}
+    drop = dict(zip(keys, masks))
+    quad = lambda a, b: (a ** 2).sum() + (b ** 2).sum()      # noqa: E731
     names = [n for n, _ in m.named_parameters()]
-    gr = torch.autograd.grad((o1r ** 2).sum() + (o2r ** 2).sum(), [sd[n] for n in names])
-    gg = torch.autograd.grad((o1 ** 2).sum() + (o2 ** 2).sum(), list(m.parameters()))
-    errs = np.array([rel_err(a, b) for a, b in zip(gg, gr) if b.norm() > 1e-2])
-    # fp32 mode: every tensor close; TF32 mode: percent-level derivative-kink noise (see cudnn_tf32_grad_dev)
-    assert errs.max() < (1e-2 if simt else 0.3) and np.median(errs) < (1e-3 if simt else 0.15), (errs.max(), np.median(errs))
+    tol = logit_tol(mode, "2d", sd0, x, drop)
+    assert rel_err(o1, o1r) < tol and rel_err(o2, o2r) < tol
+    gr = torch.autograd.grad(quad(o1r, o2r), [sd[n] for n in names])
+    gg = torch.autograd.grad(quad(o1, o2), list(m.parameters()))
+    sel = [i for i, b in enumerate(gr) if b.norm() > 1e-2]
+    errs = np.array([rel_err(gg[i], gr[i]) for i in sel])
+    if mode == "fp32-cuda-core":
+        lim_max, lim_med = 1e-2, 1e-3
+    elif mode == "3xtf32-tensor-core":
+        lim_max, lim_med = 2e-2, 2e-3                 # plain-TF32 weight-gradient GEMM on top of split-operand fwd / dgrad
+    else:
+        # TF32: the ideal TF32 evaluation of this very network is the bar (derivative-kink flips make its gradients
+        # percent-level too): no more than 1.5x its median / maximum deviation
+        ideal = np.array(ideal_tf32_devs("2d", sd0, x, quad, [names[i] for i in sel], drop)[1])
+        lim_max, lim_med = 1.5 * ideal.max() + 1e-3, 1.5 * np.median(ideal) + 1e-4
+    assert errs.max() < lim_max and np.median(errs) < lim_med, (errs.max(), lim_max, np.median(errs), lim_med)
 
 
-def test_vnet_train_dropout3d_masks_vs_oracle(simt):
+def test_vnet_train_dropout3d_masks_vs_oracle(mode):
     m = seeded_model("dualdecoder3d", seed=4)
     for mod in m.modules():
         if hasattr(mod, "has_dropout"):
@@ -226,7 +270,7 @@ def test_vnet_train_dropout3d_masks_vs_oracle(simt):
     o1r, o2r = nets.dualdecoder3d_forward(sd, x, True, True, True, drop)
     feats = m.encoder(x.to(DEV), d5.to(DEV))
     o1, o2 = m.decoder1(feats, d9a.to(DEV)), m.decoder2(feats, d9b.to(DEV))
-    tol = 1e-3 if simt else 3e-2
+    tol = logit_tol(mode, "3d", sd, x, drop)
     assert rel_err(o1, o1r) < tol and rel_err(o2, o2r) < tol
 
 

@@ -358,3 +358,34 @@ def test_tensor_core_path_is_taken_and_accurate_to_tf32():
     s_tc = s_tc.reshape(_lib.STAT_SLOTS, -1).sum(0)
     s_ref = s_ref.reshape(_lib.STAT_SLOTS, -1).sum(0)
     assert rel_err(s_tc, s_ref) < 1e-3
+
+
+def test_feature_dropout_kernel_matches_reference_fixture():
+    """perform_dropout on the fused CUDA kernel, given the factors the reference applied (tests/golden/filter_dropout.npz,
+    generated from the unmodified reference): outputs bit-exact; backward equals autograd through the oracle restatement."""
+    from chap_b200.networks import FilterDropout as fd
+    from oracle import filter_dropout as ofd
+    g = golden("filter_dropout.npz")
+    feats = [torch.from_numpy(g["feat%d" % i]) for i in range(3)]
+    for name in ("binomial_comp", "dropout2d", "scores", "scores_comp"):
+        masks = [(torch.from_numpy(g["%s_m1_%d" % (name, i)]), torch.from_numpy(g["%s_m2_%d" % (name, i)])) if i in (0, 2) else None
+                 for i in range(3)]
+        fg = [_to_cl(f).requires_grad_(True) for f in feats]
+        mg = [None if m is None else (m[0].to(DEV), m[1].to(DEV)) for m in masks]
+        o1, o2 = fd.perform_dropout(fg, [0, 2], None, False, masks=mg)
+        for i in range(3):
+            assert o1[i].shape[0] == 6
+            np.testing.assert_allclose(o1[i].detach().cpu().numpy(), g["%s_fp1_%d" % (name, i)], rtol=2e-7, atol=0)
+            np.testing.assert_allclose(o2[i].detach().cpu().numpy(), g["%s_fp2_%d" % (name, i)], rtol=2e-7, atol=0)
+        fr = [f.clone().requires_grad_(True) for f in feats]
+        r1, r2 = ofd.perform_dropout(fr, masks)
+        ws = [torch.randn_like(t) for t in r1 + r2]
+        gr = torch.autograd.grad(sum((t * w).sum() for t, w in zip(r1 + r2, ws)), fr)
+        gg = torch.autograd.grad(sum((t * w.to(DEV)).sum() for t, w in zip(o1 + o2, ws)), fg)
+        for a, b in zip(gg, gr):
+            assert rel_err(a, b) < 1e-6
+    # drawing on the device (no explicit masks): shapes and the mean-preserving property of Dropout2d(0.5) factors
+    o1, o2 = fd.perform_dropout([_to_cl(f) for f in feats], [0, 1, 2], None, False)
+    assert all(t.shape[0] == 6 for t in o1 + o2)
+    ratio = (o1[0][4:] / _to_cl(feats[0])[2:]).flatten()
+    assert set(torch.unique(ratio[torch.isfinite(ratio)].round()).tolist()) <= {0.0, 2.0}

@@ -25,18 +25,23 @@ def _batch2d(n=8, size=32, seed=0):
     return vol, lab
 
 
-@pytest.fixture(params=[True, False], ids=["fp32-cuda-core", "tf32-tensor-core"])
-def simt(request):
+@pytest.fixture(params=["fp32-cuda-core", "tf32-tensor-core", "3xtf32-tensor-core"])
+def mode(request):
     from chap_b200 import ops
-    ops.set_force_simt(request.param)
+    ops.set_force_simt(request.param == "fp32-cuda-core")
+    ops.set_conv_precision(ops.PRECISE_ALL if request.param == "3xtf32-tensor-core" else 0)
     yield request.param
     ops.set_force_simt(False)
+    ops.set_conv_precision(0)
 
 
 @pytest.mark.parametrize("losstype", ["kl", "dice"])
-def test_vat_matches_oracle(losstype, simt):
-    """perturbation tensors <= 1e-4 relative GIVEN the same gradient field (kernel boundary), VAT loss
-    <= 1e-3 (BASELINE.json north_star tolerances)."""
+def test_vat_matches_oracle(losstype, mode):
+    """perturbation tensors <= 1e-4 relative GIVEN the same gradient field (kernel boundary); probe distance and VAT loss
+    <= 1e-3 relative in the fp32 and 3xTF32 modes (BASELINE.json north_star tolerances); in plain TF32 mode the features
+    carry one TF32 network pass of error (bounded against the ideal-TF32 yardstick in test_gpu_nets.py) and the loss sits a
+    few 1e-3 off."""
+    simt = mode != "tf32-tensor-core"
     from chap_b200 import ops
     from chap_b200.utils import losses
     m = seeded_model("dualdecoder2d", seed=11).to(DEV).train()
@@ -53,14 +58,17 @@ def test_vat_matches_oracle(losstype, simt):
     lo = L.VAT(10.0, 6.0, 4)(om, vol, soft1, soft2, mask, losstype, d_init=d_init, trace=tr_o)
     lg = losses.VAT2d(10.0, 6.0, 4)(m, vol.to(DEV), soft1.to(DEV), soft2.to(DEV), mask.to(DEV), losstype,
                                      d_init=[ops.cl(t.to(DEV)) for t in d_init], trace=tr_g)
-    k = 1.0 if simt else 10.0      # TF32 tensor-core mode: the reference's default cuDNN precision, see test_gpu_nets.py
-    assert abs(float(tr_g["dist"]) - float(tr_o["dist"])) < k * 2e-3 * max(1.0, abs(float(tr_o["dist"])))
+    tol = 1e-3 if simt else 1e-2
+    e_dist = abs(float(tr_g["dist"]) - float(tr_o["dist"])) / abs(float(tr_o["dist"]))
+    e_loss = abs(float(lg) - float(lo)) / abs(float(lo))
+    print("\n[vat %s %s] dist %.6g rel err %.2e | loss %.6g rel err %.2e" % (losstype, mode, float(tr_o["dist"]), e_dist, float(lo), e_loss))
+    assert e_dist < tol
     for lvl in range(5):
         # kernel-boundary parity: feed the ORACLE's gradient field through the CUDA generator
         (adv,) = ops.perturb([ops.cl(tr_o["g"][lvl].to(DEV))], None, 6.0, "channel_spatial", g_scale=1.0)
         assert rel_err(adv, tr_o["r"][lvl]) < 1e-4, lvl
         assert rel_err(tr_g["feats"][lvl], tr_o["feats"][lvl]) < (1e-4 if simt else 6e-3), lvl
-    assert abs(float(lg) - float(lo)) < k * 5e-3 * max(1.0, abs(float(lo)))
+    assert e_loss < tol
     names = [n for n, _ in m.named_parameters()]
     go = torch.autograd.grad(lo, [sd[n] for n in names], allow_unused=True)
     gg = torch.autograd.grad(lg, list(m.parameters()), allow_unused=True)
@@ -200,3 +208,77 @@ def test_cuda_graph_trainer_full_chap_step_runs():
         losses_seen.append(float(out["loss"]))
     assert t.graph is not None and all(np.isfinite(v) for v in losses_seen), losses_seen
     assert len(set(losses_seen)) == 5            # every replay saw new inputs / weights
+
+
+def test_dropout_branch_iteration_matches_oracle_with_shared_masks(mode):
+    """The --dropout branch (code/train_ours_2D.py:359-365; perform_dropout, FilterDropout.py:45-89) inside the full iteration:
+    same weights, inputs, copy-paste offsets, VAT noise and perform_dropout factors on both sides; eager and graph-captured."""
+    from chap_b200 import ops
+    from chap_b200.train_step import ChapTrainer
+    tol = 1e-3 if mode != "tf32-tensor-core" else 5e-3
+    for use_graph in (False, True):
+        m = seeded_model("dualdecoder2d", seed=8).to(DEV)
+        sd = nets.clone_state_dict(m.state_dict(), requires_grad=True)
+        om = oracle_step.OracleModel(sd, dims=2)
+        trainer = ChapTrainer(m, n_classes=4, labeled_bs=4, base_lr=0.01, max_iterations=100, topk=0.25, dropout=True,
+                              use_graph=use_graph, graph_warmup=1)
+        bufs = [None] * len(om.params())
+        g = torch.Generator().manual_seed(1)
+        for it in range(3):
+            vol, lab = _batch2d(8, 32, seed=it)
+            offs = (3 + it, 5 - it)
+            d_init = [torch.rand(4, c, s, s, generator=g) - 0.5 for c, s in zip((16, 32, 64, 128, 256), (32, 16, 8, 4, 2))]
+            masks = [((torch.rand(2, c, generator=g) > 0.5).float() * 2.0, (torch.rand(2, c, generator=g) > 0.5).float() * 2.0)
+                     for c in (16, 32, 64, 128, 256)]
+            ref = oracle_step.chap_train_step(om, bufs, vol, lab, 4, 4, offs, it, base_lr=0.01, max_iterations=100,
+                                              vat=L.VAT(10.0, 6.0, 4), topk=0.25, d_init=d_init, dropout_masks=masks)
+            out = trainer.step(vol.to(DEV), lab.to(DEV), mask_offsets=offs, d_init=[ops.cl(t.to(DEV)) for t in d_init],
+                               dropout_masks=[(a.to(DEV), b.to(DEV)) for a, b in masks])
+            assert float(ref["fp_loss"]) > 0.5                                     # the branch is live
+            for key in ("bcp_loss", "fp_loss", "loss"):
+                assert abs(float(out[key]) - float(ref[key])) < tol * max(1.0, abs(float(ref[key]))), (use_graph, it, key, float(out[key]), float(ref[key]))
+        assert (trainer.graph is not None) == use_graph
+        trainer.close()
+    # masks drawn like the reference (no explicit masks), graph mode: runs, finite, the fp loss moves between iterations
+    m = seeded_model("dualdecoder2d", seed=8).to(DEV)
+    t = ChapTrainer(m, 4, 4, max_iterations=100, use_graph=True, graph_warmup=1, topk=0.25, dropout=True, comp_drop=True)
+    seen = []
+    for it in range(4):
+        vol, lab = _batch2d(8, 32, seed=it)
+        seen.append(float(t.step(vol.to(DEV), lab.to(DEV))["fp_loss"]))
+    assert all(np.isfinite(v) for v in seen) and len(set(seen)) == 4
+    t.close()
+
+
+def test_flat_sgd_state_dict_roundtrip_and_torch_compat():
+    """FlatSGD.state_dict() has torch.optim.SGD's layout: resume gives bit-identical continued training, and the state loads
+    into a torch.optim.SGD over the same parameters (code/train_ours_2D.py:278)."""
+    from chap_b200 import ops
+    from chap_b200.train_step import ChapTrainer
+    ops.set_force_simt(True)
+    try:
+        def make():
+            m = seeded_model("dualdecoder2d", seed=8).to(DEV)
+            return m, ChapTrainer(m, 4, 4, max_iterations=100, adv_noise=False)
+        ma, ta = make()
+        data = [_batch2d(8, 32, seed=i) for i in range(4)]
+        for it in range(2):
+            ta.step(data[it][0].to(DEV), data[it][1].to(DEV), mask_offsets=(2, 3))
+        ckpt = {k: (v if not isinstance(v, dict) else v) for k, v in ta.state_dict().items()}
+        import copy
+        ckpt = copy.deepcopy(ckpt)
+        mb, tb = make()
+        tb.load_state_dict(ckpt)
+        assert tb.iter_num == 2
+        for it in range(2, 4):
+            la = ta.step(data[it][0].to(DEV), data[it][1].to(DEV), mask_offsets=(2, 3))["loss"]
+            lb = tb.step(data[it][0].to(DEV), data[it][1].to(DEV), mask_offsets=(2, 3))["loss"]
+            assert abs(float(la) - float(lb)) < 2e-4 * max(1.0, abs(float(la)))
+        errs = [rel_err(pb, pa) for pa, pb in zip(ma.parameters(), mb.parameters())]
+        assert np.median(errs) < 1e-4
+        sgd = torch.optim.SGD(list(mb.parameters()), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        sgd.load_state_dict(tb.opt.state_dict())                   # torch's own loader accepts the layout
+        buf0 = sgd.state[next(iter(mb.parameters()))]["momentum_buffer"]
+        assert torch.equal(buf0, tb.opt.flat_buf[:buf0.numel()].view_as(buf0))
+    finally:
+        ops.set_force_simt(False)

@@ -126,3 +126,20 @@ def test_dice_and_mix_loss_properties():
     assert abs(d.item()) < 1e-5                                         # perfect prediction -> dice loss 0
     zero = L.dice_loss_bcp(torch.softmax(perfect, 1), lab.unsqueeze(1), ones * 0, 4)
     assert abs(zero.item()) < 1e-6                                      # empty mask -> (0+e)/(0+e) -> loss 0
+
+
+def test_oracle_perform_dropout_reproduces_reference_fixture():
+    """tests/golden/filter_dropout.npz holds the reference's perform_dropout outputs and the factors it applied."""
+    from oracle import filter_dropout as ofd
+    g = golden("filter_dropout.npz")
+    feats = [torch.from_numpy(g["feat%d" % i]) for i in range(3)]
+    for name in ("binomial_comp", "dropout2d", "scores", "scores_comp"):
+        masks = [(torch.from_numpy(g["%s_m1_%d" % (name, i)]), torch.from_numpy(g["%s_m2_%d" % (name, i)])) if i in (0, 2) else None
+                 for i in range(3)]
+        o1, o2 = ofd.perform_dropout(feats, masks)
+        for i in range(3):
+            np.testing.assert_allclose(o1[i].numpy(), g["%s_fp1_%d" % (name, i)], rtol=2e-7, atol=0)
+            np.testing.assert_allclose(o2[i].numpy(), g["%s_fp2_%d" % (name, i)], rtol=2e-7, atol=0)
+        for i in (0, 2):                                  # Dropout2d / Binomial factors are 0 or 2; score masks are rescaled to mean 1
+            m = g["%s_m1_%d" % (name, i)]
+            assert m.shape == (2, feats[i].shape[1]) and (m >= 0).all()

@@ -74,12 +74,47 @@ def test_oracle_forward_bit_exact_3d_with_dropout_masks(ref):
     assert torch.equal(o1, p1) and torch.equal(o2, p2)
 
 
-def test_perform_dropout_deterministic_branch_matches_reference(ref):
+def _dropout_case(branch):
+    """(features, level, scores, comp_drop) for one branch of perform_dropout (code/networks/FilterDropout.py:54-80)."""
+    g = torch.Generator().manual_seed(31)
+    feats = [torch.randn(4, c, s, s, generator=g) for c, s in ((16, 8), (32, 4), (64, 2))]
+    level = [0, 2]                                                   # level 1 stays untouched (:82-84)
+    if branch == "binomial_comp":
+        return feats, level, None, True
+    if branch == "dropout2d":
+        return feats, level, None, False
+    if branch == "zero_scores":
+        return feats, level, [torch.zeros(c) for c in (16, 32, 64)], False
+    scores = [torch.rand(c, generator=g) + 0.1 for c in (16, 32, 64)]
+    return feats, level, scores, branch == "scores_comp"
+
+
+@pytest.mark.parametrize("branch", ["none", "binomial_comp", "dropout2d", "zero_scores", "scores", "scores_comp"])
+def test_perform_dropout_every_branch_matches_reference(ref, branch):
+    """Under the same seeds the product's mask draws (draw_dropout_masks: same generator calls in the same order) equal the
+    factors the reference applied (recovered from its outputs), and the oracle's apply step given those factors reproduces the
+    reference's outputs bit for bit.  (The product's apply step is a CUDA kernel: tests/test_gpu_ops.py against the fixture.)"""
+    import random
     from chap_b200.networks import FilterDropout as fd
-    feats = [torch.randn(4, c, 8, 8) for c in (16, 32)]
-    a1, a2 = ref.perform_dropout(feats, level=[], scores=None, comp_drop=False)
-    b1, b2 = fd.perform_dropout(feats, level=[], scores=None, comp_drop=False)
-    for u, v in zip(a1 + a2, b1 + b2):
+    from oracle import filter_dropout as ofd
+    if branch == "none":
+        feats, level, scores, comp = _dropout_case("dropout2d")
+        level = []
+    else:
+        feats, level, scores, comp = _dropout_case(branch)
+    torch.manual_seed(77); random.seed(5)
+    r1, r2 = ref.perform_dropout(feats, level=level, scores=scores, comp_drop=comp)
+    torch.manual_seed(77); random.seed(5)
+    masks = fd.draw_dropout_masks(feats, level, scores, comp)
+    rec1, rec2 = ofd.recover_masks(feats, r1, level), ofd.recover_masks(feats, r2, level)
+    for idx, m in enumerate(masks):
+        if idx not in level:
+            assert m is None
+            continue
+        assert torch.allclose(m[0].reshape(rec1[idx].shape), rec1[idx], rtol=1e-6, atol=0), (branch, idx)
+        assert torch.allclose(m[1].reshape(rec2[idx].shape), rec2[idx], rtol=1e-6, atol=0), (branch, idx)
+    o1, o2 = ofd.perform_dropout(feats, masks)
+    for u, v in zip(r1 + r2, o1 + o2):
         assert torch.equal(u, v) and u.shape[0] == 6
 
 
