@@ -99,6 +99,8 @@ SIGNATURES = {
     "chap_sgd_momentum_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
     "chap_sgd_momentum": (I, [P, P, P, L, F, F, F, F, I, P]),
     "chap_schedule_step": (I, [P, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, L, P, P, P]),
+    "chap_gather2d": (I, [P, I, P, P, I, I, I, I, I, P, P]),
+    "chap_label_overlap": (I, [P, P, L, I, P, P]),
     "chap_sw_extract": (I, [_SW, P, I, I, P, P]),
     "chap_sw_aggregate": (I, [_SW, P, I, P, P, P, P]),
 }

@@ -111,6 +111,38 @@ __global__ void schedule_kernel(long long* iter, double base_lr, double max_it, 
     *iter = it + 1;
 }
 
+// ------------------------------------------------------------------ validation helpers (code/val_2D.py:57-92)
+// Nearest-neighbour resampling of a stack of slices through per-axis index tables: out[s, Y, X] = in[s, iy[Y], ix[X]].  The
+// tables are scipy.ndimage.zoom(order=0)'s own index map (floor(o * (in - 1) / (out - 1) + 0.5) in double), computed on the
+// host, so the label maps are bit-identical to the reference's zoom -> net -> zoom back -- including scipy's quirk that an output
+// coordinate which overshoots the last sample by one ulp (o * ratio > in - 1 in double) takes the constant fill value 0.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather2d_kernel(const T* __restrict__ in, const int* __restrict__ iy, const int* __restrict__ ix, int h, int w, int H, int W,
+                int64_t total, T* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W); const int Y = (int)((i / W) % H); const int64_t s = i / ((int64_t)W * H);
+        const int sy = iy[Y], sx = ix[X];                 // -1: scipy's mode='constant' fill (coordinate beyond the last sample)
+        out[i] = (sy < 0 || sx < 0) ? T(0) : in[(s * h + sy) * w + sx];
+    }
+}
+// per-class overlap counts of two label volumes: counts[c] = {|pred == c & gt == c|, |pred == c|, |gt == c|} (Dice numerators /
+// denominators of code/val_2D.py:43-51 for every class in one pass); block-level shared-memory histogram, then one atomic per bin
+__global__ void __launch_bounds__(256)
+label_overlap_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ gt, int64_t elems, int classes,
+                     unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int h[3 * 16];
+    for (int i = threadIdx.x; i < 3 * classes; i += blockDim.x) h[i] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = pred[i], g = gt[i];
+        if (p >= 0 && p < classes) atomicAdd(&h[3 * p + 1], 1u);
+        if (g >= 0 && g < classes) { atomicAdd(&h[3 * g + 2], 1u); if (p == g) atomicAdd(&h[3 * g], 1u); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * classes; i += blockDim.x) if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+}
+
 // ------------------------------------------------------------------ sliding window
 __device__ __forceinline__ int win_start(int i, int stride, int vol, int patch) {
     int s = stride * i;
@@ -277,6 +309,25 @@ extern "C" int chap_schedule_step(int64_t* iter_dev, double base_lr, double max_
     schedule_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<long long*>(iter_dev), base_lr, max_iterations, consistency, rampup,
                                             (long long)ramp_div, lr_dev, cw_dev);
     return launched("schedule_kernel");
+}
+
+extern "C" int chap_gather2d(const void* in, int32_t elem_bytes, const int32_t* iy, const int32_t* ix, int32_t n, int32_t h, int32_t w,
+                             int32_t out_h, int32_t out_w, void* out, void* stream) {
+    CHAP_REQUIRE(in && iy && ix && out && n > 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0, CHAP_ERR_BAD_ARG, "gather2d: bad argument");
+    CHAP_REQUIRE(elem_bytes == 4 || elem_bytes == 8, CHAP_ERR_BAD_ARG, "gather2d: element size must be 4 or 8 bytes (got %d)", elem_bytes);
+    const int64_t total = (int64_t)n * out_h * out_w;
+    KernelTimer timer_("gather2d", 0.0, 2.0 * elem_bytes * (double)total, S(stream));
+    if (elem_bytes == 4) gather2d_kernel<float><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>((const float*)in, iy, ix, h, w, out_h, out_w, total, (float*)out);
+    else gather2d_kernel<int64_t><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>((const int64_t*)in, iy, ix, h, w, out_h, out_w, total, (int64_t*)out);
+    return launched("gather2d_kernel");
+}
+
+extern "C" int chap_label_overlap(const int64_t* pred, const int64_t* gt, int64_t elems, int32_t classes, uint64_t* counts, void* stream) {
+    CHAP_REQUIRE(pred && gt && counts && elems > 0 && classes >= 1 && classes <= 16, CHAP_ERR_BAD_ARG, "label_overlap: bad argument (classes %d)", classes);
+    KernelTimer timer_("label_overlap", 0.0, 16.0 * (double)elems, S(stream));
+    CHAP_TRY(zero_async(counts, (size_t)3 * classes * sizeof(uint64_t), S(stream)));
+    label_overlap_kernel<<<grid_for(elems, 256 * 8), 256, 0, S(stream)>>>(pred, gt, elems, classes, reinterpret_cast<unsigned long long*>(counts));
+    return launched("label_overlap_kernel");
 }
 
 static int check_sw(const chap_sw_desc* d) {

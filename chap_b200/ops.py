@@ -756,6 +756,47 @@ def schedule_step(iter_dev, base_lr, max_iterations, consistency, rampup, lr_dev
                                    int(ramp_div), _p(lr_dev), _p(cw_dev), _stream()))
 
 
+# ----------------------------------------------------------------------------- 2D validation helpers
+def zoom_index(in_size, out_size):
+    """scipy.ndimage.zoom(order=0, mode='constant', grid_mode=False) index map for one axis: output o reads input
+    floor(o * (in - 1) / (out - 1) + 0.5), evaluated in double like ni_interpolation.c (NI_ZoomShift) does; -1 = fill value 0."""
+    import numpy as np
+    if out_size <= 1:
+        return np.zeros(max(out_size, 0), dtype=np.int32)
+    ratio = float(in_size - 1) / float(out_size - 1)
+    cc = np.arange(out_size, dtype=np.float64) * ratio
+    idx = np.floor(cc + 0.5).astype(np.int32)
+    # mode='constant' (the default the reference uses): a coordinate outside [0, in - 1] -- which happens for the LAST output
+    # when o * ratio overshoots in - 1 by one ulp, e.g. 256 -> 200 -- reads the fill value cval = 0 (map_coordinate, NI_EXTEND_CONSTANT)
+    idx[(cc < 0) | (cc > in_size - 1)] = -1
+    return idx
+
+
+def zoom_nearest(x, out_h, out_w):
+    """scipy.ndimage.zoom(x[s], (out_h / h, out_w / w), order=0) for every slice of a CUDA stack [S, h, w] (float32 or int64)."""
+    _require_cuda(x)
+    if x.dtype not in (torch.float32, torch.int64):
+        raise RuntimeError("zoom_nearest: float32 or int64 stacks only")
+    x = x.contiguous()
+    s, h, w = x.shape
+    iy = torch.from_numpy(zoom_index(h, out_h)).to(x.device)
+    ix = torch.from_numpy(zoom_index(w, out_w)).to(x.device)
+    out = torch.empty((s, out_h, out_w), dtype=x.dtype, device=x.device)
+    check(lib().chap_gather2d(_p(x), x.element_size(), _p(iy), _p(ix), s, h, w, out_h, out_w, _p(out), _stream()))
+    return out
+
+
+def label_overlap(pred, gt, classes):
+    """int64 [classes, 3] = (|pred == c & gt == c|, |pred == c|, |gt == c|) for two int64 CUDA label volumes."""
+    _require_cuda(pred, gt)
+    pred, gt = pred.to(torch.int64).contiguous(), gt.to(torch.int64).contiguous()
+    if pred.numel() != gt.numel():
+        raise RuntimeError("label_overlap: shapes differ")
+    counts = torch.empty((classes, 3), dtype=torch.int64, device=pred.device)
+    check(lib().chap_label_overlap(_p(pred), _p(gt), pred.numel(), classes, _p(counts), _stream()))
+    return counts
+
+
 # ----------------------------------------------------------------------------- sliding window
 def sw_desc(vol, patch, nwin, stride, c):
     d = _lib.SwDesc()

@@ -284,6 +284,15 @@ int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int32_t n, int3
 int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n, int64_t elems_per_sample,
                          double* norms, float* out, void* stream);
 
+/* ------------------------------------------------------------------ 2D validation (code/val_2D.py:54-97)
+ * out[s, Y, X] = in[s, iy[Y], ix[X]] for a stack of n slices [h, w] -> [out_h, out_w]; elem_bytes 4 (float image) or 8 (int64
+ * label map).  With scipy.ndimage.zoom(order=0)'s index tables this is the reference's `zoom` (:60, :91) on the device. */
+int chap_gather2d(const void* in, int32_t elem_bytes, const int32_t* iy, const int32_t* ix, int32_t n, int32_t h, int32_t w,
+                  int32_t out_h, int32_t out_w, void* out, void* stream);
+/* counts[c] = {|pred == c and gt == c|, |pred == c|, |gt == c|} as uint64 [classes][3]: the sums medpy.metric.binary.dc needs
+ * (code/val_2D.py:43-51), for all classes in one pass over the two int64 label volumes.  classes <= 16. */
+int chap_label_overlap(const int64_t* pred, const int64_t* gt, int64_t elems, int32_t classes, uint64_t* counts, void* stream);
+
 /* ------------------------------------------------------------------ optimiser
  * torch.optim.SGD(momentum, weight_decay) step of code/train_ours_2D.py:278,383 on flat buffers:
  * g' = grad_scale*g + wd*p ; buf = first ? g' : mom*buf + g' ; p -= lr*buf */

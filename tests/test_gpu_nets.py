@@ -79,7 +79,9 @@ def assert_grads(mode, kind, mine, want, ideal_dev):
         if mode == "fp32-cuda-core":
             lim = 2e-4 if kind == "2d" else 5e-2
         elif mode == "3xtf32-tensor-core":
-            lim = 1e-2 if kind == "2d" else 5e-2
+            # weight gradients: the wgrad GEMM stays plain TF32 in this mode -> the TF32 yardstick of that tensor, with a floor for
+            # the derivative flips described above
+            lim = max(2.0 * ideal_dev[i] + 2e-3, 1e-2 if kind == "2d" else 5e-2)
         else:
             lim = 2.0 * ideal_dev[i] + 2e-3
         assert rel_err(a, b) < lim, (i, rel_err(a, b), lim)
@@ -106,18 +108,19 @@ def test_dualdecoder2d_matches_reference_fixture(mode):
     sel = ["encoder.in_conv.conv_conv.0.weight", "decoder1.out_conv.weight", "decoder2.up4.up.weight"]
     want = [g["grad_in_conv"], g["grad_out1"], g["grad_up4_t"]]
     lin = lambda a, b: (a * w.double()).sum() + (b * w.double().flip(0)).sum()      # noqa: E731
-    dev = ideal_tf32_devs("2d", sd0, x, lin, sel)[1] if mode == "tf32-tensor-core" else None
+    dev = ideal_tf32_devs("2d", sd0, x, lin, sel)[1] if mode != "fp32-cuda-core" else None
     assert_grads(mode, "2d", [grads[names.index(n)] for n in sel], want, dev)
     norms = np.array([t.double().norm().item() for t in grads])
     big = g["grad_norms"] > 1.0                      # pre-BN conv biases have analytically zero gradient
-    if mode == "tf32-tensor-core":                   # norms of ALL parameter gradients: as close as the ideal TF32 evaluation (x1.5)
+    if mode != "fp32-cuda-core":                     # norms of ALL parameter gradients: as close as the ideal TF32 evaluation (x1.5);
+        # the weight-gradient GEMM is plain TF32 in the 3xTF32 mode too, and this linear zero-mean functional cancels heavily
         all_names = [n for n in names if big[names.index(n)]]
         (_, g64) = _oracle64("2d", sd0, x, lin, all_names)
         (_, gid) = _oracle64("2d", sd0, x, lin, all_names, emulate=True)
         ideal_norm_dev = max(abs(float(a.norm()) / float(b.norm()) - 1.0) for a, b in zip(gid, g64))
         np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1.5 * ideal_norm_dev + 1e-3)
     else:
-        np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1e-3 if simt else 3e-3)
+        np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=1e-3)
     assert rel_err(m.encoder.in_conv.conv_conv[1].running_mean, g["running_mean0"]) < 1e-4
     assert rel_err(m.encoder.in_conv.conv_conv[1].running_var, g["running_var0"]) < 1e-4
     m.eval()
@@ -148,7 +151,7 @@ def test_dualdecoder3d_and_vnet_match_reference_fixture(mode):
     sel = ["encoder.block_one.conv.0.weight", "encoder.block_one_dw.conv.0.weight", "decoder2.block_eight_up.conv.0.weight"]
     want = [g["grad_block_one"], g["grad_dw"], g["grad_up_t"]]
     lin = lambda a, b: (a * w.double()).sum() + (b * w.double().flip(0)).sum()      # noqa: E731
-    dev = ideal_tf32_devs("3d", sd0, x, lin, sel)[1] if mode == "tf32-tensor-core" else None
+    dev = ideal_tf32_devs("3d", sd0, x, lin, sel)[1] if mode != "fp32-cuda-core" else None
     if dev is not None:
         dev = [d + 2.5e-2 for d in dev]               # the fp32 fixture itself is 1.7e-2 from an fp64 evaluation (see above)
     assert_grads(mode, "3d", [grads[names.index(n)] for n in sel], want, dev)

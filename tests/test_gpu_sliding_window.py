@@ -115,3 +115,75 @@ def test_val_2d_test_single_volume_batched_equals_slice_loop():
     res = test_single_volume(torch.from_numpy(image)[None], torch.from_numpy(label)[None], m, classes=4,
                              patch_size=[64, 64], model_type='logit_ensemble', device=DEV)
     assert len(res) == 3 and all(len(r) == 2 for r in res)
+
+
+def test_val_2d_device_zoom_and_dice_equal_host_protocol():
+    """On-device nearest zoom (incl. scipy's constant-fill quirk on 256 -> 200) and on-device Dice counts against the host
+    protocol of code/val_2D.py:43-51,57-92; `validate` shards volumes over ranks and the partial means add up."""
+    from scipy.ndimage import zoom
+    from conftest import seeded_model
+    from chap_b200 import ops
+    from chap_b200 import val_2D
+    rng = np.random.RandomState(3)
+    for shape, out in (((3, 200, 180), (256, 256)), ((2, 256, 256), (200, 180)), ((4, 64, 72), (64, 64))):
+        a = rng.rand(*shape).astype(np.float32) + 1.0
+        lab = (rng.rand(*shape) * 5).astype(np.int64)
+        want_f = np.stack([zoom(a[i], (out[0] / shape[1], out[1] / shape[2]), order=0) for i in range(shape[0])])
+        want_l = np.stack([zoom(lab[i], (out[0] / shape[1], out[1] / shape[2]), order=0) for i in range(shape[0])])
+        assert np.array_equal(ops.zoom_nearest(torch.from_numpy(a).to(DEV), *want_f.shape[1:]).cpu().numpy(), want_f)
+        assert np.array_equal(ops.zoom_nearest(torch.from_numpy(lab).to(DEV), *want_l.shape[1:]).cpu().numpy(), want_l)
+    pred = (rng.rand(6, 50, 40) * 4).astype(np.int64)
+    gt = (rng.rand(6, 50, 40) * 4).astype(np.int64)
+    pred[pred == 3] = 0                                           # class 3 never predicted -> (0, 0) like :50-51
+    counts = ops.label_overlap(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV), 4).cpu().numpy()
+    for c in range(4):
+        assert tuple(counts[c]) == (int(((pred == c) & (gt == c)).sum()), int((pred == c).sum()), int((gt == c).sum()))
+    m = seeded_model("dualdecoder2d", seed=9).to(DEV).eval()
+    vols = [dict(image=torch.from_numpy(rng.rand(1, 4, 48, 40).astype(np.float32)),
+                 label=torch.from_numpy((rng.rand(1, 4, 48, 40) * 4).astype(np.int64))) for _ in range(3)]
+    full = val_2D.validate(vols, m, 4, [64, 64], 'logit_ensemble', DEV)
+    for b in vols:                                                # Dice / HD95 of every volume equal the host metric on the same prediction
+        p = val_2D.predict_volume(b["image"][0].numpy(), m, (64, 64), 'logit_ensemble', DEV)
+        res = val_2D.test_single_volume(b["image"], b["label"], m, 4, [64, 64], 'logit_ensemble', DEV)
+        for i in range(1, 4):
+            d, h = val_2D.calculate_metric_percase(p == i, b["label"][0].numpy() == i)
+            assert abs(res[i - 1][0] - d) < 1e-12 and abs(res[i - 1][1] - h) < 1e-9
+    parts = [val_2D.validate(vols, m, 4, [64, 64], 'logit_ensemble', DEV, rank=r, world_size=2) for r in range(2)]
+    np.testing.assert_allclose(parts[0] + parts[1], full, rtol=1e-12)
+    assert full.shape == (3, 2)
+
+
+def test_test_all_case_reference_signature_reads_case_files(tmp_path):
+    """test_all_case(net, base_dir, method, test_list, ...) / val_3D.test_all_case(net, base_dir, test_list, ...) with the
+    reference's positional signatures (code/test_3D_util.py:91, code/val_3D.py:91): case list + per-case files on disk, metric
+    text file, and the in-memory / sharded extensions give the same numbers."""
+    from conftest import seeded_model
+    from chap_b200 import test_3D_util, val_3D
+    rng = np.random.RandomState(5)
+    base = tmp_path
+    (base / "data").mkdir()
+    cases = []
+    for i in range(3):
+        img = rng.randn(40, 36, 24).astype(np.float32)
+        lab = (rng.rand(40, 36, 24) > 0.5).astype(np.uint8)
+        np.savez(str(base / "data" / ("case%d.npz" % i)), image=img, label=lab)
+        cases.append((img, lab))
+    (base / "test.list").write_text("case0\ncase1,extra\ncase2\n")
+    net = seeded_model("vnet", seed=3).to(DEV).eval()
+    out_dir = tmp_path / "pred"
+    out_dir.mkdir()
+    got = test_3D_util.test_all_case(net, str(base), "vnet", "test.list", 2, (32, 32, 16), 16, 8, str(out_dir))
+    assert got.shape == (1, 4)
+    mem = test_3D_util.test_all_case(net, None, num_classes=2, patch_size=(32, 32, 16), stride_xy=16, stride_z=8, cases=cases)
+    np.testing.assert_allclose(got, mem, rtol=1e-12)
+    parts = [test_3D_util.test_all_case(net, None, num_classes=2, patch_size=(32, 32, 16), stride_xy=16, stride_z=8, cases=cases,
+                                        rank=r, world_size=2) for r in range(2)]
+    np.testing.assert_allclose(parts[0] + parts[1], got, rtol=1e-12)
+    text = (out_dir / "vnet.txt").read_text()
+    assert text.count("\n") == 3 and "Mean metrics" in text and (out_dir / "case1_pred.npy").exists()
+    v = val_3D.test_all_case(net, str(base), "test.list", 2, (32, 32, 16), 16, 8)
+    assert v.shape == (1, 2) and abs(v[0, 0] - got[0, 0]) < 1e-12          # same Dice through cal_metric
+    from chap_b200 import networks
+    net1 = networks.VNet(1, 1, normalization='batchnorm', has_dropout=False).to(DEV).eval()
+    lab1 = test_3D_util.test_single_case(net1, cases[0][0], 16, 8, (32, 32, 16))    # the reference's default num_classes=1
+    assert lab1.shape == cases[0][0].shape and not lab1.any()                        # softmax over one class: label 0 everywhere

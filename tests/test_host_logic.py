@@ -61,3 +61,21 @@ def test_filter_dropout_mask_helpers():
     assert m1.shape == (6, 32) and abs(float(m1.mean()) - 1.0) < 1e-5 and abs(float(m2.mean()) - 1.0) < 1e-5
     m1, m2 = fd.scores_dropoutV2(torch.rand(32), torch.rand(6, 32), True, 'sigmoid')
     assert set(torch.unique(m1 > 0).tolist()) <= {True, False} and m1.shape == (6, 32)
+
+
+def test_zoom_index_tables_reproduce_scipy_zoom_order0():
+    """ops.zoom_index is scipy.ndimage.zoom(order=0)'s index map (code/val_2D.py:60,91), including its constant-fill quirk on an
+    overshooting last coordinate; the gather kernel only applies these tables."""
+    import numpy as np
+    from scipy.ndimage import zoom
+    from chap_b200.ops import zoom_index
+    rng = np.random.RandomState(0)
+    for (h, w, hh, ww) in [(200, 180, 256, 256), (256, 256, 200, 180), (313, 257, 256, 256), (256, 256, 313, 257), (64, 64, 256, 256),
+                           (5, 7, 256, 256), (256, 256, 5, 7), (256, 256, 256, 256), (224, 208, 256, 256), (256, 256, 224, 208)]:
+        a = rng.rand(h, w).astype(np.float32) + 1.0
+        ref = zoom(a, (hh / h, ww / w), order=0)
+        oh, ow = int(round(h * (hh / h))), int(round(w * (ww / w)))
+        assert ref.shape == (oh, ow)
+        iy, ix = zoom_index(h, oh), zoom_index(w, ow)
+        got = np.where((iy[:, None] < 0) | (ix[None, :] < 0), np.float32(0), a[np.maximum(iy, 0)][:, np.maximum(ix, 0)])
+        assert np.array_equal(ref, got), (h, w, hh, ww)
