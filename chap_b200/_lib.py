@@ -22,6 +22,10 @@ class ConvDesc(ctypes.Structure):
                 ("in_w", c_int32), ("cin", c_int32), ("cout", c_int32)]
 
 
+class PackItem(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("w_fwd", c_void_p), ("w_dgrad", c_void_p), ("desc", ConvDesc)]
+
+
 class Level(ctypes.Structure):
     _fields_ = [("g", c_void_p), ("f", c_void_p), ("out", c_void_p), ("rows", c_int64), ("c", c_int32),
                 ("pad_", c_int32)]
@@ -57,13 +61,17 @@ SIGNATURES = {
     "chap_get_conv_precision": (I, []),
     "chap_conv_packed_elems": (c_size_t, [_CD]),
     "chap_conv_pack_weights": (I, [_CD, P, P, P, P]),
+    "chap_conv_pack_weights_batched": (I, [POINTER(PackItem), I, P]),
     "chap_conv_fwd": (I, [_CD, P, P, P, P, P, P]),
     "chap_conv_bn_fwd": (I, [_CD, P, P, P, P, P, P, P]),
+    "chap_conv_bn_act_fwd": (I, [_CD, P, P, P, P, F, P, P, P]),
     "chap_conv_dgrad": (I, [_CD, P, P, P, P]),
     "chap_conv_dgrad_split_supported": (I, [_CD, I]),
     "chap_conv_dgrad_split": (I, [_CD, P, P, P, I, P, P]),
     "chap_conv_wgrad_workspace_bytes": (c_size_t, [_CD]),
     "chap_conv_wgrad": (I, [_CD, P, P, P, P, P, c_size_t, P]),
+    "chap_conv_wgrad_acc": (I, [_CD, P, P, P, P, P, c_size_t, P, P]),
+    "chap_bn_act_bwd_acc": (I, [P, P, P, P, F, P, P, I, L, I, I, P, P, P, P, P]),
     "chap_channel_stats": (I, [P, L, I, P, P]),
     "chap_bn_finalize": (I, [P, I, L, P, P, F, F, P, P, P, P, P, I, P]),
     "chap_bn_eval_params": (I, [P, P, P, P, F, P, P, I, P]),

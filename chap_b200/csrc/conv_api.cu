@@ -33,6 +33,27 @@ extern "C" int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, f
     return CHAP_OK;
 }
 
+extern "C" int chap_conv_pack_weights_batched(const chap_pack_item* items, int32_t n, void* stream) {
+    CHAP_REQUIRE(items != nullptr && n >= 0, CHAP_ERR_BAD_ARG, "pack_weights_batched: bad argument");
+    static thread_local PackBatch batch;
+    batch.n = 0;
+    auto push = [&](const float* w, float* out, const PackSpec& p, bool tc) -> int {
+        PackSub& s = batch.sub[batch.n++];
+        s.w = w; s.out = out; s.sk = p.sk; s.sn = p.sn; s.taps = p.taps; s.K = p.K; s.N = p.N;
+        s.Kp = tc ? tc_pad16(p.K) : p.K; s.Np = tc ? tc_pad16(p.N) : p.N; s.flip = p.flip; s.kn_order = tc ? 0 : 1; s.pad_ = 0;
+        if (batch.n == kPackBatch) { CHAP_TRY(launch_pack_batch(batch, S(stream))); batch.n = 0; }
+        return CHAP_OK;
+    };
+    for (int i = 0; i < n; ++i) {
+        Geom g{};
+        CHAP_TRY(resolve(&items[i].desc, g));
+        CHAP_REQUIRE(items[i].w != nullptr, CHAP_ERR_BAD_ARG, "pack_weights_batched: item %d has no weight", i);
+        if (items[i].w_fwd) CHAP_TRY(push(items[i].w, items[i].w_fwd, fwd_pack(g), use_tc(g, false)));
+        if (items[i].w_dgrad) CHAP_TRY(push(items[i].w, items[i].w_dgrad, dgrad_pack(g), use_tc(g, true)));
+    }
+    return launch_pack_batch(batch, S(stream));
+}
+
 extern "C" int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
                              float* y, double* ch_sums, void* stream) {
     Geom g{};
@@ -68,6 +89,23 @@ extern "C" int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const f
     CHAP_TRY(chap_conv_fwd(d, x, w_fwd, bias, y, ch_sums, stream));
     return chap_bn_finalize(ch_sums, CHAP_STAT_SLOTS, g.out_rows, bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean,
                             bn->running_var, bn->num_batches_tracked, bn->mean_invstd, bn->scale_shift, g.cout, stream);
+}
+
+extern "C" int chap_conv_bn_act_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
+                                    const float* scale_shift, float slope, const float* residual, float* y, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    CHAP_REQUIRE(x && w_fwd && scale_shift && y, CHAP_ERR_BAD_ARG, "conv_bn_act_fwd: NULL pointer");
+    if (use_tc(g, false)) {
+        EvalEpilogue e{scale_shift, slope, residual};
+        int rc = tc_conv(g, false, x, w_fwd, bias, y, nullptr, S(stream), nullptr, 0, nullptr, &e);
+        if (rc < 0) return rc;
+        if (rc == 1) return CHAP_OK;
+    }
+    // shapes outside the fused path (Cin = 1 stems, CUDA-core mode): convolution, then the BatchNorm/activation kernel in place
+    CHAP_TRY(chap_conv_fwd(d, x, w_fwd, bias, y, nullptr, stream));
+    const int64_t rps = (int64_t)g.oD * g.oH * g.oW;
+    return chap_bn_act_fwd(y, scale_shift, slope, nullptr, nullptr, residual, g.n, rps, g.cout, y, stream);
 }
 
 extern "C" int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream) {
@@ -110,8 +148,8 @@ extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
     return (((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255) + (size_t)g.taps * g.cin * g.cout * sizeof(float);
 }
 
-extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+static int conv_wgrad_impl(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                           void* workspace, size_t workspace_bytes, float* scratch, bool accumulate, void* stream) {
     Geom g{};
     CHAP_TRY(resolve(d, g));
     CHAP_REQUIRE(x && dy && dw, CHAP_ERR_BAD_ARG, "conv_wgrad: NULL pointer");
@@ -123,18 +161,30 @@ extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const fl
     static const int thin_max = getenv("CHAP_THIN_MAX") ? atoi(getenv("CHAP_THIN_MAX")) : 0;
     const bool thin = g.kind == CHAP_CONV_K3 && g.cin % 4 == 0 && g.cout % 4 == 0 && g.cin * g.cout <= thin_max;
     if (g_force_simt.load() == 0 && tc_wgrad_supports(g) && !thin) {
-        const size_t off = ((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255;
-        float* acc_ws = (workspace && workspace_bytes >= off + (size_t)g.taps * g.cin * g.cout * sizeof(float))
-                            ? reinterpret_cast<float*>(static_cast<char*>(workspace) + off) : nullptr;
-        handled = tc_wgrad(g, x, dy, dw, S(stream), acc_ws);
+        handled = tc_wgrad(g, x, dy, dw, S(stream), scratch, accumulate);
         if (handled < 0) return handled;
     }
-    if (!handled) CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream)));
+    if (!handled) CHAP_TRY(simt_wgrad(op, x, dy, dw, (int64_t)g.taps * g.cin * g.cout, p.sk, p.sn, S(stream), accumulate));
     if (dbias) {
         CHAP_REQUIRE(workspace && workspace_bytes >= (size_t)2 * g.cout * sizeof(double), CHAP_ERR_WORKSPACE,
                      "conv_wgrad: workspace too small (%zu bytes)", workspace_bytes);
         CHAP_TRY(channel_stats(dy, g.out_rows, g.cout, (double*)workspace, S(stream)));
-        CHAP_TRY(sums_to_float((const double*)workspace, dbias, g.cout, S(stream)));
+        CHAP_TRY(sums_to_float((const double*)workspace, dbias, g.cout, S(stream), accumulate));
     }
     return CHAP_OK;
+}
+
+extern "C" int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    Geom g{};
+    CHAP_TRY(resolve(d, g));
+    const size_t off = ((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255;
+    float* scratch = (workspace && workspace_bytes >= off + (size_t)g.taps * g.cin * g.cout * sizeof(float))
+                         ? reinterpret_cast<float*>(static_cast<char*>(workspace) + off) : nullptr;
+    return conv_wgrad_impl(d, x, dy, dw, dbias, workspace, workspace_bytes, scratch, false, stream);
+}
+
+extern "C" int chap_conv_wgrad_acc(const chap_conv_desc* d, const float* x, const float* dy, float* dw_acc, float* dbias_acc,
+                                   void* workspace, size_t workspace_bytes, float* zeroed_scratch, void* stream) {
+    return conv_wgrad_impl(d, x, dy, dw_acc, dbias_acc, workspace, workspace_bytes, zeroed_scratch, true, stream);
 }

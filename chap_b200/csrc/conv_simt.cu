@@ -40,6 +40,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// All weights of a model in one launch (blockIdx.y = sub-item: one packed operand of one layer).  The trainer re-packs every
+// conv weight once per iteration (the optimiser just changed them): 72 launches of the single-layer kernel became 2 of this one.
+__global__ void pack_weights_batched_kernel(const __grid_constant__ PackBatch b) {
+    const PackSub& s = b.sub[blockIdx.y];
+    const int64_t total = (int64_t)s.taps * s.Kp * s.Np;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int t = (int)(i / ((int64_t)s.Kp * s.Np));
+        int r = (int)(i % ((int64_t)s.Kp * s.Np));
+        int k, n;
+        if (s.kn_order) { k = r / s.Np; n = r % s.Np; } else { n = r / s.Kp; k = r % s.Kp; }
+        int ts = s.flip ? (s.taps - 1 - t) : t;
+        const float v = (k < s.K && n < s.N) ? s.w[k * s.sk + n * s.sn + ts] : 0.f;
+        if (s.kn_order == 0) {                  // tensor-core operand: TF32 hi / lo halves (see pack_weights_kernel)
+            const float hi = tf32_rn(v, 1);
+            s.out[i] = hi;
+            s.out[total + i] = tf32_rn(v - hi, 1);
+        } else {
+            s.out[i] = v;
+        }
+    }
+}
+
+int launch_pack_batch(const PackBatch& b, cudaStream_t st) {
+    if (b.n <= 0) return CHAP_OK;
+    pack_weights_batched_kernel<<<dim3(24, (unsigned)b.n), 256, 0, st>>>(b);
+    return launched("pack_weights_batched_kernel");
+}
+
 int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, int64_t sn, int flip,
                 int kn_order, cudaStream_t st, int Kp, int Np) {
     if (Kp < K) Kp = K;
@@ -458,8 +486,8 @@ k1_head_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
 }
 
 int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int64_t dw_elems,
-               int64_t sk, int64_t sn, cudaStream_t st) {
-    CHAP_TRY(zero_async(dw, dw_elems * sizeof(float), st));
+               int64_t sk, int64_t sn, cudaStream_t st, bool accumulate) {
+    if (!accumulate) CHAP_TRY(zero_async(dw, dw_elems * sizeof(float), st));      // every kernel below ADDS into dw with atomics
     if (!op.up2 && op.ksz == 1 && op.K == 16 && (op.N == 2 || op.N == 4) && aligned16(a)) {
         KernelTimer timer(timer_name("conv_thin_wgrad", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * (double)op.out_rows * op.K * op.N,
                           4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N), st);

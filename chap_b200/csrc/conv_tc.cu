@@ -63,6 +63,10 @@ struct TcParams {
     float* out_b;                 // channels [ca, n_total), row stride n_total - ca (dgrad of a channel concat), or nullptr
     int ca;
     const float* bias;
+    const float* epi_ss;          // inference epilogue (eval-mode BatchNorm folded in): y = act(scale[c] * (conv + bias) + shift[c]) + residual;
+    const float* epi_res;         //   epi_ss = [scale[C], shift[C]] or nullptr (off); epi_res = tensor of the output's shape or nullptr
+    float epi_slope;              //   negative slope of the (Leaky)ReLU
+    int epi_c;                    //   C = real output channels (offset of the shift half)
     double* stats;                // [CHAP_STAT_SLOTS][2 * n_total] or nullptr
     BnFold bn;                    // bn.mi != nullptr: the last CTA turns the statistics into BatchNorm scale / shift
 };
@@ -263,7 +267,7 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
 // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of output-channel chunk blockIdx.y.  The smem ring and the
 // two TMEM accumulators run across tile boundaries, so the TMA loads of tile j + 1 and its MMAs overlap the epilogue of
 // tile j, and the per-CTA setup (barriers, TMEM allocation, resident weights) is paid once per SM instead of once per tile.
-template <bool PRECISE>
+template <bool PRECISE, bool EVAL>
 __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmTaps* tmTp, const TcParams& p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -489,6 +493,14 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
                         for (int j4 = 0; j4 < 16; ++j4) v[j4] += __ldg(p.bias + bias0 + j4);
                     }
                 }
+                if (EVAL && p.epi_ss) {                                 // eval-mode BatchNorm + activation folded into the epilogue
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4) {
+                        const float sc = __ldg(p.epi_ss + bias0 + j4), sh = __ldg(p.epi_ss + p.epi_c + bias0 + j4);
+                        const float t = fmaf(v[j4], sc, sh);
+                        v[j4] = t > 0.f ? t : t * p.epi_slope;
+                    }
+                }
                 if (valid && !TC_DBG(4) && !TC_DBG(128)) {
                     const int gc = n0 + c0;
                     float* dst;
@@ -501,6 +513,14 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
                         dst = p.out + orow * p.up_c + co;
                     } else {
                         dst = gc < p.ca ? p.out + row * p.ca + gc : p.out_b + row * cb + (gc - p.ca);
+                    }
+                    if (EVAL && p.epi_res) {                            // additive skip (vnet.py:202-215): same shape / offset as the output
+                        const float4* r4 = reinterpret_cast<const float4*>(p.epi_res + (dst - p.out));
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 rr = __ldg(r4 + j4);
+                            v[4 * j4] += rr.x; v[4 * j4 + 1] += rr.y; v[4 * j4 + 2] += rr.z; v[4 * j4 + 3] += rr.w;
+                        }
                     }
                     if (p.n_real >= 16 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
                         // two 256-bit stores (STG.256, sm_100) per 16-column chunk
@@ -598,24 +618,19 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
 }
 
 // Two entry points: the per-tap tensor maps (1 KB of kernel parameters) are only passed for the k2 s2 gathers.
-__global__ void __launch_bounds__(kTcThreadsMax, 2)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    conv_tc_kernel_body<false>(tmA, tmB, nullptr, p);
+// Entry points.  The per-tap tensor maps (1 KB of kernel parameters) are only passed for the k2 s2 gathers (`_taps`); PRECISE adds the
+// operand-splitting warps (split-operand 3xTF32, chap_set_conv_precision); EVAL compiles the inference epilogue in (eval-mode
+// BatchNorm + activation + skip add, chap_conv_bn_act_fwd) -- kept out of the training kernels, whose 96-register budget is tight.
+template <bool PRECISE, bool EVAL>
+__global__ void __launch_bounds__(PRECISE ? kTcThreadsPrecise : kTcThreadsMax, 2)
+conv_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    conv_tc_kernel_body<PRECISE, EVAL>(tmA, tmB, nullptr, p);
 }
-__global__ void __launch_bounds__(kTcThreadsMax, 2)
-conv_tc_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
-                    const TcParams p) {
-    conv_tc_kernel_body<false>(tmA, tmB, &tmT, p);
-}
-// split-operand 3xTF32 variants (chap_set_conv_precision): + 4 splitter warps
-__global__ void __launch_bounds__(kTcThreadsPrecise, 2)
-conv_tc_precise_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    conv_tc_kernel_body<true>(tmA, tmB, nullptr, p);
-}
-__global__ void __launch_bounds__(kTcThreadsPrecise, 2)
-conv_tc_precise_kernel_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
-                            const TcParams p) {
-    conv_tc_kernel_body<true>(tmA, tmB, &tmT, p);
+template <bool PRECISE, bool EVAL>
+__global__ void __launch_bounds__(PRECISE ? kTcThreadsPrecise : kTcThreadsMax, 2)
+conv_tc_k_taps(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmTaps tmT,
+               const TcParams p) {
+    conv_tc_kernel_body<PRECISE, EVAL>(tmA, tmB, &tmT, p);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -708,8 +723,9 @@ static void choose_box(int W, int H, int D, int& tw, int& th, int& td) {
 }
 
 int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const float* bias, float* out,
-            double* ch_sums, cudaStream_t st, float* out_b, int ca, const BnFold* bn) {
+            double* ch_sums, cudaStream_t st, float* out_b, int ca, const BnFold* bn, const EvalEpilogue* epi) {
     if (!tc_supports(g, dgrad)) return 0;
+    if (epi && (dgrad || out_b || ch_sums || g.cout < 16 || g.cout % 16 != 0 || !aligned16(epi->residual))) return 0;
     CHAP_REQUIRE(aligned16(in) && aligned16(wp) && aligned16(out), CHAP_ERR_ALIGNMENT, "tc_conv: buffers must be 16-byte aligned");
     int K, N;
     tc_channels(g, dgrad, K, N);
@@ -746,6 +762,17 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
     p.n_total = N; p.nt = N > 256 ? 256 : N;
     p.tiles_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    // Small-M layers (deep levels: 3D 128 -> 128 @ 10x14x14 has 31 M tiles, 2D 256 -> 256 @ 16^2 has 24) cannot fill 148 SMs with
+    // one CTA per M tile: split N across CTAs (blockIdx.y) until the grid covers half the machine (measured: 96 tiles are better
+    // left alone -- 128 -> 128 @ 12x32^2: 29 us whole, 33 us split; 24 tiles gain -- 256 -> 256 @ 12x16^2: 45 -> 38 us).  Every CTA re-reads its A boxes
+    // (L2 hits: these tensors are a few MB) and owns nt output channels end to end, so bias, stores and the BatchNorm
+    // statistics need no cross-CTA reduction (unlike split-K).  CHAP_TC_NT forces nt for experiments.
+    if (p.mode != 1) {
+        static const int nt_force = getenv("CHAP_TC_NT") ? atoi(getenv("CHAP_TC_NT")) : 0;
+        static const int fill = getenv("CHAP_TC_FILL") ? atoi(getenv("CHAP_TC_FILL")) : kNumSMs / 2;
+        while (p.nt >= 64 && p.nt % 32 == 0 && (long)p.tiles_total * (N / p.nt) < fill && !nt_force) p.nt /= 2;
+        if (nt_force >= 16 && nt_force % 16 == 0 && N % nt_force == 0 && nt_force <= p.nt) p.nt = nt_force;
+    }
     p.n_buf = p.nt <= 128 ? 2 : 1;                                       // two accumulators while 2 CTAs/SM still fit in 512 columns
     p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
@@ -818,6 +845,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.b_lo_off = p.b_resident ? p.b_area_bytes : (uint32_t)stages * p.b_stage_bytes;
     p.debug = getenv("CHAP_TC_DEBUG") ? atoi(getenv("CHAP_TC_DEBUG")) : 0;
     p.out = out; p.out_b = out_b; p.ca = out_b ? ca : p.n_real; p.bias = bias; p.stats = ch_sums;
+    if (epi) { p.epi_ss = epi->scale_shift; p.epi_res = epi->residual; p.epi_slope = epi->slope; p.epi_c = g.cout; }
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
     const size_t smem = (size_t)stages * stage + fixed + extras;
@@ -874,10 +902,16 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         CHAP_TRY(make_tensor_map(&tmB, wp, 2, wd, ws, wb, p.kc));
     }
     static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_precise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(conv_tc_precise_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    std::call_once(attr_once, [] {
+        const int big = 227 * 1024;
+        cudaFuncSetAttribute(conv_tc_k<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k_taps<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k_taps<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k_taps<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(conv_tc_k_taps<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); });
     const size_t stat_doubles = (size_t)CHAP_STAT_SLOTS * 2 * (p.mode == 1 ? g.cout : p.n_real);
     if (bn) {
         CHAP_REQUIRE(ch_sums != nullptr, CHAP_ERR_BAD_ARG, "tc_conv: the folded BatchNorm finalize needs the statistics buffer");
@@ -893,13 +927,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
                       4.0 * ((double)g.in_rows * g.cin + (double)g.out_rows * g.cout + (double)g.taps * g.cin * g.cout), st);
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
     const unsigned threads = 64 + 128 * p.epi_groups + (p.precise ? 128 : 0);
-    if (p.precise) {
-        if (p.mode == 3) conv_tc_precise_kernel_taps<<<grid, threads, smem, st>>>(tmA, tmB, tmT, p);
-        else conv_tc_precise_kernel<<<grid, threads, smem, st>>>(tmA, tmB, p);
-    } else {
-        if (p.mode == 3) conv_tc_kernel_taps<<<grid, threads, smem, st>>>(tmA, tmB, tmT, p);
-        else conv_tc_kernel<<<grid, threads, smem, st>>>(tmA, tmB, p);
-    }
+    const bool ev = epi != nullptr;
+#define CHAP_TC_LAUNCH(PR, EV) do { if (p.mode == 3) conv_tc_k_taps<PR, EV><<<grid, threads, smem, st>>>(tmA, tmB, tmT, p); \
+                                    else conv_tc_k<PR, EV><<<grid, threads, smem, st>>>(tmA, tmB, p); } while (0)
+    if (p.precise) { if (ev) CHAP_TC_LAUNCH(true, true); else CHAP_TC_LAUNCH(true, false); }
+    else           { if (ev) CHAP_TC_LAUNCH(false, true); else CHAP_TC_LAUNCH(false, false); }
+#undef CHAP_TC_LAUNCH
     CHAP_TRY(launched("conv_tc_kernel"));
     return 1;
 }

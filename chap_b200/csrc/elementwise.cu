@@ -75,12 +75,12 @@ int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_
     return launched("channel_stats_kernel");
 }
 
-__global__ void sums_to_float_kernel(const double* sums, float* out, int c) {
+__global__ void sums_to_float_kernel(const double* sums, float* out, int c, int accumulate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < c) out[i] = (float)sums[i];
+    if (i < c) out[i] = accumulate ? out[i] + (float)sums[i] : (float)sums[i];
 }
-int sums_to_float(const double* sums, float* out, int c, cudaStream_t st) {
-    sums_to_float_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, out, c);
+int sums_to_float(const double* sums, float* out, int c, cudaStream_t st, bool accumulate) {
+    sums_to_float_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, out, c, accumulate ? 1 : 0);
     return launched("sums_to_float_kernel");
 }
 
@@ -191,8 +191,14 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         const double* __restrict__ sums, float* __restrict__ dy,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c / VEC;
+    const int acc_pg = train >> 1;             // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
+    train &= 1;
     if (blockIdx.x == 0 && dgamma) {
-        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) { dbeta[ch] = (float)sums[ch]; dgamma[ch] = (float)sums[c + ch]; }
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const float db = (float)sums[ch], dg = (float)sums[c + ch];
+            dbeta[ch] = acc_pg ? dbeta[ch] + db : db;
+            dgamma[ch] = acc_pg ? dgamma[ch] + dg : dg;
+        }
     }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % cg);
@@ -373,8 +379,14 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
                               double inv_count, const double* __restrict__ sums, float* __restrict__ dy,
                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c >> 2, g = threadIdx.x % cg;
+    const int acc_pg = train >> 1;             // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
+    train &= 1;
     if (blockIdx.x == 0 && dgamma) {
-        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) { dbeta[ch] = (float)sums[ch]; dgamma[ch] = (float)sums[c + ch]; }
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const float db = (float)sums[ch], dg = (float)sums[c + ch];
+            dbeta[ch] = acc_pg ? dbeta[ch] + db : db;
+            dgamma[ch] = acc_pg ? dgamma[ch] + dg : dg;
+        }
     }
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g), mean = ld4(mi + 4 * g), istd = ld4(mi + c + 4 * g);
     float4 mz = make_float4(0.f, 0.f, 0.f, 0.f), mzx = mz;            // batch means of dz and dz * xhat (0 in eval mode)
@@ -712,10 +724,27 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     return launched("bn_act_fwd_kernel");
 }
 
+static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
+                           const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy, float* dgamma,
+                           float* dbeta, void* stream);
+
 extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* ss, const float* mi, const float* gamma,
                                float slope, const float* drop_nc, const float* drop_el, int32_t n, int64_t rps, int32_t c,
                                int32_t train, double* sums, float* dy, float* dgamma, float* dbeta, void* stream) {
     (void)gamma;
+    return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, drop_el, n, rps, c, train ? 1 : 0, sums, dy, dgamma, dbeta, stream);
+}
+
+extern "C" int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
+                                   const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy,
+                                   float* dgamma_acc, float* dbeta_acc, void* stream) {
+    CHAP_REQUIRE(dgamma_acc && dbeta_acc, CHAP_ERR_BAD_ARG, "bn_act_bwd_acc: the gradient accumulators are required");
+    return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, drop_el, n, rps, c, (train ? 1 : 0) | 2, sums, dy, dgamma_acc, dbeta_acc, stream);
+}
+
+static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
+                           const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy, float* dgamma,
+                           float* dbeta, void* stream) {
     CHAP_REQUIRE(dout && y && ss && mi && sums && dy && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_bwd: bad argument");
     CHAP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), CHAP_ERR_BAD_ARG, "bn_act_bwd: dgamma/dbeta must both be set or both NULL");
     const int64_t rows = (int64_t)n * rps, total = rows * c;
@@ -727,7 +756,7 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);
     const double inv_count = 1.0 / (double)rows;
     if (v4 && 256 % cg == 0 && all16({ss, mi, drop_nc}) && round_tf32_on() == 0) {
-        if (train || dgamma) {
+        if ((train & 1) || dgamma) {
             const int rgrid = grid_for(total / 4, 256 * kEwUnroll * 2, kNumSMs * 8);
             if (drop_el) bn_act_bwd_reduce_fixed_kernel<true><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
             else bn_act_bwd_reduce_fixed_kernel<false><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);

@@ -61,14 +61,17 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // acc [tap][M][N] -> torch-layout gradient dw[m * s_co + n * s_ci + tap]
 __global__ void __launch_bounds__(256)
-wgrad_unpack_kernel(const float* __restrict__ acc, float* __restrict__ dw, int taps, int M, int N, int64_t s_co, int64_t s_ci) {
+wgrad_unpack_kernel(float* __restrict__ acc, float* __restrict__ dw, int taps, int M, int N, int64_t s_co, int64_t s_ci, int accumulate) {
     const int64_t total = (int64_t)taps * M * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         // consecutive threads walk the torch layout's fastest index (tap) so that the writes coalesce
         const int t = (int)(i % taps);
         const int64_t r = i / taps;
         const int n = (int)(r % N), m = (int)(r / N);
-        dw[(int64_t)m * s_co + (int64_t)n * s_ci + t] = acc[((int64_t)t * M + m) * N + n];
+        float* src = acc + ((int64_t)t * M + m) * N + n;
+        float* dst = dw + (int64_t)m * s_co + (int64_t)n * s_ci + t;
+        if (accumulate) { *dst += *src; *src = 0.f; }        // gradient-sink mode: add into the arena, hand the scratch back zeroed
+        else *dst = *src;
     }
 }
 
@@ -333,7 +336,7 @@ static void choose_box8(int W, int H, int D, int& tw, int& th, int& td, int max_
             }
 }
 
-int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st, float* acc_ws) {
+int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStream_t st, float* acc_ws, bool accumulate) {
     if (!tc_wgrad_supports(g)) return 0;
     CHAP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dw), CHAP_ERR_ALIGNMENT, "tc_wgrad: buffers must be 16-byte aligned");
     // k2 s2 convolutions: dW = sum_p S[p, .] * B[2p + tap, .] with S the low-resolution tensor (tap independent: the M operand) and
@@ -487,7 +490,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
     // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
     p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
-    CHAP_TRY(zero_async(p.acc ? p.acc : dw, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
+    // the kernel ADDS (red.global.add) into its target: a fresh gradient needs it zeroed; in accumulate mode dw keeps its content
+    // and the scratch arrives zeroed (the unpack kernel of its previous use cleared it)
+    if (!accumulate) CHAP_TRY(zero_async(p.acc ? p.acc : dw, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
     const double rows = (double)(up2 ? g.in_rows : g.out_rows);     // = pixels of the low-resolution grid for the k2 s2 kinds
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
                       4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
@@ -497,7 +502,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     CHAP_TRY(launched("wgrad_tc_kernel"));
     if (p.acc) {
         const int64_t total = (int64_t)g.taps * v.cin * v.cout;
-        wgrad_unpack_kernel<<<grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st>>>(p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci);
+        wgrad_unpack_kernel<<<grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st>>>(p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci, accumulate ? 1 : 0);
         CHAP_TRY(launched("wgrad_unpack_kernel"));
     }
     return 1;

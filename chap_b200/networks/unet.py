@@ -43,6 +43,9 @@ class ConvBlock(nn.Module):
         protocol; by default the mask is drawn like nn.Dropout would.
         cat: the block runs on torch.cat([x, cat], dim=1); the concat is fused into the first convolution."""
         c1, b1, _, _, c2, b2, _ = self.conv_conv
+        if drop_mask is None and ops.eval_fusable(b1) and ops.eval_fusable(b2):      # inference (dropout inactive): conv + BatchNorm + LeakyReLU per kernel
+            a = ops.conv_bn_act_eval(x, c1.weight, c1.bias, CONV_K3, b1, LEAKY_SLOPE, cat=cat)
+            return ops.conv_bn_act_eval(a, c2.weight, c2.bias, CONV_K3, b2, LEAKY_SLOPE)
         y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training, cat=cat, bn=b1)
         if drop_mask is None:
             drop_mask = _elementwise_dropout_mask(y, self.dropout_p, self.training)

@@ -21,6 +21,8 @@ def _check_norm(normalization):
 
 
 def _conv_bn_relu(x, conv, bn, kind, residual=None, drop_nc=None):
+    if drop_nc is None and ops.eval_fusable(bn):       # inference: BatchNorm, ReLU and the skip add run in the conv epilogue
+        return ops.conv_bn_act_eval(x, conv.weight, conv.bias, kind, bn, 0.0, residual=residual)
     y, sums = ops.conv_stats(x, conv.weight, conv.bias, kind, bn.training, feeds_train_bn=bn.training, bn=bn)
     return ops.bn_act(y, bn, 0.0, sums=sums, residual=residual, drop_nc=drop_nc)
 

@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ConvDesc, check
 
-_state = {"epoch": 0, "bn_tracking": True, "weight_grad": True, "bias_grad_none": False}
+_state = {"bn_epoch": 0, "epoch": 0, "bn_tracking": True, "weight_grad": True, "bias_grad_none": False, "grad_sink": False}
 
 
 def lib():
@@ -97,6 +97,24 @@ def zero_bias_grad_as_none(flag=True):
         _state["bias_grad_none"] = old
 
 
+@contextlib.contextmanager
+def grad_sink(flag=True):
+    """Inside: parameters that carry a `_chap_sink` attribute (set by FlatSGD: a view of the flat gradient arena plus, for conv
+    weights, a persistent zeroed scratch) get their gradients ADDED straight into the arena by the kernels
+    (chap_conv_wgrad_acc / chap_bn_act_bwd_acc) and autograd receives None for them: no AccumulateGrad add kernels for
+    parameters used by several passes, no zero-fills of fresh gradient tensors, no gather copy before the optimiser."""
+    old = _state["grad_sink"]
+    _state["grad_sink"] = bool(flag)
+    try:
+        yield
+    finally:
+        _state["grad_sink"] = old
+
+
+def _sink_of(p):
+    return getattr(p, "_chap_sink", None) if p is not None else None
+
+
 def set_force_simt(flag):
     lib().chap_set_force_simt(1 if flag else 0)
     invalidate_weight_cache()
@@ -143,6 +161,51 @@ def _packs(weight, kind, nd):
     return wf, wd
 
 
+def _conv_kind_of(module):
+    """(kind, nd) of an nn.Conv / nn.ConvTranspose parameter holder on the hot path, None for anything else."""
+    import torch.nn as nn
+    if isinstance(module, (nn.ConvTranspose2d, nn.ConvTranspose3d)):
+        return _lib.CONV_UP2, (2 if isinstance(module, nn.ConvTranspose2d) else 3)
+    if isinstance(module, (nn.Conv2d, nn.Conv3d)):
+        nd = 2 if isinstance(module, nn.Conv2d) else 3
+        k, s = module.kernel_size[0], module.stride[0]
+        kind = {(3, 1): _lib.CONV_K3, (1, 1): _lib.CONV_K1, (2, 2): _lib.CONV_DOWN2}.get((k, s))
+        return (kind, nd) if kind is not None else None
+    return None
+
+
+def pack_all(model):
+    """Re-pack every conv weight of `model` in ONE batched launch (chap_conv_pack_weights_batched) and refresh the per-weight
+    pack cache that `conv_stats` consults -- called by the trainer at the top of each iteration, right after the optimiser
+    changed the weights (72 single-layer pack launches per iteration otherwise)."""
+    plan = getattr(model, "_chap_pack_plan", None)
+    mode = lib().chap_get_force_simt()
+    if plan is None or plan["mode"] != mode:
+        entries = []
+        for mod in model.modules():
+            kn = _conv_kind_of(mod)
+            if kn is None:
+                continue
+            kind, nd = kn
+            w = mod.weight
+            transposed = kind == _lib.CONV_UP2
+            cin, cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+            desc = ConvDesc(kind, nd, 1, 2, 2, 2, cin, cout) if nd == 3 else ConvDesc(kind, nd, 1, 1, 2, 2, cin, cout)
+            n = lib().chap_conv_packed_elems(ctypes.byref(desc))
+            entries.append((w, kind, nd, desc, torch.empty(n, dtype=torch.float32, device=w.device),
+                            torch.empty(n, dtype=torch.float32, device=w.device)))
+        plan = {"mode": mode, "entries": entries, "items": (_lib.PackItem * len(entries))()}
+        model._chap_pack_plan = plan
+    items = plan["items"]
+    for i, (w, kind, nd, desc, wf, wd) in enumerate(plan["entries"]):
+        if not w.is_contiguous():
+            raise RuntimeError("pack_all: parameters must be contiguous")
+        items[i] = _lib.PackItem(w.data_ptr(), wf.data_ptr(), wd.data_ptr(), desc)      # p.data may have been re-pointed (flat arena)
+    check(lib().chap_conv_pack_weights_batched(items, len(plan["entries"]), _stream()))
+    for (w, kind, nd, desc, wf, wd) in plan["entries"]:
+        w._chap_pack = ((w._version, _state["epoch"], kind, nd, mode), wf, wd)
+
+
 def _out_shape(kind, x, cout):
     sp = list(x.shape[2:])
     if kind == _lib.CONV_DOWN2:
@@ -159,6 +222,9 @@ class _Conv(Function):
     @staticmethod
     def forward(ctx, x, xb, weight, bias, kind, want_stats, wf, wd, zero_bias_grad=False, bn=None):
         _require_cuda(x, weight, bias)
+        # no zero tensors for the gradients of the (non-differentiable) statistics outputs: autograd would otherwise fill three
+        # of them per convolution backward (216 fill kernels per 2D iteration, measured with tools/step_kernels.py)
+        ctx.set_materialize_grads(False)
         x = cl(x)
         ctx.split = None
         if xb is not None:
@@ -190,6 +256,7 @@ class _Conv(Function):
             check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
         ctx.desc, ctx.has_bias, ctx.wd = desc, bias is not None, wd
         ctx.zero_bias_grad = zero_bias_grad
+        ctx.w_sink, ctx.b_sink = _sink_of(weight), _sink_of(bias)      # FlatSGD's gradient arena views (None outside a trainer)
         ctx.wshape = tuple(weight.shape)
         ctx.save_for_backward(x if ctx.needs_input_grad[2] else None)
         if want_stats:
@@ -204,6 +271,8 @@ class _Conv(Function):
     def backward(ctx, dy, _dsums, _dmi, _dss):
         (x,) = ctx.saved_tensors
         desc = ctx.desc
+        if dy is None:                                   # y itself unused downstream
+            return (None,) * 10
         dy = cl(dy)
         dx = dxb = dw = db = None
         nd = desc.nd
@@ -224,7 +293,14 @@ class _Conv(Function):
         elif ctx.needs_input_grad[0]:
             dx = empty_cl([desc.n, desc.cin] + sp, dy.device)
             check(lib().chap_conv_dgrad(ctypes.byref(desc), _p(dy), _p(ctx.wd), _p(dx), _stream()))
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] and _state["grad_sink"] and ctx.w_sink is not None:
+            # gradient-sink mode: dW (and db) are ADDED into the optimiser's flat arena by the kernels; autograd gets None
+            g_view, scratch = ctx.w_sink
+            want_b = ctx.has_bias and ctx.needs_input_grad[3] and not ctx.zero_bias_grad and ctx.b_sink is not None
+            ws = torch.empty(max(2 * desc.cout, 1), dtype=torch.float64, device=dy.device) if want_b else None
+            check(lib().chap_conv_wgrad_acc(ctypes.byref(desc), _p(x), _p(dy), _p(g_view), _p(ctx.b_sink[0]) if want_b else None,
+                                            _p(ws), 0 if ws is None else ws.numel() * 8, _p(scratch), _stream()))
+        elif ctx.needs_input_grad[2]:
             dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dy.device)
             # A bias that feeds a train-mode BatchNorm has an analytically ZERO gradient (BN subtracts the batch mean:
             # sum_r dy = scale * (sum dz - N mean(dz) - mean(dz xhat) * sum xhat) = 0); the reference computes rounding
@@ -234,7 +310,7 @@ class _Conv(Function):
             ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
             check(lib().chap_conv_wgrad(ctypes.byref(desc), _p(x), _p(dy), _p(dw), _p(db), _p(ws), ws_bytes, _stream()))
-            if ctx.has_bias and ctx.needs_input_grad[3] and ctx.zero_bias_grad:
+            if ctx.has_bias and ctx.needs_input_grad[3] and ctx.zero_bias_grad and not _state["bias_grad_none"]:
                 db = torch.zeros(desc.cout, dtype=torch.float32, device=dy.device)
         return dx, dxb, dw, db, None, None, None, None, None, None
 
@@ -256,6 +332,8 @@ def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat
     if bn is not None and want_stats and bn.training:
         # bn: the nn.BatchNormNd holder that consumes y -> (y, BnStats) and bn_act skips its own finalize launch
         update = bn.track_running_stats and _state["bn_tracking"]
+        if update:
+            _state["bn_epoch"] += 1                  # the kernel's last block updates the running statistics
         momentum = 0.1 if bn.momentum is None else bn.momentum
         pack = (bn.weight, bn.bias, float(bn.eps), float(momentum),
                 bn.running_mean if update else None, bn.running_var if update else None, bn.num_batches_tracked if update else None)
@@ -267,6 +345,46 @@ def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat
 
 def conv(x, weight, bias, kind):
     return conv_stats(x, weight, bias, kind, False)[0]
+
+
+def _eval_scale_shift(bn):
+    """float[2C] (scale, shift) of an eval-mode BatchNorm holder, cached on the module until a parameter / running statistic
+    changes (optimiser step, train-mode forward, load_state_dict)."""
+    tag = (_state["epoch"], _state["bn_epoch"], bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+    hit = getattr(bn, "_chap_eval_ss", None)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    c = bn.weight.numel()
+    mi = torch.empty(2 * c, dtype=torch.float32, device=bn.weight.device)
+    ss = torch.empty(2 * c, dtype=torch.float32, device=bn.weight.device)
+    check(lib().chap_bn_eval_params(_p(bn.weight.detach()), _p(bn.bias.detach()), _p(bn.running_mean), _p(bn.running_var),
+                                    float(bn.eps), _p(mi), _p(ss), c, _stream()))
+    bn._chap_eval_ss = (tag, ss)
+    return ss
+
+
+def eval_fusable(bn):
+    """True when conv -> bn -> act can run as ONE kernel: eval-mode BatchNorm with running statistics and no autograd."""
+    return (not bn.training) and bn.track_running_stats and not torch.is_grad_enabled()
+
+
+def conv_bn_act_eval(x, weight, bias, kind, bn, slope, residual=None, cat=None):
+    """act(BatchNorm_eval(conv(x))) + residual in one kernel (chap_conv_bn_act_fwd); inference only (no autograd)."""
+    _require_cuda(x, weight)
+    x = cl(x.detach())
+    if cat is not None:
+        x = concat_channels(x, cl(cat.detach()))
+    wf, _ = _packs(weight, kind, x.dim() - 2)
+    transposed = kind == _lib.CONV_UP2
+    cin = weight.shape[0] if transposed else weight.shape[1]
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    desc = _conv_desc(kind, x, cin, cout)
+    y = empty_cl(_out_shape(kind, x, cout), x.device)
+    res = None if residual is None else cl(residual.detach())
+    check(lib().chap_conv_bn_act_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(None if bias is None else bias.detach()),
+                                     _p(_eval_scale_shift(bn)), float(slope), _p(res), _p(y), _stream()))
+    return y
 
 
 # ----------------------------------------------------------------------------- BN + activation
@@ -306,6 +424,7 @@ class _BnAct(Function):
         check(lib().chap_bn_act_fwd(_p(y), _p(ss), slope, _p(drop_nc), _p(drop_el), _p(residual), n, rps, c, _p(out), _stream()))
         ctx.save_for_backward(y, ss, mi, g, drop_nc, drop_el)
         ctx.cfg = (n, rps, c, bool(train), float(slope), residual is not None)
+        ctx.sinks = (_sink_of(gamma), _sink_of(beta))
         return out
 
     @staticmethod
@@ -316,9 +435,14 @@ class _BnAct(Function):
         dev = dout.device
         dy = empty_cl(y.shape, dev)
         want_pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        if want_pg and _state["grad_sink"] and ctx.sinks[0] is not None and ctx.sinks[1] is not None:
+            check(lib().chap_bn_act_bwd_acc(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), _p(drop_el), n, rps, c,
+                                            1 if train else 0, _p(sums), _p(dy), _p(ctx.sinks[0][0]), _p(ctx.sinks[1][0]), _stream()))
+            dres = dout if (has_res and ctx.needs_input_grad[3]) else None
+            return (dy, None, None, dres) + (None,) * 10
         dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
         dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
-        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,
                                     1 if train else 0, _p(sums), _p(dy), _p(dgamma), _p(dbeta), _stream()))
         dres = dout if (has_res and ctx.needs_input_grad[3]) else None
@@ -331,6 +455,8 @@ def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
     train = bn.training or not bn.track_running_stats
     running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else None
     update = bn.training and bn.track_running_stats and _state["bn_tracking"]
+    if update:
+        _state["bn_epoch"] += 1                      # running statistics change: cached eval scale / shift are stale
     momentum = 0.1 if bn.momentum is None else bn.momentum
     pre = None
     if isinstance(sums, BnStats):

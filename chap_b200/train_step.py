@@ -122,9 +122,10 @@ class FlatSGD:
     (optional) is called on the flat gradient before the update -- the data-parallel all-reduce.
     The learning rate lives in a device scalar so that the update can be replayed from a CUDA graph."""
 
-    def __init__(self, params, lr, momentum=0.9, weight_decay=1e-4, grad_hook=None):
+    def __init__(self, params, lr, momentum=0.9, weight_decay=1e-4, grad_hook=None, grad_sink=True):
         self.params = [p for p in params if p.requires_grad]
         self.momentum, self.weight_decay, self.grad_hook = momentum, weight_decay, grad_hook
+        self.sink = bool(grad_sink)
         dev = self.params[0].device
         self.offsets, total = [], 0
         for p in self.params:
@@ -141,6 +142,14 @@ class FlatSGD:
                 view.copy_(p)
                 p.data = view
         self.grad_views = [self.flat_g[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        if self.sink:
+            # gradient-sink mode (ops.grad_sink): the kernels add every parameter gradient straight into flat_g.  Conv weights also
+            # get a persistent zeroed scratch (the tensor-core weight-gradient kernel reduces into a [tap][M][N] image with vector
+            # atomics, its unpack step adds that into the arena and leaves the scratch zeroed again).
+            self.flat_ws = torch.zeros(total, dtype=torch.float32, device=dev)
+            for p, off, gv in zip(self.params, self.offsets, self.grad_views):
+                scratch = self.flat_ws[off:off + p.numel()] if p.dim() >= 3 else None
+                p._chap_sink = (gv, scratch)
         ops.invalidate_weight_cache()
 
     @property
@@ -157,8 +166,18 @@ class FlatSGD:
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+        if self.sink:
+            self.flat_g.zero_()                 # ONE fill for the whole arena; the kernels accumulate into it during backward
 
     def gather_grads(self):
+        if self.sink:
+            # everything the kernels produced is already in flat_g; a gradient that still arrived through autograd (an op
+            # outside this library touching a parameter) is added on top
+            with torch.no_grad():
+                stray = [(v, p.grad) for p, v in zip(self.params, self.grad_views) if p.grad is not None]
+                if stray:
+                    torch._foreach_add_([v for v, _ in stray], [g for _, g in stray])
+            return
         with torch.no_grad():
             missing = [v for p, v in zip(self.params, self.grad_views) if p.grad is None]
             have = [(v, p.grad) for p, v in zip(self.params, self.grad_views) if p.grad is not None]
@@ -210,7 +229,7 @@ class ChapTrainer:
     def __init__(self, model, n_classes, labeled_bs, base_lr=0.01, max_iterations=30000, adv_noise=True,
                  adv_losstype="kl", noise_mag=10.0, epi=6.0, topk=0.1, consistency=1.0, consistency_rampup=50.0,
                  use_diff_mask=True, grad_hook=None, grad_scale=1.0, use_graph=False, graph_warmup=3,
-                 dropout=False, comp_drop=False, sim_score=None):
+                 dropout=False, comp_drop=False, sim_score=None, grad_sink=True):
         """dropout / comp_drop / sim_score: the --dropout feature-perturbation branch (code/train_ours_2D.py:359-365, 2D nets only:
         the reference's DualDecoder3d.forward has no such branch); sim_score stands in for the absent GradSim.get_sim()."""
         self.model, self.n_classes, self.labeled_bs = model, n_classes, labeled_bs
@@ -223,7 +242,7 @@ class ChapTrainer:
         self.vat = losses.VAT2d(xi=noise_mag, epi=epi, num_classes=n_classes) if adv_noise else None
         self.adv_losstype, self.topk, self.use_diff_mask = adv_losstype, topk, use_diff_mask
         self.consistency, self.rampup = consistency, consistency_rampup
-        self.opt = FlatSGD(model.parameters(), base_lr, grad_hook=grad_hook)
+        self.opt = FlatSGD(model.parameters(), base_lr, grad_hook=grad_hook, grad_sink=grad_sink)
         self.grad_scale = grad_scale
         self.iter_num = 0
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
@@ -239,6 +258,7 @@ class ChapTrainer:
         return draw_dropout_masks(fake, [0, 1, 2, 3, 4], None, self.comp_drop)
 
     def _iteration(self, volume, label, img_mask=None, cw=None, mask_offsets=None, d_init=None, trace=None, dropout_masks=None):
+        ops.pack_all(self.model)                 # the previous optimiser step changed every weight: one batched re-pack
         loss, aux = chap_losses_forward(self.model, volume, label, self.labeled_bs, self.n_classes, self.iter_num,
                                         vat=self.vat, adv_losstype=self.adv_losstype, topk=self.topk,
                                         use_diff_mask=self.use_diff_mask, consistency=self.consistency,
@@ -246,7 +266,7 @@ class ChapTrainer:
                                         img_mask=img_mask, cw=cw, dropout=self.dropout, comp_drop=self.comp_drop,
                                         sim_score=self.sim_score, dropout_masks=dropout_masks)
         self.opt.zero_grad()                                                            # :381
-        with ops.zero_bias_grad_as_none():
+        with ops.zero_bias_grad_as_none(), ops.grad_sink(self.opt.sink):
             loss.backward()                                                             # :382
         self.opt.step(self.grad_scale)                                                  # :383
         aux["loss"] = loss.detach()

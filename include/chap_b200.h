@@ -96,6 +96,15 @@ typedef struct {
 size_t chap_conv_packed_elems(const chap_conv_desc* d);
 /* torch-layout weight -> packed forward operand and packed data-gradient operand (either may be NULL) */
 int chap_conv_pack_weights(const chap_conv_desc* d, const float* w, float* w_fwd, float* w_dgrad, void* stream);
+/* The same for many layers in one or two launches (a trainer re-packs every conv weight once per optimiser step):
+ * items[i] = {w, w_fwd, w_dgrad (either output nullable), desc}; the item table is read on the host during the call. */
+typedef struct {
+    const float* w;
+    float* w_fwd;
+    float* w_dgrad;
+    chap_conv_desc desc;
+} chap_pack_item;
+int chap_conv_pack_weights_batched(const chap_pack_item* items, int32_t n, void* stream);
 /* y = conv(x) + bias.  ch_sums (nullable): double[CHAP_STAT_SLOTS][2*cout], receives partial per-channel
  * sum(y), sum(y*y) (zeroed by the call) -- the BatchNorm batch statistics of the following layer. */
 int chap_conv_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
@@ -117,6 +126,13 @@ typedef struct chap_bn_train_args {
 } chap_bn_train_args;
 int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias, float* y,
                      double* ch_sums, const chap_bn_train_args* bn, void* stream);
+/* Inference form of conv -> BatchNorm(eval) -> (Leaky)ReLU (+ additive skip), the layer pattern of code/networks/vnet.py:19-28,
+ * 76-83,103-112 (and unet.py:49-57) under net.eval(): y = act(scale[c] * (conv(x) + bias[c]) + shift[c]) + residual, with
+ * scale_shift = float[2*cout] from chap_bn_eval_params and residual (nullable) a tensor of y's shape.  On the tensor-core path
+ * the affine map, the activation and the skip add run in the convolution epilogue -- no separate BatchNorm pass over y (the
+ * sliding-window inference of code/test_3D_util.py:61-64 spends a quarter of its time there otherwise). */
+int chap_conv_bn_act_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
+                         const float* scale_shift, float slope, const float* residual, float* y, void* stream);
 /* dx = conv^T(dy) (data gradient), dx has the input shape */
 int chap_conv_dgrad(const chap_conv_desc* d, const float* dy, const float* w_dgrad, float* dx, void* stream);
 /* Data gradient of a convolution whose input was torch.cat([a, b], dim=1) (the U-Net skip connection, reference
@@ -134,6 +150,14 @@ int chap_conv_dgrad_split(const chap_conv_desc* d, const float* dy, const float*
 size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d);
 int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Gradient-sink form (the trainer's flat gradient arena, code/train_ours_2D.py:381-383 `zero_grad(); backward(); step()`):
+ * dw_acc += dW and dbias_acc += db (dbias_acc nullable) instead of overwriting, so a parameter that is used by several network
+ * passes of one iteration needs no autograd accumulation kernels and no gather copy.  zeroed_scratch (nullable): taps*cin*cout
+ * floats that are ALL ZERO on entry and are left all zero on return (a persistent per-layer scratch: the tensor-core kernel
+ * reduces into it with 128-bit atomics and a small kernel adds it into dw_acc in the torch layout).  workspace: >= 2*cout
+ * doubles, only used for the bias gradient. */
+int chap_conv_wgrad_acc(const chap_conv_desc* d, const float* x, const float* dy, float* dw_acc, float* dbias_acc,
+                        void* workspace, size_t workspace_bytes, float* zeroed_scratch, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm + activation (+dropout, +skip add)
  * Replaces BatchNorm2d/3d (train and eval) + LeakyReLU(0.01)/ReLU + Dropout + the additive skip of
@@ -164,6 +188,10 @@ int chap_bn_act_bwd(const float* dout, const float* y, const float* scale_shift,
                     const float* gamma, float slope, const float* drop_nc, const float* drop_el,
                     int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
                     double* sums, float* dy, float* dgamma, float* dbeta, void* stream);
+/* same, with the BatchNorm parameter gradients ADDED into dgamma_acc / dbeta_acc (gradient-sink form, see chap_conv_wgrad_acc) */
+int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* scale_shift, const float* mean_invstd, float slope,
+                        const float* drop_nc, const float* drop_el, int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
+                        double* sums, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream);
 
 /* ------------------------------------------------------------------ pooling / upsampling / concat
  * MaxPool2d(2) code/networks/unet.py:69; Upsample(x2, bilinear|trilinear, align_corners=True)

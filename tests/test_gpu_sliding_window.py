@@ -187,3 +187,45 @@ def test_test_all_case_reference_signature_reads_case_files(tmp_path):
     net1 = networks.VNet(1, 1, normalization='batchnorm', has_dropout=False).to(DEV).eval()
     lab1 = test_3D_util.test_single_case(net1, cases[0][0], 16, 8, (32, 32, 16))    # the reference's default num_classes=1
     assert lab1.shape == cases[0][0].shape and not lab1.any()                        # softmax over one class: label 0 everywhere
+
+
+def test_eval_mode_fused_conv_bn_act_equals_separate_kernels_and_oracle():
+    """Inference path: conv + eval BatchNorm + (Leaky)ReLU + additive skip in ONE kernel (chap_conv_bn_act_fwd) vs the same
+    network run with the separate BatchNorm pass (autograd enabled -> not fused) and vs the oracle; running statistics that
+    change (a train-mode pass) invalidate the cached scale / shift."""
+    from conftest import rel_err, seeded_model
+    from chap_b200 import _lib
+    from oracle import nets
+    for kind, shape in (("vnet", (2, 1, 32, 32, 16)), ("dualdecoder2d", (3, 1, 64, 64))):
+        m = seeded_model(kind, seed=5).to(DEV)
+        x = torch.randn(*shape, device=DEV)
+        m.train()
+        with torch.no_grad():
+            m(x)                                             # moves the running statistics away from (0, 1)
+        m.eval()
+        sd = nets.clone_state_dict(m.state_dict())
+        _lib.timing_enable(True)
+        with torch.no_grad():
+            fused = m(x)
+        rep = _lib.timing_report()
+        _lib.timing_enable(False)
+        n_bn = sum(v["launches"] for k, v in rep.items() if k.split(":")[0] == "bn_act_fwd")
+        assert n_bn == 1, rep.keys()                         # only the Cin = 1 stem (CUDA-core conv) keeps its separate BatchNorm pass
+        with torch.enable_grad():
+            plain = m(x)                                     # autograd on: conv, BatchNorm pass, activation as separate kernels
+        want = nets.vnet_forward(sd, x.cpu(), False, False) if kind == "vnet" else nets.dualdecoder2d_forward(sd, x.cpu(), False, False)
+        for a, b, c in zip(fused if isinstance(fused, tuple) else (fused,), plain if isinstance(plain, tuple) else (plain,),
+                           want if isinstance(want, tuple) else (want,)):
+            assert rel_err(a, b) < 1e-5, kind                # same arithmetic, fused
+            assert rel_err(a, c) < 5e-3, kind                # TF32 convs vs the fp32 oracle
+        m.train()
+        with torch.no_grad():
+            m(x * 2.0)                                       # running statistics change -> the cached eval parameters must not be reused
+        m.eval()
+        with torch.no_grad():
+            again = m(x)
+        sd2 = nets.clone_state_dict(m.state_dict())
+        want2 = nets.vnet_forward(sd2, x.cpu(), False, False) if kind == "vnet" else nets.dualdecoder2d_forward(sd2, x.cpu(), False, False)
+        a = again[0] if isinstance(again, tuple) else again
+        c = want2[0] if isinstance(want2, tuple) else want2
+        assert rel_err(a, c) < 5e-3, kind
