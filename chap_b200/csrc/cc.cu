@@ -25,6 +25,14 @@ __device__ __forceinline__ int uf_find(int* parent, int i) {
         i = p;
     }
 }
+// read-only find (no path halving): for kernels that must not disturb what other threads wrote
+__device__ __forceinline__ int uf_find_ro(const int* parent, int i) {
+    while (true) {
+        const int p = __ldcg(parent + i);
+        if (p == i) return i;
+        i = p;
+    }
+}
 __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     while (true) {
         a = uf_find(parent, a);
@@ -113,6 +121,10 @@ cc_count_kernel(const int64_t* __restrict__ seg, int* parent, int* size, int64_t
     for (int64_t r = 0; r < rounds; ++r, i += stride) {            // whole warps iterate together (match_any)
         const bool fg = i < total && seg[i] != 0;
         int root = -1;
+        // parent[i] = root is only a shortcut for the kernels that follow: another thread's path halving (parent[i] = its
+        // grandparent, read before this store) may still land AFTER it and leave an intermediate ancestor here.  Round 1's
+        // cc_write_kernel compared parent[i] with the winning root directly and lost a few voxels per launch that way
+        // (found by tests/test_gpu_stress.py: 40 launches, 40 different outputs); it now walks to the root itself.
         if (fg) { root = uf_find(parent, (int)i); parent[i] = root; }
         const unsigned same = __match_any_sync(0xffffffffu, root);
         if (fg && lane == __ffs(same) - 1) atomicAdd(size + root, __popc(same));
@@ -139,7 +151,7 @@ cc_write_kernel(const int64_t* __restrict__ seg, const int* __restrict__ parent,
         if (c != 0) {
             const unsigned long long key = best[(i / vol) * n_classes + c];
             const unsigned root = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-            if ((unsigned)parent[i] == root) v = (float)c;
+            if ((unsigned)uf_find_ro(parent, (int)i) == root) v = (float)c;      // chains are 1-2 links long after cc_count_kernel
         }
         out[i] = v;
     }
