@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("CHAP_B200_LIB", os.path.join(_HERE, "lib", "libchap_b
 class BnTrainArgs(ctypes.Structure):          # chap_bn_train_args
     _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("momentum", c_float),
                 ("running_mean", c_void_p), ("running_var", c_void_p), ("num_batches_tracked", c_void_p),
-                ("mean_invstd", c_void_p), ("scale_shift", c_void_p)]
+                ("mean_invstd", c_void_p), ("scale_shift", c_void_p), ("stats_persistent", c_int32), ("reserved_", c_int32)]
 
 
 class ConvDesc(ctypes.Structure):
@@ -71,7 +71,7 @@ SIGNATURES = {
     "chap_conv_wgrad_workspace_bytes": (c_size_t, [_CD]),
     "chap_conv_wgrad": (I, [_CD, P, P, P, P, P, c_size_t, P]),
     "chap_conv_wgrad_acc": (I, [_CD, P, P, P, P, P, c_size_t, P, P]),
-    "chap_bn_act_bwd_acc": (I, [P, P, P, P, F, P, P, I, L, I, I, P, P, P, P, P]),
+    "chap_bn_act_bwd_acc": (I, [P, P, P, P, F, P, P, I, L, I, I, P, I, P, P, P, P]),
     "chap_channel_stats": (I, [P, L, I, P, P]),
     "chap_bn_finalize": (I, [P, I, L, P, P, F, F, P, P, P, P, P, I, P]),
     "chap_bn_eval_params": (I, [P, P, P, P, F, P, P, I, P]),

@@ -81,14 +81,18 @@ extern "C" int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const f
     CHAP_REQUIRE((bn->running_mean == nullptr) == (bn->running_var == nullptr), CHAP_ERR_BAD_ARG, "conv_bn_fwd: running_mean / running_var must both be set or both NULL");
     if (use_tc(g, false) && getenv("CHAP_NO_BN_FOLD") == nullptr) {
         BnFold f{bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean, bn->running_var,
-                 reinterpret_cast<long long*>(bn->num_batches_tracked), bn->mean_invstd, bn->scale_shift, 0.0, nullptr};
+                 reinterpret_cast<long long*>(bn->num_batches_tracked), bn->mean_invstd, bn->scale_shift, 0.0, nullptr,
+                 bn->stats_persistent ? 1 : 0};
         int rc = tc_conv(g, false, x, w_fwd, bias, y, ch_sums, S(stream), nullptr, 0, &f);
         if (rc < 0) return rc;
         if (rc == 1) return CHAP_OK;
     }
     CHAP_TRY(chap_conv_fwd(d, x, w_fwd, bias, y, ch_sums, stream));
-    return chap_bn_finalize(ch_sums, CHAP_STAT_SLOTS, g.out_rows, bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean,
-                            bn->running_var, bn->num_batches_tracked, bn->mean_invstd, bn->scale_shift, g.cout, stream);
+    CHAP_TRY(chap_bn_finalize(ch_sums, CHAP_STAT_SLOTS, g.out_rows, bn->gamma, bn->beta, bn->eps, bn->momentum, bn->running_mean,
+                              bn->running_var, bn->num_batches_tracked, bn->mean_invstd, bn->scale_shift, g.cout, stream));
+    if (bn->stats_persistent)          // the three-launch path of unsupported shapes must also hand a persistent buffer back zeroed
+        CHAP_TRY(zero_async(ch_sums, ((size_t)CHAP_STAT_SLOTS * 2 * g.cout + 1) * sizeof(double), S(stream)));
+    return CHAP_OK;
 }
 
 extern "C" int chap_conv_bn_act_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias,

@@ -77,6 +77,7 @@ struct BnFold {
     float* mi; float* ss;
     double count;                // elements per channel (N * spatial of the output)
     unsigned* counter;           // zero-initialised ticket counter (the double after the statistics slots)
+    int rezero;                  // 1: the statistics buffer is persistent -- zero on entry, zeroed again by the finalizing block
 };
 // out_b != nullptr: output channels [0, ca) go to `out` (row stride ca), [ca, N) to `out_b` (row stride N - ca)
 // inference epilogue: y = act(scale[c] * (conv + bias) + shift[c]) (+ residual of the output's shape); forward only

@@ -601,7 +601,14 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
                             p.bn.rmean[c] = (1.f - p.bn.momentum) * p.bn.rmean[c] + p.bn.momentum * (float)mean;
                             p.bn.rvar[c] = (1.f - p.bn.momentum) * p.bn.rvar[c] + p.bn.momentum * (float)unbiased;
                         }
+                        if (p.bn.rezero) {                       // persistent statistics buffer: hand it back zeroed (no zero-fill launch per conv)
+                            for (int sl = 0; sl < CHAP_STAT_SLOTS; ++sl) {
+                                p.stats[(size_t)sl * 2 * n_ch + c] = 0.0;
+                                p.stats[(size_t)sl * 2 * n_ch + n_ch + c] = 0.0;
+                            }
+                        }
                     }
+                    if (e == 0 && p.bn.rezero) *p.bn.counter = 0u;
                     if (e == 0 && p.bn.nbt) *p.bn.nbt += 1;
                 }
             }
@@ -919,7 +926,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         p.bn.count = (double)g.out_rows;
         p.bn.counter = reinterpret_cast<unsigned*>(ch_sums + stat_doubles);
     }
-    if (ch_sums) CHAP_TRY(zero_async(ch_sums, (stat_doubles + (bn ? 1 : 0)) * sizeof(double), st));
+    if (ch_sums && !(bn && bn->rezero)) CHAP_TRY(zero_async(ch_sums, (stat_doubles + (bn ? 1 : 0)) * sizeof(double), st));
     const double rows = (double)(g.kind == CHAP_CONV_UP2 ? g.in_rows : g.out_rows);
     KernelTimer timer(timer_name(p.precise ? (dgrad ? "conv_tc3x_dgrad" : "conv_tc3x_fwd") : (dgrad ? "conv_tc_dgrad" : "conv_tc_fwd"), g.taps,
                                  dgrad ? g.cout : g.cin, dgrad ? g.cin : g.cout, g.iW, g.iH, g.iD, g.in_rows),       // real channel counts

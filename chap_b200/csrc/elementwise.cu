@@ -191,7 +191,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         const double* __restrict__ sums, float* __restrict__ dy,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c / VEC;
-    const int acc_pg = train >> 1;             // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
+    const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
     train &= 1;
     if (blockIdx.x == 0 && dgamma) {
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -376,10 +376,11 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
                               const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
                               const float* __restrict__ drop_el, int64_t rows_per_sample, int c, int64_t total_vec, int train,
-                              double inv_count, const double* __restrict__ sums, float* __restrict__ dy,
+                              double inv_count, double* __restrict__ sums, float* __restrict__ dy,
                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c >> 2, g = threadIdx.x % cg;
-    const int acc_pg = train >> 1;             // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
+    const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
+    const int persist = (train >> 2) & 1;      // bit 2: `sums` is a persistent buffer (2c sums + a ticket word) that must be handed back zeroed
     train &= 1;
     if (blockIdx.x == 0 && dgamma) {
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -395,6 +396,21 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
                          (float)(sums[4 * g + 2] * inv_count), (float)(sums[4 * g + 3] * inv_count));
         mzx = make_float4((float)(sums[c + 4 * g] * inv_count), (float)(sums[c + 4 * g + 1] * inv_count),
                           (float)(sums[c + 4 * g + 2] * inv_count), (float)(sums[c + 4 * g + 3] * inv_count));
+    }
+    if (persist) {
+        // every block has read what it needs from `sums` above; the block that draws the last ticket zeroes the buffer (and the
+        // ticket) for the next use of this BatchNorm layer -- no zero-fill launch per backward call
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(reinterpret_cast<unsigned*>(sums + 2 * c), 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            for (int ch = threadIdx.x; ch < 2 * c; ch += blockDim.x) sums[ch] = 0.0;
+            if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(sums + 2 * c) = 0u;
+        }
     }
     const int64_t per_sample = rows_per_sample * cg;
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -736,10 +752,11 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
 }
 
 extern "C" int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
-                                   const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy,
-                                   float* dgamma_acc, float* dbeta_acc, void* stream) {
+                                   const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums,
+                                   int32_t sums_persistent, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream) {
     CHAP_REQUIRE(dgamma_acc && dbeta_acc, CHAP_ERR_BAD_ARG, "bn_act_bwd_acc: the gradient accumulators are required");
-    return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, drop_el, n, rps, c, (train ? 1 : 0) | 2, sums, dy, dgamma_acc, dbeta_acc, stream);
+    return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, drop_el, n, rps, c, (train ? 1 : 0) | 2 | (sums_persistent ? 4 : 0), sums, dy,
+                           dgamma_acc, dbeta_acc, stream);
 }
 
 static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
@@ -749,13 +766,18 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
     CHAP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), CHAP_ERR_BAD_ARG, "bn_act_bwd: dgamma/dbeta must both be set or both NULL");
     const int64_t rows = (int64_t)n * rps, total = rows * c;
     cudaStream_t st = S(stream);
-    CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));
-    KernelTimer timer("bn_act_bwd", 0.0, 4.0 * total * (3 + (drop_el ? 1 : 0)), st);   // algorithmic: read dout, y; write dy
     const bool v4 = c % 4 == 0 && all16({dout, y, drop_el, dy});
     const int cg = v4 ? c / 4 : c;
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);
+    const bool fixed = v4 && 256 % cg == 0 && all16({ss, mi, drop_nc}) && round_tf32_on() == 0;
+    // persistent sums (bit 2): zero on entry, re-zeroed by the last block of the apply kernel -- only the fixed-group kernels do that;
+    // on the generic path the buffer is zeroed before AND after by launches (it must come back zeroed either way)
+    const bool persist = (train & 4) != 0;
+    if (!persist) CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));
+    if (!fixed) train &= ~4;
+    KernelTimer timer("bn_act_bwd", 0.0, 4.0 * total * (3 + (drop_el ? 1 : 0)), st);   // algorithmic: read dout, y; write dy
     const double inv_count = 1.0 / (double)rows;
-    if (v4 && 256 % cg == 0 && all16({ss, mi, drop_nc}) && round_tf32_on() == 0) {
+    if (fixed) {
         if ((train & 1) || dgamma) {
             const int rgrid = grid_for(total / 4, 256 * kEwUnroll * 2, kNumSMs * 8);
             if (drop_el) bn_act_bwd_reduce_fixed_kernel<true><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
@@ -774,7 +796,9 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
     CHAP_TRY(launched("bn_act_bwd_reduce_kernel"));
     if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
     else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
-    return launched("bn_act_bwd_apply_kernel");
+    CHAP_TRY(launched("bn_act_bwd_apply_kernel"));
+    if (persist) CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));      // hand the persistent buffer back zeroed
+    return CHAP_OK;
 }
 
 extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, void* stream) {

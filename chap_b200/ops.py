@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ConvDesc, check
 
-_state = {"bn_epoch": 0, "epoch": 0, "bn_tracking": True, "weight_grad": True, "bias_grad_none": False, "grad_sink": False}
+_state = {"persistent_stats": True, "bn_epoch": 0, "epoch": 0, "bn_tracking": True, "weight_grad": True, "bias_grad_none": False, "grad_sink": False}
 
 
 def lib():
@@ -109,6 +109,17 @@ def grad_sink(flag=True):
         yield
     finally:
         _state["grad_sink"] = old
+
+
+def _persistent_zeros(holder, attr, n):
+    """A float64 zero buffer of n elements that lives on `holder` (a BatchNorm module).  The kernels that use it hand it back
+    zeroed, so it is allocated and cleared exactly once (saves one zero-fill launch per convolution / BatchNorm backward)."""
+    buf = getattr(holder, attr, None)
+    dev = holder.weight.device
+    if buf is None or buf.numel() != n or buf.device != dev:
+        buf = torch.zeros(n, dtype=torch.float64, device=dev)
+        setattr(holder, attr, buf)
+    return buf
 
 
 def _sink_of(p):
@@ -242,15 +253,20 @@ class _Conv(Function):
         desc = _conv_desc(kind, x, cin, cout)
         y = empty_cl(_out_shape(kind, x, cout), x.device)
         fold = bn is not None and want_stats                      # +1 double: the kernel's block ticket counter
-        sums = torch.empty(_lib.STAT_SLOTS * 2 * cout + (1 if fold else 0), dtype=torch.float64, device=x.device) if want_stats else None
+        persistent = fold and len(bn) > 7 and bn[7] is not None
+        if persistent:
+            sums = bn[7]            # per-layer persistent statistics buffer: zero on entry, zeroed again by the kernel's finalizing block
+        else:
+            sums = torch.empty(_lib.STAT_SLOTS * 2 * cout + (1 if fold else 0), dtype=torch.float64, device=x.device) if want_stats else None
         b = None if bias is None else bias.detach()
         mi = ss = None
         if fold:
             # train-mode BatchNorm follows: its finalize step (scale / shift, running statistics) runs inside the conv kernel
-            gamma, beta, eps, momentum, rm, rv, nbt = bn
+            gamma, beta, eps, momentum, rm, rv, nbt = bn[:7]
             mi = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
             ss = torch.empty(2 * cout, dtype=torch.float32, device=x.device)
-            args = _lib.BnTrainArgs(_p(gamma.detach()), _p(beta.detach()), eps, momentum, _p(rm), _p(rv), _p(nbt), _p(mi), _p(ss))
+            args = _lib.BnTrainArgs(_p(gamma.detach()), _p(beta.detach()), eps, momentum, _p(rm), _p(rv), _p(nbt), _p(mi), _p(ss),
+                                    1 if persistent else 0, 0)
             check(lib().chap_conv_bn_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), ctypes.byref(args), _stream()))
         else:
             check(lib().chap_conv_fwd(ctypes.byref(desc), _p(x), _p(wf), _p(b), _p(y), _p(sums), _stream()))
@@ -336,7 +352,8 @@ def conv_stats(x, weight, bias, kind, want_stats=True, feeds_train_bn=False, cat
             _state["bn_epoch"] += 1                  # the kernel's last block updates the running statistics
         momentum = 0.1 if bn.momentum is None else bn.momentum
         pack = (bn.weight, bn.bias, float(bn.eps), float(momentum),
-                bn.running_mean if update else None, bn.running_var if update else None, bn.num_batches_tracked if update else None)
+                bn.running_mean if update else None, bn.running_var if update else None, bn.num_batches_tracked if update else None,
+                _persistent_zeros(bn, "_chap_stats", _lib.STAT_SLOTS * 2 * bn.weight.numel() + 1) if _state["persistent_stats"] else None)
     y, sums, mi, ss = _Conv.apply(x, cat, weight, bias, kind, bool(want_stats), wf, wd, bool(feeds_train_bn), pack)
     if mi is not None:
         return y, BnStats((sums, mi, ss))
@@ -425,6 +442,7 @@ class _BnAct(Function):
         ctx.save_for_backward(y, ss, mi, g, drop_nc, drop_el)
         ctx.cfg = (n, rps, c, bool(train), float(slope), residual is not None)
         ctx.sinks = (_sink_of(gamma), _sink_of(beta))
+        ctx.bwd_sums = getattr(gamma, "_chap_bwd_sums", None)          # persistent zeroed reduction buffer (set up by FlatSGD)
         return out
 
     @staticmethod
@@ -435,12 +453,15 @@ class _BnAct(Function):
         dev = dout.device
         dy = empty_cl(y.shape, dev)
         want_pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         if want_pg and _state["grad_sink"] and ctx.sinks[0] is not None and ctx.sinks[1] is not None:
+            psums = ctx.bwd_sums if _state["persistent_stats"] else None
+            sums = psums if psums is not None else torch.empty(2 * c, dtype=torch.float64, device=dev)
             check(lib().chap_bn_act_bwd_acc(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), _p(drop_el), n, rps, c,
-                                            1 if train else 0, _p(sums), _p(dy), _p(ctx.sinks[0][0]), _p(ctx.sinks[1][0]), _stream()))
+                                            1 if train else 0, _p(sums), 1 if psums is not None else 0, _p(dy), _p(ctx.sinks[0][0]),
+                                            _p(ctx.sinks[1][0]), _stream()))
             dres = dout if (has_res and ctx.needs_input_grad[3]) else None
             return (dy, None, None, dres) + (None,) * 10
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
         dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
         check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,

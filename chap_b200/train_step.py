@@ -150,6 +150,8 @@ class FlatSGD:
             for p, off, gv in zip(self.params, self.offsets, self.grad_views):
                 scratch = self.flat_ws[off:off + p.numel()] if p.dim() >= 3 else None
                 p._chap_sink = (gv, scratch)
+                if p.dim() == 1:        # BatchNorm gammas (and, harmlessly, other vectors): persistent zeroed reduction buffer of the
+                    p._chap_bwd_sums = torch.zeros(2 * p.numel() + 1, dtype=torch.float64, device=dev)    # BatchNorm backward
         ops.invalidate_weight_cache()
 
     @property

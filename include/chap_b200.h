@@ -123,6 +123,9 @@ typedef struct chap_bn_train_args {
     int64_t* num_batches_tracked;
     float* mean_invstd;              /* out: float[2*cout] */
     float* scale_shift;              /* out: float[2*cout] */
+    int32_t stats_persistent;        /* 1: ch_sums is a persistent per-layer buffer that is ALL ZERO on entry; the call leaves it all
+                                      * zero again (the finalizing block clears it) and launches no zero-fill.  0: zeroed by the call. */
+    int32_t reserved_;
 } chap_bn_train_args;
 int chap_conv_bn_fwd(const chap_conv_desc* d, const float* x, const float* w_fwd, const float* bias, float* y,
                      double* ch_sums, const chap_bn_train_args* bn, void* stream);
@@ -189,9 +192,11 @@ int chap_bn_act_bwd(const float* dout, const float* y, const float* scale_shift,
                     int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
                     double* sums, float* dy, float* dgamma, float* dbeta, void* stream);
 /* same, with the BatchNorm parameter gradients ADDED into dgamma_acc / dbeta_acc (gradient-sink form, see chap_conv_wgrad_acc) */
+/* sums_persistent = 1: `sums` holds 2c + 1 doubles, is ALL ZERO on entry and is left all zero (cleared by the last block of the
+ * apply kernel): no zero-fill launch per call.  0: `sums` (2c doubles) is zeroed by the call. */
 int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* scale_shift, const float* mean_invstd, float slope,
                         const float* drop_nc, const float* drop_el, int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
-                        double* sums, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream);
+                        double* sums, int32_t sums_persistent, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream);
 
 /* ------------------------------------------------------------------ pooling / upsampling / concat
  * MaxPool2d(2) code/networks/unet.py:69; Upsample(x2, bilinear|trilinear, align_corners=True)
