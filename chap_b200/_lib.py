@@ -104,6 +104,7 @@ SIGNATURES = {
     "chap_perturb_workspace_elems": (c_size_t, [POINTER(Level), I, I]),
     "chap_perturb_fwd": (I, [POINTER(Level), I, I, I, F, F, P, c_size_t, P]),
     "chap_l2n_sample_axpy": (I, [P, P, F, I, L, P, P, P]),
+    "chap_l2n_sample_axpy_batched": (I, [POINTER(Level), I, I, F, P, P]),
     "chap_sgd_momentum_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
     "chap_sgd_momentum": (I, [P, P, P, L, F, F, F, F, I, P]),
     "chap_schedule_step": (I, [P, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, L, P, P, P]),

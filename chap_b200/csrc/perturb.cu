@@ -8,8 +8,10 @@
 //   P1  chan_sq[n, c]   = sum_rows g^2                                  (skipped for SAMPLE / SPATIAL)
 //   P2  samp_sq[n]      = sum u^2,  u = combine(g / (||g||_chan + e), g / (||g||_row + e))
 //   P3  out             = f + eps * u / (sqrt(samp_sq) + e)
-// Algorithmic traffic is 12 B / element (read g, read f, write out); this first version re-reads g in
-// P2/P3 (20 B / element, the re-reads mostly hit the 126 MB L2 for 2D levels).
+// Algorithmic traffic is 12 B / element (read g, read f, write out); g is re-read in P2 / P3 (20 B / element touched, the
+// re-reads mostly hit the 126 MB L2: the five 2D levels of 12 samples are 97 MB).  The two grid-wide reductions are real data
+// dependencies, so a level cannot be ONE pass; what can go is the launch count: every phase runs for ALL levels and samples in
+// ONE launch through a descriptor table (round 1: 3 launches + a zero-fill per level = 16 per call; now 3 + 1).
 #include "common.cuh"
 
 namespace chap {
@@ -17,18 +19,29 @@ namespace chap {
 constexpr float kEps = 1e-8f;
 
 // P1: per-(sample, channel) sum of squares.  grid = (blocks_per_sample, n)
+// one level of one call, as the batched kernels see it
+struct PLevel {
+    const float* g; const float* f; float* out;
+    double* chan_sq; double* samp_sq;
+    int64_t rows;
+    int c, tpr;
+    int bps_chan, bps_rows;          // blocks per sample in the channel-norm phase / the row phases
+    int blk0_chan, blk0_rows;        // first block of this level in the flattened grids
+};
+constexpr int kMaxLevels = 8;
+struct PBatch { PLevel lv[kMaxLevels]; int n_levels, n; float eps, gs; };
+
 template <int VEC>
-__global__ void __launch_bounds__(256)
-chan_sq_kernel(const float* __restrict__ g, int64_t rows, int c, float gs, double* __restrict__ chan_sq) {
-    __shared__ float part[256 * 4];
+__device__ __forceinline__ void chan_sq_body(const float* __restrict__ g, int64_t rows, int c, float gs, double* __restrict__ chan_sq,
+                                             int bx, int nbx, int sample, float* part) {
     const int cg = c / VEC, rpb = 256 / cg;
     const int gi = threadIdx.x % cg, rl = threadIdx.x / cg;
-    const float* base = g + (int64_t)blockIdx.y * rows * c;
+    const float* base = g + (int64_t)sample * rows * c;
     float q[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) q[v] = 0.f;
     if (rl < rpb)
-        for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < rows; r += (int64_t)gridDim.x * rpb) {
+        for (int64_t r = (int64_t)bx * rpb + rl; r < rows; r += (int64_t)nbx * rpb) {
             if (VEC == 4) {
                 float4 t = __ldg(reinterpret_cast<const float4*>(base + r * c) + gi);
                 t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
@@ -43,9 +56,19 @@ chan_sq_kernel(const float* __restrict__ g, int64_t rows, int c, float gs, doubl
         for (int v = 0; v < VEC; ++v) {
             double a = 0.0;
             for (int l = 0; l < rpb; ++l) a += (double)part[(l * cg + threadIdx.x) * VEC + v];
-            atomicAdd(chan_sq + (int64_t)blockIdx.y * c + threadIdx.x * VEC + v, a);
+            atomicAdd(chan_sq + (int64_t)sample * c + threadIdx.x * VEC + v, a);
         }
     }
+}
+// P1 for all levels: flattened grid, block -> (level, sample, block in sample)
+__global__ void __launch_bounds__(256)
+chan_sq_all_kernel(const __grid_constant__ PBatch b) {
+    __shared__ float part[256 * 4];
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_chan) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_chan;
+    chan_sq_body<4>(L.g, L.rows, L.c, b.gs, L.chan_sq, rel % L.bps_chan, L.bps_chan, rel / L.bps_chan, part);
 }
 
 // u for one row.  One WARP handles one row when c >= 128 elements would not fit a thread; here a
@@ -61,12 +84,10 @@ __device__ __forceinline__ float unit_value(float gv, float inv_chan, float inv_
 // P2 / P3 share the row traversal.  grid = (blocks_per_sample, n); block = 256 threads = 256/tpr rows.
 // smem: inv_chan[c]
 template <int MODE, bool APPLY>
-__global__ void __launch_bounds__(256)
-perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, float* __restrict__ out,
-                    int64_t rows, int c, int tpr, float eps, float gs, int rt, const double* __restrict__ chan_sq,
-                    double* __restrict__ samp_sq) {
-    extern __shared__ float inv_chan[];
-    const int n = blockIdx.y;
+__device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, const float* __restrict__ f, float* __restrict__ out,
+                                                  int64_t rows, int c, int tpr, float eps, float gs, int rt,
+                                                  const double* __restrict__ chan_sq, double* __restrict__ samp_sq,
+                                                  int bx, int nbx, int n, float* inv_chan, float* red) {
     if (MODE == CHAP_PERTURB_CHANNEL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
         for (int ch = threadIdx.x; ch < c; ch += 256)
             inv_chan[ch] = 1.f / (sqrtf((float)chan_sq[(int64_t)n * c + ch]) + kEps);
@@ -80,7 +101,7 @@ perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, fl
     const float* fb = f ? f + (int64_t)n * rows * c : nullptr;
     float* ob = out + (int64_t)n * rows * c;
     float acc = 0.f;
-    for (int64_t r0 = (int64_t)blockIdx.x * rpb; r0 < rows; r0 += (int64_t)gridDim.x * rpb) {
+    for (int64_t r0 = (int64_t)bx * rpb; r0 < rows; r0 += (int64_t)nbx * rpb) {
         const int64_t r = r0 + rl;
         const bool live = r < rows;
         float inv_row = 0.f;
@@ -119,7 +140,6 @@ perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, fl
         }
     }
     if (!APPLY) {
-        __shared__ float red[8];
         float t = warp_sum(acc);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
         __syncthreads();
@@ -130,32 +150,31 @@ perturb_rows_kernel(const float* __restrict__ g, const float* __restrict__ f, fl
         }
     }
 }
+// P2 (APPLY = false) / P3 (APPLY = true) for all levels in one launch
+template <int MODE, bool APPLY>
+__global__ void __launch_bounds__(256)
+perturb_rows_all_kernel(const __grid_constant__ PBatch b) {
+    __shared__ float inv_chan[1024];
+    __shared__ float red[8];
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_rows;
+    perturb_rows_body<MODE, APPLY>(L.g, APPLY ? L.f : nullptr, APPLY ? L.out : nullptr, L.rows, L.c, L.tpr, b.eps, b.gs, 0, L.chan_sq, L.samp_sq,
+                                   rel % L.bps_rows, L.bps_rows, rel / L.bps_rows, inv_chan, red);
+}
 
 template <int MODE>
-static int run_level(const chap_level& L, int n, float eps, float gs, double* chan_sq, double* samp_sq, cudaStream_t st) {
-    const int c = L.c;
-    KernelTimer timer("perturb_level", 0.0, 12.0 * (double)n * L.rows * c, st);   // algorithmic: read g, read f, write out
-    int tpr = 1;                                   // lanes per row: keep <= 16 channels (4 float4) per lane
-    while (tpr < 32 && c / tpr > 16 && (c / (tpr * 2)) % 4 == 0) tpr *= 2;
-    const int rpb = 256 / tpr;
-    int bps = (int)((L.rows + rpb * 4 - 1) / (rpb * 4));
-    int cap = (kNumSMs * 8 + n - 1) / n;
-    if (bps > cap) bps = cap;
-    if (bps < 1) bps = 1;
-    dim3 grid((unsigned)bps, (unsigned)n);
-    const size_t smem = (size_t)c * sizeof(float);
+static int run_all(const PBatch& b, int blocks_chan, int blocks_rows, double alg_bytes, cudaStream_t st) {
+    KernelTimer timer("perturb_level", 0.0, alg_bytes, st);       // algorithmic: read g, read f, write out (all levels of the call)
     if (MODE == CHAP_PERTURB_CHANNEL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
-        const int cg = c / 4, rpb1 = 256 / cg;
-        int b1 = (int)((L.rows + rpb1 * 8 - 1) / (rpb1 * 8));
-        if (b1 > cap) b1 = cap;
-        if (b1 < 1) b1 = 1;
-        chan_sq_kernel<4><<<dim3((unsigned)b1, (unsigned)n), 256, 0, st>>>(L.g, L.rows, c, gs, chan_sq);
-        CHAP_TRY(launched("chan_sq_kernel"));
+        chan_sq_all_kernel<<<blocks_chan, 256, 0, st>>>(b);
+        CHAP_TRY(launched("chan_sq_all_kernel"));
     }
-    perturb_rows_kernel<MODE, false><<<grid, 256, smem, st>>>(L.g, nullptr, nullptr, L.rows, c, tpr, eps, gs, 0, chan_sq, samp_sq);
-    CHAP_TRY(launched("perturb_rows_kernel<reduce>"));
-    perturb_rows_kernel<MODE, true><<<grid, 256, smem, st>>>(L.g, L.f, L.out, L.rows, c, tpr, eps, gs, round_tf32_on(), chan_sq, samp_sq);
-    return launched("perturb_rows_kernel<apply>");
+    perturb_rows_all_kernel<MODE, false><<<blocks_rows, 256, 0, st>>>(b);
+    CHAP_TRY(launched("perturb_rows_all_kernel<reduce>"));
+    perturb_rows_all_kernel<MODE, true><<<blocks_rows, 256, 0, st>>>(b);
+    return launched("perturb_rows_all_kernel<apply>");
 }
 
 // out = base + xi * d / (||d|| + 1e-8) per sample
@@ -185,9 +204,82 @@ l2n_axpy_kernel(const float* __restrict__ d, const float* __restrict__ base, flo
         out[off + i] = tf32_rn(fmaf(s, d[off + i], base ? base[off + i] : 0.f), rt);
 }
 
+// the same two phases for several tensors at once (the five levels of the VAT probe): PLevel.g = d, .f = base, .samp_sq = norms
+__global__ void __launch_bounds__(256)
+sample_sq_all_kernel(const __grid_constant__ PBatch b) {
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_rows, bx = rel % L.bps_rows, n = rel / L.bps_rows;
+    const int64_t eps_ = L.rows * L.c;
+    const float4* d4 = reinterpret_cast<const float4*>(L.g + (int64_t)n * eps_);
+    float acc = 0.f;
+    for (int64_t i = (int64_t)bx * 256 + threadIdx.x; i < eps_ / 4; i += (int64_t)L.bps_rows * 256) {
+        const float4 v = __ldg(d4 + i);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    __shared__ float red[8];
+    float t = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int w = 0; w < 8; ++w) a += (double)red[w];
+        atomicAdd(L.samp_sq + n, a);
+    }
+}
+__global__ void __launch_bounds__(256)
+l2n_axpy_all_kernel(const __grid_constant__ PBatch b) {
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_rows, bx = rel % L.bps_rows, n = rel / L.bps_rows;
+    const int64_t eps_ = L.rows * L.c, off = (int64_t)n * eps_;
+    const float s = b.eps / (sqrtf((float)L.samp_sq[n]) + kEps);              // b.eps carries xi here
+    const float4* d4 = reinterpret_cast<const float4*>(L.g + off);
+    const float4* f4 = L.f ? reinterpret_cast<const float4*>(L.f + off) : nullptr;
+    float4* o4 = reinterpret_cast<float4*>(L.out + off);
+    for (int64_t i = (int64_t)bx * 256 + threadIdx.x; i < eps_ / 4; i += (int64_t)L.bps_rows * 256) {
+        const float4 v = ldg_stream(d4 + i);
+        float4 o = f4 ? ldg_stream(f4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x = fmaf(s, v.x, o.x); o.y = fmaf(s, v.y, o.y); o.z = fmaf(s, v.z, o.z); o.w = fmaf(s, v.w, o.w);
+        o4[i] = o;
+    }
+}
+
 }  // namespace chap
 
 using namespace chap;
+
+extern "C" int chap_l2n_sample_axpy_batched(const chap_level* levels, int32_t n_levels, int32_t n, float xi, double* norms, void* stream) {
+    CHAP_REQUIRE(levels && n_levels > 0 && n_levels <= kMaxLevels && n > 0 && norms, CHAP_ERR_BAD_ARG, "l2n_sample_axpy_batched: bad argument");
+    cudaStream_t st = S(stream);
+    static thread_local PBatch b;
+    b.n_levels = n_levels; b.n = n; b.eps = xi; b.gs = 1.f;
+    double total = 0.0;
+    for (int l = 0; l < n_levels; ++l) total += (double)levels[l].rows * levels[l].c;
+    int blocks = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const chap_level& L = levels[l];
+        CHAP_REQUIRE(L.g && L.out && L.rows > 0 && L.c > 0 && (L.rows * L.c) % 4 == 0, CHAP_ERR_BAD_ARG, "l2n_sample_axpy_batched: level %d: bad shape / pointer", l);
+        CHAP_REQUIRE(aligned16(L.g) && aligned16(L.out) && (!L.f || aligned16(L.f)), CHAP_ERR_ALIGNMENT, "l2n_sample_axpy_batched: level %d misaligned", l);
+        PLevel& P = b.lv[l];
+        P.g = L.g; P.f = L.f; P.out = L.out; P.rows = L.rows; P.c = L.c; P.tpr = 1; P.chan_sq = nullptr;
+        P.samp_sq = norms + (size_t)l * n;
+        const int share = (int)(kNumSMs * 16 * ((double)L.rows * L.c / total) / n) + 1;
+        int bps = (int)((L.rows * L.c / 4 + 256 * 4 - 1) / (256 * 4));
+        if (bps > share) bps = share;
+        if (bps < 1) bps = 1;
+        P.bps_rows = bps; P.bps_chan = 0; P.blk0_rows = blocks; P.blk0_chan = 0;
+        blocks += bps * n;
+    }
+    KernelTimer timer_("l2n_sample_axpy", 0.0, 12.0 * total * n, st);        // algorithmic: read d, read base, write out
+    CHAP_TRY(zero_async(norms, (size_t)n_levels * n * sizeof(double), st));
+    sample_sq_all_kernel<<<blocks, 256, 0, st>>>(b);
+    CHAP_TRY(launched("sample_sq_all_kernel"));
+    l2n_axpy_all_kernel<<<blocks, 256, 0, st>>>(b);
+    return launched("l2n_axpy_all_kernel");
+}
 
 extern "C" size_t chap_perturb_workspace_elems(const chap_level* levels, int32_t n_levels, int32_t n) {
     size_t total = 0;
@@ -200,26 +292,50 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
     CHAP_REQUIRE(levels && n_levels > 0 && n > 0 && workspace, CHAP_ERR_BAD_ARG, "perturb_fwd: bad argument");
     CHAP_REQUIRE(mode >= CHAP_PERTURB_SAMPLE && mode <= CHAP_PERTURB_CHANNEL_SPATIAL, CHAP_ERR_BAD_ARG, "perturb_fwd: unknown mode %d", mode);
     CHAP_REQUIRE(ws_elems >= chap_perturb_workspace_elems(levels, n_levels, n), CHAP_ERR_WORKSPACE, "perturb_fwd: workspace too small");
+    CHAP_REQUIRE(n_levels <= kMaxLevels, CHAP_ERR_BAD_ARG, "perturb_fwd: at most %d levels per call (got %d)", kMaxLevels, n_levels);
     cudaStream_t st = S(stream);
     CHAP_TRY(zero_async(workspace, chap_perturb_workspace_elems(levels, n_levels, n) * sizeof(double), st));
+    static thread_local PBatch b;
+    b.n_levels = n_levels; b.n = n; b.eps = eps; b.gs = g_scale;
     double* ws = workspace;
+    int blocks_chan = 0, blocks_rows = 0;
+    double alg_bytes = 0.0;
+    // blocks per (level, sample): enough to fill the machine a few times over across ALL levels of the launch
+    double total_elems = 0.0;
+    for (int l = 0; l < n_levels; ++l) total_elems += (double)levels[l].rows * levels[l].c;
+    const int block_budget = kNumSMs * 16;
     for (int l = 0; l < n_levels; ++l) {
         const chap_level& L = levels[l];
         CHAP_REQUIRE(L.g && L.out && L.rows > 0 && L.c > 0, CHAP_ERR_BAD_ARG, "perturb_fwd: level %d has a NULL pointer or empty shape", l);
         CHAP_REQUIRE(L.c % 4 == 0 && L.c <= 1024, CHAP_ERR_BAD_ARG, "perturb_fwd: level %d channel count %d must be a multiple of 4", l, L.c);
         CHAP_REQUIRE(aligned16(L.g) && aligned16(L.out) && (!L.f || aligned16(L.f)), CHAP_ERR_ALIGNMENT, "perturb_fwd: level %d misaligned", l);
-        double* chan_sq = ws; ws += (size_t)n * L.c;
-        double* samp_sq = ws; ws += n;
-        int rc;
-        switch (mode) {
-            case CHAP_PERTURB_SAMPLE: rc = run_level<CHAP_PERTURB_SAMPLE>(L, n, eps, g_scale, chan_sq, samp_sq, st); break;
-            case CHAP_PERTURB_CHANNEL: rc = run_level<CHAP_PERTURB_CHANNEL>(L, n, eps, g_scale, chan_sq, samp_sq, st); break;
-            case CHAP_PERTURB_SPATIAL: rc = run_level<CHAP_PERTURB_SPATIAL>(L, n, eps, g_scale, chan_sq, samp_sq, st); break;
-            default: rc = run_level<CHAP_PERTURB_CHANNEL_SPATIAL>(L, n, eps, g_scale, chan_sq, samp_sq, st); break;
-        }
-        CHAP_TRY(rc);
+        PLevel& P = b.lv[l];
+        P.g = L.g; P.f = L.f; P.out = L.out; P.rows = L.rows; P.c = L.c;
+        P.chan_sq = ws; ws += (size_t)n * L.c;
+        P.samp_sq = ws; ws += n;
+        int tpr = 1;                                   // lanes per row: keep <= 16 channels (4 float4) per lane
+        while (tpr < 32 && L.c / tpr > 16 && (L.c / (tpr * 2)) % 4 == 0) tpr *= 2;
+        P.tpr = tpr;
+        const int share = (int)(block_budget * ((double)L.rows * L.c / total_elems) / n) + 1;      // this level's share of the grid, per sample
+        const int rpb = 256 / tpr;
+        int bps = (int)((L.rows + rpb * 4 - 1) / (rpb * 4));
+        if (bps > share) bps = share;
+        if (bps < 1) bps = 1;
+        const int cg = L.c / 4, rpb1 = cg <= 256 ? 256 / cg : 1;
+        int b1 = (int)((L.rows + rpb1 * 8 - 1) / (rpb1 * 8));
+        if (b1 > share) b1 = share;
+        if (b1 < 1) b1 = 1;
+        P.bps_rows = bps; P.bps_chan = b1;
+        P.blk0_rows = blocks_rows; P.blk0_chan = blocks_chan;
+        blocks_rows += bps * n; blocks_chan += b1 * n;
+        alg_bytes += 12.0 * (double)n * L.rows * L.c;
     }
-    return CHAP_OK;
+    switch (mode) {
+        case CHAP_PERTURB_SAMPLE: return run_all<CHAP_PERTURB_SAMPLE>(b, blocks_chan, blocks_rows, alg_bytes, st);
+        case CHAP_PERTURB_CHANNEL: return run_all<CHAP_PERTURB_CHANNEL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+        case CHAP_PERTURB_SPATIAL: return run_all<CHAP_PERTURB_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+        default: return run_all<CHAP_PERTURB_CHANNEL_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+    }
 }
 
 extern "C" int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n, int64_t elems_per_sample,

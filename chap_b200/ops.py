@@ -879,6 +879,24 @@ def l2n_sample_axpy(d, base, xi):
     return out
 
 
+def l2n_sample_axpy_all(ds, bases, xi):
+    """[base_l + xi * d_l / (||d_l||_2 per sample + 1e-8)] for all levels in TWO launches (VAT step 2); no autograd."""
+    n = ds[0].shape[0]
+    levels = (_lib.Level * len(ds))()
+    keep, outs = [], []
+    for i, d in enumerate(ds):
+        _require_cuda(d)
+        d = cl(d.detach())
+        base = None if bases is None or bases[i] is None else cl(bases[i].detach())
+        out = torch.empty_like(d)
+        levels[i] = _lib.Level(d.data_ptr(), 0 if base is None else base.data_ptr(), out.data_ptr(), d.numel() // n, 1, 0)
+        keep += [d, base]
+        outs.append(out)
+    norms = torch.empty(len(ds) * n, dtype=torch.float64, device=ds[0].device)
+    check(lib().chap_l2n_sample_axpy_batched(levels, len(ds), n, float(xi), _p(norms), _stream()))
+    return outs
+
+
 # ----------------------------------------------------------------------------- optimiser
 def sgd_momentum_(flat_p, flat_g, flat_buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
     _require_cuda(flat_p, flat_g, flat_buf)

@@ -107,7 +107,7 @@ class VAT2d:
             feats = model.encoder(x_u)
             if d_init is None:
                 d_init = [torch.rand_like(f) - 0.5 for f in feats]
-            hat = [ops.l2n_sample_axpy(d, f, self.xi).requires_grad_(True) for d, f in zip(d_init, feats)]
+            hat = [h.requires_grad_(True) for h in ops.l2n_sample_axpy_all(d_init, feats, self.xi)]
             with ops.no_weight_grad():
                 # the probe distance is always 'batchmean' (direction only; keeps |g| far above the 1e-8 of the norms)
                 dist = consistency_distance(model.decoder1(hat), soft2, mask, losstype, "batchmean") + \

@@ -316,6 +316,9 @@ int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int32_t n, int3
 /* out = base + xi * d / (||d||_2 per sample + 1e-8)  (base nullable); norms: double[n] scratch */
 int chap_l2n_sample_axpy(const float* d, const float* base, float xi, int32_t n, int64_t elems_per_sample,
                          double* norms, float* out, void* stream);
+/* the same for several tensors in two launches (the five levels of the VAT probe, hat_l = f_l + xi * l2n(d_l)): levels[l] =
+ * {g = d_l, f = base_l (nullable), out, rows * c = elements per sample (multiple of 4)}; norms: double[n_levels * n] scratch */
+int chap_l2n_sample_axpy_batched(const chap_level* levels, int32_t n_levels, int32_t n, float xi, double* norms, void* stream);
 
 /* ------------------------------------------------------------------ 2D validation (code/val_2D.py:54-97)
  * out[s, Y, X] = in[s, iy[Y], ix[X]] for a stack of n slices [h, w] -> [out_h, out_w]; elem_bytes 4 (float image) or 8 (int64

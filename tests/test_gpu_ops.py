@@ -319,12 +319,42 @@ def test_perturbation_generator(mode):
     assert rel_err(og, gf[key]) < 1e-4
 
 
+def test_perturbation_generator_all_levels_one_call():
+    """The five pyramid levels (different C, rows) of 3 samples through ONE chap_perturb_fwd call = 3 launches + a zero-fill
+    (every phase runs for all levels through a descriptor table): each level <= 1e-4 of the oracle, with and without f."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    shapes = [(3, 16, 32, 32), (3, 32, 16, 16), (3, 64, 8, 8), (3, 128, 4, 4), (3, 256, 2, 2)]
+    gs = [torch.randn(s, generator=g) * (10.0 ** (-i)) for i, s in enumerate(shapes)]          # very different magnitudes per level
+    fs = [torch.randn(s, generator=g) for s in shapes]
+    for mode in ("channel_spatial", "channel", "spatial", "sample"):
+        outs = ops.perturb([_to_cl(t) for t in gs], [_to_cl(t) for t in fs], 6.0, mode, g_scale=10.0)
+        for o, gg, ff in zip(outs, gs, fs):
+            want = ff + L.perturbation(gg * 10.0, 6.0, mode)
+            assert rel_err(o - ff.to(DEV), want - ff) < 1e-4, mode          # the perturbation itself, not f + r
+    outs = ops.perturb([_to_cl(t) for t in gs], None, 6.0, "channel_spatial")
+    for o, gg in zip(outs, gs):
+        assert rel_err(o, L.perturbation(gg, 6.0, "channel_spatial")) < 1e-4
+    # 3D levels
+    g3 = [torch.randn(2, c, s, s, s, generator=g) for c, s in ((16, 8), (32, 4), (64, 2))]
+    outs = ops.perturb([_to_cl(t) for t in g3], None, 6.0, "channel_spatial")
+    for o, gg in zip(outs, g3):
+        assert rel_err(o, L.perturbation(gg, 6.0, "channel_spatial")) < 1e-4
+
+
 def test_l2n_axpy_and_sgd():
     ops = _ops()
     torch.manual_seed(2)
     d, base = torch.randn(3, 16, 5, 7) - 0.5, torch.randn(3, 16, 5, 7)
     out = ops.l2n_sample_axpy(_to_cl(d), _to_cl(base), 10.0)
     assert rel_err(out, base + 10.0 * L.l2n_sample(d)) < 1e-6
+    # all levels of the VAT probe in two launches (ragged shapes, one level without a base)
+    ds = [torch.randn(3, c, s, s + 1) - 0.5 for c, s in ((16, 12), (32, 6), (64, 3), (128, 2), (256, 1))]
+    bs = [torch.randn_like(t) for t in ds]
+    bs[3] = None
+    outs = ops.l2n_sample_axpy_all([_to_cl(t) for t in ds], [None if t is None else _to_cl(t) for t in bs], 10.0)
+    for o, t, bb in zip(outs, ds, bs):
+        assert rel_err(o, (0 if bb is None else bb) + 10.0 * L.l2n_sample(t)) < 1e-6
     p, g = torch.randn(1003), torch.randn(1003)
     pr, buf = p.clone(), [None]
     pg, gg, bg = p.to(DEV), g.to(DEV), torch.zeros(1003, device=DEV)
