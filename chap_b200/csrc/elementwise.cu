@@ -240,26 +240,39 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
 // tensor are in flight per thread.
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// Traversal direction of the streaming kernels.  A kernel that re-reads what its predecessor just streamed (BatchNorm apply after
+// the conv wrote y; BatchNorm-backward apply after the reduce pass read dout / y) finds the END of those tensors in the 126 MB L2,
+// not the beginning: walking the 256-vector chunks backwards turns the first part of the pass into L2 hits.  Chunks are reversed
+// whole, so a thread keeps its channel group (i % cg == threadIdx.x % cg).  MEASURED on the 2D iteration (CHAP_EW_REVERSE = 0 / 1 / 2 / 3,
+// same box, back to back): 13.51 / 13.55 / 13.54 / 13.58 ms, BatchNorm families unchanged within noise -- the re-read tensors already hit
+// L2 (50 MB level-0 tensors in a 126 MB cache).  Off by default; kept as an experiment knob.
+__device__ __forceinline__ int64_t ew_index(int64_t i, int64_t nchunks, int reverse) {
+    return reverse ? (((nchunks - 1 - (i >> 8)) << 8) | (i & 255)) : i;
+}
+
 template <bool EL, bool RES>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ ss, float slope,
                         const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
-                        const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec, float* __restrict__ out) {
+                        const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec, int reverse,
+                        float* __restrict__ out) {
     const int cg = c >> 2, g = threadIdx.x % cg;
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g);
     const int64_t per_sample = rows_per_sample * cg;
     const int64_t stride = (int64_t)gridDim.x * 256;
+    const int64_t nchunks = (total_vec + 255) >> 8, span = nchunks << 8;
     const float4* y4 = reinterpret_cast<const float4*>(y);
     const float4* e4 = reinterpret_cast<const float4*>(drop_el);
     const float4* r4 = reinterpret_cast<const float4*>(res);
     float4* o4 = reinterpret_cast<float4*>(out);
     auto act = [&](float v, float s, float h) { float z = fmaf(v, s, h); return z > 0.f ? z : slope * z; };
-    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < span; i0 += kEwUnroll * stride) {
         float4 v[kEwUnroll], e[kEwUnroll], r[kEwUnroll];
 #pragma unroll
         for (int u = 0; u < kEwUnroll; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < total_vec) {
+            const int64_t iv = i0 + u * stride;
+            const int64_t i = ew_index(iv, nchunks, reverse);
+            if (iv < span && i < total_vec) {
                 v[u] = ldg_stream(y4 + i);
                 if (EL) e[u] = ldg_stream(e4 + i);
                 if (RES) r[u] = ldg_stream(r4 + i);
@@ -267,8 +280,10 @@ bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ s
         }
 #pragma unroll
         for (int u = 0; u < kEwUnroll; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i >= total_vec) break;
+            const int64_t iv = i0 + u * stride;
+            if (iv >= span) break;
+            const int64_t i = ew_index(iv, nchunks, reverse);
+            if (i >= total_vec) continue;
             float4 o = make_float4(act(v[u].x, sc.x, sh.x), act(v[u].y, sc.y, sh.y), act(v[u].z, sc.z, sh.z), act(v[u].w, sc.w, sh.w));
             if (drop_nc) {
                 const float4 f = ld4(drop_nc + (i / per_sample) * c + 4 * g);
@@ -379,6 +394,7 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
                               double inv_count, double* __restrict__ sums, float* __restrict__ dy,
                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int cg = c >> 2, g = threadIdx.x % cg;
+    const int train_bits = train;
     const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
     const int persist = (train >> 2) & 1;      // bit 2: `sums` is a persistent buffer (2c sums + a ticket word) that must be handed back zeroed
     train &= 1;
@@ -422,20 +438,25 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
         const float dz = bn_dz(dd, yv, s_, h_, slope);
         return train ? s_ * (dz - mz_ - (yv - m_) * is_ * mzx_) : s_ * dz;
     };
-    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total_vec; i0 += kEwUnroll * stride) {
+    const int reverse = (train_bits >> 3) & 1;     // bit 3: walk the chunks backwards (the reduce pass just streamed dout / y forwards)
+    const int64_t nchunks = (total_vec + 255) >> 8, span = nchunks << 8;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < span; i0 += kEwUnroll * stride) {
         float4 d[kEwUnroll], v[kEwUnroll], e[kEwUnroll];
 #pragma unroll
         for (int u = 0; u < kEwUnroll; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < total_vec) {
+            const int64_t iv = i0 + u * stride;
+            const int64_t i = ew_index(iv, nchunks, reverse);
+            if (iv < span && i < total_vec) {
                 d[u] = ldg_stream(d4 + i); v[u] = ldg_stream(y4 + i);
                 if (EL) e[u] = ldg_stream(e4 + i);
             }
         }
 #pragma unroll
         for (int u = 0; u < kEwUnroll; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i >= total_vec) break;
+            const int64_t iv = i0 + u * stride;
+            if (iv >= span) break;
+            const int64_t i = ew_index(iv, nchunks, reverse);
+            if (i >= total_vec) continue;
             float4 dd = d[u];
             if (EL) { dd.x *= e[u].x; dd.y *= e[u].y; dd.z *= e[u].z; dd.w *= e[u].w; }
             if (drop_nc) { const float4 f = ld4(drop_nc + (i / per_sample) * c + 4 * g); dd.x *= f.x; dd.y *= f.y; dd.z *= f.z; dd.w *= f.w; }
@@ -728,7 +749,8 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     KernelTimer timer("bn_act_fwd", 0.0, 4.0 * total * (2 + (drop_el ? 1 : 0) + (residual ? 1 : 0)), S(stream));
     if (c % 4 == 0 && 256 % (c / 4) == 0 && all16({y, drop_el, residual, out, ss, drop_nc}) && round_tf32_on() == 0) {
         const int grid = grid_for(total / 4, 256 * kEwUnroll);
-#define CHAP_FWD_FIXED(EL, RES) bn_act_fwd_fixed_kernel<EL, RES><<<grid, 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, out)
+        static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
+#define CHAP_FWD_FIXED(EL, RES) bn_act_fwd_fixed_kernel<EL, RES><<<grid, 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, rev & 1, out)
         if (drop_el) { if (residual) CHAP_FWD_FIXED(true, true); else CHAP_FWD_FIXED(true, false); }
         else         { if (residual) CHAP_FWD_FIXED(false, true); else CHAP_FWD_FIXED(false, false); }
 #undef CHAP_FWD_FIXED
@@ -785,8 +807,10 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
             CHAP_TRY(launched("bn_act_bwd_reduce_fixed_kernel"));
         }
         const int agrid = grid_for(total / 4, 256 * kEwUnroll);
-        if (drop_el) bn_act_bwd_apply_fixed_kernel<true><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
-        else bn_act_bwd_apply_fixed_kernel<false><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, inv_count, sums, dy, dgamma, dbeta);
+        static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
+        const int tb = train | ((rev & 2) ? 8 : 0);
+        if (drop_el) bn_act_bwd_apply_fixed_kernel<true><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
+        else bn_act_bwd_apply_fixed_kernel<false><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
         return launched("bn_act_bwd_apply_fixed_kernel");
     }
     const int rpb = 256 / cg;
