@@ -46,7 +46,8 @@ struct WgParams {
     int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
     int b_rows;                     // rows (pixels) per x channel chunk in smem
     int debug;                      // CHAP_WG_DEBUG bit 0: skip the MMAs, bit 1: skip the TMA loads (timing experiments only)
-    int stages, tmem_cols;
+    int stages, tmem_cols;          // stages: ring slots of the per-tap N-operand (x) boxes
+    int a_stages;                   // ring slots of the M-operand (dy) box, which is loaded ONCE per pixel block and shared by all taps
     int blocks_total, blocks_per_cta;
     uint32_t a_stage_bytes, b_stage_bytes;
     int64_t s_co, s_ci;             // gradient strides in floats (torch layout), tap stride is 1
@@ -89,13 +90,18 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t r
 __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TmTaps* tmTp, const WgParams& p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // The dy box of a pixel block is the same for every tap: it has its own small ring (a_stages slots, one fill per BLOCK),
+    // the x boxes shifted by the tap keep the per-tap ring.  Round 1 re-loaded dy with every tap: 3x (2D) / 9x (3D) its bytes
+    // through the L2 -> shared-memory path that bounds this kernel (679 MB for a 100 MB layer, profiles/r02_conv_ncu_full_summary.md).
     uint8_t* a_base = smem;
-    uint8_t* b_base = smem + (size_t)p.stages * p.a_stage_bytes;
+    uint8_t* b_base = smem + (size_t)p.a_stages * p.a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.stages * p.b_stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    uint64_t* a_full = tmem_full + 1;
+    uint64_t* a_empty = a_full + p.a_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + p.a_stages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = p.cout / p.m_tile;
@@ -111,6 +117,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -118,7 +125,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
     if (p.p_box != p.P) {
         // the TMA boxes cover p_box < P rows of every channel chunk: the remaining rows of the last K atom must read as zero
         float4* z = reinterpret_cast<float4*>(smem);
-        const int n16 = (int)(((size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes)) >> 4);
+        const int n16 = (int)(((size_t)p.a_stages * p.a_stage_bytes + (size_t)p.stages * p.b_stage_bytes) >> 4);
         for (int i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -136,6 +143,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
     if (nblk > 0 && warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
             for (int b = 0; b < nblk; ++b) {
                 int t = blk0 + b;
                 const int tx = t % p.tiles_w; t /= p.tiles_w;
@@ -143,6 +151,19 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
                 const int tz = t % p.tiles_d;
                 const int img = t / p.tiles_d;
                 const int w0 = tx * p.tw, h0 = ty * p.th, d0 = tz * p.td;
+                {   // the dy box of this block: once, for all taps
+                    mbar_wait(&a_empty[as], aph ^ 1);
+                    if (p.debug & 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[as])) : "memory");
+                    else {
+                        mbar_expect_tx(&a_full[as], (uint32_t)p.a_groups * (uint32_t)p.p_box * 128u);
+                        uint8_t* a_dst = a_base + (size_t)as * p.a_stage_bytes;
+                        for (int g = 0; g < p.a_groups; ++g) {
+                            if (p.nd == 2) tma_load_4d(a_dst + (size_t)g * a_chunk, &tmA, &a_full[as], m0 + g * p.a_cpg, w0, h0, img);
+                            else tma_load_5d(a_dst + (size_t)g * a_chunk, &tmA, &a_full[as], m0 + g * p.a_cpg, w0, h0, d0, img);
+                        }
+                    }
+                    if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                }
                 for (int ti = 0; ti < ntaps; ++ti) {
                     const int tap = tap0 + ti;
                     int kx, ky, kz;
@@ -150,13 +171,8 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
                     else if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
                     mbar_wait(&empty[s], ph ^ 1);
                     if (p.debug & 2) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory"); if (++s == p.stages) { s = 0; ph ^= 1; } continue; }
-                    mbar_expect_tx(&full[s], ((uint32_t)p.a_groups * (uint32_t)p.p_box + (uint32_t)p.b_groups * (uint32_t)(p.reuse ? p.b_rows : p.p_box)) * 128u);
-                    uint8_t* a_dst = a_base + (size_t)s * p.a_stage_bytes;
+                    mbar_expect_tx(&full[s], (uint32_t)p.b_groups * (uint32_t)(p.reuse ? p.b_rows : p.p_box) * 128u);
                     uint8_t* b_dst = b_base + (size_t)s * p.b_stage_bytes;
-                    for (int g = 0; g < p.a_groups; ++g) {
-                        if (p.nd == 2) tma_load_4d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, img);
-                        else tma_load_5d(a_dst + (size_t)g * a_chunk, &tmA, &full[s], m0 + g * p.a_cpg, w0, h0, d0, img);
-                    }
                     for (int g = 0; g < p.b_groups; ++g) {
                         if (p.k2s2 && p.nd == 2) tma_load_4d(b_dst + (size_t)g * b_chunk, &tmTp->m[tap], &full[s], n0 + g * p.b_cpg, w0, h0, img);
                         else if (p.k2s2) tma_load_5d(b_dst + (size_t)g * b_chunk, &tmTp->m[tap], &full[s], n0 + g * p.b_cpg, w0, h0, d0, img);
@@ -195,9 +211,11 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
         const uint32_t id = swap ? ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(p.n_mma >> 3) << 17)) : idesc;
         const uint32_t d_stride = swap ? (uint32_t)p.n_mma : (uint32_t)(nky * p.n_tile);
         int s = 0; uint32_t ph = 0;
+        int as = 0; uint32_t aph = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0;
         for (int b = 0; b < nblk; ++b) {
             uint32_t d_tap = tmem_base;
+            mbar_wait(&a_full[as], aph);                         // this block's dy box (shared by all its taps)
             for (int ti = 0; ti < ntaps; ++ti) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
@@ -231,12 +249,15 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
                         }
                     }
                     tc_commit(&empty[s]);
+                    if (ti == ntaps - 1) tc_commit(&a_empty[as]);          // all MMAs that read this dy box are in flight behind this commit
                 }
                 __syncwarp();
                 d_tap += d_stride;
-                a_lo += a_stage; b_lo += b_stage;
-                if (++s == p.stages) { s = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+                b_lo += b_stage;
+                if (++s == p.stages) { s = 0; ph ^= 1; b_lo = b_lo0; }
             }
+            a_lo += a_stage;
+            if (++as == p.a_stages) { as = 0; aph ^= 1; a_lo = a_lo0; }
         }
         if (elect_one()) tc_commit(tmem_full);
         __syncwarp();
@@ -359,9 +380,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
         choose_box8(p.W, p.H, p.D, tw, th, td, 128);
         const int m_pre = v.cout > 128 ? 128 : v.cout;
         const int P = (tw * th * td + 7) / 8 * 8;
-        const size_t st_bytes = (size_t)(((m_pre + 31) / 32) * 32 + n_tile_pre) * P * 4;
+        const size_t a_bytes = (size_t)(((m_pre + 31) / 32) * 32) * P * 4, b_bytes = (size_t)n_tile_pre * P * 4;
         const long blocks = (long)g.n * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th) * ((p.D + td - 1) / td);
-        if (st_bytes * 3 <= 198 * 1024 && blocks >= 4 * kNumSMs && getenv("CHAP_WG_BOX") == nullptr) { p.tw = tw; p.th = th; p.td = td; }
+        if (a_bytes * 2 + b_bytes * 3 <= 198 * 1024 && blocks >= 4 * kNumSMs && getenv("CHAP_WG_BOX") == nullptr) { p.tw = tw; p.th = th; p.td = td; }
     }
     // Row-reuse mode (large images, <= 128 input channels per CTA): in-plane 8 x 8 pixel block; the x box is loaded once
     // per (kz, kx) with an h-halo of one row above and below and serves the three ky taps -> 3 (9) x-boxes of 10 rows
@@ -379,9 +400,9 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
             const int tw = c[0], th = c[1], P = tw * th;
             if (force && P != force) continue;
             if (p.W < tw || p.H < th + 2) continue;
-            const size_t st_bytes = (size_t)((m_tile_pre + 31) / 32) * 32 * P * 4 + (size_t)n_tile_pre * tw * (th + 2) * 4;
+            const size_t a_bytes = (size_t)((m_tile_pre + 31) / 32) * 32 * P * 4, b_bytes = (size_t)n_tile_pre * tw * (th + 2) * 4;
             const long blocks = (long)g.n * p.D * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th);
-            if (st_bytes * (force ? 2 : 3) > 198 * 1024 || blocks < 4 * kNumSMs) continue;
+            if (a_bytes * 2 + b_bytes * (force ? 2 : 3) > 198 * 1024 || blocks < 4 * kNumSMs) continue;
             p.tw = tw; p.th = th;
             break;
         }
@@ -399,7 +420,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.b_cpg = 32; p.b_groups = p.n_tile / 32;
     p.a_stage_bytes = ((uint32_t)p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
     p.b_stage_bytes = ((uint32_t)p.n_tile * p.b_rows * 4u + 1023u) & ~1023u;
-    const size_t stage = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    p.a_stages = 2;
+    const size_t a_ring = (size_t)p.a_stages * p.a_stage_bytes, stage = p.b_stage_bytes;      // `stage` = one per-tap ring slot (x box)
     p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
     const int n_tiles = v.cin > 256 ? v.cin / 256 : 1;
     const int zdim = (v.cout / p.m_tile) * n_tiles;
@@ -421,7 +443,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     for (int tg = (512 / cols_per_unit < units ? 512 / cols_per_unit : units); tg >= 1; --tg) {
         const int groups = (units + tg - 1) / tg;
         if ((units + groups - 1) / groups != tg) continue;                     // keep the groups balanced
-        const bool two = tg * cols_per_unit <= 256 && 3 * stage <= 100 * 1024;
+        const bool two = tg * cols_per_unit <= 256 && a_ring + 3 * stage <= 100 * 1024;
         const int target = two ? 2 * kNumSMs : kNumSMs;
         long splits = (target + groups * zdim - 1) / (groups * zdim);
         if (splits > max_splits) splits = max_splits;
@@ -435,8 +457,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.tmem_cols = 32; while (p.tmem_cols < tg * cols_per_unit) p.tmem_cols *= 2;
     p.acc2 = p.swap && p.P % 64 == 0 && p.tmem_cols <= 256 && getenv("CHAP_WG_ACC2") != nullptr;
     if (p.acc2) p.tmem_cols *= 2;
-    const bool two_per_sm = p.tmem_cols <= 256 && 3 * stage <= 100 * 1024;
-    int stages = (int)(((two_per_sm ? 100 : 200) * 1024 - 2048) / stage);
+    const bool two_per_sm = p.tmem_cols <= 256 && a_ring + 3 * stage <= 100 * 1024;
+    int stages = (int)(((two_per_sm ? 100 : 200) * 1024 - 2048 - a_ring) / stage);
     if (stages > 8) stages = 8;
     CHAP_REQUIRE(stages >= 2, CHAP_ERR_BAD_ARG, "tc_wgrad: tile does not fit shared memory");
     p.stages = stages;
@@ -486,7 +508,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(wgrad_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16 +
+    const size_t smem = 1024 + a_ring + (size_t)stages * stage + (2 * stages + 1 + 2 * p.a_stages) * sizeof(uint64_t) + 16 +
                         (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
     // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
     p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
