@@ -53,6 +53,9 @@ struct TcParams {
     int colsplit;                 // two groups: 1 = both work on every tile, half the columns each; 0 = they alternate tiles
     int cps;                      // k chunks per pipeline stage (1, 2 or 4): fewer, fatter stages for the deep layers
     int thin2d;                   // 1: row-reuse layer (2D or 3D) with one k chunk and resident weights -> the lean issue / producer loops
+    int sup;                      // 1 (thin2d only): SUPER TILES -- one haloed box of 2 th + 2 rows per (kz, kx) serves TWO vertically adjacent
+                                  // M tiles (rows 0.. and th..), one per TMEM accumulator: half the TMA issues / ring round trips per tile and
+                                  // 1.25x instead of 1.5x halo overhead.  tiles_h / tiles_total then count super tiles.
     int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
     int precise;                  // 1: split-operand 3xTF32 (kernel template PRECISE): 4 extra warps split every A stage into TF32 hi / lo halves
@@ -170,6 +173,42 @@ __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_ba
     mbar_wait(b_full, 0);
     int s = 0; uint32_t ph = 0, a_s = a0;
     int j = 0;
+    if (p.sup) {
+        // super tiles: unit k = tiles j = 2k (accumulator 0, box rows 0..) and j = 2k + 1 (accumulator 1, box rows th * tw..)
+        const uint32_t a_sub = ((uint32_t)(p.th * p.tw) * row_bytes) >> 4;
+        for (int unit = blockIdx.x; unit < p.tiles_total; unit += gridDim.x, ++j) {
+            mbar_wait(&tmem_empty[0], (uint32_t)(j & 1) ^ 1u);
+            mbar_wait(&tmem_empty[1], (uint32_t)(j & 1) ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const int kx = g % 3, kz = g / 3;                               // compile time after unrolling
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int sb = 0; sb < 2; ++sb) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(sb * p.nt);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k)
+                                mma_term<PRECISE>(d_tmem, a_s + (uint32_t)sb * a_sub + (uint32_t)ky * a_ky + 2u * k,
+                                                  b0 + (uint32_t)((kz * 3 + ky) * 3 + kx) * b_box + 2u * k, hi, idesc,
+                                                  (g | ky | k) == 0 ? 0u : 1u, a_lo_off, b_lo_off);
+                        }
+                    }
+                    tc_commit(&empty[s]);
+                }
+                __syncwarp();
+                a_s += a_stage;
+                if (++s == p.stages) { s = 0; ph ^= 1u; a_s = a0; }
+            }
+            if (elect_one()) { tc_commit(&tmem_full[0]); tc_commit(&tmem_full[1]); }
+            __syncwarp();
+        }
+        return;
+    }
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
         const int buf = j & 1;
         mbar_wait(&tmem_empty[buf], (uint32_t)((j >> 1) & 1) ^ 1u);          // the epilogue has drained this accumulator
@@ -334,7 +373,7 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             const int ng = p.nd == 2 ? 3 : 9;
             TileIter tj;
             for (tj.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d); tj.tile < p.tiles_total; tj.next(p.tiles_w, p.tiles_h, p.tiles_d)) {
-                const int w0 = tj.tx * p.tw - 1, h0 = tj.ty * p.th - 1, d0 = tj.tz * p.td - 1;
+                const int w0 = tj.tx * p.tw - 1, h0 = tj.ty * (p.sup ? 2 * p.th : p.th) - 1, d0 = tj.tz * p.td - 1;
                 for (int g = 0; g < ng; ++g) {
                     const int kx = g % 3, kz = g / 3;
                     mbar_wait(&empty[s], ph ^ 1u);
@@ -456,13 +495,20 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
         const int c_begin = colsplit ? eg * (p.nt >> 1) : 0, c_end = colsplit ? c_begin + (p.nt >> 1) : p.nt;
         float* scratch = red + (size_t)p.epi_groups * 8 * p.nt + (size_t)(warp - 2) * (32 * 17);   // warp-private transpose scratch
         const bool bias_vec = (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;     // parameters may sit at any 4-byte offset of an arena
-        int jj = alternate ? eg : 0;                                   // index of the tile among this CTA's tiles
+        int jj0 = alternate ? eg : 0;                                  // index of the tile among this CTA's tiles
+        // super tiles: the iteration units are pairs of tiles (j = 2k, 2k + 1 <-> accumulators 0, 1); with alternating groups, group e
+        // takes sub-tile e of EVERY unit, otherwise both sub-tiles of a unit are processed one after the other
+        const bool sup = p.sup != 0;
+        const bool split_units = alternate && !sup;                    // no super tiles: the groups take alternate tiles
+        const int sub_lo = sup ? (alternate ? eg : 0) : 0, sub_hi = sup ? (alternate ? eg + 1 : 2) : 1;
         TileIter ti;
-        for (ti.init(blockIdx.x + (alternate ? eg * (int)gridDim.x : 0), (alternate ? 2 : 1) * (int)gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d);
-             ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), jj += alternate ? 2 : 1) {
+        for (ti.init(blockIdx.x + (split_units ? eg * (int)gridDim.x : 0), (split_units ? 2 : 1) * (int)gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d);
+             ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), jj0 += (sup || alternate) ? 2 : 1)
+        for (int sb = sub_lo; sb < sub_hi; ++sb) {
+            const int jj = jj0 + ((sup && !alternate) ? sb : 0);
             const int buf = p.n_buf == 2 ? (jj & 1) : 0;
             const uint32_t use = p.n_buf == 2 ? (uint32_t)(jj >> 1) : (uint32_t)jj;
-            const int ow = ti.tx * p.tw + dx, oh = ti.ty * p.th + dy, od = ti.tz * p.td + dz;
+            const int ow = ti.tx * p.tw + dx, oh = (sup ? 2 * ti.ty + sb : ti.ty) * p.th + dy, od = ti.tz * p.td + dz;
             const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
             const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
             TC_WAIT(&tmem_full[buf], use & 1u);
@@ -789,8 +835,19 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.precise = (pmc > 0 && (g.cin > g.cout ? g.cin : g.cout) <= pmc) ? 1 : 0;
     const uint32_t dup = p.precise ? 2u : 1u;
     p.b_resident = dup * p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
+    // Super tiles for the thin row-reuse layers (the conditions of the lean thin2d loops, known at this point).  MEASURED (round 2,
+    // tools/conv_bench.py, same box): correct, but NOT faster -- 16 -> 16 @ 12x256^2 forward 44.0 us with, 42.1 us without; 3D 16 -> 16 @
+    // 2x112x112x80 173 vs 150 us (4 ring stages of 20 KB instead of 6 of 13 KB).  Halving the TMA issues and ring round trips per tile
+    // does not move these kernels, nor do polling mbarrier waits (-DCHAP_MBAR_POLL: 44.9 vs 43.2 us) -- so neither the TMA issue rate
+    // nor barrier wake-up latency is what bounds the thin layers.  Opt-in (CHAP_TC_SUPER=1) experiment, off by default.
+    p.sup = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.b_resident && p.n_buf == 2 && p.H >= 2 * p.th + 2 && TC_DBG_HOST_OFF &&
+             getenv("CHAP_TC_NO_THIN2D") == nullptr && getenv("CHAP_TC_SUPER") != nullptr) ? 1 : 0;
+    if (p.sup) {
+        p.tiles_h = (p.tiles_h + 1) / 2;                                 // rows of super tiles (an odd last row gets a phantom second tile: all rows masked)
+        p.tiles_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
+    }
     if (p.reuse) {
-        p.a_box_bytes = (uint32_t)(p.tw * (p.th + 2)) * p.kc * 4u;
+        p.a_box_bytes = (uint32_t)(p.tw * ((p.sup ? 2 * p.th : p.th) + 2)) * p.kc * 4u;
         p.a_chunk_bytes = (p.a_box_bytes + 1023u) & ~1023u;              // 128 + 2 tw rows: every ky view of 128 rows stays inside
         p.b_chunk_bytes = 3u * p.b_box_bytes;
     } else {
@@ -847,6 +904,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     // lean issue / producer loops for the thin row-reuse layers (see issue_mmas_thin)
     p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 && stages >= 2 &&
                 TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
+    CHAP_REQUIRE(!p.sup || p.thin2d, CHAP_ERR_BAD_ARG, "tc_conv: super tiles need the thin-layer loops (stages %d, cps %d)", stages, p.cps);
     p.stages = stages;
     p.a_lo_off = (uint32_t)stages * p.a_stage_bytes;
     p.b_lo_off = p.b_resident ? p.b_area_bytes : (uint32_t)stages * p.b_stage_bytes;
@@ -893,12 +951,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         } else if (g.nd == 2) {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H;
-            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = 1;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? (p.sup ? 2 * p.th : p.th) + 2 : p.th; box[3] = 1;
             CHAP_TRY(make_tensor_map(&tmA, in, 4, dims, str, box, p.kc, false, p.precise));
         } else {
             dims[0] = C; dims[1] = p.W; dims[2] = p.H; dims[3] = p.D; dims[4] = g.n;
             str[0] = C * 4; str[1] = str[0] * p.W; str[2] = str[1] * p.H; str[3] = str[2] * p.D;
-            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? p.th + 2 : p.th; box[3] = p.td; box[4] = 1;
+            box[0] = p.kc; box[1] = p.tw; box[2] = p.reuse ? (p.sup ? 2 * p.th : p.th) + 2 : p.th; box[3] = p.td; box[4] = 1;
             CHAP_TRY(make_tensor_map(&tmA, in, 5, dims, str, box, p.kc, false, p.precise));
         }
         // packed weights: [hi half | lo half], each [w_taps * N rows][K]; the plain TF32 kernel only ever addresses the hi rows

@@ -17,7 +17,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifdef CHAP_MBAR_POLL
+__device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_poll(bar, parity); }
+__device__ __forceinline__ void mbar_wait_suspending(uint64_t* bar, uint32_t parity) {
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
