@@ -314,7 +314,7 @@ def time_training(args, w, d, dev, steps, warmup, use_graph, kernel_timing, cloc
         dist.all_reduce(flat_g)
     trainer = ChapTrainer(model, n_classes=w["classes"], labeled_bs=w["labeled"], max_iterations=30000,
                           grad_hook=allreduce if d.world > 1 else None, grad_scale=1.0 / d.world,
-                          use_graph=use_graph, graph_warmup=2)
+                          use_graph=use_graph, graph_warmup=2, overlap_allreduce=not args.no_overlap)
     n_in = max(2, min(4, steps))
     host = [synth_batch(w, 1000 * d.rank + i) for i in range(n_in)]
     host = [(v.pin_memory(), l.pin_memory()) for v, l in host]
@@ -585,6 +585,7 @@ def main():
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel eagerly instead of replaying one CUDA graph per step")
+    ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the backward instead of the overlapped two-bucket scheme")
     ap.add_argument("--force-simt", action="store_true", help="debug: fp32 CUDA-core convolutions only")
     ap.add_argument("--conv-precision", type=int, default=None,
                     help="split-operand 3xTF32 tensor-core convolutions for layers with max(Cin, Cout) <= this (0: plain TF32)")

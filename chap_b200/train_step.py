@@ -61,7 +61,7 @@ def feature_dropout_loss(model, uimg_ab, ps1, ps2, sim_score=None, comp_drop=Fal
 def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, vat=None, adv_losstype="kl",
                         topk=0.1, use_diff_mask=True, consistency=1.0, rampup=50.0, mask_offsets=None,
                         d_init=None, trace=None, img_mask=None, cw=None, dropout=False, comp_drop=False, sim_score=None,
-                        dropout_masks=None):
+                        dropout_masks=None, on_decoders_done=None):
     """Forward part of the iteration; returns (loss, aux).  Line numbers: code/train_ours_2D.py.
     img_mask (int64 [*spatial]) / cw (float or 0-dim device tensor) may be supplied by the caller (the CUDA-graph
     trainer keeps them in static device buffers); otherwise they are drawn / computed here like the reference does."""
@@ -86,7 +86,24 @@ def chap_losses_forward(model, volume, label, labeled_bs, n_classes, iter_num, v
         net_input_l = ops.mask_mix(img_b, uimg_b, img_mask)                             # :336
         net_input_mix = torch.cat((net_input_l, net_input_unl))                         # :338
 
-    out1, out2 = model(net_input_mix)                                                   # :339
+    if on_decoders_done is not None and hasattr(model, "encoder"):
+        # The mix pass is the FIRST pass recorded with gradients, so autograd back-propagates it LAST (the engine runs the most
+        # recently recorded nodes first): when the gradients of all its encoder features have arrived, every use of the decoder
+        # weights in this iteration has been back-propagated -- the decoders' gradient bucket is final while the encoder
+        # backward of this pass is still to come.  (Same computation as model(net_input_mix), code/networks/unet.py:277-292.)
+        feats = model.encoder(net_input_mix)
+        out1, out2 = model.decoder1(feats), model.decoder2(feats)                       # :339
+        pending = [len(feats)]
+
+        def _arrived(grad):
+            pending[0] -= 1
+            if pending[0] == 0:
+                on_decoders_done()
+            return None
+        for f in feats:
+            f.register_hook(_arrived)
+    else:
+        out1, out2 = model(net_input_mix)                                               # :339
     out_l1, out_unl1 = out1[:sub_l], out1[sub_l:]
     out_l2, out_unl2 = out2[:sub_l], out2[sub_l:]
     lu_o1, ll_i1, m1 = losses.mix_loss(out_unl1, plab_a2, lab_a, loss_mask, u_weight=0.5, unlab=True)   # :345
@@ -188,10 +205,34 @@ class FlatSGD:
             if have:
                 torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
 
+    # -- data-parallel all-reduce in two buckets: the tail bucket [tail_start, end) -- the decoders -- is final as soon as the
+    #    last network pass has back-propagated through the decoders, i.e. BEFORE the encoder backward of that pass; its
+    #    all-reduce runs on a side stream underneath that encoder backward (ChapTrainer triggers it), the head bucket follows here.
+    def set_tail_bucket(self, first_tail_param):
+        """Parameters from `first_tail_param` on (arena order = model.parameters() order) form the early bucket."""
+        idx = next(i for i, p in enumerate(self.params) if p is first_tail_param)
+        self.tail_start = self.offsets[idx]
+        self.comm_stream = torch.cuda.Stream(device=self.flat_g.device)
+        self._tail_pending = False
+
+    def early_reduce_tail(self):
+        if self.grad_hook is None or getattr(self, "tail_start", None) is None or not self.sink or self._tail_pending:
+            return
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)                     # everything that accumulated into the tail bucket is ordered before
+        with torch.cuda.stream(self.comm_stream):
+            self.grad_hook(self.flat_g[self.tail_start:])
+        self._tail_pending = True
+
     def step(self, grad_scale=1.0):
         self.gather_grads()
         if self.grad_hook is not None:
-            self.grad_hook(self.flat_g)
+            if getattr(self, "_tail_pending", False):
+                self.grad_hook(self.flat_g[:self.tail_start])                       # head bucket (encoder), on the main stream
+                torch.cuda.current_stream().wait_stream(self.comm_stream)           # join the overlapped tail all-reduce
+                self._tail_pending = False
+            else:
+                self.grad_hook(self.flat_g)
         ops.sgd_momentum_lrdev_(self.flat_p, self.flat_g, self.flat_buf, self.lr_dev, self.momentum, self.weight_decay, grad_scale)
 
     # -- optimizer-state save / resume.  The reference only saves model.state_dict() (code/train_ours_2D.py:428-435) and has no
@@ -231,7 +272,7 @@ class ChapTrainer:
     def __init__(self, model, n_classes, labeled_bs, base_lr=0.01, max_iterations=30000, adv_noise=True,
                  adv_losstype="kl", noise_mag=10.0, epi=6.0, topk=0.1, consistency=1.0, consistency_rampup=50.0,
                  use_diff_mask=True, grad_hook=None, grad_scale=1.0, use_graph=False, graph_warmup=3,
-                 dropout=False, comp_drop=False, sim_score=None, grad_sink=True):
+                 dropout=False, comp_drop=False, sim_score=None, grad_sink=True, overlap_allreduce=True):
         """dropout / comp_drop / sim_score: the --dropout feature-perturbation branch (code/train_ours_2D.py:359-365, 2D nets only:
         the reference's DualDecoder3d.forward has no such branch); sim_score stands in for the absent GradSim.get_sim()."""
         self.model, self.n_classes, self.labeled_bs = model, n_classes, labeled_bs
@@ -245,6 +286,10 @@ class ChapTrainer:
         self.adv_losstype, self.topk, self.use_diff_mask = adv_losstype, topk, use_diff_mask
         self.consistency, self.rampup = consistency, consistency_rampup
         self.opt = FlatSGD(model.parameters(), base_lr, grad_hook=grad_hook, grad_sink=grad_sink)
+        # overlapped two-bucket gradient all-reduce (data parallel only): decoders early on a side stream, encoder at the end
+        self.overlap = bool(overlap_allreduce and grad_hook is not None and grad_sink and hasattr(model, "decoder1"))
+        if self.overlap:
+            self.opt.set_tail_bucket(next(iter(model.decoder1.parameters())))
         self.grad_scale = grad_scale
         self.iter_num = 0
         self.use_graph, self.graph_warmup = use_graph, graph_warmup
@@ -266,7 +311,8 @@ class ChapTrainer:
                                         use_diff_mask=self.use_diff_mask, consistency=self.consistency,
                                         rampup=self.rampup, mask_offsets=mask_offsets, d_init=d_init, trace=trace,
                                         img_mask=img_mask, cw=cw, dropout=self.dropout, comp_drop=self.comp_drop,
-                                        sim_score=self.sim_score, dropout_masks=dropout_masks)
+                                        sim_score=self.sim_score, dropout_masks=dropout_masks,
+                                        on_decoders_done=self.opt.early_reduce_tail if self.overlap else None)
         self.opt.zero_grad()                                                            # :381
         with ops.zero_bias_grad_as_none(), ops.grad_sink(self.opt.sink):
             loss.backward()                                                             # :382
