@@ -52,3 +52,39 @@ def gather_rows(rows, world_size):
     out = [None] * world_size
     dist.all_gather_object(out, rows)
     return out
+
+
+class DevicePrefetcher:
+    """Host -> device input pipeline for the training loop (the reference's DataLoader uses pin_memory=True and then a blocking
+    `.cuda()` per batch, code/train_ours_2D.py:274,304-305): batch i + 1 is copied from pinned host memory on a side stream while
+    iteration i computes.  Iterating yields tuples of device tensors; every yielded tensor is safe to use on the current stream."""
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.next = None
+        self._load()
+
+    def _load(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self.next = tuple(t.to(self.device, non_blocking=True) for t in batch)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)                       # the copy of THIS batch has finished before it is used
+        batch = self.next
+        for t in batch:
+            t.record_stream(cur)                           # allocated on the side stream, consumed on the current one
+        self._load()                                       # start the next copy; it overlaps with the caller's iteration
+        return batch

@@ -77,11 +77,16 @@ def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1,
     vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(device)
     out = sliding_window_device(net, vol, stride_xy, stride_z, patch_size, num_classes, batch_windows, return_maps,
                                 window_logits_hook)
+    def labels_to_host(label):
+        # int64 like np.argmax in the reference (:72); the class index crosses the bus as one byte per voxel and is widened on the host
+        if num_classes <= 255:
+            return label.to(torch.uint8).cpu().numpy().astype(np.int64)
+        return label.cpu().numpy()
     if return_maps:
         label, score, cnt = out
-        label_map, score_map, cnt_map = label.cpu().numpy(), score.cpu().numpy(), cnt.cpu().numpy()
+        label_map, score_map, cnt_map = labels_to_host(label), score.cpu().numpy(), cnt.cpu().numpy()
     else:
-        label_map = out.cpu().numpy()
+        label_map = labels_to_host(out)
     if add_pad:
         (wl, _), (hl, _), (dl, _) = pads
         label_map = label_map[wl:wl + w, hl:hl + h, dl:dl + d]

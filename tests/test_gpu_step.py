@@ -315,3 +315,15 @@ def test_gradient_sink_equals_autograd_accumulation(mode):
     assert float(t.opt.flat_ws.abs().max()) == 0.0                                    # every scratch was handed back zeroed
     errs = np.array([rel_err(a, b) for a, b in zip(runs[True][1], runs[False][1])])
     assert np.median(errs) < 10 * tol and errs.max() < 0.2, (np.median(errs), errs.max())
+
+
+def test_device_prefetcher_yields_every_batch_intact():
+    from chap_b200.parallel import DevicePrefetcher
+    host = [(torch.full((4, 1, 64, 64), float(i)).pin_memory(), torch.full((4, 64, 64), i, dtype=torch.int64).pin_memory()) for i in range(7)]
+    seen = []
+    for v, l in DevicePrefetcher(iter(host), DEV):
+        assert v.is_cuda and l.is_cuda
+        junk = torch.randn(2048, 2048, device=DEV) @ torch.randn(2048, 2048, device=DEV)       # work on the current stream while the next copy runs
+        seen.append((float(v.mean()), int(l.max())))
+        del junk
+    assert seen == [(float(i), i) for i in range(7)]
