@@ -149,7 +149,40 @@ extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
     if (resolve(d, g) != CHAP_OK) return 0;
     // [2 * cout doubles for the bias gradient][pad to 256][taps * cin * cout floats: the tensor-core kernel accumulates the
     // gradient in a [tap][M][N] layout with vector reductions, then a small kernel writes the torch layout]
-    return (((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255) + (size_t)g.taps * g.cin * g.cout * sizeof(float);
+    // pair-packed weight gradient of the 16 -> 16 layers: [+ 4 x that for the gradient of the equivalent 32 -> 32 convolution]
+    const size_t base = (((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255) + (size_t)g.taps * g.cin * g.cout * sizeof(float);
+    return ((base + 255) & ~(size_t)255) + (size_t)4 * g.taps * g.cin * g.cout * sizeof(float);
+}
+
+// Pair-packed weight gradient (round 2).  The tensor-core weight gradient of the thin layers is bound by the NUMBER of
+// tcgen05.mma instructions the single issuing thread can emit (K = 8 pixels per MMA whatever M and N are: 295 k MMAs per launch for
+// 16 -> 16 @ 12x256^2 = 2,000 per CTA x ~40 ns = the measured 85 us), and a 16-channel tensor wastes half of every 128-byte operand
+// row on zero fill.  A channels-last [.., W, 16] tensor IS a [.., W/2, 32] tensor (two pixels per row), so the layer is handed to the same
+// kernel as a 32 -> 32 convolution on the half-width image: half the MMAs (N = 32 costs the same issue slot), no zero fill.  Its gradient
+// dW'[(p', co), (p, ci), ky, e] = sum_j dy[2j + p', co] x[2(j + e) + p, ci] holds every product of pixels q = 2j + p' and q + s with
+// s = 2e + p - p'; the 3x3 gradient is the fold  dW[.., kx = s + 1] = sum over {(e, p, p') : 2e + p - p' = s}:
+//   s =  0: (0,0,0) + (0,1,1)      s = +1: (0,1,0) + (+1,0,1)      s = -1: (0,0,1) + (-1,1,0)
+// Image-row ends are exact because W is even: pixel -1 / W live in pairs -1 / W/2, which the TMA zero-fills as a whole.
+static bool pair_wgrad_ok(const Geom& g) {
+    static const bool off = getenv("CHAP_WG_NO_PAIR") != nullptr;
+    return !off && g.kind == CHAP_CONV_K3 && g.cin == 16 && g.cout == 16 && g.iW % 2 == 0 && g.iW / 2 >= 8 && g.iH >= 10;
+}
+
+__global__ void __launch_bounds__(256)
+pair_fold_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int planes, int accumulate) {
+    // dwp: torch layout [32 (p', co)][32 (p, ci)][planes (kz, ky)][3 (e + 1)]; dw: [16 co][16 ci][planes][3 kx]
+    const int total = 16 * 16 * planes * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kx = i % 3, pl = (i / 3) % planes, ci = (i / (3 * planes)) % 16, co = i / (3 * planes * 16);
+        auto at = [&](int pq, int pp, int e1) {               // pq = p' (dy parity), pp = p (x parity), e1 = e + 1
+            return dwp[((size_t)((pq * 16 + co) * 32 + (pp * 16 + ci)) * planes + pl) * 3 + e1];
+        };
+        float v;
+        if (kx == 1) v = at(0, 0, 1) + at(1, 1, 1);
+        else if (kx == 2) v = at(0, 1, 1) + at(1, 0, 2);
+        else v = at(1, 0, 1) + at(0, 1, 0);
+        dw[i] = accumulate ? dw[i] + v : v;
+    }
 }
 
 static int conv_wgrad_impl(const chap_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
@@ -164,7 +197,22 @@ static int conv_wgrad_impl(const chap_conv_desc* d, const float* x, const float*
     // ~130 cycles, so the register-tiled CUDA-core kernel wins (measured; threshold overridable for experiments)
     static const int thin_max = getenv("CHAP_THIN_MAX") ? atoi(getenv("CHAP_THIN_MAX")) : 0;
     const bool thin = g.kind == CHAP_CONV_K3 && g.cin % 4 == 0 && g.cout % 4 == 0 && g.cin * g.cout <= thin_max;
-    if (g_force_simt.load() == 0 && tc_wgrad_supports(g) && !thin) {
+    const size_t pair_off = ((((size_t)2 * g.cout * sizeof(double) + 255) & ~(size_t)255) + (size_t)g.taps * g.cin * g.cout * sizeof(float) + 255) & ~(size_t)255;
+    if (g_force_simt.load() == 0 && !thin && pair_wgrad_ok(g) && workspace &&
+        workspace_bytes >= pair_off + (size_t)4 * g.taps * g.cin * g.cout * sizeof(float)) {
+        Geom g2 = g;                                   // the same memory seen as a 32 -> 32 convolution on the half-width image
+        g2.cin = 32; g2.cout = 32; g2.iW = g.iW / 2; g2.oW = g.oW / 2; g2.in_rows = g.in_rows / 2; g2.out_rows = g.out_rows / 2;
+        if (tc_wgrad_supports(g2)) {
+            float* dwp = reinterpret_cast<float*>(static_cast<char*>(workspace) + pair_off);
+            handled = tc_wgrad(g2, x, dy, dwp, S(stream), nullptr, false);
+            if (handled < 0) return handled;
+            if (handled) {
+                pair_fold_kernel<<<(16 * 16 * g.taps + 255) / 256, 256, 0, S(stream)>>>(dwp, dw, g.taps / 3, accumulate ? 1 : 0);
+                CHAP_TRY(launched("pair_fold_kernel"));
+            }
+        }
+    }
+    if (!handled && g_force_simt.load() == 0 && tc_wgrad_supports(g) && !thin) {
         handled = tc_wgrad(g, x, dy, dw, S(stream), scratch, accumulate);
         if (handled < 0) return handled;
     }

@@ -313,9 +313,10 @@ class _Conv(Function):
             # gradient-sink mode: dW (and db) are ADDED into the optimiser's flat arena by the kernels; autograd gets None
             g_view, scratch = ctx.w_sink
             want_b = ctx.has_bias and ctx.needs_input_grad[3] and not ctx.zero_bias_grad and ctx.b_sink is not None
-            ws = torch.empty(max(2 * desc.cout, 1), dtype=torch.float64, device=dy.device) if want_b else None
+            ws_bytes = lib().chap_conv_wgrad_workspace_bytes(ctypes.byref(desc))      # bias sums + scratch of the pair-packed 16 -> 16 path
+            ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.float64, device=dy.device)
             check(lib().chap_conv_wgrad_acc(ctypes.byref(desc), _p(x), _p(dy), _p(g_view), _p(ctx.b_sink[0]) if want_b else None,
-                                            _p(ws), 0 if ws is None else ws.numel() * 8, _p(scratch), _stream()))
+                                            _p(ws), ws_bytes, _p(scratch), _stream()))
         elif ctx.needs_input_grad[2]:
             dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dy.device)
             # A bias that feeds a train-mode BatchNorm has an analytically ZERO gradient (BN subtracts the batch mean:

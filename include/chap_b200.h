@@ -157,8 +157,9 @@ int chap_conv_wgrad(const chap_conv_desc* d, const float* x, const float* dy, fl
  * dw_acc += dW and dbias_acc += db (dbias_acc nullable) instead of overwriting, so a parameter that is used by several network
  * passes of one iteration needs no autograd accumulation kernels and no gather copy.  zeroed_scratch (nullable): taps*cin*cout
  * floats that are ALL ZERO on entry and are left all zero on return (a persistent per-layer scratch: the tensor-core kernel
- * reduces into it with 128-bit atomics and a small kernel adds it into dw_acc in the torch layout).  workspace: >= 2*cout
- * doubles, only used for the bias gradient. */
+ * reduces into it with 128-bit atomics and a small kernel adds it into dw_acc in the torch layout).  workspace:
+ * chap_conv_wgrad_workspace_bytes(d) bytes (bias sums; scratch of the pair-packed 16 -> 16 path); >= 2*cout doubles is the minimum,
+ * a smaller-than-full workspace only disables the pair-packed path. */
 int chap_conv_wgrad_acc(const chap_conv_desc* d, const float* x, const float* dy, float* dw_acc, float* dbias_acc,
                         void* workspace, size_t workspace_bytes, float* zeroed_scratch, void* stream);
 
