@@ -165,17 +165,18 @@ extern "C" size_t chap_conv_wgrad_workspace_bytes(const chap_conv_desc* d) {
 // Image-row ends are exact because W is even: pixel -1 / W live in pairs -1 / W/2, which the TMA zero-fills as a whole.
 static bool pair_wgrad_ok(const Geom& g) {
     static const bool off = getenv("CHAP_WG_NO_PAIR") != nullptr;
-    return !off && g.kind == CHAP_CONV_K3 && g.cin == 16 && g.cout == 16 && g.iW % 2 == 0 && g.iW / 2 >= 8 && g.iH >= 10;
+    // cout = 4: the class heads (dy pairs are 8 floats, zero-filled to a 128-byte row by the TMA like the 4-channel rows were before)
+    return !off && g.kind == CHAP_CONV_K3 && g.cin == 16 && (g.cout == 16 || g.cout == 4) && g.iW % 2 == 0 && g.iW / 2 >= 8 && g.iH >= 10;
 }
 
 __global__ void __launch_bounds__(256)
-pair_fold_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int planes, int accumulate) {
-    // dwp: torch layout [32 (p', co)][32 (p, ci)][planes (kz, ky)][3 (e + 1)]; dw: [16 co][16 ci][planes][3 kx]
-    const int total = 16 * 16 * planes * 3;
+pair_fold_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cout, int planes, int accumulate) {
+    // dwp: torch layout [2 cout (p', co)][32 (p, ci)][planes (kz, ky)][3 (e + 1)]; dw: [cout][16 ci][planes][3 kx]
+    const int total = cout * 16 * planes * 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int kx = i % 3, pl = (i / 3) % planes, ci = (i / (3 * planes)) % 16, co = i / (3 * planes * 16);
         auto at = [&](int pq, int pp, int e1) {               // pq = p' (dy parity), pp = p (x parity), e1 = e + 1
-            return dwp[((size_t)((pq * 16 + co) * 32 + (pp * 16 + ci)) * planes + pl) * 3 + e1];
+            return dwp[((size_t)((pq * cout + co) * 32 + (pp * 16 + ci)) * planes + pl) * 3 + e1];
         };
         float v;
         if (kx == 1) v = at(0, 0, 1) + at(1, 1, 1);
@@ -201,13 +202,13 @@ static int conv_wgrad_impl(const chap_conv_desc* d, const float* x, const float*
     if (g_force_simt.load() == 0 && !thin && pair_wgrad_ok(g) && workspace &&
         workspace_bytes >= pair_off + (size_t)4 * g.taps * g.cin * g.cout * sizeof(float)) {
         Geom g2 = g;                                   // the same memory seen as a 32 -> 32 convolution on the half-width image
-        g2.cin = 32; g2.cout = 32; g2.iW = g.iW / 2; g2.oW = g.oW / 2; g2.in_rows = g.in_rows / 2; g2.out_rows = g.out_rows / 2;
+        g2.cin = 32; g2.cout = 2 * g.cout; g2.iW = g.iW / 2; g2.oW = g.oW / 2; g2.in_rows = g.in_rows / 2; g2.out_rows = g.out_rows / 2;
         if (tc_wgrad_supports(g2)) {
             float* dwp = reinterpret_cast<float*>(static_cast<char*>(workspace) + pair_off);
             handled = tc_wgrad(g2, x, dy, dwp, S(stream), nullptr, false);
             if (handled < 0) return handled;
             if (handled) {
-                pair_fold_kernel<<<(16 * 16 * g.taps + 255) / 256, 256, 0, S(stream)>>>(dwp, dw, g.taps / 3, accumulate ? 1 : 0);
+                pair_fold_kernel<<<(g.cout * 16 * g.taps + 255) / 256, 256, 0, S(stream)>>>(dwp, dw, g.cout, g.taps / 3, accumulate ? 1 : 0);
                 CHAP_TRY(launched("pair_fold_kernel"));
             }
         }
