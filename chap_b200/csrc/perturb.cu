@@ -4,14 +4,21 @@
 //
 // Layout: g, f, out are channels-last [n, rows, c]; the spatial-wise norm (over c) of a position is
 // local to one row (contiguous words), the channel-wise norm (over rows) and the per-sample norm are
-// grid-wide reductions -> three streaming passes per level over g:
+// grid-wide reductions.  Round 1 ran three streaming passes per level over g:
 //   P1  chan_sq[n, c]   = sum_rows g^2                                  (skipped for SAMPLE / SPATIAL)
 //   P2  samp_sq[n]      = sum u^2,  u = combine(g / (||g||_chan + e), g / (||g||_row + e))
 //   P3  out             = f + eps * u / (sqrt(samp_sq) + e)
-// Algorithmic traffic is 12 B / element (read g, read f, write out); g is re-read in P2 / P3 (20 B / element touched, the
-// re-reads mostly hit the 126 MB L2: the five 2D levels of 12 samples are 97 MB).  The two grid-wide reductions are real data
-// dependencies, so a level cannot be ONE pass; what can go is the launch count: every phase runs for ALL levels and samples in
-// ONE launch through a descriptor table (round 1: 3 launches + a zero-fill per level = 16 per call; now 3 + 1).
+// Round 2 (default): P2 is gone.  With S_c = sum_r g_rc^2, the row norms nr_r = sqrt(sum_c g_rc^2) + e being LOCAL to a row, and
+//   Q_c = sum_r g_rc^2 / nr_r,   Z = sum_r (sum_c g_rc^2) / nr_r^2
+// the per-sample norm of the combined field is a function of these per-channel sums alone:
+//   ||u||^2 = 1/4 [ sum_c S_c / nc_c^2  +  Z  +  2 sum_c Q_c / nc_c ],     nc_c = sqrt(S_c) + e
+// so ONE statistics pass (S, Q, Z) and ONE apply pass remain -- the minimum for a computation with one dependent grid-wide
+// reduction: 16 B / element touched (g twice, f, out) for 12 B algorithmic, and every pass runs for ALL levels and samples in ONE
+// launch through a descriptor table (round 1: 3 launches + a zero-fill per level = 16 per call; now 2 + 1).
+// Measured, all five 2D levels of 12 samples (97 MB of g; tools/perturb_bench.py): three-phase 137.4 us, two-pass 129.0 us
+// (statistics 45 us + apply 69 us = 4.2 TB/s over its 12 B / element); 3D b2: 222 -> 199 us.  The statistics pass keeps <= 16
+// channel accumulators x (S, Q) per thread and folds them with warp shuffles (a shared-memory fold over the row lanes made it
+// SLOWER than three-phase: 165 us).  CHAP_PERTURB_3PHASE=1 selects the three-phase path (also the fallback for c > 256).
 #include "common.cuh"
 
 namespace chap {
@@ -22,7 +29,8 @@ constexpr float kEps = 1e-8f;
 // one level of one call, as the batched kernels see it
 struct PLevel {
     const float* g; const float* f; float* out;
-    double* chan_sq; double* samp_sq;
+    double* chan_sq; double* samp_sq;       // S[n][c]; (three-phase path) ||u||^2 per sample / (batched l2n) ||d||^2
+    double* chan_q; double* row_z;          // Q[n][c], Z[n] of the two-pass scheme
     int64_t rows;
     int c, tpr;
     int bps_chan, bps_rows;          // blocks per sample in the channel-norm phase / the row phases
@@ -86,7 +94,7 @@ __device__ __forceinline__ float unit_value(float gv, float inv_chan, float inv_
 template <int MODE, bool APPLY>
 __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, const float* __restrict__ f, float* __restrict__ out,
                                                   int64_t rows, int c, int tpr, float eps, float gs, int rt,
-                                                  const double* __restrict__ chan_sq, double* __restrict__ samp_sq,
+                                                  const double* __restrict__ chan_sq, double* __restrict__ samp_sq, int samp_idx,
                                                   int bx, int nbx, int n, float* inv_chan, float* red) {
     if (MODE == CHAP_PERTURB_CHANNEL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
         for (int ch = threadIdx.x; ch < c; ch += 256)
@@ -94,7 +102,7 @@ __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, c
         __syncthreads();
     }
     float scale = 0.f;
-    if (APPLY) scale = eps / (sqrtf((float)samp_sq[n]) + kEps);
+    if (APPLY) scale = eps / (sqrtf((float)samp_sq[samp_idx]) + kEps);
     const int lane = threadIdx.x % tpr, rl = threadIdx.x / tpr, rpb = 256 / tpr;
     const int cpl = c / tpr;                       // channels per lane (multiple of 4 when c % (4 tpr) == 0)
     const float* gb = g + (int64_t)n * rows * c;
@@ -105,22 +113,40 @@ __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, c
         const int64_t r = r0 + rl;
         const bool live = r < rows;
         float inv_row = 0.f;
+        // the row's slice of g is loaded ONCE into registers (<= 16 channels per lane) and serves both the row norm and u
+        // (round 1 loaded it twice: the second, dependent load made the reduce phase latency-bound at 28 % of HBM under ncu)
+        const bool in_regs = cpl <= 16;
+        float4 tg[4];
+        if (live && in_regs) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+                if (4 * k4 < cpl) {
+                    float4 t = __ldg(reinterpret_cast<const float4*>(gb + r * c + lane * cpl) + k4);
+                    t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
+                    tg[k4] = t;
+                }
+        }
         if (MODE == CHAP_PERTURB_SPATIAL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
             float q = 0.f;
-            if (live)
-                for (int k = 0; k < cpl; k += 4) {
-                    float4 t = __ldg(reinterpret_cast<const float4*>(gb + r * c + lane * cpl + k));
-                    t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
-                    q += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+            if (live) {
+                if (in_regs) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        if (4 * k4 < cpl) q += tg[k4].x * tg[k4].x + tg[k4].y * tg[k4].y + tg[k4].z * tg[k4].z + tg[k4].w * tg[k4].w;
+                } else {
+                    for (int k = 0; k < cpl; k += 4) {
+                        float4 t = __ldg(reinterpret_cast<const float4*>(gb + r * c + lane * cpl + k));
+                        t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
+                        q += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+                    }
                 }
+            }
             for (int o = tpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
             inv_row = 1.f / (sqrtf(q) + kEps);
         }
         if (!live) continue;
-        for (int k = 0; k < cpl; k += 4) {
+        auto emit = [&](float4 t, const int k) {            // u for 4 channels of this row: accumulate ||u||^2 or write f + scale * u
             const int ch = lane * cpl + k;
-            float4 t = __ldg(reinterpret_cast<const float4*>(gb + r * c + ch));
-            t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
             float ic0 = 0.f, ic1 = 0.f, ic2 = 0.f, ic3 = 0.f;
             if (MODE == CHAP_PERTURB_CHANNEL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
                 ic0 = inv_chan[ch]; ic1 = inv_chan[ch + 1]; ic2 = inv_chan[ch + 2]; ic3 = inv_chan[ch + 3];
@@ -137,6 +163,17 @@ __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, c
             } else {
                 acc += u0 * u0 + u1 * u1 + u2 * u2 + u3 * u3;
             }
+        };
+        if (in_regs) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)                  // static indices: tg stays in registers
+                if (4 * k4 < cpl) emit(tg[k4], 4 * k4);
+        } else {
+            for (int k = 0; k < cpl; k += 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(gb + r * c + lane * cpl + k));
+                t.x *= gs; t.y *= gs; t.z *= gs; t.w *= gs;
+                emit(t, k);
+            }
         }
     }
     if (!APPLY) {
@@ -146,7 +183,7 @@ __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, c
         if (threadIdx.x == 0) {
             double a = 0.0;
             for (int w = 0; w < 8; ++w) a += (double)red[w];
-            atomicAdd(samp_sq + n, a);
+            atomicAdd(samp_sq + samp_idx, a);
         }
     }
 }
@@ -161,7 +198,121 @@ perturb_rows_all_kernel(const __grid_constant__ PBatch b) {
     const PLevel& L = b.lv[l];
     const int rel = (int)blockIdx.x - L.blk0_rows;
     perturb_rows_body<MODE, APPLY>(L.g, APPLY ? L.f : nullptr, APPLY ? L.out : nullptr, L.rows, L.c, L.tpr, b.eps, b.gs, 0, L.chan_sq, L.samp_sq,
-                                   rel % L.bps_rows, L.bps_rows, rel / L.bps_rows, inv_chan, red);
+                                   rel / L.bps_rows, rel % L.bps_rows, L.bps_rows, rel / L.bps_rows, inv_chan, red);
+}
+
+// Statistics pass of the two-pass scheme, all levels in one launch: per sample S_c, Q_c (double atomics, one per channel and block) and Z.
+// Row layout of the apply pass (tpr lanes per row, <= 16 channels per lane); a thread walks many rows and keeps its 2 x cpl partial
+// sums in registers, the block folds them through shared memory once at the end.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+perturb_stats_all_kernel(const __grid_constant__ PBatch b) {
+    __shared__ float fold[2][8][256];              // [S | Q][warp][channel]: warp totals (c <= 256 on this path)
+    __shared__ float redz[8];
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_chan) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_chan, bx = rel % L.bps_chan, nbx = L.bps_chan, n = rel / L.bps_chan;
+    const int c = L.c, tpr = L.tpr, cpl = c / tpr, rpb = 256 / tpr;
+    const int lane = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+    const float* gb = L.g + (int64_t)n * L.rows * c;
+    float sacc[16], qacc[16], zacc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { sacc[j] = 0.f; qacc[j] = 0.f; }
+    for (int64_t r0 = (int64_t)bx * rpb; r0 < L.rows; r0 += (int64_t)nbx * rpb) {
+        const int64_t r = r0 + rl;
+        const bool live = r < L.rows;
+        float4 tg[4];
+        float q = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+            if (4 * k4 < cpl) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) { t = ldg_stream(reinterpret_cast<const float4*>(gb + r * c + lane * cpl) + k4); t.x *= b.gs; t.y *= b.gs; t.z *= b.gs; t.w *= b.gs; }
+                t.x *= t.x; t.y *= t.y; t.z *= t.z; t.w *= t.w;          // squares from here on
+                tg[k4] = t;
+                q += t.x + t.y + t.z + t.w;
+            }
+        for (int o = tpr >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);      // R_r: the row's sum of squares
+        const float inv = 1.f / (sqrtf(q) + kEps);                                           // 1 / nr_r
+        if (live && lane == 0) zacc = fmaf(q * inv, inv, zacc);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+            if (4 * k4 < cpl) {
+                sacc[4 * k4] += tg[k4].x; sacc[4 * k4 + 1] += tg[k4].y; sacc[4 * k4 + 2] += tg[k4].z; sacc[4 * k4 + 3] += tg[k4].w;
+                qacc[4 * k4] = fmaf(tg[k4].x, inv, qacc[4 * k4]); qacc[4 * k4 + 1] = fmaf(tg[k4].y, inv, qacc[4 * k4 + 1]);
+                qacc[4 * k4 + 2] = fmaf(tg[k4].z, inv, qacc[4 * k4 + 2]); qacc[4 * k4 + 3] = fmaf(tg[k4].w, inv, qacc[4 * k4 + 3]);
+            }
+    }
+    // fold over the block's row lanes: inside a warp the threads that own the same channel slice are tpr apart -> xor shuffles over
+    // the offsets >= tpr; the 8 warp totals meet in shared memory
+    (void)rl; (void)rpb;
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < cpl) {
+            float s1 = sacc[j], q1 = qacc[j];
+            for (int o = 16; o >= tpr; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+            if (wl < tpr) { fold[0][wid][lane * cpl + j] = s1; fold[1][wid][lane * cpl + j] = q1; }
+        }
+    float z = warp_sum(zacc);
+    if ((threadIdx.x & 31) == 0) redz[threadIdx.x >> 5] = z;
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += 256) {
+        double s1 = 0.0, q1 = 0.0;
+        for (int w = 0; w < 8; ++w) { s1 += (double)fold[0][w][ch]; q1 += (double)fold[1][w][ch]; }
+        atomicAdd(L.chan_sq + (int64_t)n * c + ch, s1);
+        if (MODE == CHAP_PERTURB_CHANNEL_SPATIAL) atomicAdd(L.chan_q + (int64_t)n * c + ch, q1);
+    }
+    if (threadIdx.x == 0 && (MODE == CHAP_PERTURB_SPATIAL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL)) {
+        double zz = 0.0;
+        for (int w = 0; w < 8; ++w) zz += (double)redz[w];
+        atomicAdd(L.row_z + n, zz);
+    }
+}
+
+// Apply pass of the two-pass scheme: every block first derives ||u||^2 of its sample from S, Q, Z (c <= 1024 channels: a block
+// reduction over at most 4 values per thread), then streams g and f once.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+perturb_apply_all_kernel(const __grid_constant__ PBatch b) {
+    __shared__ float inv_chan[1024];
+    __shared__ float red[8];
+    __shared__ double part[8];
+    __shared__ double samp_local;
+    int l = 0;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
+    const PLevel& L = b.lv[l];
+    const int rel = (int)blockIdx.x - L.blk0_rows, n = rel / L.bps_rows;
+    double acc = 0.0;
+    for (int ch = threadIdx.x; ch < L.c; ch += 256) {
+        const double S = L.chan_sq[(int64_t)n * L.c + ch];
+        const float ic = 1.f / (sqrtf((float)S) + kEps);
+        if (MODE == CHAP_PERTURB_SAMPLE) acc += S;
+        else if (MODE == CHAP_PERTURB_CHANNEL) acc += S * (double)ic * (double)ic;
+        else if (MODE == CHAP_PERTURB_CHANNEL_SPATIAL) acc += S * (double)ic * (double)ic + 2.0 * L.chan_q[(int64_t)n * L.c + ch] * (double)ic;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        if (MODE == CHAP_PERTURB_SPATIAL) t = L.row_z[n];
+        else if (MODE == CHAP_PERTURB_CHANNEL_SPATIAL) t = 0.25 * (t + L.row_z[n]);
+        samp_local = t;
+    }
+    __syncthreads();
+    perturb_rows_body<MODE, true>(L.g, L.f, L.out, L.rows, L.c, L.tpr, b.eps, b.gs, 0, L.chan_sq, &samp_local, 0, rel % L.bps_rows, L.bps_rows, n, inv_chan, red);
+}
+
+template <int MODE>
+static int run_two_pass(const PBatch& b, int blocks_stats, int blocks_rows, double alg_bytes, cudaStream_t st) {
+    KernelTimer timer("perturb_level", 0.0, alg_bytes, st);       // algorithmic: read g, read f, write out (all levels of the call)
+    perturb_stats_all_kernel<MODE><<<blocks_stats, 256, 0, st>>>(b);
+    CHAP_TRY(launched("perturb_stats_all_kernel"));
+    perturb_apply_all_kernel<MODE><<<blocks_rows, 256, 0, st>>>(b);
+    return launched("perturb_apply_all_kernel");
 }
 
 template <int MODE>
@@ -283,7 +434,7 @@ extern "C" int chap_l2n_sample_axpy_batched(const chap_level* levels, int32_t n_
 
 extern "C" size_t chap_perturb_workspace_elems(const chap_level* levels, int32_t n_levels, int32_t n) {
     size_t total = 0;
-    for (int l = 0; l < n_levels; ++l) total += (size_t)n * levels[l].c + (size_t)n;
+    for (int l = 0; l < n_levels; ++l) total += 2 * ((size_t)n * levels[l].c + (size_t)n);      // S, ||u||^2, Q, Z per level
     return total;
 }
 
@@ -300,6 +451,7 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
     double* ws = workspace;
     int blocks_chan = 0, blocks_rows = 0;
     double alg_bytes = 0.0;
+    bool two_pass_ok = true;
     // blocks per (level, sample): enough to fill the machine a few times over across ALL levels of the launch
     double total_elems = 0.0;
     for (int l = 0; l < n_levels; ++l) total_elems += (double)levels[l].rows * levels[l].c;
@@ -313,9 +465,12 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
         P.g = L.g; P.f = L.f; P.out = L.out; P.rows = L.rows; P.c = L.c;
         P.chan_sq = ws; ws += (size_t)n * L.c;
         P.samp_sq = ws; ws += n;
+        P.chan_q = ws; ws += (size_t)n * L.c;
+        P.row_z = ws; ws += n;
         int tpr = 1;                                   // lanes per row: keep <= 16 channels (4 float4) per lane
         while (tpr < 32 && L.c / tpr > 16 && (L.c / (tpr * 2)) % 4 == 0) tpr *= 2;
         P.tpr = tpr;
+        if (L.c / tpr > 16 || L.c > 256) two_pass_ok = false;            // the statistics pass keeps <= 16 channels per lane in registers
         const int share = (int)(block_budget * ((double)L.rows * L.c / total_elems) / n) + 1;      // this level's share of the grid, per sample
         const int rpb = 256 / tpr;
         int bps = (int)((L.rows + rpb * 4 - 1) / (rpb * 4));
@@ -329,6 +484,15 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
         P.blk0_rows = blocks_rows; P.blk0_chan = blocks_chan;
         blocks_rows += bps * n; blocks_chan += b1 * n;
         alg_bytes += 12.0 * (double)n * L.rows * L.c;
+    }
+    static const bool three_phase = getenv("CHAP_PERTURB_3PHASE") != nullptr;
+    if (two_pass_ok && !three_phase) {
+        switch (mode) {
+            case CHAP_PERTURB_SAMPLE: return run_two_pass<CHAP_PERTURB_SAMPLE>(b, blocks_chan, blocks_rows, alg_bytes, st);
+            case CHAP_PERTURB_CHANNEL: return run_two_pass<CHAP_PERTURB_CHANNEL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+            case CHAP_PERTURB_SPATIAL: return run_two_pass<CHAP_PERTURB_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+            default: return run_two_pass<CHAP_PERTURB_CHANNEL_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+        }
     }
     switch (mode) {
         case CHAP_PERTURB_SAMPLE: return run_all<CHAP_PERTURB_SAMPLE>(b, blocks_chan, blocks_rows, alg_bytes, st);
