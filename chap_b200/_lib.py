@@ -57,6 +57,8 @@ SIGNATURES = {
     "chap_timing_report": (I, [ctypes.c_char_p, c_size_t]),
     "chap_set_force_simt": (None, [I]),
     "chap_get_force_simt": (I, []),
+    "chap_set_pdl": (None, [I]),
+    "chap_get_pdl": (I, []),
     "chap_set_conv_precision": (None, [I]),
     "chap_get_conv_precision": (I, []),
     "chap_conv_packed_elems": (c_size_t, [_CD]),

@@ -49,6 +49,7 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 // resolved by a ballot instead of atomics, so the union phase only touches run boundaries.
 __global__ void __launch_bounds__(256)
 cc_init_kernel(const int64_t* __restrict__ seg, int* parent, int* size, unsigned long long* best, int W, int64_t total, int nbest) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t rounds = (total + stride - 1) / stride;
@@ -73,6 +74,7 @@ cc_init_kernel(const int64_t* __restrict__ seg, int* parent, int* size, unsigned
 //   * the diagonals only when up is a different class, and only from the end of the run that touches them.
 __global__ void __launch_bounds__(256)
 cc_unite_kernel(const int64_t* __restrict__ seg, int* parent, int nd, int D, int H, int W, int64_t total) {
+    pdl_enter();
     const int64_t vol = (int64_t)D * H * W;
     const int lane = threadIdx.x & 31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,6 +114,7 @@ cc_unite_kernel(const int64_t* __restrict__ seg, int* parent, int nd, int D, int
 
 __global__ void __launch_bounds__(256)
 cc_count_kernel(const int64_t* __restrict__ seg, int* parent, int* size, int64_t total) {
+    pdl_enter();
     // Warp-aggregated: the lanes of a warp that found the same root add their count with ONE atomic (a blob's voxels share one
     // root: per-voxel atomics on that single address serialised at ~1 ns each and dominated the 3D filter).
     const int lane = threadIdx.x & 31;
@@ -134,6 +137,7 @@ cc_count_kernel(const int64_t* __restrict__ seg, int* parent, int* size, int64_t
 __global__ void __launch_bounds__(256)
 cc_best_kernel(const int64_t* __restrict__ seg, const int* __restrict__ parent, const int* __restrict__ size,
                unsigned long long* best, int64_t vol, int n_classes, int64_t total) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = seg[i];
         if (c == 0 || parent[i] != (int)i) continue;               // roots only
@@ -145,6 +149,7 @@ cc_best_kernel(const int64_t* __restrict__ seg, const int* __restrict__ parent, 
 __global__ void __launch_bounds__(256)
 cc_write_kernel(const int64_t* __restrict__ seg, const int* __restrict__ parent, const unsigned long long* __restrict__ best,
                 int64_t vol, int n_classes, int64_t total, float* __restrict__ out) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = seg[i];
         float v = 0.f;
@@ -180,14 +185,14 @@ extern "C" int chap_largest_cc(const int64_t* seg, int32_t nd, int32_t n, int32_
     int* size = parent + total;
     cudaStream_t st = S(stream);
     const int grid = grid_for(total, 256 * 2);
-    cc_init_kernel<<<grid, 256, 0, st>>>(seg, parent, size, best, w, total, n * n_classes);
+    launch_k(cc_init_kernel, grid, 256, 0, st, seg, parent, size, best, w, total, n * n_classes);
     CHAP_TRY(launched("cc_init_kernel"));
-    cc_unite_kernel<<<grid, 256, 0, st>>>(seg, parent, nd, d, h, w, total);
+    launch_k(cc_unite_kernel, grid, 256, 0, st, seg, parent, nd, d, h, w, total);
     CHAP_TRY(launched("cc_unite_kernel"));
-    cc_count_kernel<<<grid, 256, 0, st>>>(seg, parent, size, total);
+    launch_k(cc_count_kernel, grid, 256, 0, st, seg, parent, size, total);
     CHAP_TRY(launched("cc_count_kernel"));
-    cc_best_kernel<<<grid, 256, 0, st>>>(seg, parent, size, best, vol, n_classes, total);
+    launch_k(cc_best_kernel, grid, 256, 0, st, seg, parent, size, best, vol, n_classes, total);
     CHAP_TRY(launched("cc_best_kernel"));
-    cc_write_kernel<<<grid, 256, 0, st>>>(seg, parent, best, vol, n_classes, total, out);
+    launch_k(cc_write_kernel, grid, 256, 0, st, seg, parent, best, vol, n_classes, total, out);
     return launched("cc_write_kernel");
 }

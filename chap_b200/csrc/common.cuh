@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <utility>
 #include "../../include/chap_b200.h"
 
 namespace chap {
@@ -12,6 +13,7 @@ namespace chap {
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_force_simt;
+extern std::atomic<int> g_pdl;            // 1: kernels are launched with programmatic stream serialization (see launch_k)
 extern std::atomic<int> g_precise_max_c;  // 3xTF32 split-operand convolutions for layers with max(K, N) <= this (0: plain TF32)
 
 inline int fail(int code, const char* fmt, ...) {
@@ -32,6 +34,46 @@ inline int launched(const char* what) {
     }
     return CHAP_OK;
 }
+
+// Programmatic dependent launch.  EVERY kernel of this library starts with pdl_enter() (or pdl_trigger() ... pdl_wait() around a
+// prologue that touches no global memory) and is launched through launch_k() with cudaLaunchAttributeProgrammaticStreamSerialization:
+//   griddepcontrol.launch_dependents  -- the NEXT kernel of the stream may be scheduled as soon as every CTA of this one has started
+//                                        (its CTAs become resident on whatever the tail of this kernel leaves free and run their prologue)
+//   griddepcontrol.wait               -- returns when the PREVIOUS kernel has completed and its memory is visible
+// Nothing reads or writes global memory before the wait, so the stream order semantics are unchanged (158 GPU tests pass either way).
+// MEASURED (tools/pdl_chain_bench.py, B200): a replayed CUDA graph already runs a dependent chain at 1.2-1.4 us per small kernel node;
+// the attribute changes that by -0.14 us (16 KB tensors) to +0.4 us (1 MB tensors, the early-resident CTAs get in the way), and the
+// whole 2D iteration by +0.2 ms (13.71 vs 13.49 ms).  griddepcontrol.wait waits for the COMPLETION of the previous grid, so only a
+// prologue can overlap, never the tails -- not worth it here.  Worse: the two instructions are NOT free in a kernel launched without
+// the attribute -- same box, same step, library built with and without them: 13.49 vs 13.26 ms (0.23 us for each of 980 kernels).
+// So the default build compiles them out (pdl_* are empty, the attribute is never set); `make -C chap_b200/csrc pdl` builds
+// lib/libchap_b200_pdl.so with them (-DCHAP_PDL_INSN), where CHAP_PDL=1 / chap_set_pdl(1) turn the attribute on.
+#ifdef __CUDACC__
+#ifndef CHAP_PDL_INSN          // default build: no griddepcontrol instructions at all (see above: their presence alone costs 0.23 ms per iteration)
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+template <typename... P, typename... A>
+inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+#ifdef CHAP_PDL_INSN
+    cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1u : 0u;
+#else
+    cfg.numAttrs = 0u;            // kernels without griddepcontrol.wait must never be launched with the attribute
+#endif
+    (void)cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);      // errors are picked up by launched()
+}
+#endif
 
 #define CHAP_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::chap::fail(code, __VA_ARGS__); } while (0)

@@ -171,6 +171,7 @@ static bool pair_wgrad_ok(const Geom& g) {
 
 __global__ void __launch_bounds__(256)
 pair_fold_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cout, int planes, int accumulate) {
+    pdl_enter();
     // dwp: torch layout [2 cout (p', co)][32 (p, ci)][planes (kz, ky)][3 (e + 1)]; dw: [cout][16 ci][planes][3 kx]
     const int total = cout * 16 * planes * 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -208,7 +209,7 @@ static int conv_wgrad_impl(const chap_conv_desc* d, const float* x, const float*
             handled = tc_wgrad(g2, x, dy, dwp, S(stream), nullptr, false);
             if (handled < 0) return handled;
             if (handled) {
-                pair_fold_kernel<<<(g.cout * 16 * g.taps + 255) / 256, 256, 0, S(stream)>>>(dwp, dw, g.cout, g.taps / 3, accumulate ? 1 : 0);
+                launch_k(pair_fold_kernel, (g.cout * 16 * g.taps + 255) / 256, 256, 0, S(stream), dwp, dw, g.cout, g.taps / 3, accumulate ? 1 : 0);
                 CHAP_TRY(launched("pair_fold_kernel"));
             }
         }

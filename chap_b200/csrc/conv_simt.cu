@@ -22,6 +22,7 @@ __device__ __forceinline__ void decode_row(int64_t m, int D, int H, int W, int& 
 // zero-padded to Kp x Np (tensor-core path of the 4- / 8-channel heads: the MMA needs K, N >= 16)
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ out,
                                     int taps, int K, int N, int Kp, int Np, int64_t sk, int64_t sn, int flip, int kn_order, int rt) {
+    pdl_enter();
     int64_t total = (int64_t)taps * Kp * Np;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int t = (int)(i / ((int64_t)Kp * Np));
@@ -43,6 +44,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 // All weights of a model in one launch (blockIdx.y = sub-item: one packed operand of one layer).  The trainer re-packs every
 // conv weight once per iteration (the optimiser just changed them): 72 launches of the single-layer kernel became 2 of this one.
 __global__ void pack_weights_batched_kernel(const __grid_constant__ PackBatch b) {
+    pdl_enter();
     const PackSub& s = b.sub[blockIdx.y];
     const int64_t total = (int64_t)s.taps * s.Kp * s.Np;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -64,7 +66,7 @@ __global__ void pack_weights_batched_kernel(const __grid_constant__ PackBatch b)
 
 int launch_pack_batch(const PackBatch& b, cudaStream_t st) {
     if (b.n <= 0) return CHAP_OK;
-    pack_weights_batched_kernel<<<dim3(24, (unsigned)b.n), 256, 0, st>>>(b);
+    launch_k(pack_weights_batched_kernel, dim3(24, (unsigned)b.n), 256, 0, st, b);
     return launched("pack_weights_batched_kernel");
 }
 
@@ -73,7 +75,7 @@ int launch_pack(const float* w, float* out, int taps, int K, int N, int64_t sk, 
     if (Kp < K) Kp = K;
     if (Np < N) Np = N;
     int64_t total = (int64_t)taps * Kp * Np;
-    pack_weights_kernel<<<grid_for(total, 256, 1024), 256, 0, st>>>(w, out, taps, K, N, Kp, Np, sk, sn, flip, kn_order,
+    launch_k(pack_weights_kernel, grid_for(total, 256, 1024), 256, 0, st, w, out, taps, K, N, Kp, Np, sk, sn, flip, kn_order,
                                                                     kn_order == 0 ? 1 : 0);   // kn_order 0 = tensor-core operand
     return launched("pack_weights_kernel");
 }
@@ -83,6 +85,7 @@ template <int CO_T, bool VEC4>
 __global__ void __launch_bounds__(128)
 conv_gather_kernel(SimtOp op, int all_w, const float* __restrict__ in, const float* __restrict__ wp,
                    const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_enter();
     extern __shared__ float ws_all[];              // [K][CO_T] per tap, or [taps][K][CO_T] when everything fits (all_w)
     const int n0 = blockIdx.y * CO_T;
     const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -165,6 +168,7 @@ template <int CO_T, bool VEC4>
 __global__ void __launch_bounds__(128)
 conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, const float* __restrict__ wp,
                 const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_enter();
     extern __shared__ float ws[];                  // [K][CO_T]
     const int t = blockIdx.x / blocks_per_tap;
     const int n0 = blockIdx.y * CO_T;
@@ -216,6 +220,7 @@ conv_up2_kernel(SimtOp op, int blocks_per_tap, const float* __restrict__ in, con
 template <int PX>
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(SimtOp op, const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float ws[27 * 16];
     for (int i = threadIdx.x; i < op.taps * 16; i += 128) ws[i] = wp[i];            // packed [tap][K = 1][N = 16]
     __syncthreads();
@@ -278,7 +283,7 @@ int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* b
     if (!op.up2 && op.K == 1 && op.N == 16 && op.ksz == 3 && op.stride == 1 && op.pad == 1 && aligned16(out)) {
         constexpr int PX = 4;
         const int64_t threads = op.out_rows / op.oW * ((op.oW + PX - 1) / PX);
-        stem_conv_kernel<PX><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(op, in, wp, bias, out);
+        launch_k(stem_conv_kernel<PX>, (unsigned)((threads + 127) / 128), 128, 0, st, op, in, wp, bias, out);
         return launched("stem_conv_kernel");
     }
     const bool vec4 = (op.K % 4 == 0) && aligned16(in);
@@ -290,11 +295,11 @@ int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* b
         int bpt = (int)((op.in_rows + 127) / 128);
         dim3 grid((unsigned)(bpt * op.taps), (unsigned)((op.N + co_t - 1) / co_t));
         if (small) {
-            if (vec4) conv_up2_kernel<4, true><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
-            else conv_up2_kernel<4, false><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+            if (vec4) launch_k(conv_up2_kernel<4, true>, grid, block, smem, st, op, bpt, in, wp, bias, out);
+            else launch_k(conv_up2_kernel<4, false>, grid, block, smem, st, op, bpt, in, wp, bias, out);
         } else {
-            if (vec4) conv_up2_kernel<16, true><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
-            else conv_up2_kernel<16, false><<<grid, block, smem, st>>>(op, bpt, in, wp, bias, out);
+            if (vec4) launch_k(conv_up2_kernel<16, true>, grid, block, smem, st, op, bpt, in, wp, bias, out);
+            else launch_k(conv_up2_kernel<16, false>, grid, block, smem, st, op, bpt, in, wp, bias, out);
         }
         return launched("conv_up2_kernel");
     }
@@ -302,11 +307,11 @@ int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* b
     const int all_w = (size_t)op.taps * smem <= 40 * 1024 ? 1 : 0;      // all taps' weights resident: no per-tap barrier
     const size_t gsmem = all_w ? (size_t)op.taps * smem : smem;
     if (small) {
-        if (vec4) conv_gather_kernel<4, true><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
-        else conv_gather_kernel<4, false><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
+        if (vec4) launch_k(conv_gather_kernel<4, true>, grid, block, gsmem, st, op, all_w, in, wp, bias, out);
+        else launch_k(conv_gather_kernel<4, false>, grid, block, gsmem, st, op, all_w, in, wp, bias, out);
     } else {
-        if (vec4) conv_gather_kernel<16, true><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
-        else conv_gather_kernel<16, false><<<grid, block, gsmem, st>>>(op, all_w, in, wp, bias, out);
+        if (vec4) launch_k(conv_gather_kernel<16, true>, grid, block, gsmem, st, op, all_w, in, wp, bias, out);
+        else launch_k(conv_gather_kernel<16, false>, grid, block, gsmem, st, op, all_w, in, wp, bias, out);
     }
     return launched("conv_gather_kernel");
 }
@@ -318,6 +323,7 @@ int simt_conv(const SimtOp& op, const float* in, const float* wp, const float* b
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(SimtOp op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dw,
                   int64_t sk, int64_t sn, int64_t rows_per_split) {
+    pdl_enter();
     __shared__ float As[64][16];
     __shared__ float Bs[64][16];
     __shared__ int64_t rowA[64], rowB[64];
@@ -381,6 +387,7 @@ conv_wgrad_kernel(SimtOp op, const float* __restrict__ a, const float* __restric
 template <int KC, int NC>
 __global__ void __launch_bounds__(128)
 thin_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t sk, int64_t sn) {
+    pdl_enter();
     constexpr int NA = 9 * KC * NC;
     __shared__ float red[NA];
     const int kz = blockIdx.y;
@@ -448,6 +455,7 @@ thin_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restric
 template <int K, int N>
 __global__ void __launch_bounds__(256)
 k1_head_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t rows, int64_t sk, int64_t sn) {
+    pdl_enter();
     float acc[N][K];
 #pragma unroll
     for (int c = 0; c < N; ++c)
@@ -492,8 +500,8 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
         KernelTimer timer(timer_name("conv_thin_wgrad", op.taps, op.K, op.N, op.oW, op.oH, op.oD, op.out_rows), 2.0 * (double)op.out_rows * op.K * op.N,
                           4.0 * ((double)op.in_rows * op.K + (double)op.out_rows * op.N), st);
         const int grid = grid_for(op.out_rows, 256 * 8, kNumSMs * 4);
-        if (op.N == 2) k1_head_wgrad_kernel<16, 2><<<grid, 256, 0, st>>>(a, b, dw, op.out_rows, sk, sn);
-        else k1_head_wgrad_kernel<16, 4><<<grid, 256, 0, st>>>(a, b, dw, op.out_rows, sk, sn);
+        if (op.N == 2) launch_k(k1_head_wgrad_kernel<16, 2>, grid, 256, 0, st, a, b, dw, op.out_rows, sk, sn);
+        else launch_k(k1_head_wgrad_kernel<16, 4>, grid, 256, 0, st, a, b, dw, op.out_rows, sk, sn);
         return launched("k1_head_wgrad_kernel");
     }
     const bool stem = op.K == 1 && op.N % 16 == 0;
@@ -507,8 +515,8 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
         const int cap = (kNumSMs * 6) / (planes * zdim);
         if (slices > cap) slices = cap < 1 ? 1 : cap;
         dim3 grid((unsigned)slices, (unsigned)planes, (unsigned)zdim);
-        if (stem) thin_wgrad_kernel<1, 16><<<grid, 128, 0, st>>>(op, a, b, dw, sk, sn);
-        else thin_wgrad_kernel<4, 4><<<grid, 128, 0, st>>>(op, a, b, dw, sk, sn);
+        if (stem) launch_k(thin_wgrad_kernel<1, 16>, grid, 128, 0, st, op, a, b, dw, sk, sn);
+        else launch_k(thin_wgrad_kernel<4, 4>, grid, 128, 0, st, op, a, b, dw, sk, sn);
         return launched("thin_wgrad_kernel");
     }
     const int64_t rows = op.up2 ? op.in_rows : op.out_rows;
@@ -522,7 +530,7 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
     int64_t rps = ((rows + splits - 1) / splits + 63) / 64 * 64;
     splits = (rows + rps - 1) / rps;
     dim3 grid((unsigned)tiles, (unsigned)op.taps, (unsigned)splits);
-    conv_wgrad_kernel<<<grid, 256, 0, st>>>(op, a, b, dw, sk, sn, rps);
+    launch_k(conv_wgrad_kernel, grid, 256, 0, st, op, a, b, dw, sk, sn, rps);
     return launched("conv_wgrad_kernel");
 }
 

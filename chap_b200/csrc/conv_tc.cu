@@ -41,7 +41,7 @@ struct TcParams {
     int kc, kchunks;              // channels per k chunk (32 or 16), chunks per tap
     int n_total, nt;              // output channels, channels per CTA
     int stages, tmem_cols;
-    int n_buf;                    // TMEM accumulators (2: the epilogue of tile j overlaps the MMAs of tile j + 1)
+    int n_buf, n_buf_lg;          // TMEM accumulators (1, 2 or 4: the epilogue of tile j overlaps the MMAs of tiles j + 1 ..) and log2 of it
     int reuse;                    // 1: one h-haloed A box per (kz, kx) serves the three ky taps (row-offset descriptors)
     int n_real;                   // output channels that exist (< nt = 16 for the zero-padded 4- / 8-channel heads)
     int mode;                     // 0: stride-1 conv; 1: k2 s2 scatter (transposed conv forward, strided conv data gradient): one GEMM over
@@ -101,18 +101,33 @@ __device__ long long g_tc_trace[8];
 // (the epilogue is one latency-bound instruction stream per warp, so instruction count is what matters).  Lane l sums
 // column l % 16 over rows 16 * (l / 16) ..; the two halves meet in one shuffle and lanes 0..15 add into dst (one owner
 // per column and warp: no race).
+// The scratch is addressed through explicit shared-space instructions: behind the generic `red` pointer the compiler emitted generic
+// LD.E / ST.E (ncu source view of round 2: 42 % of the epilogue warps' samples sat on this function, mostly on those loads).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ void warp_column_sums(const float (&v)[16], const bool valid, const int lane, float* scratch,
                                                  float* dst_s, float* dst_q) {
+    const uint32_t sc = smem_u32(scratch);
+    const uint32_t wr = sc + (uint32_t)(lane * 17) * 4u;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) scratch[lane * 17 + j] = valid ? v[j] : 0.f;
+    for (int j = 0; j < 16; ++j) sts_f32(wr + 4u * j, valid ? v[j] : 0.f);
     __syncwarp();
     const int col = lane & 15, r0 = (lane >> 4) * 16;
-    float s = 0.f, q = 0.f;
+    const uint32_t rd = sc + (uint32_t)(r0 * 17 + col) * 4u;
+    float x[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) { const float x = scratch[(r0 + r) * 17 + col]; s += x; q = fmaf(x, x, q); }
+    for (int r = 0; r < 16; ++r) x[r] = lds_f32(rd + (uint32_t)(r * 17) * 4u);
+    // two independent chains per statistic instead of one 16-deep dependent chain
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; r += 2) { s0 += x[r]; q0 = fmaf(x[r], x[r], q0); s1 += x[r + 1]; q1 = fmaf(x[r + 1], x[r + 1], q1); }
+    float s = s0 + s1, q = q0 + q1;
     s += __shfl_xor_sync(0xffffffffu, s, 16);
     q += __shfl_xor_sync(0xffffffffu, q, 16);
-    if (lane < 16) { dst_s[col] += s; dst_q[col] += q; }
+    if (lane < 16) {
+        const uint32_t ds = smem_u32(dst_s + col), dq = smem_u32(dst_q + col);
+        sts_f32(ds, lds_f32(ds) + s); sts_f32(dq, lds_f32(dq) + q);
+    }
     __syncwarp();
 }
 
@@ -210,8 +225,8 @@ __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_ba
         return;
     }
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
-        const int buf = j & 1;
-        mbar_wait(&tmem_empty[buf], (uint32_t)((j >> 1) & 1) ^ 1u);          // the epilogue has drained this accumulator
+        const int buf = j & (p.n_buf - 1);
+        mbar_wait(&tmem_empty[buf], (uint32_t)((j >> p.n_buf_lg) & 1) ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
 #pragma unroll
@@ -262,8 +277,8 @@ __device__ __forceinline__ void issue_mmas(const TcParams& p, uint8_t* a_base, u
     uint32_t a_lo = a_lo0, b_lo_s = b_lo0;
     int j = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++j) {
-        const int buf = p.n_buf == 2 ? (j & 1) : 0;
-        const uint32_t use = p.n_buf == 2 ? (uint32_t)(j >> 1) : (uint32_t)j;
+        const int buf = j & (p.n_buf - 1);
+        const uint32_t use = (uint32_t)(j >> p.n_buf_lg);
         TC_WAIT(&tmem_empty[buf], (use & 1u) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
@@ -317,9 +332,9 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)dup * (p.b_resident ? (size_t)p.b_area_bytes : (size_t)p.stages * p.b_stage_bytes));
     uint64_t* full = bars;                              // TMA bytes of a ring slot have landed
     uint64_t* empty = bars + p.stages;
-    uint64_t* tmem_full = bars + 2 * p.stages;          // [2]
-    uint64_t* tmem_empty = tmem_full + 2;               // [2]
-    uint64_t* b_full = tmem_empty + 2;
+    uint64_t* tmem_full = bars + 2 * p.stages;          // [4]
+    uint64_t* tmem_empty = tmem_full + 4;               // [4]
+    uint64_t* b_full = tmem_empty + 4;
     uint64_t* split = b_full + 1;                       // [stages] precise: the slot's A data has been split into hi / lo
     uint64_t* ready = PRECISE ? split : full;           // what the MMA warp waits for
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split + (PRECISE ? p.stages : 0));
@@ -328,12 +343,13 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * p.nt;
     if (threadIdx.x == 0) TC_TRACE(0);
+    pdl_trigger();          // the prologue below (barriers, TMEM, statistics scratch) touches no global memory: it overlaps the previous kernel's tail
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); if (PRECISE) mbar_init(&split[s], 4); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.epi_groups == 2 && p.colsplit) ? 8 : 4); }
+        for (int b = 0; b < 4; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], (p.epi_groups == 2 && p.colsplit) ? 8 : 4); }
         mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -348,6 +364,7 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();             // the previous kernel has completed: activations, weights, statistics slots may be touched from here on
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TC_TRACE(1);
     // reuse mode: one stage = (kz, kx, k-chunk) and covers 3 taps (ky = 0..2)
@@ -506,8 +523,8 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
              ti.tile < p.tiles_total; ti.next(p.tiles_w, p.tiles_h, p.tiles_d), jj0 += (sup || alternate) ? 2 : 1)
         for (int sb = sub_lo; sb < sub_hi; ++sb) {
             const int jj = jj0 + ((sup && !alternate) ? sb : 0);
-            const int buf = p.n_buf == 2 ? (jj & 1) : 0;
-            const uint32_t use = p.n_buf == 2 ? (uint32_t)(jj >> 1) : (uint32_t)jj;
+            const int buf = jj & (p.n_buf - 1);
+            const uint32_t use = (uint32_t)(jj >> p.n_buf_lg);
             const int ow = ti.tx * p.tw + dx, oh = (sup ? 2 * ti.ty + sb : ti.ty) * p.th + dy, od = ti.tz * p.td + dz;
             const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
             const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
@@ -826,7 +843,12 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         while (p.nt >= 64 && p.nt % 32 == 0 && (long)p.tiles_total * (N / p.nt) < fill && !nt_force) p.nt /= 2;
         if (nt_force >= 16 && nt_force % 16 == 0 && N % nt_force == 0 && nt_force <= p.nt) p.nt = nt_force;
     }
-    p.n_buf = p.nt <= 128 ? 2 : 1;                                       // two accumulators while 2 CTAs/SM still fit in 512 columns
+    // Accumulators: two while 2 CTAs/SM still fit in 512 columns; FOUR for nt <= 64 -- the ncu source view of the thin layers shows the
+    // MMA warp waiting 14 % of its time for an accumulator (the two epilogue groups are ~75 % busy, so their jitter reaches it)
+    static const int nbuf_force = getenv("CHAP_TC_NBUF") ? atoi(getenv("CHAP_TC_NBUF")) : 0;
+    p.n_buf = p.nt <= 64 ? 4 : (p.nt <= 128 ? 2 : 1);
+    if ((nbuf_force == 1 || nbuf_force == 2 || nbuf_force == 4) && nbuf_force * p.nt <= 256) p.n_buf = nbuf_force;
+    p.n_buf_lg = p.n_buf == 4 ? 2 : (p.n_buf == 2 ? 1 : 0);
     p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
     p.b_area_bytes = (uint32_t)p.taps * p.kchunks * p.b_box_bytes;
@@ -840,9 +862,10 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     // 2x112x112x80 173 vs 150 us (4 ring stages of 20 KB instead of 6 of 13 KB).  Halving the TMA issues and ring round trips per tile
     // does not move these kernels, nor do polling mbarrier waits (-DCHAP_MBAR_POLL: 44.9 vs 43.2 us) -- so neither the TMA issue rate
     // nor barrier wake-up latency is what bounds the thin layers.  Opt-in (CHAP_TC_SUPER=1) experiment, off by default.
-    p.sup = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.b_resident && p.n_buf == 2 && p.H >= 2 * p.th + 2 && TC_DBG_HOST_OFF &&
+    p.sup = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.b_resident && p.n_buf >= 2 && p.H >= 2 * p.th + 2 && TC_DBG_HOST_OFF &&
              getenv("CHAP_TC_NO_THIN2D") == nullptr && getenv("CHAP_TC_SUPER") != nullptr) ? 1 : 0;
     if (p.sup) {
+        p.n_buf = 2; p.n_buf_lg = 1;                                     // a super tile IS the pair of accumulators
         p.tiles_h = (p.tiles_h + 1) / 2;                                 // rows of super tiles (an odd last row gets a phantom second tile: all rows masked)
         p.tiles_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
     }
@@ -898,11 +921,11 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     const long stage_uses = (long)iters * ((p.tiles_total + grid_x - 1) / grid_x);     // ring slots one CTA ever fills
     const int stage_cap = getenv("CHAP_TC_STAGES") ? atoi(getenv("CHAP_TC_STAGES")) : 6;
     if (stages > stage_cap) stages = stage_cap;
-    if (stages > (p.precise ? 8 : 12)) stages = p.precise ? 8 : 12;          // barrier block: 3 (2) barriers per stage + 5 in 256 bytes
+    if (stages > (p.precise ? 7 : 10)) stages = p.precise ? 7 : 10;          // barrier block: 3 (2) barriers per stage + 9 in 256 bytes
     if (stages > stage_uses) stages = (int)stage_uses;
     if (stages < 2) stages = stage_uses < 2 ? 1 : 2;
     // lean issue / producer loops for the thin row-reuse layers (see issue_mmas_thin)
-    p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf == 2 && stages >= 2 &&
+    p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf >= 2 && stages >= 2 &&
                 TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
     CHAP_REQUIRE(!p.sup || p.thin2d, CHAP_ERR_BAD_ARG, "tc_conv: super tiles need the thin-layer loops (stages %d, cps %d)", stages, p.cps);
     p.stages = stages;
@@ -914,7 +937,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     CHAP_REQUIRE(!out_b || (ca > 0 && ca < N && ca % 16 == 0 && (N - ca) % 16 == 0 && aligned16(out_b)), CHAP_ERR_BAD_ARG,
                  "tc_conv: split output needs 16-channel aligned parts (ca %d of %d)", ca, N);
     const size_t smem = (size_t)stages * stage + fixed + extras;
-    static_assert(2 * 12 + 5 <= 256 / 8 - 2 && 3 * 8 + 5 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
+    static_assert(2 * 10 + 9 <= 256 / 8 - 2 && 3 * 7 + 9 <= 256 / 8 - 2, "barrier block fits the 256-byte slot");
 
     // tensor maps: activations [C, W, H, (D,) N] (channels-last), weights [K, taps * N]
     CUtensorMap tmA, tmB;
@@ -993,8 +1016,8 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     dim3 grid((unsigned)grid_x, (unsigned)(N / p.nt));
     const unsigned threads = 64 + 128 * p.epi_groups + (p.precise ? 128 : 0);
     const bool ev = epi != nullptr;
-#define CHAP_TC_LAUNCH(PR, EV) do { if (p.mode == 3) conv_tc_k_taps<PR, EV><<<grid, threads, smem, st>>>(tmA, tmB, tmT, p); \
-                                    else conv_tc_k<PR, EV><<<grid, threads, smem, st>>>(tmA, tmB, p); } while (0)
+#define CHAP_TC_LAUNCH(PR, EV) do { if (p.mode == 3) launch_k(conv_tc_k_taps<PR, EV>, grid, threads, smem, st, tmA, tmB, tmT, p); \
+                                    else launch_k(conv_tc_k<PR, EV>, grid, threads, smem, st, tmA, tmB, p); } while (0)
     if (p.precise) { if (ev) CHAP_TC_LAUNCH(true, true); else CHAP_TC_LAUNCH(true, false); }
     else           { if (ev) CHAP_TC_LAUNCH(false, true); else CHAP_TC_LAUNCH(false, false); }
 #undef CHAP_TC_LAUNCH

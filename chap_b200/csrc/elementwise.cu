@@ -45,6 +45,7 @@ __device__ __forceinline__ void channel_reduce(int64_t rows, int c, double* sums
 
 template <int VEC>
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ y, int64_t rows, int c, double* sums) {
+    pdl_enter();
     channel_reduce<VEC>(rows, c, sums, [&](int64_t r, int g, float* s, float* q) {
         if (VEC == 4) {
             float4 v = ldg_stream(reinterpret_cast<const float4*>(y + r * c) + g);
@@ -69,18 +70,19 @@ int channel_stats(const float* y, int64_t rows, int c, double* sums, cudaStream_
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "channel_stats: too many channels (%d)", c);
     const int rpb = 256 / cg;
     int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
-    if (v4 && 256 % cg == 0) channel_stats_fixed_kernel<<<grid_for(rows * cg, 256 * kEwUnroll * 2, kNumSMs * 8), 256, 0, st>>>(y, rows * cg, c, sums);
-    else if (v4) channel_stats_kernel<4><<<grid, 256, 0, st>>>(y, rows, c, sums);
-    else channel_stats_kernel<1><<<grid, 256, 0, st>>>(y, rows, c, sums);
+    if (v4 && 256 % cg == 0) launch_k(channel_stats_fixed_kernel, grid_for(rows * cg, 256 * kEwUnroll * 2, kNumSMs * 8), 256, 0, st, y, rows * cg, c, sums);
+    else if (v4) launch_k(channel_stats_kernel<4>, grid, 256, 0, st, y, rows, c, sums);
+    else launch_k(channel_stats_kernel<1>, grid, 256, 0, st, y, rows, c, sums);
     return launched("channel_stats_kernel");
 }
 
 __global__ void sums_to_float_kernel(const double* sums, float* out, int c, int accumulate) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c) out[i] = accumulate ? out[i] + (float)sums[i] : (float)sums[i];
 }
 int sums_to_float(const double* sums, float* out, int c, cudaStream_t st, bool accumulate) {
-    sums_to_float_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, out, c, accumulate ? 1 : 0);
+    launch_k(sums_to_float_kernel, (c + 127) / 128, 128, 0, st, sums, out, c, accumulate ? 1 : 0);
     return launched("sums_to_float_kernel");
 }
 
@@ -88,6 +90,7 @@ int sums_to_float(const double* sums, float* out, int c, cudaStream_t st, bool a
 __global__ void bn_finalize_kernel(const double* sums, int slots, int64_t count, const float* gamma, const float* beta,
                                    float eps, float momentum, float* rmean, float* rvar, int64_t* nbt,
                                    float* mean_invstd, float* scale_shift, int c) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && nbt) *nbt += 1;
     if (i >= c) return;
@@ -109,6 +112,7 @@ __global__ void bn_finalize_kernel(const double* sums, int slots, int64_t count,
 
 __global__ void bn_eval_params_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar,
                                       float eps, float* mean_invstd, float* scale_shift, int c) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     float invstd = 1.f / sqrtf(rvar[i] + eps);
@@ -124,6 +128,7 @@ bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ ss, flo
                   const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
                   const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec,
                   int rt, float* __restrict__ out) {
+    pdl_enter();
     const int cg = c / VEC;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % cg);
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
                          const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
                          const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t rows, int c, double* sums) {
+    pdl_enter();
     channel_reduce<VEC>(rows, c, sums, [&](int64_t r, int g, float* s, float* q) {
         const int64_t n = r / rows_per_sample;
 #pragma unroll
@@ -190,6 +196,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         int64_t rows_per_sample, int c, int64_t total_vec, int train, int rt, double inv_count,
                         const double* __restrict__ sums, float* __restrict__ dy,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_enter();
     const int cg = c / VEC;
     const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
     train &= 1;
@@ -256,6 +263,7 @@ bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ s
                         const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
                         const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec, int reverse,
                         float* __restrict__ out) {
+    pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g);
     const int64_t per_sample = rows_per_sample * cg;
@@ -326,6 +334,7 @@ __device__ __forceinline__ void channel_reduce_finish(float4 s, float4 q, int c,
 
 __global__ void __launch_bounds__(256)
 channel_stats_fixed_kernel(const float* __restrict__ y, int64_t total_vec, int c, double* sums) {
+    pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
     const int64_t stride = (int64_t)gridDim.x * 256;
     const float4* y4 = reinterpret_cast<const float4*>(y);
@@ -351,6 +360,7 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_fixed_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
                                const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
                                const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t total_vec, int c, double* sums) {
+    pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g), mean = ld4(mi + 4 * g), istd = ld4(mi + c + 4 * g);
     const int64_t per_sample = rows_per_sample * cg;
@@ -393,6 +403,7 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
                               const float* __restrict__ drop_el, int64_t rows_per_sample, int c, int64_t total_vec, int train,
                               double inv_count, double* __restrict__ sums, float* __restrict__ dy,
                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
     const int train_bits = train;
     const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
@@ -470,6 +481,7 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
 template <int VEC>
 __global__ void __launch_bounds__(256)
 maxpool2_fwd_kernel(const float* __restrict__ x, int h, int w, int c, int64_t total_vec, float* __restrict__ y) {
+    pdl_enter();
     const int cg = c / VEC, oh = h / 2, ow = w / 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -487,6 +499,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int h, int w, int c,
                     int64_t total_vec, float* __restrict__ dx) {
+    pdl_enter();
     const int cg = c / VEC, oh = h / 2, ow = w / 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -518,6 +531,7 @@ __device__ __forceinline__ void lerp_src(int o, int in, int out, int& i0, int& i
 template <int VEC>
 __global__ void __launch_bounds__(256)
 upsample2x_fwd_kernel(const float* __restrict__ x, int d, int h, int w, int c, int nd, int64_t total_vec, int rt, float* __restrict__ y) {
+    pdl_enter();
     const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -563,6 +577,7 @@ __device__ __forceinline__ int contrib(int i, int in, int out, int* oi, float* w
 template <int VEC>
 __global__ void __launch_bounds__(256)
 upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, int nd, int64_t total_vec, int rt, float* __restrict__ dx) {
+    pdl_enter();
     const int cg = c / VEC, od = nd == 3 ? 2 * d : 1, oh = 2 * h, ow = 2 * w;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         int g = (int)(i % cg); int64_t r = i / cg;
@@ -595,6 +610,7 @@ upsample2x_bwd_kernel(const float* __restrict__ dy, int d, int h, int w, int c, 
 // ------------------------------------------------------------------ concat / split / misc
 __global__ void __launch_bounds__(256)
 concat_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int ca, int cb, float* __restrict__ out) {
+    pdl_enter();
     const int ct = ca + cb;
     const int64_t total = rows * ct;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -604,6 +620,7 @@ concat_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t 
 }
 __global__ void __launch_bounds__(256)
 concat4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t rows, int ca4, int cb4, float4* __restrict__ out) {
+    pdl_enter();
     const int ct = ca4 + cb4;
     const int64_t total = rows * ct;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -613,6 +630,7 @@ concat4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64
 }
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ in, int64_t rows, int ca, int cb, float* __restrict__ a, float* __restrict__ b) {
+    pdl_enter();
     const int ct = ca + cb;
     const int64_t total = rows * ct;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -623,6 +641,7 @@ split_kernel(const float* __restrict__ in, int64_t rows, int ca, int cb, float* 
 }
 __global__ void __launch_bounds__(256)
 channel_scale_kernel(const float* __restrict__ x, const float* __restrict__ s, int64_t rows_per_sample, int c, int64_t total, float* __restrict__ out) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int ch = (int)(i % c); int64_t n = i / (rows_per_sample * c);
         out[i] = x[i] * s[n * c + ch];
@@ -635,6 +654,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 feature_dropout_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ m1, const float* __restrict__ m2,
                            int n, int nu, int64_t rps, int c, float* __restrict__ out1, float* __restrict__ out2) {
+    pdl_enter();
     const int cv = c / VEC;
     const int64_t per_sample = rps * cv, total = (int64_t)n * per_sample;
     const int nl = n - nu;
@@ -669,6 +689,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 feature_dropout_bwd_kernel(const float* __restrict__ d1, const float* __restrict__ d2, const float* __restrict__ m1, const float* __restrict__ m2,
                            int n, int nu, int64_t rps, int c, float* __restrict__ dfeat) {
+    pdl_enter();
     const int cv = c / VEC;
     const int64_t per_sample = rps * cv, total = (int64_t)n * per_sample;
     const int nl = n - nu;
@@ -699,12 +720,14 @@ feature_dropout_bwd_kernel(const float* __restrict__ d1, const float* __restrict
 
 __global__ void __launch_bounds__(256)
 axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, int64_t total, float* __restrict__ out) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = fmaf(alpha, b[i], a[i]);
 }
 __global__ void __launch_bounds__(256)
 mask_mix_kernel(const float* __restrict__ a, const float* __restrict__ b, const int64_t* __restrict__ m,
                 int64_t rows_per_sample, int c, int64_t total, float* __restrict__ out) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = (i / c) % rows_per_sample;
         float mm = (float)m[r];
@@ -725,7 +748,7 @@ extern "C" int chap_bn_finalize(const double* sums, int32_t slots, int64_t count
                                 float* mean_invstd, float* scale_shift, int32_t c, void* stream) {
     CHAP_REQUIRE(sums && gamma && beta && mean_invstd && scale_shift && c > 0 && count > 0 && slots >= 1, CHAP_ERR_BAD_ARG, "bn_finalize: bad argument");
     CHAP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CHAP_ERR_BAD_ARG, "bn_finalize: running stats must both be set or both NULL");
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(sums, slots, count, gamma, beta, eps, momentum, running_mean,
+    launch_k(bn_finalize_kernel, (c + 127) / 128, 128, 0, S(stream), sums, slots, count, gamma, beta, eps, momentum, running_mean,
                                                                running_var, running_mean ? nbt : nullptr, mean_invstd, scale_shift, c);
     return launched("bn_finalize_kernel");
 }
@@ -733,7 +756,7 @@ extern "C" int chap_bn_finalize(const double* sums, int32_t slots, int64_t count
 extern "C" int chap_bn_eval_params(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                    float* mean_invstd, float* scale_shift, int32_t c, void* stream) {
     CHAP_REQUIRE(gamma && beta && rm && rv && mean_invstd && scale_shift && c > 0, CHAP_ERR_BAD_ARG, "bn_eval_params: bad argument");
-    bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, S(stream)>>>(gamma, beta, rm, rv, eps, mean_invstd, scale_shift, c);
+    launch_k(bn_eval_params_kernel, (c + 127) / 128, 128, 0, S(stream), gamma, beta, rm, rv, eps, mean_invstd, scale_shift, c);
     return launched("bn_eval_params_kernel");
 }
 
@@ -750,14 +773,14 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     if (c % 4 == 0 && 256 % (c / 4) == 0 && all16({y, drop_el, residual, out, ss, drop_nc}) && round_tf32_on() == 0) {
         const int grid = grid_for(total / 4, 256 * kEwUnroll);
         static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
-#define CHAP_FWD_FIXED(EL, RES) bn_act_fwd_fixed_kernel<EL, RES><<<grid, 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, rev & 1, out)
+#define CHAP_FWD_FIXED(EL, RES) launch_k(bn_act_fwd_fixed_kernel<EL, RES>, grid, 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, rev & 1, out)
         if (drop_el) { if (residual) CHAP_FWD_FIXED(true, true); else CHAP_FWD_FIXED(true, false); }
         else         { if (residual) CHAP_FWD_FIXED(false, true); else CHAP_FWD_FIXED(false, false); }
 #undef CHAP_FWD_FIXED
     } else if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
-        bn_act_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, round_tf32_on(), out);
+        launch_k(bn_act_fwd_kernel<4>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, round_tf32_on(), out);
     } else {
-        bn_act_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(y, ss, slope, drop_nc, drop_el, residual, rps, c, total, round_tf32_on(), out);
+        launch_k(bn_act_fwd_kernel<1>, grid_for(total, 256 * 4), 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total, round_tf32_on(), out);
     }
     return launched("bn_act_fwd_kernel");
 }
@@ -802,24 +825,24 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
     if (fixed) {
         if ((train & 1) || dgamma) {
             const int rgrid = grid_for(total / 4, 256 * kEwUnroll * 2, kNumSMs * 8);
-            if (drop_el) bn_act_bwd_reduce_fixed_kernel<true><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
-            else bn_act_bwd_reduce_fixed_kernel<false><<<rgrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
+            if (drop_el) launch_k(bn_act_bwd_reduce_fixed_kernel<true>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
+            else launch_k(bn_act_bwd_reduce_fixed_kernel<false>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
             CHAP_TRY(launched("bn_act_bwd_reduce_fixed_kernel"));
         }
         const int agrid = grid_for(total / 4, 256 * kEwUnroll);
         static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
         const int tb = train | ((rev & 2) ? 8 : 0);
-        if (drop_el) bn_act_bwd_apply_fixed_kernel<true><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
-        else bn_act_bwd_apply_fixed_kernel<false><<<agrid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
+        if (drop_el) launch_k(bn_act_bwd_apply_fixed_kernel<true>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
+        else launch_k(bn_act_bwd_apply_fixed_kernel<false>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
         return launched("bn_act_bwd_apply_fixed_kernel");
     }
     const int rpb = 256 / cg;
     int grid = grid_for(rows, rpb * 8, kNumSMs * 8);
-    if (v4) bn_act_bwd_reduce_kernel<4><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
-    else bn_act_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
+    if (v4) launch_k(bn_act_bwd_reduce_kernel<4>, grid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
+    else launch_k(bn_act_bwd_reduce_kernel<1>, grid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, rows, c, sums);
     CHAP_TRY(launched("bn_act_bwd_reduce_kernel"));
-    if (v4) bn_act_bwd_apply_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
-    else bn_act_bwd_apply_kernel<1><<<grid_for(total, 256 * 4), 256, 0, st>>>(dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
+    if (v4) launch_k(bn_act_bwd_apply_kernel<4>, grid_for(total / 4, 256 * 4), 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
+    else launch_k(bn_act_bwd_apply_kernel<1>, grid_for(total, 256 * 4), 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total, train, round_tf32_on(), inv_count, sums, dy, dgamma, dbeta);
     CHAP_TRY(launched("bn_act_bwd_apply_kernel"));
     if (persist) CHAP_TRY(zero_async(sums, (size_t)2 * c * sizeof(double), st));      // hand the persistent buffer back zeroed
     return CHAP_OK;
@@ -829,8 +852,8 @@ extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w
     KernelTimer timer_("maxpool2_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_fwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
-    if (c % 4 == 0) maxpool2_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, h, w, c, total / 4, y);
-    else maxpool2_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, h, w, c, total, y);
+    if (c % 4 == 0) launch_k(maxpool2_fwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, h, w, c, total / 4, y);
+    else launch_k(maxpool2_fwd_kernel<1>, grid_for(total, 256 * 2), 256, 0, S(stream), x, h, w, c, total, y);
     return launched("maxpool2_fwd_kernel");
 }
 
@@ -838,8 +861,8 @@ extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int
     KernelTimer timer_("maxpool2_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_bwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
-    if (c % 4 == 0) maxpool2_bwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, dy, h, w, c, total / 4, dx);
-    else maxpool2_bwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, dy, h, w, c, total, dx);
+    if (c % 4 == 0) launch_k(maxpool2_bwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, dy, h, w, c, total / 4, dx);
+    else launch_k(maxpool2_bwd_kernel<1>, grid_for(total, 256 * 2), 256, 0, S(stream), x, dy, h, w, c, total, dx);
     return launched("maxpool2_bwd_kernel");
 }
 
@@ -847,8 +870,8 @@ extern "C" int chap_upsample2x_fwd(const float* x, int32_t nd, int32_t n, int32_
     KernelTimer timer_("upsample2x_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && y && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_fwd: bad argument");
     const int64_t total = (int64_t)n * (nd == 3 ? 2 * d : 1) * 2 * h * 2 * w * c;
-    if (c % 4 == 0) upsample2x_fwd_kernel<4><<<grid_for(total / 4, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total / 4, round_tf32_on(), y);
-    else upsample2x_fwd_kernel<1><<<grid_for(total, 256 * 2), 256, 0, S(stream)>>>(x, d, h, w, c, nd, total, round_tf32_on(), y);
+    if (c % 4 == 0) launch_k(upsample2x_fwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, d, h, w, c, nd, total / 4, round_tf32_on(), y);
+    else launch_k(upsample2x_fwd_kernel<1>, grid_for(total, 256 * 2), 256, 0, S(stream), x, d, h, w, c, nd, total, round_tf32_on(), y);
     return launched("upsample2x_fwd_kernel");
 }
 
@@ -856,8 +879,8 @@ extern "C" int chap_upsample2x_bwd(const float* dy, int32_t nd, int32_t n, int32
     KernelTimer timer_("upsample2x_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(dy && dx && (nd == 2 || nd == 3) && n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && (nd == 3 || d == 1), CHAP_ERR_BAD_ARG, "upsample2x_bwd: bad argument");
     const int64_t total = (int64_t)n * d * h * w * c;
-    if (c % 4 == 0) upsample2x_bwd_kernel<4><<<grid_for(total / 4, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total / 4, round_tf32_on(), dx);
-    else upsample2x_bwd_kernel<1><<<grid_for(total, 256), 256, 0, S(stream)>>>(dy, d, h, w, c, nd, total, round_tf32_on(), dx);
+    if (c % 4 == 0) launch_k(upsample2x_bwd_kernel<4>, grid_for(total / 4, 256), 256, 0, S(stream), dy, d, h, w, c, nd, total / 4, round_tf32_on(), dx);
+    else launch_k(upsample2x_bwd_kernel<1>, grid_for(total, 256), 256, 0, S(stream), dy, d, h, w, c, nd, total, round_tf32_on(), dx);
     return launched("upsample2x_bwd_kernel");
 }
 
@@ -866,16 +889,16 @@ extern "C" int chap_concat_channels(const float* a, const float* b, int64_t rows
     CHAP_REQUIRE(a && b && out && rows > 0 && ca > 0 && cb > 0, CHAP_ERR_BAD_ARG, "concat_channels: bad argument");
     const int64_t total = rows * (ca + cb);
     if (ca % 4 == 0 && cb % 4 == 0 && all16({a, b, out}))
-        concat4_kernel<<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>((const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
+        launch_k(concat4_kernel, grid_for(total / 4, 256 * 4), 256, 0, S(stream), (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
     else
-        concat_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(a, b, rows, ca, cb, out);
+        launch_k(concat_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), a, b, rows, ca, cb, out);
     return launched("concat_kernel");
 }
 
 extern "C" int chap_split_channels(const float* in, int64_t rows, int32_t ca, int32_t cb, float* a, float* b, void* stream) {
     KernelTimer timer_("split_channels", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(in && rows > 0 && ca > 0 && cb > 0 && (a || b), CHAP_ERR_BAD_ARG, "split_channels: bad argument");
-    split_kernel<<<grid_for(rows * (ca + cb), 256 * 4), 256, 0, S(stream)>>>(in, rows, ca, cb, a, b);
+    launch_k(split_kernel, grid_for(rows * (ca + cb), 256 * 4), 256, 0, S(stream), in, rows, ca, cb, a, b);
     return launched("split_kernel");
 }
 
@@ -883,7 +906,7 @@ extern "C" int chap_channel_scale(const float* x, const float* s, int32_t n, int
     KernelTimer timer_("channel_scale", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && s && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "channel_scale: bad argument");
     const int64_t total = (int64_t)n * rps * c;
-    channel_scale_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(x, s, rps, c, total, out);
+    launch_k(channel_scale_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), x, s, rps, c, total, out);
     return launched("channel_scale_kernel");
 }
 
@@ -894,8 +917,8 @@ extern "C" int chap_feature_dropout_fwd(const float* feat, const float* m1, cons
     KernelTimer timer_("feature_dropout_fwd", 0.0, 4.0 * (elems + 2.0 * (elems + extra)), S(stream));       // read feat once, write both outputs
     const bool v4 = c % 4 == 0 && aligned16(feat) && aligned16(out1) && aligned16(out2);
     const int64_t total = (int64_t)n * rps * c;
-    if (v4) feature_dropout_fwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(feat, m1, m2, n, nu, rps, c, out1, out2);
-    else feature_dropout_fwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(feat, m1, m2, n, nu, rps, c, out1, out2);
+    if (v4) launch_k(feature_dropout_fwd_kernel<4>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), feat, m1, m2, n, nu, rps, c, out1, out2);
+    else launch_k(feature_dropout_fwd_kernel<1>, grid_for(total, 256 * 4), 256, 0, S(stream), feat, m1, m2, n, nu, rps, c, out1, out2);
     return launched("feature_dropout_fwd_kernel");
 }
 
@@ -906,15 +929,15 @@ extern "C" int chap_feature_dropout_bwd(const float* d1, const float* d2, const 
     KernelTimer timer_("feature_dropout_bwd", 0.0, 4.0 * (elems + ((d1 ? 1.0 : 0.0) + (d2 ? 1.0 : 0.0)) * (elems + extra)), S(stream));
     const bool v4 = c % 4 == 0 && aligned16(dfeat) && (!d1 || aligned16(d1)) && (!d2 || aligned16(d2));
     const int64_t total = (int64_t)n * rps * c;
-    if (v4) feature_dropout_bwd_kernel<4><<<grid_for(total / 4, 256 * 4), 256, 0, S(stream)>>>(d1, d2, m1, m2, n, nu, rps, c, dfeat);
-    else feature_dropout_bwd_kernel<1><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(d1, d2, m1, m2, n, nu, rps, c, dfeat);
+    if (v4) launch_k(feature_dropout_bwd_kernel<4>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), d1, d2, m1, m2, n, nu, rps, c, dfeat);
+    else launch_k(feature_dropout_bwd_kernel<1>, grid_for(total, 256 * 4), 256, 0, S(stream), d1, d2, m1, m2, n, nu, rps, c, dfeat);
     return launched("feature_dropout_bwd_kernel");
 }
 
 extern "C" int chap_axpy(const float* a, const float* b, float alpha, int64_t elems, float* out, void* stream) {
     KernelTimer timer_("axpy", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && b && out && elems > 0, CHAP_ERR_BAD_ARG, "axpy: bad argument");
-    axpy_kernel<<<grid_for(elems, 256 * 4), 256, 0, S(stream)>>>(a, b, alpha, elems, out);
+    launch_k(axpy_kernel, grid_for(elems, 256 * 4), 256, 0, S(stream), a, b, alpha, elems, out);
     return launched("axpy_kernel");
 }
 
@@ -922,6 +945,6 @@ extern "C" int chap_mask_mix(const float* a, const float* b, const int64_t* mask
     KernelTimer timer_("mask_mix", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(a && b && mask && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "mask_mix: bad argument");
     const int64_t total = (int64_t)n * rps * c;
-    mask_mix_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(a, b, mask, rps, c, total, out);
+    launch_k(mask_mix_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), a, b, mask, rps, c, total, out);
     return launched("mask_mix_kernel");
 }

@@ -75,6 +75,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 pseudo_label_kernel(const float* __restrict__ pre1, const float* __restrict__ pre2, int64_t rows,
                     float* soft1, float* soft2, int64_t* arg1, int64_t* arg2, float* knowledge) {
+    pdl_enter();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
         float x1[C], x2[C], p1[C], p2[C];
         load_row<C>(pre1, r, x1); load_row<C>(pre2, r, x2);
@@ -96,6 +97,7 @@ pseudo_label_kernel(const float* __restrict__ pre1, const float* __restrict__ pr
 template <int C>
 __global__ void __launch_bounds__(256)
 softmax_kernel(const float* __restrict__ logits, int64_t rows, float* __restrict__ out) {
+    pdl_enter();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
         float x[C], p[C];
         load_row<C>(logits, r, x);
@@ -107,6 +109,7 @@ softmax_kernel(const float* __restrict__ logits, int64_t rows, float* __restrict
 template <int C>
 __global__ void __launch_bounds__(256)
 argmax_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t rows, int64_t* __restrict__ out) {
+    pdl_enter();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
         float x[C], p[C];
         load_row<C>(a, r, x);
@@ -131,6 +134,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 dice_ce_fwd_kernel(const float* __restrict__ logits, const void* __restrict__ labels, int dtype,
                    const int64_t* __restrict__ mask, int invert, int64_t rps, int64_t rows, double* sums) {
+    pdl_enter();
     float v[3 * C + 2];
 #pragma unroll
     for (int k = 0; k < 3 * C + 2; ++k) v[k] = 0.f;
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(256)
 dice_ce_bwd_kernel(const float* __restrict__ logits, const void* __restrict__ labels, int dtype,
                    const int64_t* __restrict__ mask, int invert, int64_t rps, int64_t rows,
                    const float* __restrict__ coef, int accumulate, float* __restrict__ dlogits) {
+    pdl_enter();
     float ci[C], cs[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) { ci[k] = coef[k]; cs[k] = coef[C + k]; }
@@ -200,6 +205,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 consistency_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                        const float* __restrict__ mask, int dist, int64_t rows, double* sums) {
+    pdl_enter();
     float v[3 * C + 1];
 #pragma unroll
     for (int k = 0; k < 3 * C + 1; ++k) v[k] = 0.f;
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(256)
 consistency_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                        const float* __restrict__ mask, int dist, int64_t rows, const float* __restrict__ coef,
                        float* __restrict__ dlogits) {
+    pdl_enter();
     float c0[C], c1[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) { c0[k] = coef[k]; c1[k] = dist == CHAP_DIST_KL ? 0.f : coef[C + k]; }
@@ -264,6 +271,7 @@ consistency_bwd_kernel(const float* __restrict__ logits, const float* __restrict
 __global__ void __launch_bounds__(256)
 patch_score_kernel(const float* __restrict__ know, const int64_t* __restrict__ a1, const int64_t* __restrict__ a2,
                    int nd, int d, int h, int w, int s, int64_t total, float* __restrict__ score) {
+    pdl_enter();
     const int pd = nd == 3 ? d / s : 1, ph = h / s, pw = w / s;
     const int sd = nd == 3 ? s : 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -284,6 +292,7 @@ patch_score_kernel(const float* __restrict__ know, const int64_t* __restrict__ a
 __global__ void __launch_bounds__(256)
 patch_mask_kernel(const float* __restrict__ score, const float* __restrict__ kth, int nd, int d, int h, int w, int s,
                   int64_t total, float* __restrict__ mask) {
+    pdl_enter();
     const int pd = nd == 3 ? d / s : 1, ph = h / s, pw = w / s;
     const int sd = nd == 3 ? s : 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -315,7 +324,7 @@ extern "C" int chap_pseudo_label(const float* pre1, const float* pre2, int64_t r
     CHAP_REQUIRE(pre1 && pre2 && rows > 0, CHAP_ERR_BAD_ARG, "pseudo_label: bad argument");
     CHAP_REQUIRE(row_aligned(pre1, c) && row_aligned(pre2, c) && row_aligned(soft1, c) && row_aligned(soft2, c), CHAP_ERR_ALIGNMENT, "pseudo_label: misaligned");
     int grid = grid_for(rows, 256 * 2);
-    DISPATCH_C(c, (pseudo_label_kernel<C><<<grid, 256, 0, S(stream)>>>(pre1, pre2, rows, soft1, soft2, arg1, arg2, knowledge)));
+    DISPATCH_C(c, (launch_k(pseudo_label_kernel<C>, grid, 256, 0, S(stream), pre1, pre2, rows, soft1, soft2, arg1, arg2, knowledge)));
     return launched("pseudo_label_kernel");
 }
 
@@ -324,7 +333,7 @@ extern "C" int chap_softmax(const float* logits, int64_t rows, int32_t c, float*
     CHAP_REQUIRE(logits && out && rows > 0, CHAP_ERR_BAD_ARG, "softmax: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(out, c), CHAP_ERR_ALIGNMENT, "softmax: misaligned");
     int grid = grid_for(rows, 256 * 2);
-    DISPATCH_C(c, (softmax_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, rows, out)));
+    DISPATCH_C(c, (launch_k(softmax_kernel<C>, grid, 256, 0, S(stream), logits, rows, out)));
     return launched("softmax_kernel");
 }
 
@@ -333,7 +342,7 @@ extern "C" int chap_argmax(const float* a, const float* b, int64_t rows, int32_t
     CHAP_REQUIRE(a && out && rows > 0, CHAP_ERR_BAD_ARG, "argmax: bad argument");
     CHAP_REQUIRE(row_aligned(a, c) && row_aligned(b, c), CHAP_ERR_ALIGNMENT, "argmax: misaligned");
     int grid = grid_for(rows, 256 * 2);
-    DISPATCH_C(c, (argmax_kernel<C><<<grid, 256, 0, S(stream)>>>(a, b, rows, out)));
+    DISPATCH_C(c, (launch_k(argmax_kernel<C>, grid, 256, 0, S(stream), a, b, rows, out)));
     return launched("argmax_kernel");
 }
 
@@ -345,7 +354,7 @@ extern "C" int chap_dice_ce_fwd(const float* logits, const void* labels, int32_t
     CHAP_TRY(zero_async(sums, (size_t)(3 * c + 2) * sizeof(double), S(stream)));
     const int64_t rows = (int64_t)n * rps;
     int grid = grid_for(rows, 256 * 4, kNumSMs * 4);
-    DISPATCH_C(c, (dice_ce_fwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, labels, dtype, mask, invert, rps, rows, sums)));
+    DISPATCH_C(c, (launch_k(dice_ce_fwd_kernel<C>, grid, 256, 0, S(stream), logits, labels, dtype, mask, invert, rps, rows, sums)));
     return launched("dice_ce_fwd_kernel");
 }
 
@@ -356,7 +365,7 @@ extern "C" int chap_dice_ce_bwd(const float* logits, const void* labels, int32_t
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(dlogits, c), CHAP_ERR_ALIGNMENT, "dice_ce_bwd: misaligned");
     const int64_t rows = (int64_t)n * rps;
     int grid = grid_for(rows, 256 * 2);
-    DISPATCH_C(c, (dice_ce_bwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, labels, dtype, mask, invert, rps, rows, coef, accumulate, dlogits)));
+    DISPATCH_C(c, (launch_k(dice_ce_bwd_kernel<C>, grid, 256, 0, S(stream), logits, labels, dtype, mask, invert, rps, rows, coef, accumulate, dlogits)));
     return launched("dice_ce_bwd_kernel");
 }
 
@@ -372,6 +381,7 @@ __device__ __forceinline__ void dice_ce_from_sums(const double* s, int c, double
     ce = s[3 * c] / (s[3 * c + 1] + 1e-16);
 }
 __global__ void mix_loss_finalize_kernel(const double* s_img, const double* s_patch, int c, float w_img, float w_patch, float* out3) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double d1, c1, d2, c2;
     dice_ce_from_sums(s_img, c, d1, c1);
@@ -392,6 +402,7 @@ __device__ __forceinline__ void dice_ce_coef(const double* s, int c, double up, 
 }
 __global__ void mix_loss_coef_kernel(const double* s_img, const double* s_patch, int c, float w_img, float w_patch,
                                      const float* g3, float* coef_img, float* coef_patch) {
+    pdl_enter();
     const int k = threadIdx.x;
     // loss_image = w_img (dice1 + ce1) / 2, loss_patch = w_patch (dice2 + ce2) / 2, total = their sum
     dice_ce_coef(s_img, c, 0.5 * w_img * ((double)g3[0] + (double)g3[2]), coef_img, k);
@@ -402,7 +413,7 @@ __global__ void mix_loss_coef_kernel(const double* s_img, const double* s_patch,
 extern "C" int chap_mix_loss_finalize(const double* sums_img, const double* sums_patch, int32_t c, float w_img, float w_patch,
                                       float* out3, void* stream) {
     CHAP_REQUIRE(sums_img && sums_patch && out3 && c > 0 && c <= 64, CHAP_ERR_BAD_ARG, "mix_loss_finalize: bad argument");
-    mix_loss_finalize_kernel<<<1, 32, 0, S(stream)>>>(sums_img, sums_patch, c, w_img, w_patch, out3);
+    launch_k(mix_loss_finalize_kernel, 1, 32, 0, S(stream), sums_img, sums_patch, c, w_img, w_patch, out3);
     return launched("mix_loss_finalize_kernel");
 }
 
@@ -410,7 +421,7 @@ extern "C" int chap_mix_loss_coef(const double* sums_img, const double* sums_pat
                                   const float* grad_out3, float* coef_img, float* coef_patch, void* stream) {
     CHAP_REQUIRE(sums_img && sums_patch && grad_out3 && coef_img && coef_patch && c > 0 && c <= 64, CHAP_ERR_BAD_ARG,
                  "mix_loss_coef: bad argument");
-    mix_loss_coef_kernel<<<1, 64, 0, S(stream)>>>(sums_img, sums_patch, c, w_img, w_patch, grad_out3, coef_img, coef_patch);
+    launch_k(mix_loss_coef_kernel, 1, 64, 0, S(stream), sums_img, sums_patch, c, w_img, w_patch, grad_out3, coef_img, coef_patch);
     return launched("mix_loss_coef_kernel");
 }
 
@@ -421,7 +432,7 @@ extern "C" int chap_consistency_fwd(const float* logits, const float* target, co
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(target, c), CHAP_ERR_ALIGNMENT, "consistency_fwd: misaligned");
     CHAP_TRY(zero_async(sums, (size_t)(3 * c + 1) * sizeof(double), S(stream)));
     int grid = grid_for(rows, 256 * 4, kNumSMs * 4);
-    DISPATCH_C(c, (consistency_fwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, target, mask, dist, rows, sums)));
+    DISPATCH_C(c, (launch_k(consistency_fwd_kernel<C>, grid, 256, 0, S(stream), logits, target, mask, dist, rows, sums)));
     return launched("consistency_fwd_kernel");
 }
 
@@ -431,7 +442,7 @@ extern "C" int chap_consistency_bwd(const float* logits, const float* target, co
     CHAP_REQUIRE(logits && target && coef && dlogits && rows > 0 && (dist == CHAP_DIST_KL || dist == CHAP_DIST_DICE), CHAP_ERR_BAD_ARG, "consistency_bwd: bad argument");
     CHAP_REQUIRE(row_aligned(logits, c) && row_aligned(target, c) && row_aligned(dlogits, c), CHAP_ERR_ALIGNMENT, "consistency_bwd: misaligned");
     int grid = grid_for(rows, 256 * 2);
-    DISPATCH_C(c, (consistency_bwd_kernel<C><<<grid, 256, 0, S(stream)>>>(logits, target, mask, dist, rows, coef, dlogits)));
+    DISPATCH_C(c, (launch_k(consistency_bwd_kernel<C>, grid, 256, 0, S(stream), logits, target, mask, dist, rows, coef, dlogits)));
     return launched("consistency_bwd_kernel");
 }
 
@@ -441,7 +452,7 @@ extern "C" int chap_patch_score(const float* knowledge, const int64_t* arg1, con
     CHAP_REQUIRE(knowledge && arg1 && arg2 && score && (nd == 2 || nd == 3) && n > 0 && s > 0, CHAP_ERR_BAD_ARG, "patch_score: bad argument");
     CHAP_REQUIRE(h % s == 0 && w % s == 0 && (nd == 2 ? d == 1 : d % s == 0), CHAP_ERR_BAD_ARG, "patch_score: size not divisible by scale_factor");
     const int64_t total = (int64_t)n * (nd == 3 ? d / s : 1) * (h / s) * (w / s);
-    patch_score_kernel<<<grid_for(total, 256), 256, 0, S(stream)>>>(knowledge, arg1, arg2, nd, d, h, w, s, total, score);
+    launch_k(patch_score_kernel, grid_for(total, 256), 256, 0, S(stream), knowledge, arg1, arg2, nd, d, h, w, s, total, score);
     return launched("patch_score_kernel");
 }
 
@@ -450,6 +461,6 @@ extern "C" int chap_patch_mask(const float* score, const float* kth, int32_t nd,
     KernelTimer timer_("patch_mask", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(score && kth && mask && (nd == 2 || nd == 3) && n > 0 && s > 0, CHAP_ERR_BAD_ARG, "patch_mask: bad argument");
     const int64_t total = (int64_t)n * d * h * w;
-    patch_mask_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(score, kth, nd, d, h, w, s, total, mask);
+    launch_k(patch_mask_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), score, kth, nd, d, h, w, s, total, mask);
     return launched("patch_mask_kernel");
 }

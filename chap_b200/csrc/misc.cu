@@ -10,6 +10,8 @@ namespace chap {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_force_simt{0};
+static int pdl_default() { const char* e = getenv("CHAP_PDL"); return (e && e[0] == '1') ? 1 : 0; }
+std::atomic<int> g_pdl{pdl_default()};
 std::atomic<int> g_precise_max_c{getenv("CHAP_PRECISE_MAX_C") ? atoi(getenv("CHAP_PRECISE_MAX_C")) : 0};
 
 // ------------------------------------------------------------------ live kernel timing
@@ -49,6 +51,7 @@ KernelTimer::~KernelTimer() {
 
 // ------------------------------------------------------------------ zero fill
 __global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, int64_t n4, int64_t n) {
+    pdl_enter();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < n4; i += stride) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -61,7 +64,7 @@ int zero_async(void* ptr, size_t bytes, cudaStream_t st) {
     const int64_t n = (int64_t)(bytes >> 2);
     const bool vec = (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
     const int64_t n4 = vec ? n / 4 : 0;
-    zero_kernel<<<grid_for(vec ? n4 + 1 : n, 256 * 4, kNumSMs * 4), 256, 0, st>>>(reinterpret_cast<uint32_t*>(ptr), n4, n);
+    launch_k(zero_kernel, grid_for(vec ? n4 + 1 : n, 256 * 4, kNumSMs * 4), 256, 0, st, reinterpret_cast<uint32_t*>(ptr), n4, n);
     return launched("zero_kernel");
 }
 
@@ -69,6 +72,7 @@ int zero_async(void* ptr, size_t bytes, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n4, int64_t n,
            float lr, const float* __restrict__ lr_dev, float mom, float wd, float gs, int first) {
+    pdl_enter();
     if (lr_dev) lr = *lr_dev;          // learning rate read from device memory: the launch is CUDA-graph replayable
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -96,6 +100,7 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
 // with a host that runs iterations ahead.  One thread; double math (the host oracle computes these in Python floats).
 __global__ void schedule_kernel(long long* iter, double base_lr, double max_it, double consistency, double rampup, long long ramp_div,
                                 float* lr, float* cw) {
+    pdl_enter();
     const long long it = *iter;
     double frac = 1.0 - (double)it / max_it;
     if (frac < 0.0) frac = 0.0;
@@ -120,6 +125,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gather2d_kernel(const T* __restrict__ in, const int* __restrict__ iy, const int* __restrict__ ix, int h, int w, int H, int W,
                 int64_t total, T* __restrict__ out) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int X = (int)(i % W); const int Y = (int)((i / W) % H); const int64_t s = i / ((int64_t)W * H);
         const int sy = iy[Y], sx = ix[X];                 // -1: scipy's mode='constant' fill (coordinate beyond the last sample)
@@ -131,6 +137,7 @@ gather2d_kernel(const T* __restrict__ in, const int* __restrict__ iy, const int*
 __global__ void __launch_bounds__(256)
 label_overlap_kernel(const int64_t* __restrict__ pred, const int64_t* __restrict__ gt, int64_t elems, int classes,
                      unsigned long long* __restrict__ counts) {
+    pdl_enter();
     __shared__ unsigned int h[3 * 16];
     for (int i = threadIdx.x; i < 3 * classes; i += blockDim.x) h[i] = 0u;
     __syncthreads();
@@ -152,6 +159,7 @@ __device__ __forceinline__ int win_start(int i, int stride, int vol, int patch) 
 
 __global__ void __launch_bounds__(256)
 sw_extract_kernel(chap_sw_desc d, const float* __restrict__ vol, int first, int64_t total, float* __restrict__ patches) {
+    pdl_enter();
     const int64_t pvol = (int64_t)d.patch[0] * d.patch[1] * d.patch[2];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int wi = first + (int)(i / pvol);
@@ -172,6 +180,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 sw_aggregate_kernel(chap_sw_desc d, const float* __restrict__ win, int is_prob, float* __restrict__ score,
                     float* __restrict__ cnt, int64_t* __restrict__ label) {
+    pdl_enter();
     const int64_t nvox = (int64_t)d.vol[0] * d.vol[1] * d.vol[2];
     const int64_t pvol = (int64_t)d.patch[0] * d.patch[1] * d.patch[2];
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
@@ -237,6 +246,8 @@ extern "C" uint64_t chap_launch_count(void) { return g_launches.load(); }
 extern "C" void chap_reset_launch_count(void) { g_launches.store(0); }
 extern "C" void chap_set_force_simt(int flag) { g_force_simt.store(flag ? 1 : 0); }
 extern "C" int chap_get_force_simt(void) { return g_force_simt.load(); }
+extern "C" void chap_set_pdl(int flag) { g_pdl.store(flag ? 1 : 0); }
+extern "C" int chap_get_pdl(void) { return g_pdl.load(); }
 extern "C" void chap_set_conv_precision(int max_channels) { g_precise_max_c.store(max_channels < 0 ? 0 : max_channels); }
 extern "C" int chap_get_conv_precision(void) { return g_precise_max_c.load(); }
 
@@ -290,7 +301,7 @@ extern "C" int chap_sgd_momentum(float* p, const float* g, float* buf, int64_t e
     KernelTimer timer_("sgd_momentum", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(p && g && buf && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum: bad argument");
     CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum: buffers must be 16-byte aligned");
-    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, lr, nullptr, momentum, weight_decay, grad_scale, first_step);
+    launch_k(sgd_kernel, grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream), p, g, buf, elems / 4, elems, lr, nullptr, momentum, weight_decay, grad_scale, first_step);
     return launched("sgd_kernel");
 }
 
@@ -299,14 +310,14 @@ extern "C" int chap_sgd_momentum_lrdev(float* p, const float* g, float* buf, int
     KernelTimer timer_("sgd_momentum_lrdev", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(p && g && buf && lr_dev && elems > 0, CHAP_ERR_BAD_ARG, "sgd_momentum_lrdev: bad argument");
     CHAP_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), CHAP_ERR_ALIGNMENT, "sgd_momentum_lrdev: buffers must be 16-byte aligned");
-    sgd_kernel<<<grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream)>>>(p, g, buf, elems / 4, elems, 0.f, lr_dev, momentum, weight_decay, grad_scale, 0);
+    launch_k(sgd_kernel, grid_for(elems / 4 + 1, 256 * 2), 256, 0, S(stream), p, g, buf, elems / 4, elems, 0.f, lr_dev, momentum, weight_decay, grad_scale, 0);
     return launched("sgd_kernel");
 }
 
 extern "C" int chap_schedule_step(int64_t* iter_dev, double base_lr, double max_iterations, double consistency, double rampup,
                                   int64_t ramp_div, float* lr_dev, float* cw_dev, void* stream) {
     CHAP_REQUIRE(iter_dev && lr_dev && cw_dev && max_iterations > 0 && ramp_div > 0, CHAP_ERR_BAD_ARG, "schedule_step: bad argument");
-    schedule_kernel<<<1, 1, 0, S(stream)>>>(reinterpret_cast<long long*>(iter_dev), base_lr, max_iterations, consistency, rampup,
+    launch_k(schedule_kernel, 1, 1, 0, S(stream), reinterpret_cast<long long*>(iter_dev), base_lr, max_iterations, consistency, rampup,
                                             (long long)ramp_div, lr_dev, cw_dev);
     return launched("schedule_kernel");
 }
@@ -317,8 +328,8 @@ extern "C" int chap_gather2d(const void* in, int32_t elem_bytes, const int32_t* 
     CHAP_REQUIRE(elem_bytes == 4 || elem_bytes == 8, CHAP_ERR_BAD_ARG, "gather2d: element size must be 4 or 8 bytes (got %d)", elem_bytes);
     const int64_t total = (int64_t)n * out_h * out_w;
     KernelTimer timer_("gather2d", 0.0, 2.0 * elem_bytes * (double)total, S(stream));
-    if (elem_bytes == 4) gather2d_kernel<float><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>((const float*)in, iy, ix, h, w, out_h, out_w, total, (float*)out);
-    else gather2d_kernel<int64_t><<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>((const int64_t*)in, iy, ix, h, w, out_h, out_w, total, (int64_t*)out);
+    if (elem_bytes == 4) launch_k(gather2d_kernel<float>, grid_for(total, 256 * 4), 256, 0, S(stream), (const float*)in, iy, ix, h, w, out_h, out_w, total, (float*)out);
+    else launch_k(gather2d_kernel<int64_t>, grid_for(total, 256 * 4), 256, 0, S(stream), (const int64_t*)in, iy, ix, h, w, out_h, out_w, total, (int64_t*)out);
     return launched("gather2d_kernel");
 }
 
@@ -326,7 +337,7 @@ extern "C" int chap_label_overlap(const int64_t* pred, const int64_t* gt, int64_
     CHAP_REQUIRE(pred && gt && counts && elems > 0 && classes >= 1 && classes <= 16, CHAP_ERR_BAD_ARG, "label_overlap: bad argument (classes %d)", classes);
     KernelTimer timer_("label_overlap", 0.0, 16.0 * (double)elems, S(stream));
     CHAP_TRY(zero_async(counts, (size_t)3 * classes * sizeof(uint64_t), S(stream)));
-    label_overlap_kernel<<<grid_for(elems, 256 * 8), 256, 0, S(stream)>>>(pred, gt, elems, classes, reinterpret_cast<unsigned long long*>(counts));
+    launch_k(label_overlap_kernel, grid_for(elems, 256 * 8), 256, 0, S(stream), pred, gt, elems, classes, reinterpret_cast<unsigned long long*>(counts));
     return launched("label_overlap_kernel");
 }
 
@@ -345,7 +356,7 @@ extern "C" int chap_sw_extract(const chap_sw_desc* d, const float* volume, int32
     const int total_win = d->nwin[0] * d->nwin[1] * d->nwin[2];
     CHAP_REQUIRE(volume && patches && first >= 0 && count > 0 && first + count <= total_win, CHAP_ERR_BAD_ARG, "sw_extract: bad window range");
     const int64_t total = (int64_t)count * d->patch[0] * d->patch[1] * d->patch[2];
-    sw_extract_kernel<<<grid_for(total, 256 * 4), 256, 0, S(stream)>>>(*d, volume, first, total, patches);
+    launch_k(sw_extract_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), *d, volume, first, total, patches);
     return launched("sw_extract_kernel");
 }
 
@@ -360,12 +371,12 @@ extern "C" int chap_sw_aggregate(const chap_sw_desc* d, const float* win, int32_
                                                 (double)nvox * ((score ? 4.0 * d->c : 0.0) + (cnt ? 4.0 : 0.0) + 8.0), S(stream));
     int grid = grid_for(nvox, 256);
     switch (d->c) {
-        case 1: sw_aggregate_kernel<1><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;   // the reference's default num_classes=1
+        case 1: launch_k(sw_aggregate_kernel<1>, grid, 256, 0, S(stream), *d, win, is_prob, score, cnt, label); break;   // the reference's default num_classes=1
         case 2: CHAP_REQUIRE(((uintptr_t)win & 7u) == 0, CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
-                sw_aggregate_kernel<2><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
-        case 3: sw_aggregate_kernel<3><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
+                launch_k(sw_aggregate_kernel<2>, grid, 256, 0, S(stream), *d, win, is_prob, score, cnt, label); break;
+        case 3: launch_k(sw_aggregate_kernel<3>, grid, 256, 0, S(stream), *d, win, is_prob, score, cnt, label); break;
         case 4: CHAP_REQUIRE(aligned16(win), CHAP_ERR_ALIGNMENT, "sw_aggregate: misaligned");
-                sw_aggregate_kernel<4><<<grid, 256, 0, S(stream)>>>(*d, win, is_prob, score, cnt, label); break;
+                launch_k(sw_aggregate_kernel<4>, grid, 256, 0, S(stream), *d, win, is_prob, score, cnt, label); break;
         default: return fail(CHAP_ERR_BAD_ARG, "sw_aggregate: unsupported class count %d", d->c);
     }
     return launched("sw_aggregate_kernel");

@@ -71,6 +71,7 @@ __device__ __forceinline__ void chan_sq_body(const float* __restrict__ g, int64_
 // P1 for all levels: flattened grid, block -> (level, sample, block in sample)
 __global__ void __launch_bounds__(256)
 chan_sq_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     __shared__ float part[256 * 4];
     int l = 0;
     while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_chan) ++l;
@@ -191,6 +192,7 @@ __device__ __forceinline__ void perturb_rows_body(const float* __restrict__ g, c
 template <int MODE, bool APPLY>
 __global__ void __launch_bounds__(256)
 perturb_rows_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     __shared__ float inv_chan[1024];
     __shared__ float red[8];
     int l = 0;
@@ -207,6 +209,7 @@ perturb_rows_all_kernel(const __grid_constant__ PBatch b) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 perturb_stats_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     __shared__ float fold[2][8][256];              // [S | Q][warp][channel]: warp totals (c <= 256 on this path)
     __shared__ float redz[8];
     int l = 0;
@@ -276,6 +279,7 @@ perturb_stats_all_kernel(const __grid_constant__ PBatch b) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 perturb_apply_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     __shared__ float inv_chan[1024];
     __shared__ float red[8];
     __shared__ double part[8];
@@ -309,9 +313,9 @@ perturb_apply_all_kernel(const __grid_constant__ PBatch b) {
 template <int MODE>
 static int run_two_pass(const PBatch& b, int blocks_stats, int blocks_rows, double alg_bytes, cudaStream_t st) {
     KernelTimer timer("perturb_level", 0.0, alg_bytes, st);       // algorithmic: read g, read f, write out (all levels of the call)
-    perturb_stats_all_kernel<MODE><<<blocks_stats, 256, 0, st>>>(b);
+    launch_k(perturb_stats_all_kernel<MODE>, blocks_stats, 256, 0, st, b);
     CHAP_TRY(launched("perturb_stats_all_kernel"));
-    perturb_apply_all_kernel<MODE><<<blocks_rows, 256, 0, st>>>(b);
+    launch_k(perturb_apply_all_kernel<MODE>, blocks_rows, 256, 0, st, b);
     return launched("perturb_apply_all_kernel");
 }
 
@@ -319,18 +323,19 @@ template <int MODE>
 static int run_all(const PBatch& b, int blocks_chan, int blocks_rows, double alg_bytes, cudaStream_t st) {
     KernelTimer timer("perturb_level", 0.0, alg_bytes, st);       // algorithmic: read g, read f, write out (all levels of the call)
     if (MODE == CHAP_PERTURB_CHANNEL || MODE == CHAP_PERTURB_CHANNEL_SPATIAL) {
-        chan_sq_all_kernel<<<blocks_chan, 256, 0, st>>>(b);
+        launch_k(chan_sq_all_kernel, blocks_chan, 256, 0, st, b);
         CHAP_TRY(launched("chan_sq_all_kernel"));
     }
-    perturb_rows_all_kernel<MODE, false><<<blocks_rows, 256, 0, st>>>(b);
+    launch_k(perturb_rows_all_kernel<MODE, false>, blocks_rows, 256, 0, st, b);
     CHAP_TRY(launched("perturb_rows_all_kernel<reduce>"));
-    perturb_rows_all_kernel<MODE, true><<<blocks_rows, 256, 0, st>>>(b);
+    launch_k(perturb_rows_all_kernel<MODE, true>, blocks_rows, 256, 0, st, b);
     return launched("perturb_rows_all_kernel<apply>");
 }
 
 // out = base + xi * d / (||d|| + 1e-8) per sample
 __global__ void __launch_bounds__(256)
 sample_sq_kernel(const float* __restrict__ d, int64_t eps_, double* __restrict__ norms) {
+    pdl_enter();
     const float* b = d + (int64_t)blockIdx.y * eps_;
     float acc = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < eps_; i += (int64_t)gridDim.x * blockDim.x) {
@@ -349,6 +354,7 @@ sample_sq_kernel(const float* __restrict__ d, int64_t eps_, double* __restrict__
 __global__ void __launch_bounds__(256)
 l2n_axpy_kernel(const float* __restrict__ d, const float* __restrict__ base, float xi, int rt, int64_t eps_,
                 const double* __restrict__ norms, float* __restrict__ out) {
+    pdl_enter();
     const int64_t off = (int64_t)blockIdx.y * eps_;
     const float s = xi / (sqrtf((float)norms[blockIdx.y]) + kEps);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < eps_; i += (int64_t)gridDim.x * blockDim.x)
@@ -358,6 +364,7 @@ l2n_axpy_kernel(const float* __restrict__ d, const float* __restrict__ base, flo
 // the same two phases for several tensors at once (the five levels of the VAT probe): PLevel.g = d, .f = base, .samp_sq = norms
 __global__ void __launch_bounds__(256)
 sample_sq_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     int l = 0;
     while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
     const PLevel& L = b.lv[l];
@@ -381,6 +388,7 @@ sample_sq_all_kernel(const __grid_constant__ PBatch b) {
 }
 __global__ void __launch_bounds__(256)
 l2n_axpy_all_kernel(const __grid_constant__ PBatch b) {
+    pdl_enter();
     int l = 0;
     while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_rows) ++l;
     const PLevel& L = b.lv[l];
@@ -426,9 +434,9 @@ extern "C" int chap_l2n_sample_axpy_batched(const chap_level* levels, int32_t n_
     }
     KernelTimer timer_("l2n_sample_axpy", 0.0, 12.0 * total * n, st);        // algorithmic: read d, read base, write out
     CHAP_TRY(zero_async(norms, (size_t)n_levels * n * sizeof(double), st));
-    sample_sq_all_kernel<<<blocks, 256, 0, st>>>(b);
+    launch_k(sample_sq_all_kernel, blocks, 256, 0, st, b);
     CHAP_TRY(launched("sample_sq_all_kernel"));
-    l2n_axpy_all_kernel<<<blocks, 256, 0, st>>>(b);
+    launch_k(l2n_axpy_all_kernel, blocks, 256, 0, st, b);
     return launched("l2n_axpy_all_kernel");
 }
 
@@ -513,8 +521,8 @@ extern "C" int chap_l2n_sample_axpy(const float* d, const float* base, float xi,
     if (bps > cap) bps = cap;
     if (bps < 1) bps = 1;
     dim3 grid((unsigned)bps, (unsigned)n);
-    sample_sq_kernel<<<grid, 256, 0, st>>>(d, elems_per_sample, norms);
+    launch_k(sample_sq_kernel, grid, 256, 0, st, d, elems_per_sample, norms);
     CHAP_TRY(launched("sample_sq_kernel"));
-    l2n_axpy_kernel<<<grid, 256, 0, st>>>(d, base, xi, round_tf32_on(), elems_per_sample, norms, out);
+    launch_k(l2n_axpy_kernel, grid, 256, 0, st, d, base, xi, round_tf32_on(), elems_per_sample, norms, out);
     return launched("l2n_axpy_kernel");
 }

@@ -63,6 +63,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // acc [tap][M][N] -> torch-layout gradient dw[m * s_co + n * s_ci + tap]
 __global__ void __launch_bounds__(256)
 wgrad_unpack_kernel(float* __restrict__ acc, float* __restrict__ dw, int taps, int M, int N, int64_t s_co, int64_t s_ci, int accumulate) {
+    pdl_enter();
     const int64_t total = (int64_t)taps * M * N;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         // consecutive threads walk the torch layout's fastest index (tap) so that the writes coalesce
@@ -113,6 +114,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
     const int blk0 = blockIdx.x * p.blocks_per_cta;
     const int nblk = min(p.blocks_per_cta, p.blocks_total - blk0);
 
+    pdl_trigger();          // prologue (barriers, shared-memory zero fill, TMEM) overlaps the previous kernel's tail
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -136,6 +138,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_row = (uint32_t)p.a_cpg * 4u, b_row = (uint32_t)p.b_cpg * 4u;
     const uint32_t a_chunk = (uint32_t)p.P * a_row, b_chunk = (uint32_t)p.b_rows * b_row;     // bytes of one channel chunk
@@ -519,12 +522,12 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     KernelTimer timer(timer_name("conv_tc_wgrad", g.taps, v.cin, v.cout, g.iW, g.iH, g.iD, g.in_rows), 2.0 * rows * v.cin * v.cout * g.taps,
                       4.0 * (rows * v.cin + rows * v.cout + (double)g.taps * v.cin * v.cout), st);
     dim3 grid((unsigned)splits, (unsigned)groups, (unsigned)zdim);
-    if (p.k2s2) wgrad_tc_kernel_taps<<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmT, p);
-    else wgrad_tc_kernel<<<grid, kWgThreads, smem, st>>>(tmA, tmB, p);
+    if (p.k2s2) launch_k(wgrad_tc_kernel_taps, grid, kWgThreads, smem, st, tmA, tmB, tmT, p);
+    else launch_k(wgrad_tc_kernel, grid, kWgThreads, smem, st, tmA, tmB, p);
     CHAP_TRY(launched("wgrad_tc_kernel"));
     if (p.acc) {
         const int64_t total = (int64_t)g.taps * v.cin * v.cout;
-        wgrad_unpack_kernel<<<grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st>>>(p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci, accumulate ? 1 : 0);
+        launch_k(wgrad_unpack_kernel, grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st, p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci, accumulate ? 1 : 0);
         CHAP_TRY(launched("wgrad_unpack_kernel"));
     }
     return 1;

@@ -128,6 +128,11 @@ def _sink_of(p):
 
 def set_force_simt(flag):
     lib().chap_set_force_simt(1 if flag else 0)
+
+
+def set_pdl(flag):
+    """Programmatic dependent launch between the library's kernels (default off: measured without gain; results are identical either way)."""
+    lib().chap_set_pdl(1 if flag else 0)
     invalidate_weight_cache()
 
 

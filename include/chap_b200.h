@@ -55,6 +55,14 @@ void chap_timing_enable(int on);
 int chap_timing_report(char* buf, size_t cap);
 void chap_set_force_simt(int flag);
 int chap_get_force_simt(void);
+/* Programmatic dependent launch between the kernels of this library.  Only effective in the experiment build (`make pdl`,
+ * -DCHAP_PDL_INSN): measured without gain inside a replayed CUDA graph, so the default build compiles it out and these two calls only
+ * record the flag.  There, every kernel is
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization and waits (griddepcontrol.wait) before its first global-memory
+ * access, so results are identical; only the launch latency between dependent kernels overlaps.  No counterpart in the reference
+ * (its kernels are launched by ATen / cuDNN in plain stream order, e.g. every nn.Module call of code/networks/unet.py:49-57). */
+void chap_set_pdl(int flag);
+int chap_get_pdl(void);
 /* Arithmetic of the tensor-core convolutions (forward and data gradient).
  *   0 (default): plain TF32 -- operands rounded to nearest by the TMA unit, fp32 accumulation in TMEM; per layer this is
  *       exactly cuDNN's TF32 arithmetic (reference default: torch.backends.cudnn.allow_tf32, code/train_ours_2D.py:542-547).
