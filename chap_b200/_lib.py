@@ -17,6 +17,10 @@ class BnTrainArgs(ctypes.Structure):          # chap_bn_train_args
                 ("mean_invstd", c_void_p), ("scale_shift", c_void_p), ("stats_persistent", c_int32), ("reserved_", c_int32)]
 
 
+class DropoutRng(ctypes.Structure):           # chap_dropout_rng
+    _fields_ = [("p", c_float), ("seed", ctypes.c_uint64), ("subsequence", ctypes.c_uint64), ("epoch_dev", c_void_p)]
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("nd", c_int32), ("n", c_int32), ("in_d", c_int32), ("in_h", c_int32),
                 ("in_w", c_int32), ("cin", c_int32), ("cout", c_int32)]
@@ -79,6 +83,8 @@ SIGNATURES = {
     "chap_bn_eval_params": (I, [P, P, P, P, F, P, P, I, P]),
     "chap_bn_act_fwd": (I, [P, P, F, P, P, P, I, L, I, P, P]),
     "chap_bn_act_bwd": (I, [P, P, P, P, P, F, P, P, I, L, I, I, P, P, P, P, P]),
+    "chap_bn_act_fwd_rng": (I, [P, P, F, P, ctypes.POINTER(DropoutRng), P, I, L, I, P, P]),
+    "chap_bn_act_bwd_rng": (I, [P, P, P, P, F, P, ctypes.POINTER(DropoutRng), I, L, I, I, P, I, P, P, P, I, P]),
     "chap_maxpool2_fwd": (I, [P, I, I, I, I, P, P]),
     "chap_maxpool2_bwd": (I, [P, P, I, I, I, I, P, P]),
     "chap_upsample2x_fwd": (I, [P, I, I, I, I, I, I, P, P]),

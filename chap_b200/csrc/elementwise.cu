@@ -257,14 +257,43 @@ __device__ __forceinline__ int64_t ew_index(int64_t i, int64_t nchunks, int reve
     return reverse ? (((nchunks - 1 - (i >> 8)) << 8) | (i & 255)) : i;
 }
 
+// Elementwise dropout without a mask tensor (nn.Dropout(p) inside ConvBlock, code/networks/unet.py:53): the 1/(1-p)-scaled keep
+// mask of vector i is recomputed wherever it is needed -- forward, backward reduce, backward apply -- from Philox4x32-10 keyed by
+// (seed, device-side epoch) with counter (i, subsequence).  The epoch word is read from device memory (the trainer's iteration
+// counter), so a replayed CUDA graph draws fresh masks every iteration; the subsequence separates the layers / passes of one iteration.
+// Replaces bernoulli_ + div_ (two torch launches, three passes over a tensor of the activation's size) and the mask reads.
+struct DropRng {
+    uint32_t seed_lo, seed_hi, sub_lo, sub_hi;
+    uint32_t thresh;            // keep iff random word < thresh  (thresh = keep * 2^32)
+    float scale;                // 1 / keep
+    const long long* epoch;     // nullable
+    int on;
+};
+__device__ __forceinline__ uint2 drop_key(const DropRng& r) {
+    const unsigned long long e = r.epoch ? (unsigned long long)*r.epoch : 0ull;
+    return make_uint2(r.seed_lo ^ (uint32_t)(e * 0x9E3779B97F4A7C15ull >> 32), r.seed_hi ^ (uint32_t)e);
+}
+__device__ __forceinline__ float4 drop_mask4(const DropRng& r, uint2 key, int64_t i) {
+    uint4 c = make_uint4((uint32_t)i, (uint32_t)((uint64_t)i >> 32), r.sub_lo, r.sub_hi);
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.x, lo1, hi0 ^ c.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return make_float4(c.x < r.thresh ? r.scale : 0.f, c.y < r.thresh ? r.scale : 0.f, c.z < r.thresh ? r.scale : 0.f, c.w < r.thresh ? r.scale : 0.f);
+}
+
 template <bool EL, bool RES>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ ss, float slope,
                         const float* __restrict__ drop_nc, const float* __restrict__ drop_el,
                         const float* __restrict__ res, int64_t rows_per_sample, int c, int64_t total_vec, int reverse,
-                        float* __restrict__ out) {
+                        float* __restrict__ out, const DropRng rng) {
     pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
+    const uint2 key = (EL && rng.on) ? drop_key(rng) : make_uint2(0u, 0u);
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g);
     const int64_t per_sample = rows_per_sample * cg;
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -282,7 +311,7 @@ bn_act_fwd_fixed_kernel(const float* __restrict__ y, const float* __restrict__ s
             const int64_t i = ew_index(iv, nchunks, reverse);
             if (iv < span && i < total_vec) {
                 v[u] = ldg_stream(y4 + i);
-                if (EL) e[u] = ldg_stream(e4 + i);
+                if (EL) e[u] = rng.on ? drop_mask4(rng, key, i) : ldg_stream(e4 + i);
                 if (RES) r[u] = ldg_stream(r4 + i);
             }
         }
@@ -359,9 +388,11 @@ template <bool EL>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_fixed_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ ss,
                                const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
-                               const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t total_vec, int c, double* sums) {
+                               const float* __restrict__ drop_el, int64_t rows_per_sample, int64_t total_vec, int c, double* sums,
+                               const DropRng rng) {
     pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
+    const uint2 key = (EL && rng.on) ? drop_key(rng) : make_uint2(0u, 0u);
     const float4 sc = ld4(ss + 4 * g), sh = ld4(ss + c + 4 * g), mean = ld4(mi + 4 * g), istd = ld4(mi + c + 4 * g);
     const int64_t per_sample = rows_per_sample * cg;
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -376,7 +407,7 @@ bn_act_bwd_reduce_fixed_kernel(const float* __restrict__ dout, const float* __re
             const int64_t i = i0 + u * stride;
             if (i < total_vec) {
                 d[u] = ldg_stream(d4 + i); v[u] = ldg_stream(y4 + i);
-                if (EL) e[u] = ldg_stream(e4 + i);
+                if (EL) e[u] = rng.on ? drop_mask4(rng, key, i) : ldg_stream(e4 + i);
             }
         }
 #pragma unroll
@@ -402,9 +433,10 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
                               const float* __restrict__ mi, float slope, const float* __restrict__ drop_nc,
                               const float* __restrict__ drop_el, int64_t rows_per_sample, int c, int64_t total_vec, int train,
                               double inv_count, double* __restrict__ sums, float* __restrict__ dy,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                              float* __restrict__ dgamma, float* __restrict__ dbeta, const DropRng rng) {
     pdl_enter();
     const int cg = c >> 2, g = threadIdx.x % cg;
+    const uint2 key = (EL && rng.on) ? drop_key(rng) : make_uint2(0u, 0u);
     const int train_bits = train;
     const int acc_pg = (train >> 1) & 1;       // bit 1 of `train`: ADD the parameter gradients into dgamma / dbeta (gradient-sink mode)
     const int persist = (train >> 2) & 1;      // bit 2: `sums` is a persistent buffer (2c sums + a ticket word) that must be handed back zeroed
@@ -459,7 +491,7 @@ bn_act_bwd_apply_fixed_kernel(const float* __restrict__ dout, const float* __res
             const int64_t i = ew_index(iv, nchunks, reverse);
             if (iv < span && i < total_vec) {
                 d[u] = ldg_stream(d4 + i); v[u] = ldg_stream(y4 + i);
-                if (EL) e[u] = ldg_stream(e4 + i);
+                if (EL) e[u] = rng.on ? drop_mask4(rng, key, i) : ldg_stream(e4 + i);
             }
         }
 #pragma unroll
@@ -765,18 +797,38 @@ static bool all16(std::initializer_list<const void*> ps) {
     return true;
 }
 
-extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, const float* drop_nc, const float* drop_el,
-                               const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+// host side of DropRng: the C ABI struct -> kernel argument (p in (0, 1), validated by the callers)
+static DropRng make_rng(const chap_dropout_rng* r) {
+    DropRng d{};
+    if (!r) return d;
+    const double keep = 1.0 - (double)r->p;
+    const double t = keep * 4294967296.0;
+    d.seed_lo = (uint32_t)r->seed; d.seed_hi = (uint32_t)(r->seed >> 32);
+    d.sub_lo = (uint32_t)r->subsequence; d.sub_hi = (uint32_t)(r->subsequence >> 32);
+    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    d.scale = (float)(1.0 / keep);
+    d.epoch = reinterpret_cast<const long long*>(r->epoch_dev);
+    d.on = 1;
+    return d;
+}
+static bool rng_ok(const chap_dropout_rng* r) { return !r || (r->p > 0.f && r->p < 1.f); }
+
+static int bn_act_fwd_impl(const float* y, const float* ss, float slope, const float* drop_nc, const float* drop_el, const chap_dropout_rng* rng_in,
+                           const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
     CHAP_REQUIRE(y && ss && out && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_fwd: bad argument");
+    CHAP_REQUIRE(rng_ok(rng_in) && !(rng_in && drop_el), CHAP_ERR_BAD_ARG, "bn_act_fwd: dropout needs 0 < p < 1 and either a mask or a generator");
+    const DropRng rng = make_rng(rng_in);
     const int64_t total = (int64_t)n * rps * c;
     KernelTimer timer("bn_act_fwd", 0.0, 4.0 * total * (2 + (drop_el ? 1 : 0) + (residual ? 1 : 0)), S(stream));
     if (c % 4 == 0 && 256 % (c / 4) == 0 && all16({y, drop_el, residual, out, ss, drop_nc}) && round_tf32_on() == 0) {
         const int grid = grid_for(total / 4, 256 * kEwUnroll);
         static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
-#define CHAP_FWD_FIXED(EL, RES) launch_k(bn_act_fwd_fixed_kernel<EL, RES>, grid, 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, rev & 1, out)
-        if (drop_el) { if (residual) CHAP_FWD_FIXED(true, true); else CHAP_FWD_FIXED(true, false); }
+#define CHAP_FWD_FIXED(EL, RES) launch_k(bn_act_fwd_fixed_kernel<EL, RES>, grid, 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, rev & 1, out, rng)
+        if (drop_el || rng.on) { if (residual) CHAP_FWD_FIXED(true, true); else CHAP_FWD_FIXED(true, false); }
         else         { if (residual) CHAP_FWD_FIXED(false, true); else CHAP_FWD_FIXED(false, false); }
 #undef CHAP_FWD_FIXED
+    } else if (rng.on) {
+        return fail(CHAP_ERR_BAD_ARG, "bn_act_fwd: generated dropout needs c %% 4 == 0, 256 %% (c / 4) == 0 and 16-byte aligned buffers (c = %d)", c);
     } else if (c % 4 == 0 && all16({y, drop_el, residual, out})) {
         launch_k(bn_act_fwd_kernel<4>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), y, ss, slope, drop_nc, drop_el, residual, rps, c, total / 4, round_tf32_on(), out);
     } else {
@@ -785,9 +837,27 @@ extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, con
     return launched("bn_act_fwd_kernel");
 }
 
+extern "C" int chap_bn_act_fwd(const float* y, const float* ss, float slope, const float* drop_nc, const float* drop_el,
+                               const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    return bn_act_fwd_impl(y, ss, slope, drop_nc, drop_el, nullptr, residual, n, rps, c, out, stream);
+}
+extern "C" int chap_bn_act_fwd_rng(const float* y, const float* ss, float slope, const float* drop_nc, const chap_dropout_rng* rng,
+                                   const float* residual, int32_t n, int64_t rps, int32_t c, float* out, void* stream) {
+    CHAP_REQUIRE(rng != nullptr, CHAP_ERR_BAD_ARG, "bn_act_fwd_rng: the generator description is required");
+    return bn_act_fwd_impl(y, ss, slope, drop_nc, nullptr, rng, residual, n, rps, c, out, stream);
+}
+
 static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
                            const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy, float* dgamma,
-                           float* dbeta, void* stream);
+                           float* dbeta, void* stream, const chap_dropout_rng* rng_in = nullptr);
+
+extern "C" int chap_bn_act_bwd_rng(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
+                                   const chap_dropout_rng* rng, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums,
+                                   int32_t sums_persistent, float* dy, float* dgamma, float* dbeta, int32_t accumulate, void* stream) {
+    CHAP_REQUIRE(rng != nullptr, CHAP_ERR_BAD_ARG, "bn_act_bwd_rng: the generator description is required");
+    return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, nullptr, n, rps, c, (train ? 1 : 0) | (accumulate ? 2 : 0) | (sums_persistent ? 4 : 0),
+                           sums, dy, dgamma, dbeta, stream, rng);
+}
 
 extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* ss, const float* mi, const float* gamma,
                                float slope, const float* drop_nc, const float* drop_el, int32_t n, int64_t rps, int32_t c,
@@ -799,15 +869,16 @@ extern "C" int chap_bn_act_bwd(const float* dout, const float* y, const float* s
 extern "C" int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
                                    const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums,
                                    int32_t sums_persistent, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream) {
-    CHAP_REQUIRE(dgamma_acc && dbeta_acc, CHAP_ERR_BAD_ARG, "bn_act_bwd_acc: the gradient accumulators are required");
     return bn_act_bwd_impl(dout, y, ss, mi, slope, drop_nc, drop_el, n, rps, c, (train ? 1 : 0) | 2 | (sums_persistent ? 4 : 0), sums, dy,
                            dgamma_acc, dbeta_acc, stream);
 }
 
 static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, const float* mi, float slope, const float* drop_nc,
                            const float* drop_el, int32_t n, int64_t rps, int32_t c, int32_t train, double* sums, float* dy, float* dgamma,
-                           float* dbeta, void* stream) {
+                           float* dbeta, void* stream, const chap_dropout_rng* rng_in) {
     CHAP_REQUIRE(dout && y && ss && mi && sums && dy && n > 0 && rps > 0 && c > 0, CHAP_ERR_BAD_ARG, "bn_act_bwd: bad argument");
+    CHAP_REQUIRE(rng_ok(rng_in) && !(rng_in && drop_el), CHAP_ERR_BAD_ARG, "bn_act_bwd: dropout needs 0 < p < 1 and either a mask or a generator");
+    const DropRng rng = make_rng(rng_in);
     CHAP_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), CHAP_ERR_BAD_ARG, "bn_act_bwd: dgamma/dbeta must both be set or both NULL");
     const int64_t rows = (int64_t)n * rps, total = rows * c;
     cudaStream_t st = S(stream);
@@ -815,6 +886,7 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
     const int cg = v4 ? c / 4 : c;
     CHAP_REQUIRE(cg <= 256, CHAP_ERR_BAD_ARG, "bn_act_bwd: too many channels (%d)", c);
     const bool fixed = v4 && 256 % cg == 0 && all16({ss, mi, drop_nc}) && round_tf32_on() == 0;
+    CHAP_REQUIRE(fixed || !rng.on, CHAP_ERR_BAD_ARG, "bn_act_bwd: generated dropout needs c %% 4 == 0, 256 %% (c / 4) == 0 and 16-byte aligned buffers (c = %d)", c);
     // persistent sums (bit 2): zero on entry, re-zeroed by the last block of the apply kernel -- only the fixed-group kernels do that;
     // on the generic path the buffer is zeroed before AND after by launches (it must come back zeroed either way)
     const bool persist = (train & 4) != 0;
@@ -825,15 +897,15 @@ static int bn_act_bwd_impl(const float* dout, const float* y, const float* ss, c
     if (fixed) {
         if ((train & 1) || dgamma) {
             const int rgrid = grid_for(total / 4, 256 * kEwUnroll * 2, kNumSMs * 8);
-            if (drop_el) launch_k(bn_act_bwd_reduce_fixed_kernel<true>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
-            else launch_k(bn_act_bwd_reduce_fixed_kernel<false>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums);
+            if (drop_el || rng.on) launch_k(bn_act_bwd_reduce_fixed_kernel<true>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums, rng);
+            else launch_k(bn_act_bwd_reduce_fixed_kernel<false>, rgrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, total / 4, c, sums, rng);
             CHAP_TRY(launched("bn_act_bwd_reduce_fixed_kernel"));
         }
         const int agrid = grid_for(total / 4, 256 * kEwUnroll);
         static const int rev = getenv("CHAP_EW_REVERSE") ? atoi(getenv("CHAP_EW_REVERSE")) : 0;
         const int tb = train | ((rev & 2) ? 8 : 0);
-        if (drop_el) launch_k(bn_act_bwd_apply_fixed_kernel<true>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
-        else launch_k(bn_act_bwd_apply_fixed_kernel<false>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta);
+        if (drop_el || rng.on) launch_k(bn_act_bwd_apply_fixed_kernel<true>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta, rng);
+        else launch_k(bn_act_bwd_apply_fixed_kernel<false>, agrid, 256, 0, st, dout, y, ss, mi, slope, drop_nc, drop_el, rps, c, total / 4, tb, inv_count, sums, dy, dgamma, dbeta, rng);
         return launched("bn_act_bwd_apply_fixed_kernel");
     }
     const int rpb = 256 / cg;

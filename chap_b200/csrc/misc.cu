@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, int
 int zero_async(void* ptr, size_t bytes, cudaStream_t st) {
     static const bool use_memset = getenv("CHAP_ZERO_MEMSET") != nullptr;
     if (bytes == 0) return CHAP_OK;
+    static const bool trace = getenv("CHAP_ZERO_TRACE") != nullptr;      // developer aid: which callers still need a zero-fill launch
+    if (trace) fprintf(stderr, "zero_async %zu\n", bytes);
     if (use_memset || (bytes & 3u) || (reinterpret_cast<uintptr_t>(ptr) & 3u)) { CHAP_CUDA(cudaMemsetAsync(ptr, 0, bytes, st)); return CHAP_OK; }
     const int64_t n = (int64_t)(bytes >> 2);
     const bool vec = (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;

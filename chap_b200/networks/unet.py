@@ -47,9 +47,12 @@ class ConvBlock(nn.Module):
             a = ops.conv_bn_act_eval(x, c1.weight, c1.bias, CONV_K3, b1, LEAKY_SLOPE, cat=cat)
             return ops.conv_bn_act_eval(a, c2.weight, c2.bias, CONV_K3, b2, LEAKY_SLOPE)
         y, sums = ops.conv_stats(x, c1.weight, c1.bias, CONV_K3, b1.training, feeds_train_bn=b1.training, cat=cat, bn=b1)
-        if drop_mask is None:
-            drop_mask = _elementwise_dropout_mask(y, self.dropout_p, self.training)
-        a = ops.bn_act(y, b1, LEAKY_SLOPE, sums=sums, drop_el=drop_mask)
+        rng = None
+        if drop_mask is None and self.training:
+            rng = ops.dropout_rng(self.dropout_p, y.shape[1])          # nn.Dropout(p) with the mask generated inside the kernels
+            if rng is None:
+                drop_mask = _elementwise_dropout_mask(y, self.dropout_p, self.training)
+        a = ops.bn_act(y, b1, LEAKY_SLOPE, sums=sums, drop_el=drop_mask, drop_rng=rng)
         y, sums = ops.conv_stats(a, c2.weight, c2.bias, CONV_K3, b2.training, feeds_train_bn=b2.training, bn=b2)
         return ops.bn_act(y, b2, LEAKY_SLOPE, sums=sums)
 

@@ -413,7 +413,7 @@ def conv_bn_act_eval(x, weight, bias, kind, bn, slope, residual=None, cat=None):
 # ----------------------------------------------------------------------------- BN + activation
 class _BnAct(Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, residual, sums, running, train, update, slope, eps, momentum, drop_nc, drop_el, pre=None):
+    def forward(ctx, y, gamma, beta, residual, sums, running, train, update, slope, eps, momentum, drop_nc, drop_el, pre=None, rng=None):
         _require_cuda(y, gamma, beta)
         y = cl(y)
         n, c = y.shape[0], y.shape[1]
@@ -444,7 +444,12 @@ class _BnAct(Function):
         if drop_el is not None:
             drop_el = cl(drop_el)
         out = empty_cl(y.shape, dev)
-        check(lib().chap_bn_act_fwd(_p(y), _p(ss), slope, _p(drop_nc), _p(drop_el), _p(residual), n, rps, c, _p(out), _stream()))
+        ctx.rng = rng
+        if rng is not None:           # generated elementwise dropout: (p, seed, subsequence, epoch tensor or None)
+            check(lib().chap_bn_act_fwd_rng(_p(y), _p(ss), slope, _p(drop_nc), ctypes.byref(_rng_struct(rng)), _p(residual), n, rps, c,
+                                            _p(out), _stream()))
+        else:
+            check(lib().chap_bn_act_fwd(_p(y), _p(ss), slope, _p(drop_nc), _p(drop_el), _p(residual), n, rps, c, _p(out), _stream()))
         ctx.save_for_backward(y, ss, mi, g, drop_nc, drop_el)
         ctx.cfg = (n, rps, c, bool(train), float(slope), residual is not None)
         ctx.sinks = (_sink_of(gamma), _sink_of(beta))
@@ -459,26 +464,61 @@ class _BnAct(Function):
         dev = dout.device
         dy = empty_cl(y.shape, dev)
         want_pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        if want_pg and _state["grad_sink"] and ctx.sinks[0] is not None and ctx.sinks[1] is not None:
-            psums = ctx.bwd_sums if _state["persistent_stats"] else None
+        rng = None if ctx.rng is None else ctypes.byref(_rng_struct(ctx.rng))
+        psums = ctx.bwd_sums if _state["persistent_stats"] else None         # zero on entry, handed back zeroed: no zero-fill launch
+        sink = want_pg and _state["grad_sink"] and ctx.sinks[0] is not None and ctx.sinks[1] is not None
+        dres = dout if (has_res and ctx.needs_input_grad[3]) else None
+        if sink or (not want_pg and psums is not None):
+            # parameter gradients ADDED into the optimiser's arena (sink), or none wanted at all (the feature-gradient probe of VAT2d)
             sums = psums if psums is not None else torch.empty(2 * c, dtype=torch.float64, device=dev)
-            check(lib().chap_bn_act_bwd_acc(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), _p(drop_el), n, rps, c,
-                                            1 if train else 0, _p(sums), 1 if psums is not None else 0, _p(dy), _p(ctx.sinks[0][0]),
-                                            _p(ctx.sinks[1][0]), _stream()))
-            dres = dout if (has_res and ctx.needs_input_grad[3]) else None
-            return (dy, None, None, dres) + (None,) * 10
+            dg, db = (ctx.sinks[0][0], ctx.sinks[1][0]) if sink else (None, None)
+            if rng is not None:
+                check(lib().chap_bn_act_bwd_rng(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), rng, n, rps, c, 1 if train else 0, _p(sums),
+                                                1 if psums is not None else 0, _p(dy), _p(dg), _p(db), 1, _stream()))
+            else:
+                check(lib().chap_bn_act_bwd_acc(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), _p(drop_el), n, rps, c,
+                                                1 if train else 0, _p(sums), 1 if psums is not None else 0, _p(dy), _p(dg), _p(db), _stream()))
+            return (dy, None, None, dres) + (None,) * 11
         sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
         dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
         dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_pg else None
-        check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,
-                                    1 if train else 0, _p(sums), _p(dy), _p(dgamma), _p(dbeta), _stream()))
-        dres = dout if (has_res and ctx.needs_input_grad[3]) else None
-        return (dy, dgamma, dbeta, dres) + (None,) * 10
+        if rng is not None:
+            check(lib().chap_bn_act_bwd_rng(_p(dout), _p(y), _p(ss), _p(mi), slope, _p(drop_nc), rng, n, rps, c, 1 if train else 0, _p(sums), 0,
+                                            _p(dy), _p(dgamma), _p(dbeta), 0, _stream()))
+        else:
+            check(lib().chap_bn_act_bwd(_p(dout), _p(y), _p(ss), _p(mi), _p(g), slope, _p(drop_nc), _p(drop_el), n, rps, c,
+                                        1 if train else 0, _p(sums), _p(dy), _p(dgamma), _p(dbeta), _stream()))
+        return (dy, dgamma, dbeta, dres) + (None,) * 11
 
 
-def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
+def _rng_struct(rng):
+    p, seed, sub, epoch = rng
+    return _lib.DropoutRng(float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(sub) & 0xFFFFFFFFFFFFFFFF, _p(epoch))
+
+
+def set_generated_dropout(flag):
+    """Elementwise dropout masks generated inside the BatchNorm / activation kernels (default on) instead of bernoulli_ mask tensors."""
+    _state["drop_rng"] = bool(flag)
+
+
+def set_dropout_epoch(epoch_dev):
+    """int64 CUDA tensor (or None) mixed into the dropout generator's key at RUN time: a trainer hands in its device-side iteration
+    counter so that every replay of a captured iteration draws new masks."""
+    _state["drop_epoch"] = epoch_dev
+
+
+def dropout_rng(p, c):
+    """Generator description for bn_act(drop_rng=...) or None when the generated form does not apply (inactive, unsupported layout)."""
+    if not _state.get("drop_rng", True) or not (0.0 < p < 1.0) or c % 4 != 0 or 256 % (c // 4) != 0:
+        return None
+    _state["drop_calls"] = _state.get("drop_calls", 0) + 1
+    return (p, torch.initial_seed(), _state["drop_calls"], _state.get("drop_epoch"))
+
+
+def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None, drop_rng=None):
     """act(BatchNorm(y)) * drop + residual with the semantics of the nn.BatchNormNd holder `bn`
-    (train/eval, eps, momentum, running statistics)."""
+    (train/eval, eps, momentum, running statistics).  drop_rng: dropout_rng(p, C) description -- nn.Dropout(p) with the mask
+    generated inside the kernels (exclusive with drop_el)."""
     train = bn.training or not bn.track_running_stats
     running = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if bn.track_running_stats else None
     update = bn.training and bn.track_running_stats and _state["bn_tracking"]
@@ -489,7 +529,7 @@ def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None):
     if isinstance(sums, BnStats):
         sums, pre = sums[0], (sums[1], sums[2])
     return _BnAct.apply(y, bn.weight, bn.bias, residual, sums, running, train, update, float(slope), float(bn.eps),
-                        float(momentum), drop_nc, drop_el, pre)
+                        float(momentum), drop_nc, drop_el, pre, drop_rng)
 
 
 # ----------------------------------------------------------------------------- pooling / upsampling / concat

@@ -377,10 +377,14 @@ class ChapTrainer:
         ops.invalidate_weight_cache()
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            ops.schedule_step(st["iter"], self.base_lr, self.max_iterations, self.consistency, self.rampup, self.opt.lr_dev, st["cw"])
-            st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"][0], d_init=st["d_init"],
-                                        dropout_masks=st["drop"])
+        ops.set_dropout_epoch(st["iter"])          # generated nn.Dropout masks: the device-side iteration counter keys every replay differently
+        try:
+            with torch.cuda.graph(self.graph):
+                ops.schedule_step(st["iter"], self.base_lr, self.max_iterations, self.consistency, self.rampup, self.opt.lr_dev, st["cw"])
+                st["aux"] = self._iteration(st["volume"], st["label"], img_mask=st["mask"], cw=st["cw"][0], d_init=st["d_init"],
+                                            dropout_masks=st["drop"])
+        finally:
+            ops.set_dropout_epoch(None)
         self.static = st
 
     def close(self):

@@ -203,9 +203,31 @@ int chap_bn_act_bwd(const float* dout, const float* y, const float* scale_shift,
 /* same, with the BatchNorm parameter gradients ADDED into dgamma_acc / dbeta_acc (gradient-sink form, see chap_conv_wgrad_acc) */
 /* sums_persistent = 1: `sums` holds 2c + 1 doubles, is ALL ZERO on entry and is left all zero (cleared by the last block of the
  * apply kernel): no zero-fill launch per call.  0: `sums` (2c doubles) is zeroed by the call. */
+/* dgamma_acc / dbeta_acc may both be NULL (data gradient only, e.g. the feature-gradient probe of VAT2d) */
 int chap_bn_act_bwd_acc(const float* dout, const float* y, const float* scale_shift, const float* mean_invstd, float slope,
                         const float* drop_nc, const float* drop_el, int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
                         double* sums, int32_t sums_persistent, float* dy, float* dgamma_acc, float* dbeta_acc, void* stream);
+/* nn.Dropout(p) of ConvBlock (code/networks/unet.py:53, after the first LeakyReLU) WITHOUT a mask tensor: the 1/(1-p)-scaled keep
+ * mask is generated inside the kernels (Philox4x32-10, counter = (vector index, subsequence), key = (seed, *epoch_dev)) and
+ * regenerated identically by the backward given the same description.  epoch_dev (nullable) is an int64 in DEVICE memory read at
+ * run time -- a trainer's iteration counter -- so that a replayed CUDA graph draws new masks every iteration; subsequence separates
+ * the layers / passes inside one iteration.  Replaces `empty_like().bernoulli_(1-p).div_(1-p)` (two launches and three passes over
+ * an activation-sized tensor per dropout) plus the mask reads of the forward and both backward passes.  Needs c % 4 == 0 and
+ * 256 % (c / 4) == 0 (every layer of the two networks).  The draws are NOT torch's Bernoulli stream (masks are random either way;
+ * parity tests pass explicit masks through drop_el). */
+typedef struct {
+    float p;                  /* drop probability, 0 < p < 1 */
+    uint64_t seed;
+    uint64_t subsequence;
+    const int64_t* epoch_dev; /* nullable */
+} chap_dropout_rng;
+int chap_bn_act_fwd_rng(const float* y, const float* scale_shift, float slope, const float* drop_nc, const chap_dropout_rng* rng,
+                        const float* residual, int32_t n, int64_t rows_per_sample, int32_t c, float* out, void* stream);
+/* backward; accumulate = 1 adds dgamma / dbeta into their targets (gradient-sink form); dgamma / dbeta may both be NULL;
+ * sums / sums_persistent as in chap_bn_act_bwd_acc */
+int chap_bn_act_bwd_rng(const float* dout, const float* y, const float* scale_shift, const float* mean_invstd, float slope,
+                        const float* drop_nc, const chap_dropout_rng* rng, int32_t n, int64_t rows_per_sample, int32_t c, int32_t train,
+                        double* sums, int32_t sums_persistent, float* dy, float* dgamma, float* dbeta, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------ pooling / upsampling / concat
  * MaxPool2d(2) code/networks/unet.py:69; Upsample(x2, bilinear|trilinear, align_corners=True)

@@ -203,6 +203,47 @@ def test_bn_act_fwd_bwd(nd, train, with_res, drop):
         assert int(bn_g.num_batches_tracked) == int(bn.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("p,c", [(0.05, 16), (0.5, 256), (0.3, 64)])
+def test_generated_dropout_equals_its_own_mask_and_has_the_right_rate(p, c):
+    """nn.Dropout(p) generated inside the BatchNorm / activation kernels (chap_bn_act_{fwd,bwd}_rng, unet.py:53): the mask the
+    forward applied is recovered with an identity BatchNorm on ones; the generated backward must equal the explicit-mask backward
+    on that mask; keep rate = 1 - p within 5 sigma; subsequence and the device-side epoch word change the draw, equal keys repeat it."""
+    ops = _ops()
+    torch.manual_seed(3)
+    n, h, w = 4, 24, 20
+    bn = torch.nn.BatchNorm2d(c).to(DEV).eval()                       # identity: scale 1 / sqrt(1 + eps), shift 0
+    ones = _to_cl(torch.ones(n, c, h, w, device=DEV))
+    epoch = torch.zeros(1, dtype=torch.int64, device=DEV)
+    rng = (p, 1234, 7, epoch)
+    inv = float(torch.sqrt(torch.tensor(1.0 + bn.eps)))
+    mask = ops.bn_act(ones, bn, 1.0, drop_rng=rng) * inv
+    vals = torch.unique(mask)
+    keep = 1.0 - p
+    assert vals.numel() == 2 and abs(float(vals[0])) == 0.0 and abs(float(vals[1]) - 1.0 / keep) < 1e-5
+    rate = float((mask > 0).double().mean())
+    assert abs(rate - keep) < 5.0 * (keep * p / mask.numel()) ** 0.5, (rate, keep)
+    for ch in (0, c - 1):                                              # no channel / position structure
+        assert abs(float((mask[:, ch] > 0).double().mean()) - keep) < 6.0 * (keep * p / mask[:, ch].numel()) ** 0.5
+    assert torch.equal(mask, ops.bn_act(ones, bn, 1.0, drop_rng=rng) * inv)
+    assert not torch.equal(mask, ops.bn_act(ones, bn, 1.0, drop_rng=(p, 1234, 8, epoch)) * inv)
+    epoch.fill_(5)
+    assert not torch.equal(mask, ops.bn_act(ones, bn, 1.0, drop_rng=rng) * inv)
+    epoch.fill_(0)
+    # train-mode layer: generated forward / backward == explicit-mask forward / backward on the recovered mask
+    bn_a = torch.nn.BatchNorm2d(c).to(DEV).train()
+    bn_b = torch.nn.BatchNorm2d(c).to(DEV).train()
+    y = _to_cl(torch.randn(n, c, h, w, device=DEV) * 2 + 0.3)
+    gout = _to_cl(torch.randn(n, c, h, w, device=DEV))
+    ya, yb = y.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    out_a = ops.bn_act(ya, bn_a, 0.01, drop_rng=rng)
+    out_b = ops.bn_act(yb, bn_b, 0.01, drop_el=mask)
+    assert torch.equal(out_a, out_b)
+    ga = torch.autograd.grad(out_a, [ya, bn_a.weight, bn_a.bias], gout)
+    gb = torch.autograd.grad(out_b, [yb, bn_b.weight, bn_b.bias], gout)
+    for a_, b_, nm in zip(ga, gb, ["dy", "dgamma", "dbeta"]):
+        assert rel_err(a_, b_) < 1e-6, nm
+
+
 def test_bn_tracking_disabled_keeps_running_stats():
     ops = _ops()
     bn = torch.nn.BatchNorm2d(16).to(DEV).train()
