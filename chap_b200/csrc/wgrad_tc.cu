@@ -12,6 +12,10 @@
 //   * row reuse (k3, <= 128 input channels per CTA): the x box carries an h-halo and serves the three ky taps at row offsets;
 //   * swap (row reuse and cin <= 32): x is the M operand, its LBO is tw rows so that chunk g IS tap ky = g (one MMA = 3 taps),
 //     dy is the N operand with N = cout (>= 16; the 4-channel heads are zero-filled);
+//   * taps-in-N (row reuse and cout <= 64; supersedes swap): dW[ky, kx] = sum_q x[q + (ky - 1) W] dy[q - (kx - 1)], so the kx shift can sit on
+//     dy: x is the M operand as in swap mode (chunk g = tap ky) and dy is loaded three times, shifted by kx, as ONE N operand
+//     [3 kx][cout chunks] (LBO = box stride).  One MMA per K step covers all nine taps at N = 96 / 192 where swap needed three (N = cout)
+//     and the plain mode nine -- these kernels are bound by the NUMBER of K = 8 MMAs (~40 ns each), not by their width;
 //   * transposed conv: M = x (tap independent), N = dy gathered per tap through its [2C, W, 2, H, N] view.
 // Work split: blockIdx.z = (M tile, N tile), blockIdx.y = tap group (as many taps as fit the TMEM columns), blockIdx.x = slice
 // of the pixel blocks.  Each CTA accumulates its slice in TMEM (fp32) and adds it either straight into the torch-layout
@@ -41,6 +45,10 @@ struct WgParams {
     int k2s2;                       // 1: k2 s2 convolution (strided or transposed): the N operand is the high-resolution tensor gathered per
                                     // tap through one tensor map per tap; the pixel blocks tile the LOW-resolution grid
     int swap;                       // 1 (reuse mode, cin <= 32): x is the M operand (M = 4 "ky" chunks x 32 ci, chunk stride tw rows), dy the N operand
+    int tapn;                       // 1 (row-reuse geometry, cout <= 64): ALL NINE in-plane taps per MMA -- x is the M operand (4 "ky" chunks of one
+                                    // 32-channel group, chunk stride tw rows of the h-haloed box), dy the N operand loaded THREE times shifted by
+                                    // kx (N = 3 kx x cout rounded up to 32); one MMA per K step and 32-channel group of x
+    int n_cols;                     // tapn: N of the MMA = 3 * a_groups * 32 = accumulator columns per (unit, x channel group)
     int acc2;                       // experiment (CHAP_WG_ACC2): alternate K steps between two TMEM accumulators, summed in the epilogue
     int n_mma;                      // swap mode: MMA N = cout of this CTA rounded up to 16
     int reuse;                      // 1: the x box carries an h-halo (th + 2 rows) and serves the 3 ky taps at row offsets ky * tw
@@ -108,7 +116,7 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
     const int m_tiles = p.cout / p.m_tile;
     const int m0 = (blockIdx.z % m_tiles) * p.m_tile, n0 = (blockIdx.z / m_tiles) * p.n_tile;      // n0 > 0 only when cin > 256
     const int tap0 = blockIdx.y * p.tg;
-    const int units = p.reuse ? p.taps / 3 : p.taps;               // scheduling units: taps, or (kz, kx) pairs
+    const int units = p.tapn ? p.taps / 9 : (p.reuse ? p.taps / 3 : p.taps);   // scheduling units: taps, (kz, kx) pairs, or kz planes
     const int ntaps = min(p.tg, units - tap0);
     const int nky = p.reuse ? 3 : 1;
     const int blk0 = blockIdx.x * p.blocks_per_cta;
@@ -157,7 +165,17 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
                 {   // the dy box of this block: once, for all taps
                     mbar_wait(&a_empty[as], aph ^ 1);
                     if (p.debug & 2) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[as])) : "memory");
-                    else {
+                    else if (p.tapn) {
+                        // three copies of the dy box shifted by kx: chunk (kx, g) holds dy[q - (kx - 1)] for the block's pixels q
+                        mbar_expect_tx(&a_full[as], 3u * (uint32_t)p.a_groups * (uint32_t)p.p_box * 128u);
+                        uint8_t* a_dst = a_base + (size_t)as * p.a_stage_bytes;
+                        for (int kx = 0; kx < 3; ++kx)
+                            for (int g = 0; g < p.a_groups; ++g) {
+                                uint8_t* dst = a_dst + (size_t)(kx * p.a_groups + g) * a_chunk;
+                                if (p.nd == 2) tma_load_4d(dst, &tmA, &a_full[as], m0 + g * p.a_cpg, w0 + 1 - kx, h0, img);
+                                else tma_load_5d(dst, &tmA, &a_full[as], m0 + g * p.a_cpg, w0 + 1 - kx, h0, d0, img);
+                            }
+                    } else {
                         mbar_expect_tx(&a_full[as], (uint32_t)p.a_groups * (uint32_t)p.p_box * 128u);
                         uint8_t* a_dst = a_base + (size_t)as * p.a_stage_bytes;
                         for (int g = 0; g < p.a_groups; ++g) {
@@ -170,7 +188,8 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
                 for (int ti = 0; ti < ntaps; ++ti) {
                     const int tap = tap0 + ti;
                     int kx, ky, kz;
-                    if (p.reuse) { kx = tap % 3; kz = tap / 3; ky = 0; }               // box origin one row above the tile
+                    if (p.tapn) { kx = 1; kz = tap; ky = 0; }                          // unit = kz; no kx shift on x (it sits on dy)
+                    else if (p.reuse) { kx = tap % 3; kz = tap / 3; ky = 0; }          // box origin one row above the tile
                     else if (p.ksz == 3) { kx = tap % 3; ky = (tap / 3) % 3; kz = tap / 9; } else { kx = ky = kz = 0; }
                     mbar_wait(&empty[s], ph ^ 1);
                     if (p.debug & 2) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory"); if (++s == p.stages) { s = 0; ph ^= 1; } continue; }
@@ -197,9 +216,9 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
         // on the M side: the "channel chunk" stride (LBO) of its descriptor is tw rows of the h-haloed box, i.e. chunk g IS
         // tap ky = g (chunk 3 is junk that is never stored), and dy is the N operand with N = cout.  One MMA per K step
         // covers three taps at N = cout (16..128) instead of N = 3 * 32 with 16 of 128 rows in use.
-        const bool swap = p.swap != 0;
+        const bool swap = p.swap != 0 || p.tapn != 0;
         // the extra M chunks alias chunk 0 (one chunk, LBO = 0) or read whatever follows in shared memory: never stored
-        const uint32_t a_lbo = p.a_groups >= 2 ? a_chunk : 0u;
+        const uint32_t a_lbo = (p.a_groups >= 2 || p.tapn) ? a_chunk : 0u;
         const uint32_t b_lbo = swap ? (uint32_t)p.tw * b_row : b_chunk;
         // descriptor words: lo = start >> 4 | (LBO >> 4) << 16; hi = SBO >> 4 (4 rows) | version 1 (bit 46) | layout 1 (bit 61)
         const uint32_t a_hi = ((4u * a_row) >> 4) | (1u << 14) | (1u << 29);
@@ -211,8 +230,9 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
         const uint32_t b_ky = ((uint32_t)p.tw * b_row) >> 4;                     // reuse mode: tap ky starts ky * tw rows further down
         const int ksteps = (p.debug & 1) ? 0 : p.P / 8;
         const int n_sub = swap ? 1 : nky;
-        const uint32_t id = swap ? ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(p.n_mma >> 3) << 17)) : idesc;
-        const uint32_t d_stride = swap ? (uint32_t)p.n_mma : (uint32_t)(nky * p.n_tile);
+        const uint32_t n_mma = p.tapn ? (uint32_t)p.n_cols : (uint32_t)p.n_mma;
+        const uint32_t id = swap ? ((idesc & ~(0x3Fu << 17)) | ((n_mma >> 3) << 17)) : idesc;
+        const uint32_t d_stride = p.tapn ? (uint32_t)(p.b_groups * p.n_cols) : (swap ? (uint32_t)p.n_mma : (uint32_t)(nky * p.n_tile));
         int s = 0; uint32_t ph = 0;
         int as = 0; uint32_t aph = 0;
         uint32_t a_lo = a_lo0, b_lo = b_lo0;
@@ -222,6 +242,28 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
             for (int ti = 0; ti < ntaps; ++ti) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
+                if (p.tapn) {
+                    if (elect_one()) {
+                        // per 32-channel group of x: ONE MMA per K step, M = (ky, ci), N = (kx, co)
+                        for (int g = 0; g < p.b_groups; ++g) {
+                            const uint32_t d_tmem = d_tap + (uint32_t)(g * p.n_cols);
+                            uint32_t m_d = b_lo + (uint32_t)g * (b_chunk >> 4), n_d = a_lo;
+                            if ((ksteps & 7) == 0) {
+                                for (int k0 = 0; k0 < ksteps; k0 += 8) {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k)
+                                        tc_mma_tf32_lh(d_tmem, m_d + (uint32_t)k * b_k, b_hi, n_d + (uint32_t)k * a_k, a_hi, id, (uint32_t)((b | k0 | k) != 0));
+                                    m_d += 8u * b_k; n_d += 8u * a_k;
+                                }
+                            } else {
+                                for (int k = 0; k < ksteps; ++k)
+                                    tc_mma_tf32_lh(d_tmem, m_d + (uint32_t)k * b_k, b_hi, n_d + (uint32_t)k * a_k, a_hi, id, (uint32_t)((b | k) != 0));
+                            }
+                        }
+                        tc_commit(&empty[s]);
+                        if (ti == ntaps - 1) tc_commit(&a_empty[as]);
+                    }
+                } else
                 if (elect_one()) {
                     for (int ky = 0; ky < n_sub; ++ky) {
                         const uint32_t d_tmem = d_tap + (uint32_t)(ky * p.n_tile);
@@ -270,7 +312,37 @@ __device__ __forceinline__ void wgrad_tc_kernel_body(const CUtensorMap& tmA, con
         const bool valid = row < p.m_tile && row < p.mma_m;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (p.swap) {
+        if (p.tapn) {
+            // accumulator row = (ky = lane quarter, ci = lane of x channel group g); columns = [unit kz][g][kx][co chunk][32 co]
+            const int ky = lg;
+            if (ky < 3) {
+                for (int ti = 0; ti < ntaps; ++ti) {
+                    const int kz = tap0 + ti;
+                    for (int g = 0; g < p.b_groups; ++g) {
+                        const int ci = n0 + g * 32 + lane;
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int tap = (kz * 3 + ky) * 3 + kx;
+                            for (int c0 = 0; c0 < p.a_groups * 32; c0 += 16) {
+                                float v[16];
+                                tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((ti * p.b_groups + g) * p.n_cols + kx * p.a_groups * 32 + c0), v);
+                                if (ci < p.cin && c0 < p.m_tile) {                  // else: zero-filled channels of x / dy
+                                    if (p.acc) {                                    // [tap][ci][co] scratch, 128-bit reductions (cout % 16 == 0)
+                                        float* a = p.acc + ((int64_t)tap * p.cin + ci) * p.cout + m0 + c0;
+#pragma unroll
+                                        for (int j = 0; j < 16; j += 4) red_add_v4(a + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                    } else {
+                                        float* dst = p.dw + (int64_t)ci * p.s_ci + tap;
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j)
+                                            if (c0 + j < p.m_tile) atomicAdd(dst + (int64_t)(m0 + c0 + j) * p.s_co, v[j]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (p.swap) {
             // accumulator row = (ky = lane quarter, ci = lane); columns = [unit (kz, kx)][co]
             const int ky = lg, ci = lane;
             if (ky < 3) {
@@ -376,14 +448,23 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.W = g.iW; p.H = g.iH; p.D = g.iD; p.n_img = g.n;
     if (down2) { p.W = g.oW; p.H = g.oH; p.D = g.oD; }
     choose_box8(p.W, p.H, p.D, p.tw, p.th, p.td);
-    const int n_tile_pre = v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin);
+    // taps-in-N mode (see the header): row-reuse geometry, dy has <= 64 channels.  x is split into 32-channel groups; a CTA takes as many
+    // groups as fit the 512 TMEM columns (n_cols accumulator columns per group and kz plane), the rest goes to blockIdx.z.
+    const bool tapn = g.kind == CHAP_CONV_K3 && v.cout <= 64 && p.W >= 8 && p.H >= 10 && getenv("CHAP_NO_ROW_REUSE") == nullptr &&
+                      getenv("CHAP_WG_NO_TAPN") == nullptr;
+    const int cin_groups = (v.cin + 31) / 32;
+    const int tapn_cols = 3 * ((v.cout + 31) / 32) * 32;
+    int tapn_bg = cin_groups;
+    while (tapn && (tapn_bg * tapn_cols > 512 || cin_groups % tapn_bg != 0)) --tapn_bg;
+    const int a_mult = tapn ? 3 : 1;                               // the dy stage holds three kx-shifted copies
+    const int n_tile_pre = tapn ? 32 * tapn_bg : (v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin));
     {
         // 128-pixel blocks (16 MMAs per pipeline stage instead of 8) when three stages still fit and the blocks fill the GPU
         int tw, th, td;
         choose_box8(p.W, p.H, p.D, tw, th, td, 128);
         const int m_pre = v.cout > 128 ? 128 : v.cout;
         const int P = (tw * th * td + 7) / 8 * 8;
-        const size_t a_bytes = (size_t)(((m_pre + 31) / 32) * 32) * P * 4, b_bytes = (size_t)n_tile_pre * P * 4;
+        const size_t a_bytes = (size_t)a_mult * (((m_pre + 31) / 32) * 32) * P * 4, b_bytes = (size_t)n_tile_pre * P * 4;
         const long blocks = (long)g.n * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th) * ((p.D + td - 1) / td);
         if (a_bytes * 2 + b_bytes * 3 <= 198 * 1024 && blocks >= 4 * kNumSMs && getenv("CHAP_WG_BOX") == nullptr) { p.tw = tw; p.th = th; p.td = td; }
     }
@@ -391,7 +472,7 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     // per (kz, kx) with an h-halo of one row above and below and serves the three ky taps -> 3 (9) x-boxes of 10 rows
     // instead of 9 (27) boxes of 8 rows per block.
     p.reuse = 0;
-    if (g.kind == CHAP_CONV_K3 && n_tile_pre <= 128 && p.W >= 8 && p.H >= 10 && getenv("CHAP_NO_ROW_REUSE") == nullptr) {
+    if (g.kind == CHAP_CONV_K3 && (n_tile_pre <= 128 || tapn) && p.W >= 8 && p.H >= 10 && getenv("CHAP_NO_ROW_REUSE") == nullptr) {
         p.reuse = 1; p.tw = 8; p.th = 8; p.td = 1;
         // The MMA-issuing warp pays a fixed ~0.4 us of scalar work per pipeline stage (measured), so large images use
         // larger pixel blocks (16 x 8 or 16 x 16: 16 / 32 MMAs per stage instead of 8) as long as >= 3 stages still fit
@@ -403,9 +484,11 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
             const int tw = c[0], th = c[1], P = tw * th;
             if (force && P != force) continue;
             if (p.W < tw || p.H < th + 2) continue;
-            const size_t a_bytes = (size_t)((m_tile_pre + 31) / 32) * 32 * P * 4, b_bytes = (size_t)n_tile_pre * tw * (th + 2) * 4;
+            const size_t a_bytes = (size_t)a_mult * ((m_tile_pre + 31) / 32) * 32 * P * 4, b_bytes = (size_t)n_tile_pre * tw * (th + 2) * 4;
             const long blocks = (long)g.n * p.D * ((p.W + tw - 1) / tw) * ((p.H + th - 1) / th);
-            if (a_bytes * 2 + b_bytes * (force ? 2 : 3) > 198 * 1024 || blocks < 4 * kNumSMs) continue;
+            // (taps-in-N: dy and x both advance once per block and plane, so two x slots pair with the two dy slots -- 64 -> 32 @ 12x128^2:
+            //  47.9 us with 8 x 8 blocks and three slots, 40.2 us with 16 x 8 blocks and two)
+            if (a_bytes * 2 + b_bytes * ((force || tapn) ? 2 : 3) > 198 * 1024 || blocks < 4 * kNumSMs) continue;
             p.tw = tw; p.th = th;
             break;
         }
@@ -417,26 +500,28 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.cout = v.cout; p.cin = v.cin;
     p.m_tile = v.cout > 128 ? 128 : v.cout;
-    p.n_tile = v.cin > 256 ? 256 : (v.cin < 32 ? 32 : v.cin);     // 16-channel tensors: the TMA box is 32 wide, channels 16..31 zero-filled
+    p.n_tile = n_tile_pre;                                        // 16-channel tensors: the TMA box is 32 wide, channels 16..31 zero-filled
+    p.tapn = (tapn && p.reuse) ? 1 : 0;
+    p.n_cols = tapn_cols;
     p.mma_m = 128;           // M = 64 has a different TMEM lane mapping; M = 128 costs the same tensor time
     p.a_cpg = 32; p.a_groups = (p.m_tile + 31) / 32;
     p.b_cpg = 32; p.b_groups = p.n_tile / 32;
-    p.a_stage_bytes = ((uint32_t)p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
+    p.a_stage_bytes = ((uint32_t)a_mult * p.a_groups * 32u * p.P * 4u + 1023u) & ~1023u;
     p.b_stage_bytes = ((uint32_t)p.n_tile * p.b_rows * 4u + 1023u) & ~1023u;
     p.a_stages = 2;
     const size_t a_ring = (size_t)p.a_stages * p.a_stage_bytes, stage = p.b_stage_bytes;      // `stage` = one per-tap ring slot (x box)
     p.blocks_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
-    const int n_tiles = v.cin > 256 ? v.cin / 256 : 1;
+    const int n_tiles = p.tapn ? cin_groups / tapn_bg : (v.cin > 256 ? v.cin / 256 : 1);
     const int zdim = (v.cout / p.m_tile) * n_tiles;
     // Work split.  Parallelism comes from (channel tiles) x (tap groups) x (pixel splits).  Every pixel split adds one
     // fp32 atomic per (padded) weight element in the epilogue, so splits are capped by an atomic budget (measured: a
     // 256x256x9 layer with 24 splits spent >80% of its 106 us in 14 M atomics); tap groups are made smaller instead.
     // Two CTAs share an SM when a CTA needs <= 256 TMEM columns and <= 100 KB of smem.
     const long weights_pad = (long)v.cout * p.n_tile * n_tiles * g.taps;
-    const int units = p.reuse ? g.taps / 3 : g.taps;          // what a CTA's tap group is made of
-    p.swap = p.reuse && p.b_groups == 1 && getenv("CHAP_WG_NO_SWAP") == nullptr;
+    const int units = p.tapn ? g.taps / 9 : (p.reuse ? g.taps / 3 : g.taps);          // what a CTA's tap group is made of
+    p.swap = !p.tapn && p.reuse && p.b_groups == 1 && getenv("CHAP_WG_NO_SWAP") == nullptr;
     p.n_mma = p.m_tile < 16 ? 16 : p.m_tile;
-    const int cols_per_unit = p.swap ? p.n_mma : (p.reuse ? 3 : 1) * p.n_tile;
+    const int cols_per_unit = p.tapn ? p.b_groups * p.n_cols : (p.swap ? p.n_mma : (p.reuse ? 3 : 1) * p.n_tile);
     // (measured with the 128-bit reduction path: 4 M elements is still the best budget, 8 M / 16 M are 5-15 % slower)
     const long budget = getenv("CHAP_WG_BUDGET") ? atol(getenv("CHAP_WG_BUDGET")) : 4000000L;
     long max_splits = budget / weights_pad;
@@ -512,9 +597,10 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(wgrad_tc_kernel_taps, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     const size_t smem = 1024 + a_ring + (size_t)stages * stage + (2 * stages + 1 + 2 * p.a_stages) * sizeof(uint64_t) + 16 +
-                        (p.swap ? (size_t)p.tw * 128 + 1024 : 0);      // swap mode: the junk 4th M chunk reads tw rows past the last x box
+                        ((p.swap || p.tapn) ? (size_t)p.tw * 128 + 1024 : 0);      // x on M: the junk 4th M chunk reads tw rows past the last x box
     // non-swap mode with scratch: vector reductions into [tap][M][N], then one transposing copy into the torch layout
-    p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && v.cin % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
+    // (taps-in-N: the scratch is [tap][cin][cout] -- the accumulator columns run along cout)
+    p.acc = (!p.swap && acc_ws && aligned16(acc_ws) && (p.tapn ? v.cout : v.cin) % 16 == 0 && getenv("CHAP_WG_NO_V4") == nullptr) ? acc_ws : nullptr;
     // the kernel ADDS (red.global.add) into its target: a fresh gradient needs it zeroed; in accumulate mode dw keeps its content
     // and the scratch arrives zeroed (the unpack kernel of its previous use cleared it)
     if (!accumulate) CHAP_TRY(zero_async(p.acc ? p.acc : dw, (size_t)g.taps * v.cin * v.cout * sizeof(float), st));
@@ -527,7 +613,8 @@ int tc_wgrad(const Geom& g, const float* x, const float* dy, float* dw, cudaStre
     CHAP_TRY(launched("wgrad_tc_kernel"));
     if (p.acc) {
         const int64_t total = (int64_t)g.taps * v.cin * v.cout;
-        launch_k(wgrad_unpack_kernel, grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st, p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci, accumulate ? 1 : 0);
+        if (p.tapn) launch_k(wgrad_unpack_kernel, grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st, p.acc, dw, g.taps, v.cin, v.cout, p.s_ci, p.s_co, accumulate ? 1 : 0);
+        else launch_k(wgrad_unpack_kernel, grid_for(total, 256 * 2, kNumSMs * 4), 256, 0, st, p.acc, dw, g.taps, v.cout, v.cin, p.s_co, p.s_ci, accumulate ? 1 : 0);
         CHAP_TRY(launched("wgrad_unpack_kernel"));
     }
     return 1;
