@@ -56,6 +56,12 @@ struct TcParams {
     int sup;                      // 1 (thin2d only): SUPER TILES -- one haloed box of 2 th + 2 rows per (kz, kx) serves TWO vertically adjacent
                                   // M tiles (rows 0.. and th..), one per TMEM accumulator: half the TMA issues / ring round trips per tile and
                                   // 1.25x instead of 1.5x halo overhead.  tiles_h / tiles_total then count super tiles.
+    int kxn;                      // 1 (thin2d only): the three kx taps sit in the N dimension -- ONE haloed box (th + 2 rows x 32 pixels) per (kz)
+                                  // and tile, 3 x KSTEPS MMAs with N = 3 nt (weight boxes of taps (ky, 0..2) are contiguous rows), and the
+                                  // epilogue adds the three column groups shifted by one pixel (warp = one image row of the tile, lane = x:
+                                  // out[x] = D0[x - 1] + D1[x] + D2[x + 1] through two shuffles).  Lanes 0 and 31 are halo: a tile yields
+                                  // step_w = 30 output pixels per row.  A third of the tcgen05.mma count and of the TMA boxes.
+    int step_w;                   // output pixels per tile row (tw, or 30 with kxn)
     int debug;                    // CHAP_TC_DEBUG bit mask (only with -DCHAP_TC_DEBUG_HOOKS)
     int b_resident;               // 1: all weight boxes [tap][kchunk] are loaded once per CTA and stay in shared memory
     int precise;                  // 1: split-operand 3xTF32 (kernel template PRECISE): 4 extra warps split every A stage into TF32 hi / lo halves
@@ -174,10 +180,11 @@ __device__ __forceinline__ void mma_term(uint32_t d_tmem, uint32_t a_lo, uint32_
     }
 }
 
-template <int KSTEPS, int NG, bool PRECISE>
+template <int KSTEPS, int NG, bool PRECISE, bool KXN = false>
 __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* full, uint64_t* empty,
                                                 uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base) {
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t n_mma = KXN ? 3u * (uint32_t)p.nt : (uint32_t)p.nt;          // KXN: columns = [kx][nt]
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_mma >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t row_bytes = KSTEPS * 32u;
     constexpr uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
     const uint32_t a_lo_off = p.a_lo_off >> 4, b_lo_off = p.b_lo_off >> 4;
@@ -228,11 +235,10 @@ __device__ __forceinline__ void issue_mmas_thin(const TcParams& p, uint8_t* a_ba
         const int buf = j & (p.n_buf - 1);
         mbar_wait(&tmem_empty[buf], (uint32_t)((j >> p.n_buf_lg) & 1) ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.nt);
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * n_mma;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-            constexpr int dummy = 0; (void)dummy;
-            const int kx = g % 3, kz = g / 3;                               // compile time after unrolling
+            const int kx = KXN ? 0 : g % 3, kz = KXN ? g : g / 3;            // compile time after unrolling
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (elect_one()) {
@@ -387,12 +393,12 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             // twin of issue_mmas_thin: one haloed box per (kz, kx) slot, only the ring position is carried
             int s = 0; uint32_t ph = 0;
             uint8_t* a_dst = a_base;
-            const int ng = p.nd == 2 ? 3 : 9;
+            const int ng = p.kxn ? (p.nd == 2 ? 1 : 3) : (p.nd == 2 ? 3 : 9);
             TileIter tj;
             for (tj.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.tiles_d); tj.tile < p.tiles_total; tj.next(p.tiles_w, p.tiles_h, p.tiles_d)) {
-                const int w0 = tj.tx * p.tw - 1, h0 = tj.ty * (p.sup ? 2 * p.th : p.th) - 1, d0 = tj.tz * p.td - 1;
+                const int w0 = tj.tx * p.step_w - 1, h0 = tj.ty * (p.sup ? 2 * p.th : p.th) - 1, d0 = tj.tz * p.td - 1;
                 for (int g = 0; g < ng; ++g) {
-                    const int kx = g % 3, kz = g / 3;
+                    const int kx = p.kxn ? 0 : g % 3, kz = p.kxn ? g : g / 3;
                     mbar_wait(&empty[s], ph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(&full[s], p.a_box_bytes);
@@ -452,6 +458,12 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
         }   // generic producer
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        if (p.thin2d && p.kxn) {
+            if (p.nd == 2) { if (p.kc == 32) issue_mmas_thin<4, 1, PRECISE, true>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 1, PRECISE, true>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base); }
+            else           { if (p.kc == 32) issue_mmas_thin<4, 3, PRECISE, true>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base);
+                             else issue_mmas_thin<2, 3, PRECISE, true>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base); }
+        } else
         if (p.thin2d) {
             if (p.nd == 2) { if (p.kc == 32) issue_mmas_thin<4, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base);
                              else issue_mmas_thin<2, 3, PRECISE>(p, a_base, b_base, ready, empty, tmem_full, tmem_empty, b_full, tmem_base); }
@@ -525,13 +537,13 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             const int jj = jj0 + ((sup && !alternate) ? sb : 0);
             const int buf = jj & (p.n_buf - 1);
             const uint32_t use = (uint32_t)(jj >> p.n_buf_lg);
-            const int ow = ti.tx * p.tw + dx, oh = (sup ? 2 * ti.ty + sb : ti.ty) * p.th + dy, od = ti.tz * p.td + dz;
-            const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D;
+            const int ow = p.kxn ? ti.tx * p.step_w + dx - 1 : ti.tx * p.tw + dx, oh = (sup ? 2 * ti.ty + sb : ti.ty) * p.th + dy, od = ti.tz * p.td + dz;
+            const bool valid = (dz < p.td) && ow < p.W && oh < p.H && od < p.D && (!p.kxn || (dx >= 1 && dx <= p.step_w));
             const int64_t row = (((int64_t)ti.img * p.D + od) * p.H + oh) * p.W + ow;
             TC_WAIT(&tmem_full[buf], use & 1u);
             if (jj == 0 && threadIdx.x == 64) TC_TRACE(3);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * p.nt);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * (p.kxn ? 3 * p.nt : p.nt));
             // one 16-column chunk: +bias, store, BatchNorm statistics
             auto process = [&](const uint32_t (&raw)[16], const int c0) {
                 float v[16];
@@ -608,6 +620,26 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             };
             uint32_t ra[16], rb[16];
             int c0 = c_begin;
+            if (p.kxn) {
+                // columns [kx][nt]: out[x] = D0[x - 1] + D1[x] + D2[x + 1]; this warp is one image row of the tile, lane = x
+                for (; c0 < c_end; c0 += 16) {
+                    tc_ld16_issue(t_addr + (uint32_t)c0, ra);
+                    tc_ld16_issue(t_addr + (uint32_t)(p.nt + c0), rb);
+                    tc_ld16_fence(ra); tc_ld16_fence(rb);
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4)
+                        rb[j4] = __float_as_uint(__uint_as_float(__shfl_up_sync(0xffffffffu, ra[j4], 1)) + __uint_as_float(rb[j4]));
+                    tc_ld16_issue(t_addr + (uint32_t)(2 * p.nt + c0), ra);
+                    tc_ld16_fence(ra);
+                    if (c0 + 16 >= c_end) release();
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4)
+                        rb[j4] = __float_as_uint(__uint_as_float(rb[j4]) + __uint_as_float(__shfl_down_sync(0xffffffffu, ra[j4], 1)));
+                    process(rb, c0);
+                }
+                if (threadIdx.x == 64) { if (jj == 0) TC_TRACE(4); TC_TRACE(5); }
+                continue;
+            }
             tc_ld16_issue(t_addr + (uint32_t)c0, ra);
             while (true) {
                 tc_ld16_fence(ra);
@@ -828,7 +860,23 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         }
         if (best_tw) { p.reuse = 1; p.tw = best_tw; p.th = 128 / best_tw; p.td = 1; }
     }
-    p.tiles_w = (p.W + p.tw - 1) / p.tw; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
+    // kx-in-N (see TcParams::kxn): thin layers (one k chunk, N <= 32), plain output, training kernels.  MEASURED on what bounds those
+    // layers: the tensor pipe spends ~36 cycles per M128 x K8 TF32 MMA whatever N is (the ncu source view shows the issuing warp
+    // stalled on the MMA queue 54 % of its time), so 18 (2D) / 54 (3D) MMAs of N = 16 per tile become 6 / 18 of N = 48.
+    // Result (tools/conv_bench.py): 3D 16 -> 16 @ 2x112x112x80 forward 149 -> 105 us, data gradient 148 -> 88 us.  In 2D the 18 MMAs
+    // were not the only bound: with 12 % more tiles (30 of 32 columns useful) and three TMEM reads + 32 shuffles per tile in the
+    // epilogue the layer gets SLOWER (16 -> 16 @ 12x256^2: 40.3 -> 43.5 us), so 2D keeps the three-box tile (CHAP_TC_KXN2D=1 to try).
+    // resident weights up to 112 KB for these layers (3D 32 -> 32: 27 taps x 4 KB = 108 KB): one CTA per SM then, which the shorter
+    // MMA stream of the kx-in-N tile more than pays for (CHAP_TC_KXN_RES overrides the cap in KB)
+    static const size_t kxn_res_cap = (getenv("CHAP_TC_KXN_RES") ? (size_t)atoi(getenv("CHAP_TC_KXN_RES")) : 112u) * 1024u;
+    p.step_w = p.tw;
+    p.kxn = (p.reuse && p.mode == 0 && K <= 32 && N <= 32 && !out_b && !epi && p.W >= 32 && p.H >= 6 && TC_DBG_HOST_OFF &&
+             (g.nd == 3 || getenv("CHAP_TC_KXN2D") != nullptr) &&
+             (size_t)p.taps * N * K * 4 <= kxn_res_cap && getenv("CHAP_NO_RESIDENT_B") == nullptr &&        // weights resident (thin2d loops)
+             g_precise_max_c.load(std::memory_order_relaxed) == 0 && getenv("CHAP_TC_NO_KXN") == nullptr && getenv("CHAP_TC_NO_THIN2D") == nullptr &&
+             getenv("CHAP_TC_SUPER") == nullptr) ? 1 : 0;
+    if (p.kxn) { p.tw = 32; p.th = 4; p.td = 1; p.step_w = 30; }
+    p.tiles_w = (p.W + p.step_w - 1) / p.step_w; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
     p.n_total = N; p.nt = N > 256 ? 256 : N;
     p.tiles_total = g.n * p.tiles_d * p.tiles_h * p.tiles_w;
@@ -847,16 +895,17 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     // MMA warp waiting 14 % of its time for an accumulator (the two epilogue groups are ~75 % busy, so their jitter reaches it)
     static const int nbuf_force = getenv("CHAP_TC_NBUF") ? atoi(getenv("CHAP_TC_NBUF")) : 0;
     p.n_buf = p.nt <= 64 ? 4 : (p.nt <= 128 ? 2 : 1);
+    if (p.kxn && p.nt > 16) p.n_buf = 2;                                  // three column groups per accumulator: 2 x 96 columns for nt = 32
     if ((nbuf_force == 1 || nbuf_force == 2 || nbuf_force == 4) && nbuf_force * p.nt <= 256) p.n_buf = nbuf_force;
     p.n_buf_lg = p.n_buf == 4 ? 2 : (p.n_buf == 2 ? 1 : 0);
-    p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * p.nt) p.tmem_cols *= 2;
+    p.tmem_cols = 32; while (p.tmem_cols < p.n_buf * (p.kxn ? 3 : 1) * p.nt) p.tmem_cols *= 2;
     p.b_box_bytes = (uint32_t)p.nt * p.kc * 4u;
     p.b_area_bytes = (uint32_t)p.taps * p.kchunks * p.b_box_bytes;
     // split-operand 3xTF32 (chap_set_conv_precision): every A stage and every weight box exists twice (hi / lo halves)
     const int pmc = g_precise_max_c.load(std::memory_order_relaxed);
     p.precise = (pmc > 0 && (g.cin > g.cout ? g.cin : g.cout) <= pmc) ? 1 : 0;
     const uint32_t dup = p.precise ? 2u : 1u;
-    p.b_resident = dup * p.b_area_bytes <= 40u * 1024u && getenv("CHAP_NO_RESIDENT_B") == nullptr;
+    p.b_resident = (dup * p.b_area_bytes <= 40u * 1024u || p.kxn) && getenv("CHAP_NO_RESIDENT_B") == nullptr;
     // Super tiles for the thin row-reuse layers (the conditions of the lean thin2d loops, known at this point).  MEASURED (round 2,
     // tools/conv_bench.py, same box): correct, but NOT faster -- 16 -> 16 @ 12x256^2 forward 44.0 us with, 42.1 us without; 3D 16 -> 16 @
     // 2x112x112x80 173 vs 150 us (4 ring stages of 20 KB instead of 6 of 13 KB).  Halving the TMA issues and ring round trips per tile
@@ -928,6 +977,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     p.thin2d = (p.mode == 0 && p.reuse && p.kchunks == 1 && p.cps == 1 && p.b_resident && p.n_buf >= 2 && stages >= 2 &&
                 TC_DBG_HOST_OFF && getenv("CHAP_TC_NO_THIN2D") == nullptr) ? 1 : 0;
     CHAP_REQUIRE(!p.sup || p.thin2d, CHAP_ERR_BAD_ARG, "tc_conv: super tiles need the thin-layer loops (stages %d, cps %d)", stages, p.cps);
+    CHAP_REQUIRE(!p.kxn || p.thin2d, CHAP_ERR_BAD_ARG, "tc_conv: the kx-in-N tile needs the thin-layer loops (stages %d, cps %d, resident %d)", stages, p.cps, p.b_resident);
     p.stages = stages;
     p.a_lo_off = (uint32_t)stages * p.a_stage_bytes;
     p.b_lo_off = p.b_resident ? p.b_area_bytes : (uint32_t)stages * p.b_stage_bytes;
