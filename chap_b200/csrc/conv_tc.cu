@@ -860,7 +860,7 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
         }
         if (best_tw) { p.reuse = 1; p.tw = best_tw; p.th = 128 / best_tw; p.td = 1; }
     }
-    // kx-in-N (see TcParams::kxn): thin layers (one k chunk, N <= 32), plain output, training kernels.  MEASURED on what bounds those
+    // kx-in-N (see TcParams::kxn): thin layers (one k chunk, N <= 32), plain output, training and inference kernels.  MEASURED on what bounds those
     // layers: the tensor pipe spends ~36 cycles per M128 x K8 TF32 MMA whatever N is (the ncu source view shows the issuing warp
     // stalled on the MMA queue 54 % of its time), so 18 (2D) / 54 (3D) MMAs of N = 16 per tile become 6 / 18 of N = 48.
     // Result (tools/conv_bench.py): 3D 16 -> 16 @ 2x112x112x80 forward 149 -> 105 us, data gradient 148 -> 88 us.  In 2D the 18 MMAs
@@ -870,9 +870,11 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     // MMA stream of the kx-in-N tile more than pays for (CHAP_TC_KXN_RES overrides the cap in KB)
     static const size_t kxn_res_cap = (getenv("CHAP_TC_KXN_RES") ? (size_t)atoi(getenv("CHAP_TC_KXN_RES")) : 112u) * 1024u;
     p.step_w = p.tw;
-    p.kxn = (p.reuse && p.mode == 0 && K <= 32 && N <= 32 && !out_b && !epi && p.W >= 32 && p.H >= 6 && TC_DBG_HOST_OFF &&
+    p.kxn = (p.reuse && p.mode == 0 && K <= 32 && N <= 32 && !out_b && p.W >= 32 && p.H >= 6 && TC_DBG_HOST_OFF &&
              (g.nd == 3 || getenv("CHAP_TC_KXN2D") != nullptr) &&
-             (size_t)p.taps * N * K * 4 <= kxn_res_cap && getenv("CHAP_NO_RESIDENT_B") == nullptr &&        // weights resident (thin2d loops)
+             // weights resident (thin2d loops).  Inference epilogue: only while two CTAs per SM still fit (32 -> 32 @ 4x56x56x40 with
+             // one CTA per SM: 116 us against 101 us for the generic two-CTA path; 16 -> 16 @ 4x112x112x80: 213 against 284 us)
+             (size_t)p.taps * N * K * 4 <= (epi ? 40u * 1024u : kxn_res_cap) && getenv("CHAP_NO_RESIDENT_B") == nullptr &&
              g_precise_max_c.load(std::memory_order_relaxed) == 0 && getenv("CHAP_TC_NO_KXN") == nullptr && getenv("CHAP_TC_NO_THIN2D") == nullptr &&
              getenv("CHAP_TC_SUPER") == nullptr) ? 1 : 0;
     if (p.kxn) { p.tw = 32; p.th = 4; p.td = 1; p.step_w = 30; }
