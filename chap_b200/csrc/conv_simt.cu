@@ -449,6 +449,76 @@ thin_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restric
     }
 }
 
+// Weight gradient of the Cin = 1 stems (1 -> 16): dW[co][tap] = sum_p x[p + tap] * dy[p, co].  Four lanes share a pixel, each owning four
+// output channels: the dy row of a pixel is ONE coalesced 64-byte read of the quad, the nine x taps are broadcast loads, and a thread keeps
+// 9 x 4 partial sums (thin_wgrad_kernel<1, 16> kept 144 per thread at 128 threads per block: 100 us for a 100 MB dy in 2D, 261 us in 3D).
+// grid = (pixel slices, kz planes, Cout / 16); 32-bit pixel arithmetic (rows < 2^31, checked by the host).
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(SimtOp op, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int64_t sn) {
+    pdl_enter();
+    __shared__ float red[9 * 16];
+    const int kz = blockIdx.y, c0 = blockIdx.z * 16;
+    const int q = threadIdx.x & 3;                         // channel quad of this lane
+    float acc[9][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f; }
+    if (threadIdx.x < 144) red[threadIdx.x] = 0.f;
+    __syncthreads();
+    const uint32_t rows = (uint32_t)op.out_rows, W = (uint32_t)op.oW, H = (uint32_t)op.oH, D = (uint32_t)op.oD;
+    // four pixels per trip with all four dy reads issued first: one 64-byte row in flight per quad is far too little memory-level
+    // parallelism (91 us for a 100 MB dy); the loop is otherwise a chain of dependent DRAM round trips
+    constexpr int U = 4;
+    const uint32_t stride = gridDim.x * 64u;
+    for (uint32_t r0 = blockIdx.x * 64u + (threadIdx.x >> 2); r0 < rows; r0 += U * stride) {
+        float4 g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            g[u] = r < rows ? __ldg(reinterpret_cast<const float4*>(dy + (int64_t)r * op.N + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = r0 + u * stride;
+            if (r >= rows) break;
+            uint32_t m = r;
+            const int w = (int)(m % W); m /= W;
+            const int h = (int)(m % H); m /= H;
+            const int d = (int)(m % D); const uint32_t bn = m / D;
+            const int id = op.nd == 3 ? d + kz - 1 : 0;
+            if (id < 0 || id >= op.iD) continue;
+            const float* xb = x + ((int64_t)bn * op.iD + id) * op.iH * op.iW;
+            float xv[9];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ih = h + ky - 1, iw = w + kx - 1;
+                    const bool ok = ih >= 0 && ih < op.iH && iw >= 0 && iw < op.iW;
+                    xv[ky * 3 + kx] = ok ? __ldg(xb + ih * op.iW + iw) : 0.f;
+                }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                acc[t][0] = fmaf(xv[t], g[u].x, acc[t][0]); acc[t][1] = fmaf(xv[t], g[u].y, acc[t][1]);
+                acc[t][2] = fmaf(xv[t], g[u].z, acc[t][2]); acc[t][3] = fmaf(xv[t], g[u].w, acc[t][3]);
+            }
+        }
+    }
+    // lanes with the same channel quad (lane & 3) are combined over the xor offsets 4, 8, 16; lanes 0..3 then hold the warp's sums
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = acc[t][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((threadIdx.x & 31) < 4) atomicAdd(&red[t * 16 + q * 4 + c], v);
+        }
+    __syncthreads();
+    if (threadIdx.x < 144) {
+        const int t = threadIdx.x / 16, c = threadIdx.x % 16;
+        atomicAdd(dw + (int64_t)(c0 + c) * sn + (kz * 9 + t), red[threadIdx.x]);
+    }
+}
+
 // Weight gradient of the 1x1(x1) class heads (Cin = 16, Cout <= 4, e.g. the V-Net's 16 -> 2 output conv):
 //   dW[co][ci] = sum_p dy[p, co] * x[p, ci]  -- K * N <= 64 sums kept in registers over a grid-stride loop, one pass over x and dy
 // (the generic kernel re-reads the operands per 16 x 16 weight tile and spent 465 us on a 4 x 112 x 112 x 80 batch).
@@ -515,7 +585,14 @@ int simt_wgrad(const SimtOp& op, const float* a, const float* b, float* dw, int6
         const int cap = (kNumSMs * 6) / (planes * zdim);
         if (slices > cap) slices = cap < 1 ? 1 : cap;
         dim3 grid((unsigned)slices, (unsigned)planes, (unsigned)zdim);
-        if (stem) launch_k(thin_wgrad_kernel<1, 16>, grid, 128, 0, st, op, a, b, dw, sk, sn);
+        if (stem && op.out_rows < 0x7FFFFFFFll && getenv("CHAP_STEM_WGRAD_OLD") == nullptr) {
+            int sl = (int)((op.out_rows + 64 * 16 - 1) / (64 * 16));
+            // every block ends with 144 atomics on the SAME 144 addresses: the block count is what the tail costs (1184 blocks: ~60 us)
+            static const int per_sm = getenv("CHAP_STEM_WG_BLOCKS") ? atoi(getenv("CHAP_STEM_WG_BLOCKS")) : 2;
+            const int cap2 = (kNumSMs * per_sm) / (planes * zdim);
+            if (sl > cap2) sl = cap2 < 1 ? 1 : cap2;
+            launch_k(stem_wgrad_kernel, dim3((unsigned)sl, (unsigned)planes, (unsigned)zdim), 256, 0, st, op, a, b, dw, sn);
+        } else if (stem) launch_k(thin_wgrad_kernel<1, 16>, grid, 128, 0, st, op, a, b, dw, sk, sn);
         else launch_k(thin_wgrad_kernel<4, 4>, grid, 128, 0, st, op, a, b, dw, sk, sn);
         return launched("thin_wgrad_kernel");
     }
