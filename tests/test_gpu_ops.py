@@ -97,6 +97,10 @@ LARGE_CONV_CASES = [
     ("k1", 2, 9, (64, 64), 64, 32), ("k3", 2, 2, (72, 72), 128, 128), ("k3", 2, 4, (64, 80), 16, 4), ("k3", 2, 12, (128, 128), 32, 64),
     ("up2", 2, 6, (64, 72), 32, 16), ("up2", 2, 3, (32, 32), 256, 128), ("up2", 3, 2, (12, 14, 10), 32, 16), ("up2", 2, 12, (128, 128), 32, 16),
     ("down2", 3, 2, (24, 40, 48), 16, 32), ("down2", 2, 6, (64, 72), 32, 64), ("down2", 3, 2, (8, 12, 10), 128, 256), ("up2", 3, 1, (14, 14, 10), 128, 64),
+    # round 2: 3D kx-in-N convolution tile (one k chunk, N <= 32, W >= 32: tiles of 30 output columns, partial last tile; 32 -> 32 keeps 108 KB of
+    # weights resident with one CTA per SM) and the taps-in-N weight gradient (x channel groups split over CTAs when 3 * cout * groups > 512 columns)
+    ("k3", 3, 2, (10, 12, 36), 32, 32), ("k3", 3, 1, (8, 10, 33), 16, 32), ("k3", 3, 1, (6, 9, 61), 32, 16), ("k3", 3, 3, (5, 6, 32), 16, 16),
+    ("k3", 2, 2, (40, 48), 128, 64), ("k3", 2, 3, (24, 40), 64, 64), ("k3", 2, 2, (32, 32), 256, 32), ("k3", 2, 5, (56, 40), 64, 32),
 ]
 
 
@@ -264,7 +268,9 @@ def test_maxpool_upsample_concat():
     out = ops.maxpool2(xg)
     (gx,) = torch.autograd.grad(out, xg, g.float().to(DEV))
     assert max_err(out, ref) < 1e-6 and max_err(gx, gx_ref) < 1e-6
-    for nd, shape in ((2, (2, 8, 5, 7)), (3, (2, 4, 3, 5, 4)), (3, (1, 8, 1, 2, 3)), (2, (1, 4, 1, 1))):
+    # (the larger shapes have several compact pixel tiles per dimension with partial tiles at the borders: the vector kernels' tile walk)
+    for nd, shape in ((2, (2, 8, 5, 7)), (3, (2, 4, 3, 5, 4)), (3, (1, 8, 1, 2, 3)), (2, (1, 4, 1, 1)), (2, (3, 16, 21, 19)), (3, (2, 16, 7, 9, 5)),
+                      (3, (1, 64, 3, 5, 6)), (2, (2, 256, 6, 5)), (2, (1, 6, 4, 3))):
         x = torch.randn(shape, dtype=torch.float64, requires_grad=True)
         ref = F.interpolate(x, scale_factor=2, mode="bilinear" if nd == 2 else "trilinear", align_corners=True)
         g = torch.randn_like(ref)

@@ -79,3 +79,26 @@ def test_zoom_index_tables_reproduce_scipy_zoom_order0():
         iy, ix = zoom_index(h, oh), zoom_index(w, ow)
         got = np.where((iy[:, None] < 0) | (ix[None, :] < 0), np.float32(0), a[np.maximum(iy, 0)][:, np.maximum(ix, 0)])
         assert np.array_equal(ref, got), (h, w, hh, ww)
+
+
+def test_generated_dropout_description_is_host_side_bookkeeping_only():
+    """ops.dropout_rng(p, C): the (p, seed, subsequence, epoch) description handed to chap_bn_act_{fwd,bwd}_rng -- None whenever the
+    generated form does not apply (inactive dropout, channel counts outside the fixed-group kernels, switched off), a fresh
+    subsequence per call, the torch seed as key, the registered device epoch tensor passed through."""
+    from chap_b200 import ops
+    torch.manual_seed(1234)
+    assert ops.dropout_rng(0.0, 16) is None and ops.dropout_rng(1.0, 16) is None
+    assert ops.dropout_rng(0.3, 6) is None and ops.dropout_rng(0.3, 40) is None            # c % 4 != 0 / 256 % (c / 4) != 0
+    a, b = ops.dropout_rng(0.05, 16), ops.dropout_rng(0.5, 256)
+    assert a[0] == 0.05 and b[0] == 0.5 and a[1] == b[1] == 1234 and b[2] == a[2] + 1 and a[3] is None
+    marker = torch.zeros(1, dtype=torch.int64)
+    ops.set_dropout_epoch(marker)
+    try:
+        assert ops.dropout_rng(0.1, 32)[3] is marker
+    finally:
+        ops.set_dropout_epoch(None)
+    ops.set_generated_dropout(False)
+    try:
+        assert ops.dropout_rng(0.1, 32) is None
+    finally:
+        ops.set_generated_dropout(True)
