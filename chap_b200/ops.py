@@ -512,7 +512,10 @@ def dropout_rng(p, c):
     if not _state.get("drop_rng", True) or not (0.0 < p < 1.0) or c % 4 != 0 or 256 % (c // 4) != 0:
         return None
     _state["drop_calls"] = _state.get("drop_calls", 0) + 1
-    return (p, torch.initial_seed(), _state["drop_calls"], _state.get("drop_epoch"))
+    seed = torch.initial_seed()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed += 0x9E3779B97F4A7C15 * torch.distributed.get_rank()      # data-parallel ranks draw different masks from the same torch seed
+    return (p, seed, _state["drop_calls"], _state.get("drop_epoch"))
 
 
 def bn_act(y, bn, slope, sums=None, residual=None, drop_nc=None, drop_el=None, drop_rng=None):
