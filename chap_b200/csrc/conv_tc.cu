@@ -622,6 +622,24 @@ __device__ __forceinline__ void conv_tc_kernel_body(const CUtensorMap& tmA, cons
             int c0 = c_begin;
             if (p.kxn) {
                 // columns [kx][nt]: out[x] = D0[x - 1] + D1[x] + D2[x + 1]; this warp is one image row of the tile, lane = x
+                if (p.kxn == 2) {
+                    // one round trip: all three column groups of a 16-column chunk in flight together (48 registers)
+                    uint32_t rc[16];
+                    for (; c0 < c_end; c0 += 16) {
+                        tc_ld16_issue(t_addr + (uint32_t)c0, ra);
+                        tc_ld16_issue(t_addr + (uint32_t)(p.nt + c0), rb);
+                        tc_ld16_issue(t_addr + (uint32_t)(2 * p.nt + c0), rc);
+                        tc_ld16_fence(ra); tc_ld16_fence(rb); tc_ld16_fence(rc);
+                        if (c0 + 16 >= c_end) release();
+#pragma unroll
+                        for (int j4 = 0; j4 < 16; ++j4)
+                            rb[j4] = __float_as_uint(__uint_as_float(__shfl_up_sync(0xffffffffu, ra[j4], 1)) + __uint_as_float(rb[j4]) +
+                                                     __uint_as_float(__shfl_down_sync(0xffffffffu, rc[j4], 1)));
+                        process(rb, c0);
+                    }
+                    if (threadIdx.x == 64) { if (jj == 0) TC_TRACE(4); TC_TRACE(5); }
+                    continue;
+                }
                 for (; c0 < c_end; c0 += 16) {
                     tc_ld16_issue(t_addr + (uint32_t)c0, ra);
                     tc_ld16_issue(t_addr + (uint32_t)(p.nt + c0), rb);
@@ -865,19 +883,26 @@ int tc_conv(const Geom& g, bool dgrad, const float* in, const float* wp, const f
     // stalled on the MMA queue 54 % of its time), so 18 (2D) / 54 (3D) MMAs of N = 16 per tile become 6 / 18 of N = 48.
     // Result (tools/conv_bench.py): 3D 16 -> 16 @ 2x112x112x80 forward 149 -> 105 us, data gradient 148 -> 88 us.  In 2D the 18 MMAs
     // were not the only bound: with 12 % more tiles (30 of 32 columns useful) and three TMEM reads + 32 shuffles per tile in the
-    // epilogue the layer gets SLOWER (16 -> 16 @ 12x256^2: 40.3 -> 43.5 us), so 2D keeps the three-box tile (CHAP_TC_KXN2D=1 to try).
+    // epilogue the layer gets SLOWER (16 -> 16 @ 12x256^2: 40.3 -> 43.5 us), so the 16-channel 2D layers keep the three-box tile (CHAP_TC_KXN2D).
     // resident weights up to 112 KB for these layers (3D 32 -> 32: 27 taps x 4 KB = 108 KB): one CTA per SM then, which the shorter
     // MMA stream of the kx-in-N tile more than pays for (CHAP_TC_KXN_RES overrides the cap in KB)
+    // 2D: 0 off, 1 all thin layers, 32 (default): the layers with a 32-channel operand -- with the one-round-trip epilogue those gain 1-2 us
+    // per launch (32 -> 32 @ 12x128^2: 33.3 -> 31.1 / 27.3 -> 26.1 us), the 16 -> 16 layers stay on the three-box tile (41.9 vs 43.0 us);
+    // replayed 2D iteration, same box: 12.553 (off) / 12.489 (32) / 12.48-12.53 (all) ms
+    static const int kxn2d = getenv("CHAP_TC_KXN2D") ? atoi(getenv("CHAP_TC_KXN2D")) : 32;
     static const size_t kxn_res_cap = (getenv("CHAP_TC_KXN_RES") ? (size_t)atoi(getenv("CHAP_TC_KXN_RES")) : 112u) * 1024u;
     p.step_w = p.tw;
     p.kxn = (p.reuse && p.mode == 0 && K <= 32 && N <= 32 && !out_b && p.W >= 32 && p.H >= 6 && TC_DBG_HOST_OFF &&
-             (g.nd == 3 || getenv("CHAP_TC_KXN2D") != nullptr) &&
+             (g.nd == 3 || kxn2d == 1 || (kxn2d == 32 && (K == 32 || N == 32))) &&
              // weights resident (thin2d loops).  Inference epilogue: only while two CTAs per SM still fit (32 -> 32 @ 4x56x56x40 with
              // one CTA per SM: 116 us against 101 us for the generic two-CTA path; 16 -> 16 @ 4x112x112x80: 213 against 284 us)
              (size_t)p.taps * N * K * 4 <= (epi ? 40u * 1024u : kxn_res_cap) && getenv("CHAP_NO_RESIDENT_B") == nullptr &&
              g_precise_max_c.load(std::memory_order_relaxed) == 0 && getenv("CHAP_TC_NO_KXN") == nullptr && getenv("CHAP_TC_NO_THIN2D") == nullptr &&
              getenv("CHAP_TC_SUPER") == nullptr) ? 1 : 0;
     if (p.kxn) { p.tw = 32; p.th = 4; p.td = 1; p.step_w = 30; }
+    // epilogue form: 2 = all three column groups of a chunk in ONE TMEM round trip (48 registers; default: 1-4 % faster than the two
+    // round trips of form 1 on every layer measured, CHAP_TC_KXN_2RT=1 restores those)
+    if (p.kxn && getenv("CHAP_TC_KXN_2RT") == nullptr) p.kxn = 2;
     p.tiles_w = (p.W + p.step_w - 1) / p.step_w; p.tiles_h = (p.H + p.th - 1) / p.th; p.tiles_d = (p.D + p.td - 1) / p.td;
     p.kc = K == 16 ? 16 : 32; p.kchunks = K / p.kc;
     p.n_total = N; p.nt = N > 256 ? 256 : N;
