@@ -35,6 +35,8 @@ struct PLevel {
     int c, tpr;
     int bps_chan, bps_rows;          // blocks per sample in the channel-norm phase / the row phases
     int blk0_chan, blk0_rows;        // first block of this level in the flattened grids
+    int bps_stat, blk0_stat;         // the same for the statistics pass of the two-pass scheme (~16 rows per thread: its fold + 2c double
+                                     // atomics per block are a fixed cost that 2 rows per thread did not amortise)
 };
 constexpr int kMaxLevels = 8;
 struct PBatch { PLevel lv[kMaxLevels]; int n_levels, n; float eps, gs; };
@@ -213,9 +215,9 @@ perturb_stats_all_kernel(const __grid_constant__ PBatch b) {
     __shared__ float fold[2][8][256];              // [S | Q][warp][channel]: warp totals (c <= 256 on this path)
     __shared__ float redz[8];
     int l = 0;
-    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_chan) ++l;
+    while (l + 1 < b.n_levels && (int)blockIdx.x >= b.lv[l + 1].blk0_stat) ++l;
     const PLevel& L = b.lv[l];
-    const int rel = (int)blockIdx.x - L.blk0_chan, bx = rel % L.bps_chan, nbx = L.bps_chan, n = rel / L.bps_chan;
+    const int rel = (int)blockIdx.x - L.blk0_stat, bx = rel % L.bps_stat, nbx = L.bps_stat, n = rel / L.bps_stat;
     const int c = L.c, tpr = L.tpr, cpl = c / tpr, rpb = 256 / tpr;
     const int lane = threadIdx.x % tpr, rl = threadIdx.x / tpr;
     const float* gb = L.g + (int64_t)n * L.rows * c;
@@ -457,7 +459,7 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
     static thread_local PBatch b;
     b.n_levels = n_levels; b.n = n; b.eps = eps; b.gs = g_scale;
     double* ws = workspace;
-    int blocks_chan = 0, blocks_rows = 0;
+    int blocks_chan = 0, blocks_rows = 0, blocks_stat = 0;
     double alg_bytes = 0.0;
     bool two_pass_ok = true;
     // blocks per (level, sample): enough to fill the machine a few times over across ALL levels of the launch
@@ -488,18 +490,22 @@ extern "C" int chap_perturb_fwd(const chap_level* levels, int32_t n_levels, int3
         int b1 = (int)((L.rows + rpb1 * 8 - 1) / (rpb1 * 8));
         if (b1 > share) b1 = share;
         if (b1 < 1) b1 = 1;
-        P.bps_rows = bps; P.bps_chan = b1;
-        P.blk0_rows = blocks_rows; P.blk0_chan = blocks_chan;
-        blocks_rows += bps * n; blocks_chan += b1 * n;
+        static const int stat_rows = getenv("CHAP_PERTURB_STAT_ROWS") ? atoi(getenv("CHAP_PERTURB_STAT_ROWS")) : 16;      // measured: 2 rows 130.6, 8 rows 124.9, 16 rows 121.3, 32 rows 142.9 us per call
+        int b2 = (int)((L.rows + (int64_t)rpb * stat_rows - 1) / ((int64_t)rpb * stat_rows));
+        if (b2 > share) b2 = share;
+        if (b2 < 1) b2 = 1;
+        P.bps_rows = bps; P.bps_chan = b1; P.bps_stat = b2;
+        P.blk0_rows = blocks_rows; P.blk0_chan = blocks_chan; P.blk0_stat = blocks_stat;
+        blocks_rows += bps * n; blocks_chan += b1 * n; blocks_stat += b2 * n;
         alg_bytes += 12.0 * (double)n * L.rows * L.c;
     }
     static const bool three_phase = getenv("CHAP_PERTURB_3PHASE") != nullptr;
     if (two_pass_ok && !three_phase) {
         switch (mode) {
-            case CHAP_PERTURB_SAMPLE: return run_two_pass<CHAP_PERTURB_SAMPLE>(b, blocks_chan, blocks_rows, alg_bytes, st);
-            case CHAP_PERTURB_CHANNEL: return run_two_pass<CHAP_PERTURB_CHANNEL>(b, blocks_chan, blocks_rows, alg_bytes, st);
-            case CHAP_PERTURB_SPATIAL: return run_two_pass<CHAP_PERTURB_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
-            default: return run_two_pass<CHAP_PERTURB_CHANNEL_SPATIAL>(b, blocks_chan, blocks_rows, alg_bytes, st);
+            case CHAP_PERTURB_SAMPLE: return run_two_pass<CHAP_PERTURB_SAMPLE>(b, blocks_stat, blocks_rows, alg_bytes, st);
+            case CHAP_PERTURB_CHANNEL: return run_two_pass<CHAP_PERTURB_CHANNEL>(b, blocks_stat, blocks_rows, alg_bytes, st);
+            case CHAP_PERTURB_SPATIAL: return run_two_pass<CHAP_PERTURB_SPATIAL>(b, blocks_stat, blocks_rows, alg_bytes, st);
+            default: return run_two_pass<CHAP_PERTURB_CHANNEL_SPATIAL>(b, blocks_stat, blocks_rows, alg_bytes, st);
         }
     }
     switch (mode) {
