@@ -15,7 +15,8 @@
 // so ONE statistics pass (S, Q, Z) and ONE apply pass remain -- the minimum for a computation with one dependent grid-wide
 // reduction: 16 B / element touched (g twice, f, out) for 12 B algorithmic, and every pass runs for ALL levels and samples in ONE
 // launch through a descriptor table (round 1: 3 launches + a zero-fill per level = 16 per call; now 2 + 1).
-// Measured, all five 2D levels of 12 samples (97 MB of g; tools/perturb_bench.py): three-phase 137.4 us, two-pass 129.0 us
+// Measured, all five 2D levels of 12 samples (97 MB of g; tools/perturb_bench.py): three-phase 137.4 us, two-pass 129.0 us (121.3 us once the
+// statistics pass got its own grid of ~16 rows per thread)
 // (statistics 45 us + apply 69 us = 4.2 TB/s over its 12 B / element); 3D b2: 222 -> 199 us.  The statistics pass keeps <= 16
 // channel accumulators x (S, Q) per thread and folds them with warp shuffles (a shared-memory fold over the row lanes made it
 // SLOWER than three-phase: 165 us).  CHAP_PERTURB_3PHASE=1 selects the three-phase path (also the fallback for c > 256).
