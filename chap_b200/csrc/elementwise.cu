@@ -550,6 +550,49 @@ maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, i
     }
 }
 
+// Vector forms (c % 4 == 0, 16-byte aligned, < 2^31 vectors): 128-bit loads / stores and 32-bit index arithmetic.  The generic kernels above issue
+// four 32-bit accesses per tap and a 64-bit div / mod chain per vector -- more instructions than a streaming kernel of this size can hide.
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_v4_kernel(const float* __restrict__ x, int h, int w, int cg, uint32_t total_vec, float* __restrict__ y) {
+    pdl_enter();
+    const uint32_t oh = (uint32_t)h / 2, ow = (uint32_t)w / 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+        const uint32_t g = i % (uint32_t)cg; uint32_t r = i / (uint32_t)cg;
+        const uint32_t xo = r % ow; r /= ow; const uint32_t yo = r % oh; const uint32_t n = r / oh;
+        const float4* p = x4 + (((int64_t)n * h + 2 * yo) * w + 2 * xo) * cg + g;
+        const float4 a = ldg_stream(p), b = ldg_stream(p + cg), c_ = ldg_stream(p + (int64_t)w * cg), d = ldg_stream(p + (int64_t)w * cg + cg);
+        y4[i] = make_float4(fmaxf(fmaxf(fmaxf(a.x, b.x), c_.x), d.x), fmaxf(fmaxf(fmaxf(a.y, b.y), c_.y), d.y),
+                            fmaxf(fmaxf(fmaxf(a.z, b.z), c_.z), d.z), fmaxf(fmaxf(fmaxf(a.w, b.w), c_.w), d.w));
+    }
+}
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ dy, int h, int w, int cg, uint32_t total_vec, float* __restrict__ dx) {
+    pdl_enter();
+    const uint32_t oh = (uint32_t)h / 2, ow = (uint32_t)w / 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* g4 = reinterpret_cast<const float4*>(dy);
+    float4* o4 = reinterpret_cast<float4*>(dx);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+        const uint32_t g = i % (uint32_t)cg; uint32_t r = i / (uint32_t)cg;
+        const uint32_t xo = r % ow; r /= ow; const uint32_t yo = r % oh; const uint32_t n = r / oh;
+        const int64_t base = (((int64_t)n * h + 2 * yo) * w + 2 * xo) * cg + g;
+        const int64_t off[4] = {0, (int64_t)cg, (int64_t)w * cg, (int64_t)w * cg + cg};
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ldg_stream(x4 + base + off[j]);
+        const float4 gy = ldg_stream(g4 + i);
+        // first maximum wins (strict >), like the scalar kernel and torch's max_pool2d backward
+        auto pick = [](float a, float b, float c_, float d) { int best = 0; float m = a; if (b > m) { m = b; best = 1; } if (c_ > m) { m = c_; best = 2; } if (d > m) best = 3; return best; };
+        const int bx = pick(v[0].x, v[1].x, v[2].x, v[3].x), by = pick(v[0].y, v[1].y, v[2].y, v[3].y);
+        const int bz = pick(v[0].z, v[1].z, v[2].z, v[3].z), bw = pick(v[0].w, v[1].w, v[2].w, v[3].w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o4[base + off[j]] = make_float4(bx == j ? gy.x : 0.f, by == j ? gy.y : 0.f, bz == j ? gy.z : 0.f, bw == j ? gy.w : 0.f);
+    }
+}
+
 // ------------------------------------------------------------------ x2 upsample, align_corners=True
 __device__ __forceinline__ void lerp_src(int o, int in, int out, int& i0, int& i1, float& l1) {
     float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
@@ -758,14 +801,15 @@ concat_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t 
         out[i] = ch < ca ? a[r * ca + ch] : b[r * cb + ch - ca];
     }
 }
+template <typename I>         // I = uint32_t when rows * (ca + cb) / 4 < 2^31 (one 32-bit division per vector instead of a 64-bit div + mod)
 __global__ void __launch_bounds__(256)
 concat4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int64_t rows, int ca4, int cb4, float4* __restrict__ out) {
     pdl_enter();
-    const int ct = ca4 + cb4;
-    const int64_t total = rows * ct;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / ct; int ch = (int)(i % ct);
-        out[i] = ch < ca4 ? ldg_stream(a + r * ca4 + ch) : ldg_stream(b + r * cb4 + ch - ca4);
+    const I ct = (I)(ca4 + cb4);
+    const I total = (I)(rows * (ca4 + cb4));
+    for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+        const I r = i / ct; const int ch = (int)(i - r * ct);
+        out[i] = ch < ca4 ? ldg_stream(a + (int64_t)r * ca4 + ch) : ldg_stream(b + (int64_t)r * cb4 + ch - ca4);
     }
 }
 __global__ void __launch_bounds__(256)
@@ -1032,7 +1076,9 @@ extern "C" int chap_maxpool2_fwd(const float* x, int32_t n, int32_t h, int32_t w
     KernelTimer timer_("maxpool2_fwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && y && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_fwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
-    if (c % 4 == 0) launch_k(maxpool2_fwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, h, w, c, total / 4, y);
+    if (c % 4 == 0 && aligned16(x) && aligned16(y) && total / 4 < 0x7FFFFFFFll)
+        launch_k(maxpool2_fwd_v4_kernel, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, h, w, c / 4, (uint32_t)(total / 4), y);
+    else if (c % 4 == 0) launch_k(maxpool2_fwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, h, w, c, total / 4, y);
     else launch_k(maxpool2_fwd_kernel<1>, grid_for(total, 256 * 2), 256, 0, S(stream), x, h, w, c, total, y);
     return launched("maxpool2_fwd_kernel");
 }
@@ -1041,7 +1087,9 @@ extern "C" int chap_maxpool2_bwd(const float* x, const float* dy, int32_t n, int
     KernelTimer timer_("maxpool2_bwd", 0.0, 0.0, S(stream));
     CHAP_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && h % 2 == 0 && w % 2 == 0, CHAP_ERR_BAD_ARG, "maxpool2_bwd: bad argument (h, w must be even)");
     const int64_t total = (int64_t)n * (h / 2) * (w / 2) * c;
-    if (c % 4 == 0) launch_k(maxpool2_bwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, dy, h, w, c, total / 4, dx);
+    if (c % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx) && total / 4 < 0x7FFFFFFFll)
+        launch_k(maxpool2_bwd_v4_kernel, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, dy, h, w, c / 4, (uint32_t)(total / 4), dx);
+    else if (c % 4 == 0) launch_k(maxpool2_bwd_kernel<4>, grid_for(total / 4, 256 * 2), 256, 0, S(stream), x, dy, h, w, c, total / 4, dx);
     else launch_k(maxpool2_bwd_kernel<1>, grid_for(total, 256 * 2), 256, 0, S(stream), x, dy, h, w, c, total, dx);
     return launched("maxpool2_bwd_kernel");
 }
@@ -1092,7 +1140,8 @@ extern "C" int chap_concat_channels(const float* a, const float* b, int64_t rows
     CHAP_REQUIRE(a && b && out && rows > 0 && ca > 0 && cb > 0, CHAP_ERR_BAD_ARG, "concat_channels: bad argument");
     const int64_t total = rows * (ca + cb);
     if (ca % 4 == 0 && cb % 4 == 0 && all16({a, b, out}))
-        launch_k(concat4_kernel, grid_for(total / 4, 256 * 4), 256, 0, S(stream), (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
+        if (total / 4 < 0x7FFFFFFFll) launch_k(concat4_kernel<uint32_t>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
+        else launch_k(concat4_kernel<int64_t>, grid_for(total / 4, 256 * 4), 256, 0, S(stream), (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)out);
     else
         launch_k(concat_kernel, grid_for(total, 256 * 4), 256, 0, S(stream), a, b, rows, ca, cb, out);
     return launched("concat_kernel");
